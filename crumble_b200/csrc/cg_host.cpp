@@ -1,0 +1,314 @@
+/*
+ * cg_host.cpp — host-side pieces of the C ABI that need no CUDA: option defaults and
+ * level presets, the libm-built lookup tables that are uploaded to the device, and the
+ * record batcher (decoded BAM records -> structure-of-arrays).
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <math.h>
+#include <float.h>
+#include "cg_pipeline.h"
+#include "cg_host.h"
+
+/* ---- parameters ------------------------------------------------------------------------ */
+extern "C" void cg_params_default(cg_params *p) {          /* snp_score.c:91-147, 2152-2192 */
+    memset(p, 0, sizeof(*p));
+    p->reduce_qual = 1; p->binary_qual = 0;
+    p->iSTR_mul = 1.0; p->iSTR_add = 2; p->sSTR_mul = 0.0; p->sSTR_add = 0;
+    p->qlow = 5; p->qcutoff = 25; p->qhigh = 40; p->qcap = 60;
+    p->min_mqual = 0;
+    p->min_qual_A = 0; p->min_indel_A = 50; p->min_discrep_A = 2.0;
+    p->min_qual_B = 70; p->min_indel_B = 125; p->min_discrep_B = 1.5;
+    p->indel_fract = 0.0;
+    p->clip_perc = 0.2; p->low_mqual_perc = 1.0; p->ins_len_perc = 1.0; p->over_depth = 999.0; p->indel_ov_perc = 0.0;
+    p->pblock = 8;
+    p->region_tid = -1; p->region_beg = 0; p->region_end = INT_MAX;
+}
+
+extern "C" int cg_params_level(cg_params *p, int level) {  /* snp_score.c:2380-2482 */
+    switch (level) {
+    case 9: case 8:
+        p->pblock = level == 9 ? 8 : 0;
+        p->min_qual_B = 70; p->min_indel_B = 125; p->min_discrep_B = 1.5;
+        p->low_mqual_perc = 1.0; p->ins_len_perc = 1.0; p->indel_ov_perc = 0.0; p->over_depth = 999.0;
+        p->sSTR_mul = 0.0; p->sSTR_add = 0; p->iSTR_mul = 1.0; p->iSTR_add = 2; p->min_mqual = 0;
+        return 0;
+    case 7:
+        p->pblock = 0;
+        p->min_qual_B = 75; p->min_indel_B = 150; p->min_discrep_B = 1.0;
+        p->low_mqual_perc = 1.0; p->ins_len_perc = 1.0; p->indel_ov_perc = 0.0; p->over_depth = 999.0;
+        p->sSTR_mul = 0.0; p->sSTR_add = 0; p->iSTR_mul = 1.1; p->iSTR_add = 2; p->min_mqual = 0;
+        return 0;
+    case 5: case 3: case 1:
+        p->pblock = 0;
+        p->min_qual_B = 75; p->min_indel_B = 150; p->min_discrep_B = 1.0;
+        p->low_mqual_perc = 0.5; p->ins_len_perc = 0.1; p->indel_ov_perc = 0.5; p->over_depth = 3.0;
+        p->sSTR_mul = level == 5 ? 0.0 : 1.0; p->sSTR_add = level == 1 ? 5 : 0;
+        p->iSTR_mul = level == 1 ? 2.0 : 1.1; p->iSTR_add = level == 1 ? 1 : 2;
+        p->min_mqual = level == 1 ? 5 : 0;
+        return 0;
+    default:
+        return CG_ERR_BAD_ARG;
+    }
+}
+
+extern "C" const char *cg_strerror(int code) {
+    switch (code) {
+    case CG_OK: return "ok";
+    case CG_ERR_NO_DEVICE: return "no usable CUDA device (the GPU path is mandatory; there is no CPU fallback)";
+    case CG_ERR_CUDA: return "CUDA error";
+    case CG_ERR_NOMEM: return "out of memory";
+    case CG_ERR_BAD_ARG: return "bad argument";
+    case CG_ERR_UNSORTED: return "input is not coordinate sorted";
+    case CG_ERR_UNSUPPORTED: return "option not supported by the device path";
+    case CG_ERR_OVERFLOW: return "internal device list overflow";
+    case CG_ERR_STATE: return "calls made out of order";
+    default: return "unknown error";
+    }
+}
+
+extern "C" int cg_abi_version(void) { return CG_ABI_VERSION; }
+
+/* Which option combinations the device path implements today. */
+int cg_params_check(const cg_params *p, const char **why) {
+    static const char *w_mul = "negative -i/-s STR multipliers";
+    static const char *w_soft = "-S (soft-clip quantisation)";
+    static const char *w_keepq = "-k/-K/-N/-y pbccs (preserved quality values)";
+    static const char *w_bed = "-R keep.bed";
+    if (p->iSTR_mul < 0 || p->sSTR_mul < 0) { if (why) *why = w_mul; return CG_ERR_UNSUPPORTED; }
+    if (p->softclip) { if (why) *why = w_soft; return CG_ERR_UNSUPPORTED; }
+    if (p->perfect_col) { if (why) *why = w_keepq; return CG_ERR_UNSUPPORTED; }
+    for (int i = 0; i < 256; i++) if (p->preserve_qual[i]) { if (why) *why = w_keepq; return CG_ERR_UNSUPPORTED; }
+    if (p->nbed) { if (why) *why = w_bed; return CG_ERR_UNSUPPORTED; }
+    return 0;
+}
+
+void cg_devparams_from(CgDevParams *d, const cg_params *p) {
+    memset(d, 0, sizeof(*d));
+    d->reduce_qual = p->reduce_qual; d->binary_qual = p->binary_qual;
+    d->iSTR_add = p->iSTR_add; d->sSTR_add = p->sSTR_add; d->iSTR_mul = p->iSTR_mul; d->sSTR_mul = p->sSTR_mul;
+    d->qlow = p->qlow; d->qhigh = p->qhigh; d->qcap = p->qcap;
+    d->min_mqual = p->min_mqual; d->indel_fract = p->indel_fract;
+    d->min_qual_A = p->min_qual_A; d->min_indel_A = p->min_indel_A; d->min_discrep_A = p->min_discrep_A;
+    d->min_qual_B = p->min_qual_B; d->min_indel_B = p->min_indel_B; d->min_discrep_B = p->min_discrep_B;
+    d->low_mqual_perc = p->low_mqual_perc; d->clip_perc = p->clip_perc; d->ins_len_perc = p->ins_len_perc;
+    d->over_depth = p->over_depth; d->indel_ov_perc = p->indel_ov_perc;
+    d->pblock = p->pblock; d->softclip = p->softclip; d->perfect_col = p->perfect_col;
+    d->region_tid = p->region_tid; d->region_beg = p->region_beg; d->region_end = p->region_end;
+    d->str_snp = (p->sSTR_add || p->sSTR_mul != 0.0);                   /* snp_score.c:1345 */
+    for (int i = 0; i < 256; i++) if (p->preserve_qual[i]) d->any_preserve_qual = 1;
+}
+
+/* ---- tables (host libm; never recomputed on the device) ----------------------------------- */
+static double host_fast_log2(double val, double c1, double c2) {       /* snp_score.c:506-518 */
+    union { double d; int64_t i; } u; u.d = val;
+    int64_t x = u.i;
+    const int log_2 = (int)((x >> 52) & 2047) - 1024;
+    x &= ~(2047LL << 52);
+    x += 1023LL << 52;
+    u.i = x; val = u.d;
+    val = (c1 * val + 2) * val - c2;
+    return val + log_2;
+}
+
+void cg_tables_init(CgTables *T, const cg_params *p) {
+    memset(T, 0, sizeof(*T));
+    const double p_het = 1e-6;                                          /* P_HET, snp_score.c:283 */
+    for (int i = -500; i <= 500; i++) T->e_tab[i + 500] = exp((double)i);            /* 381-382 */
+    for (int i = -500; i <= 500; i++) T->e_tab2[i + 500] = exp(i / 10.);             /* 383-384 */
+    double prior[25];
+    for (int i = 0; i < 25; i++) prior[i] = p_het / 20;                              /* 389-391 */
+    prior[0] = prior[6] = prior[12] = prior[18] = prior[24] = (1 - p_het) / 5;
+    static const int pidx[15] = { 0, 1, 2, 3, 4, 6, 7, 8, 9, 12, 13, 14, 18, 19, 24 };
+    for (int j = 0; j < 15; j++) {                                                   /* 393-407 */
+        int hom = (pidx[j] % 6) == 0;
+        T->lprior15[j] = hom ? log(prior[pidx[j]]) : log(prior[pidx[j]] * 2);
+    }
+    double pMM[101], p__[101], p_M[101];
+    for (int i = 1; i < 101; i++) {                                                  /* 412-413, 464-466 */
+        double prob = 1 - pow(10, -i / 10.0);
+        pMM[i] = log(prob / 5);
+        p__[i] = log((1 - prob) / 20);
+        p_M[i] = log((exp(pMM[i]) + exp(p__[i])) / 2);
+        /* STECH_SOLEXA: tech_undercall == 1.00, the *= chain at 470-474 is the identity */
+    }
+    pMM[0] = pMM[1]; p__[0] = p__[1]; p_M[0] = p_M[1];                               /* 478-480 */
+    double q2p[101], mqual_pow[256];
+    for (int i = 0; i <= 100; i++) q2p[i] = pow(10, -i / 10.0);                      /* 564-566 */
+    for (int i = 0; i < 255; i++) mqual_pow[i] = 1 - pow(10, -(i / 2 + .05) / 10.0); /* 568-572: integer i/2 */
+    mqual_pow[255] = mqual_pow[10];                                                  /* 574 */
+    for (int q = 0; q < 128; q++) {
+        int qq = q > 100 ? 100 : q;
+        T->MM[q] = pMM[qq] - p__[qq];                                                /* 644-646 */
+        T->_M[q] = p_M[qq] - p__[qq];
+        T->q2p[q] = q2p[qq];                                                         /* 649 */
+        T->omq2p[q] = 1 - q2p[qq];                                                   /* 651 */
+    }
+    T->min_e_exp = DBL_MIN_EXP * log(2) + 1;                                         /* 540 */
+    T->log_c1 = (double)(-1.0f / 3);                                                 /* 515 */
+    T->log_c2 = (double)(2.0f / 3);
+    for (int mq = 0; mq < 256; mq++)
+        for (int q = 0; q < 256; q++) {                                              /* 632-642 */
+            double _p = mqual_pow[q], _m = mqual_pow[mq];
+            uint8_t e = (uint8_t)(-3.0103 * host_fast_log2(1 - (_m * _p + (1 - _m) / 4), T->log_c1, T->log_c2));
+            if (e < 1) e = 1;
+            if (e > 100) e = 100;          /* the reference would index past its 101-entry tables here */
+            T->effB[(mq << 8) | q] = e;
+        }
+    for (int q = 0; q < 256; q++) { int e = q < 1 ? 1 : (q > 100 ? 100 : q); T->effA[q] = (uint8_t)e; }
+    for (int i = 0; i < 256; i++) {                                                  /* init_bins 234-247 */
+        int v = i < p->qcutoff ? p->qlow : p->qhigh;
+        if (p->preserve_qual[i] > 1) v = i;
+        T->bin2[i] = (uint8_t)v;
+        T->preserve_qual[i] = p->preserve_qual[i];
+    }
+}
+
+/* ---- batch builder ----------------------------------------------------------------------- */
+void *(*cg_pinned_alloc_hook)(size_t) = NULL;
+void (*cg_pinned_free_hook)(void *) = NULL;
+
+template <class T> struct vec {
+    T *p; size_t n, cap; int pinned;
+    void init(int pin) { p = NULL; n = cap = 0; pinned = pin; }
+    void release() {
+        if (!p) return;
+        if (pinned && cg_pinned_free_hook) cg_pinned_free_hook(p); else free(p);
+        p = NULL; n = cap = 0;
+    }
+    int reserve(size_t want) {
+        if (want <= cap) return 0;
+        size_t nc = cap ? cap : 1024;
+        while (nc < want) nc += nc >> 1;
+        T *np;
+        if (pinned && cg_pinned_alloc_hook) {
+            np = (T *)cg_pinned_alloc_hook(nc * sizeof(T));
+            if (!np) return -1;
+            if (p) { memcpy(np, p, n * sizeof(T)); cg_pinned_free_hook(p); }
+        } else {
+            np = (T *)realloc(p, nc * sizeof(T));
+            if (!np) return -1;
+        }
+        p = np; cap = nc;
+        return 0;
+    }
+};
+
+struct cg_batch_builder {
+    vec<int32_t> tid, pos, l_qseq, cigar_off; vec<uint16_t> flag, n_cigar; vec<uint8_t> mapq; vec<int64_t> off;
+    vec<uint32_t> cigar; vec<uint8_t> seq, qual;
+    int64_t last_key; int unsorted; int seen_unplaced;
+};
+
+extern "C" cg_batch_builder *cgb_create(int pinned) {
+    cg_batch_builder *b = (cg_batch_builder *)calloc(1, sizeof(*b));
+    if (!b) return NULL;
+    int pin = pinned && cg_pinned_alloc_hook;
+    b->tid.init(pin); b->pos.init(pin); b->l_qseq.init(pin); b->cigar_off.init(pin); b->flag.init(pin); b->n_cigar.init(pin);
+    b->mapq.init(pin); b->off.init(pin); b->cigar.init(pin); b->seq.init(pin); b->qual.init(pin);
+    b->last_key = INT64_MIN;
+    return b;
+}
+extern "C" void cgb_reset(cg_batch_builder *b) {
+    b->tid.n = b->pos.n = b->l_qseq.n = b->cigar_off.n = b->flag.n = b->n_cigar.n = b->mapq.n = b->off.n = 0;
+    b->cigar.n = b->seq.n = b->qual.n = 0;
+    b->last_key = INT64_MIN; b->unsorted = 0; b->seen_unplaced = 0;
+}
+extern "C" void cgb_destroy(cg_batch_builder *b) {
+    if (!b) return;
+    b->tid.release(); b->pos.release(); b->l_qseq.release(); b->cigar_off.release(); b->flag.release(); b->n_cigar.release();
+    b->mapq.release(); b->off.release(); b->cigar.release(); b->seq.release(); b->qual.release();
+    free(b);
+}
+
+extern "C" int cgb_add(cg_batch_builder *b, int32_t tid, int32_t pos, uint16_t flag, uint8_t mapq, int32_t l_qseq,
+                       uint32_t n_cigar, const uint32_t *cigar, const uint8_t *seq4, const uint8_t *qual) {
+    size_t i = b->tid.n;
+    if (n_cigar > 65535 || l_qseq < 0) return CG_ERR_BAD_ARG;
+    if (b->tid.reserve(i + 1) || b->pos.reserve(i + 1) || b->l_qseq.reserve(i + 1) || b->cigar_off.reserve(i + 1) ||
+        b->flag.reserve(i + 1) || b->n_cigar.reserve(i + 1) || b->mapq.reserve(i + 1) || b->off.reserve(i + 1)) return CG_ERR_NOMEM;
+    /* quality bytes padded to 8 so that off is 8-aligned and seq sits at off/2 */
+    size_t qoff = b->qual.n, qpad = ((size_t)l_qseq + 7) & ~(size_t)7;
+    if (b->qual.reserve(qoff + qpad + 8) || b->seq.reserve((qoff + qpad) / 2 + 8) || b->cigar.reserve(b->cigar.n + n_cigar + 1)) return CG_ERR_NOMEM;
+    memcpy(b->qual.p + qoff, qual, (size_t)l_qseq);
+    memset(b->qual.p + qoff + l_qseq, 0, qpad - (size_t)l_qseq);
+    size_t sbytes = ((size_t)l_qseq + 1) >> 1;
+    memcpy(b->seq.p + qoff / 2, seq4, sbytes);
+    memset(b->seq.p + qoff / 2 + sbytes, 0, qpad / 2 - sbytes);
+    memcpy(b->cigar.p + b->cigar.n, cigar, 4u * (size_t)n_cigar);
+    b->tid.p[i] = tid; b->pos.p[i] = pos; b->flag.p[i] = flag; b->mapq.p[i] = mapq; b->l_qseq.p[i] = l_qseq;
+    b->n_cigar.p[i] = (uint16_t)n_cigar; b->off.p[i] = (int64_t)qoff; b->cigar_off.p[i] = (int32_t)b->cigar.n;
+    b->qual.n = qoff + qpad; b->seq.n = (qoff + qpad) / 2; b->cigar.n += n_cigar;
+    b->tid.n = b->pos.n = b->l_qseq.n = b->cigar_off.n = b->flag.n = b->n_cigar.n = b->mapq.n = b->off.n = i + 1;
+    /* sortedness of what enters the pileup (htslib's pileup aborts on unsorted input) */
+    if (tid >= 0 && !(flag & 4)) {
+        int64_t key = cg_key(tid, pos);
+        if (key < b->last_key || b->seen_unplaced) b->unsorted = 1;
+        b->last_key = key;
+    } else if (tid < 0) b->seen_unplaced = 1;
+    return 0;
+}
+
+extern "C" int cgb_add_bam_stream(cg_batch_builder *b, const uint8_t *buf, size_t len) {
+    if (len < 12 || memcmp(buf, "BAM\1", 4)) return CG_ERR_BAD_ARG;
+    size_t p = 4; uint32_t lt, nref;
+    memcpy(&lt, buf + p, 4); p += 4 + lt;
+    if (p + 4 > len) return CG_ERR_BAD_ARG;
+    memcpy(&nref, buf + p, 4); p += 4;
+    for (uint32_t i = 0; i < nref; i++) { uint32_t ln; if (p + 4 > len) return CG_ERR_BAD_ARG; memcpy(&ln, buf + p, 4); p += 4 + ln + 4; }
+    while (p + 4 <= len) {
+        uint32_t bs; memcpy(&bs, buf + p, 4);
+        if (bs < 32 || p + 4 + bs > len) return CG_ERR_BAD_ARG;
+        const uint8_t *r = buf + p + 4;
+        int32_t tid, pos, lseq; memcpy(&tid, r, 4); memcpy(&pos, r + 4, 4); memcpy(&lseq, r + 16, 4);
+        uint8_t lname = r[8], mapq = r[9];
+        uint16_t ncig, flag; memcpy(&ncig, r + 12, 2); memcpy(&flag, r + 14, 2);
+        const uint8_t *cig = r + 32 + lname;
+        const uint8_t *seq = cig + 4u * ncig;
+        const uint8_t *qual = seq + ((lseq + 1) >> 1);
+        if ((size_t)(qual + lseq - r) > bs) return CG_ERR_BAD_ARG;
+        uint32_t cigbuf[64], *cg = cigbuf;
+        if (ncig > 64) cg = (uint32_t *)malloc(4u * ncig);
+        memcpy(cg, cig, 4u * ncig);                 /* records are not 4-byte aligned in the stream */
+        int e = cgb_add(b, tid, pos, flag, mapq, lseq, ncig, cg, seq, qual);
+        if (cg != cigbuf) free(cg);
+        if (e) return e;
+        p += 4 + bs;
+    }
+    return 0;
+}
+
+extern "C" int cgb_finish(cg_batch_builder *b, cg_batch *o) {
+    if (b->unsorted) return CG_ERR_UNSORTED;
+    memset(o, 0, sizeof(*o));
+    o->n_reads = (int64_t)b->tid.n;
+    o->tid = b->tid.p; o->pos = b->pos.p; o->flag = b->flag.p; o->mapq = b->mapq.p; o->l_qseq = b->l_qseq.p;
+    o->n_cigar = b->n_cigar.p; o->off = b->off.p; o->cigar_off = b->cigar_off.p;
+    o->cigar = b->cigar.p; o->n_cigar_total = (int64_t)b->cigar.n;
+    o->seq = b->seq.p; o->seq_bytes = (int64_t)b->seq.n;
+    o->qual = b->qual.p; o->qual_bytes = (int64_t)b->qual.n;
+    return 0;
+}
+
+extern "C" int64_t cgb_bytes(const cg_batch_builder *b) {
+    return (int64_t)(b->tid.n * (4 + 4 + 4 + 4 + 2 + 2 + 1 + 8) + b->cigar.n * 4 + b->seq.n + b->qual.n);
+}
+
+static int batch_in_pileup(const cg_batch *in, int64_t i) {
+    if (in->tid[i] < 0 || (in->flag[i] & 4)) return 0;
+    const uint32_t *c = in->cigar + in->cigar_off[i];
+    for (int k = 0; k < in->n_cigar[i]; k++) if (cg_cig_type(cg_cig_op(c[k])) & 2) return 1;
+    return 0;
+}
+extern "C" int64_t cg_algorithmic_bytes(const cg_batch *in) {           /* SURVEY.md §8(d) */
+    int64_t s = 0;
+    for (int64_t i = 0; i < in->n_reads; i++)
+        if (batch_in_pileup(in, i)) { int64_t l = in->l_qseq[i]; s += ((l + 1) >> 1) + 2 * l + 4 * (int64_t)in->n_cigar[i] + 16; }
+    return s;
+}
+extern "C" int64_t cg_aligned_bases(const cg_batch *in) {
+    int64_t s = 0;
+    for (int64_t i = 0; i < in->n_reads; i++) if (batch_in_pileup(in, i)) s += in->l_qseq[i];
+    return s;
+}

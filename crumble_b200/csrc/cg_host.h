@@ -1,0 +1,10 @@
+/* internal declarations shared by cg_host.cpp, cg_device.cu and the test-only emulator */
+#ifndef CG_HOST_H
+#define CG_HOST_H
+#include "cg_pipeline.h"
+int  cg_params_check(const cg_params *p, const char **why);
+void cg_devparams_from(CgDevParams *d, const cg_params *p);
+void cg_tables_init(CgTables *T, const cg_params *p);
+extern void *(*cg_pinned_alloc_hook)(size_t);
+extern void (*cg_pinned_free_hook)(void *);
+#endif

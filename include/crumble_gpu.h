@@ -1,0 +1,179 @@
+/*
+ * crumble_gpu.h — C ABI of the B200-native consensus + quality-rewrite hot path.
+ *
+ * This is the drop-in boundary for ONE path of jkbonfield/crumble: everything that
+ * `int transcode(cram_lossy_params *p, samFile *in, samFile *out, bam_hdr_t *header,
+ * hts_itr_t *h_iter)` (reference snp_score.c:1336-2029) does between reading a
+ * record and writing it back: pileup construction, calculate_consensus_pileup
+ * (snp_score.c:533-797), the column heuristics (1658-1819), STR keep windows
+ * (mask_LC_regions 1230-1290, find_STR str_finder.c:135-189), the per-base quality
+ * rewrite (1822-1920), the tail/keep handling (1926-1975) and flush_bam_list's
+ * strip + P-block (1090-1100, pblock 803-834).
+ *
+ * Plain C, plain pointers and sizes; no CUDA, C++ or torch types cross this line.
+ * All compute entry points fail with CG_ERR_NO_DEVICE when no CUDA device is usable:
+ * there is no CPU fallback behind this ABI.
+ */
+#ifndef CRUMBLE_GPU_H
+#define CRUMBLE_GPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CG_ABI_VERSION 1
+
+/* ---- error codes (negative; 0 = ok).  transcode_gpu() maps any of these to -1, the
+ * value transcode() returns on failure (snp_score.c:1480-1481,1979-1980). ------------- */
+enum {
+    CG_OK               =  0,
+    CG_ERR_NO_DEVICE    = -1,   /* no CUDA device / driver: the GPU path is mandatory */
+    CG_ERR_CUDA         = -2,   /* a CUDA runtime call or kernel failed (see cg_last_error) */
+    CG_ERR_NOMEM        = -3,
+    CG_ERR_BAD_ARG      = -4,
+    CG_ERR_UNSORTED     = -5,   /* input not coordinate sorted (htslib's pileup aborts too) */
+    CG_ERR_UNSUPPORTED  = -6,   /* option combination not implemented on the device yet */
+    CG_ERR_OVERFLOW     = -7,   /* an internal fixed-size device list overflowed */
+    CG_ERR_STATE        = -8    /* calls made out of order */
+};
+
+/* ---- parameters: POD mirror of cram_lossy_params (snp_score.c:185-226) -------------- */
+typedef struct { int32_t tid, start, end; } cg_bed_reg;      /* bed.h:4-6 */
+
+typedef struct cg_params {
+    int32_t reduce_qual, binary_qual;            /* -L, -B */
+    int32_t iSTR_add, sSTR_add;                  /* -i, -s */
+    double  iSTR_mul, sSTR_mul;
+    int32_t qlow, qcutoff, qhigh, qcap;          /* -l -c -u -U */
+    int32_t min_mqual;                           /* -m */
+    double  indel_fract;                         /* -Y */
+    int32_t min_qual_A, min_indel_A;             /* -q -d */
+    double  min_discrep_A;                       /* -x */
+    int32_t min_qual_B, min_indel_B;             /* -Q -D */
+    double  min_discrep_B;                       /* -X */
+    double  low_mqual_perc, clip_perc, ins_len_perc, over_depth, indel_ov_perc;   /* -M -C -Z -P -V */
+    int32_t pblock;                              /* -p */
+    int32_t softclip;                            /* -S */
+    int32_t perfect_col;                         /* -N */
+    int32_t verbose;                             /* -v */
+    int32_t noPG;                                /* -z */
+    /* -r region (hts_itr_t beg/end, snp_score.c:1513-1518); region_tid < 0 = whole file */
+    int32_t region_tid, region_beg, region_end;
+    /* -k / -K: 0 none, 1 keep if diffs, 2 always keep (snp_score.c:232,2362-2375) */
+    uint8_t preserve_qual[256];
+    /* -R keep.bed, sorted + merged as bed.c:20-40 leaves them; borrowed pointer */
+    const cg_bed_reg *bed;
+    int32_t nbed;
+    /* BD/BI binarisation and tag lists are host-side only (purge_tags) and not part of this ABI */
+} cg_params;
+
+/* defaults = reference main() initialiser (snp_score.c:2152-2192) */
+void cg_params_default(cg_params *p);
+/* level presets -1,-3,-5,-7,-8,-9 (snp_score.c:2380-2482); returns 0 or CG_ERR_BAD_ARG */
+int  cg_params_level(cg_params *p, int level);
+
+/* ---- a batch of decoded alignment records, structure-of-arrays, host memory ----------
+ * Records are in input (coordinate-sorted) order.  Byte layout:
+ *   qual : per read l_qseq bytes at qual[off[i]], off[i] a multiple of 8
+ *   seq  : 4-bit codes =ACMGRSVTWYHKDBN, high nibble first, at seq[off[i] / 2]
+ *   cigar: BAM encoding len<<4|op at cigar[cigar_off[i]], n_cigar[i] entries
+ * Build one with the cgb_* functions below (they also pin the memory).               */
+typedef struct cg_batch {
+    int64_t  n_reads;
+    const int32_t  *tid;        /* -1 for unplaced */
+    const int32_t  *pos;        /* 0-based leftmost reference coordinate */
+    const uint16_t *flag;
+    const uint8_t  *mapq;
+    const int32_t  *l_qseq;
+    const uint16_t *n_cigar;
+    const int64_t  *off;        /* qual byte offset; seq byte offset is off/2 */
+    const int32_t  *cigar_off;
+    const uint32_t *cigar;  int64_t n_cigar_total;
+    const uint8_t  *seq;    int64_t seq_bytes;
+    const uint8_t  *qual;   int64_t qual_bytes;
+} cg_batch;
+
+/* BED_DIST-expanded suspicious-region events (snp_score.c:1496-1498,1676-1678,
+ * 1768-1770,1802-1804,1810-1812), in the order the reference prints them. */
+enum { CG_BED_VDEEP = 0, CG_BED_DEEP = 1, CG_BED_CLIP = 2, CG_BED_INDEL_LEN = 3, CG_BED_INDEL_COVERAGE = 4 };
+typedef struct { int32_t tid, pos, tag; } cg_bed_event;    /* pos = column; line is max(pos-50,0), pos+50 */
+
+/* the reference's -v counters (snp_score.c:1292-1311), same order as printed (2652-2665) */
+enum {
+    CG_CNT_DIFF = 0, CG_CNT_INDEL_QUAL, CG_CNT_INDEL,
+    CG_CNT_HET_QUAL_A, CG_CNT_HET_A, CG_CNT_HOM_QUAL_A, CG_CNT_HOM_A, CG_CNT_DISCREP_A,
+    CG_CNT_HET_QUAL_B, CG_CNT_HET_B, CG_CNT_HOM_QUAL_B, CG_CNT_HOM_B, CG_CNT_DISCREP_B,
+    CG_CNT_COLUMNS, CG_CNT_LOW_MQUAL_PERC, CG_CNT_CLIP_PERC, CG_CNT_INS_LEN_PERC,
+    CG_CNT_INDEL_OV_PERC, CG_CNT_OVER_DEPTH,
+    CG_N_COUNTERS
+};
+
+/* optional per-column dump for parity checks (consensus_t, snp_score.c:257-281) */
+typedef struct {
+    int32_t tid, pos, n_plp;
+    int32_t call, het_call, het_phred, phred;     /* mode B if enabled else mode A */
+    float   discrep;
+    uint32_t flags;       /* bit0 preserve, bit1 keep_qual, bit2 window active, bit3 processed,
+                             bit4 trigger, bit5 had_indel; bits 8-12 BED tags (1<<(8+tag)) */
+} cg_column;
+
+typedef struct cg_result {
+    uint8_t      *qual_out;        /* caller buffer, >= batch.qual_bytes; same layout as batch.qual */
+    cg_bed_event *events;          /* caller buffer or NULL */
+    int64_t       events_cap, n_events;
+    int64_t       counters[CG_N_COUNTERS];
+    cg_column    *columns;         /* caller buffer or NULL (NULL = no dump) */
+    int64_t       columns_cap, n_columns;
+} cg_result;
+
+typedef struct cg_ctx cg_ctx;
+
+/* ---- life cycle ---------------------------------------------------------------------- */
+int         cg_abi_version(void);
+int         cg_device_count(void);                                 /* 0 when no usable GPU */
+cg_ctx     *cg_create(const cg_params *p, int device, int *err);   /* NULL + *err on failure */
+void        cg_destroy(cg_ctx *ctx);
+int         cg_set_params(cg_ctx *ctx, const cg_params *p);
+const char *cg_strerror(int code);
+const char *cg_last_error(const cg_ctx *ctx);                      /* detail of the last failure */
+/* run on a caller-owned stream (cudaStream_t as void*), e.g. torch's current stream */
+int         cg_set_stream(cg_ctx *ctx, void *cuda_stream);
+
+/* ---- the hot path ---------------------------------------------------------------------
+ * cg_process  = upload + run + download: host buffers in, host buffers out (end to end).
+ * The split form lets a caller keep a batch resident and time the kernel chain alone.   */
+int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out);
+int cg_upload(cg_ctx *ctx, const cg_batch *in);
+int cg_run(cg_ctx *ctx);
+int cg_download(cg_ctx *ctx, cg_result *out);
+int cg_sync(cg_ctx *ctx);
+
+/* measurement helpers */
+enum { CG_T_TOTAL = 0, CG_T_TILES, CG_T_COLUMNS, CG_T_FLAGGED, CG_T_DEPTH, CG_T_CHAIN, CG_T_REWRITE, CG_T_PBLOCK, CG_T_EVENTS, CG_T_H2D, CG_T_D2H, CG_N_TIMERS };
+float   cg_last_ms(const cg_ctx *ctx, int which);        /* CUDA-event time of the last cg_run / copies */
+int64_t cg_last_launches(const cg_ctx *ctx);             /* kernels launched by the last cg_run */
+int64_t cg_algorithmic_bytes(const cg_batch *in);        /* sum ceil(l/2)+2l+4*n_cigar+16 over pileup reads */
+int64_t cg_aligned_bases(const cg_batch *in);            /* sum l_qseq over records entering the pileup */
+int64_t cg_n_columns(const cg_ctx *ctx);                 /* covered reference columns in the resident batch */
+
+/* ---- host batcher: decoded records -> pinned SoA (replaces pileup_callback's bam_dup1
+ * into RB-trees, snp_score.c:1113-1153) ------------------------------------------------ */
+typedef struct cg_batch_builder cg_batch_builder;
+cg_batch_builder *cgb_create(int pinned);
+void  cgb_destroy(cg_batch_builder *b);
+void  cgb_reset(cg_batch_builder *b);
+/* one record; the pointers are BAM-layout fields (bam1_t core + data) */
+int   cgb_add(cg_batch_builder *b, int32_t tid, int32_t pos, uint16_t flag, uint8_t mapq,
+              int32_t l_qseq, uint32_t n_cigar, const uint32_t *cigar, const uint8_t *seq4, const uint8_t *qual);
+/* every record of an uncompressed BAM stream (BAM\1 magic + header + records) */
+int   cgb_add_bam_stream(cg_batch_builder *b, const uint8_t *buf, size_t len);
+int   cgb_finish(cg_batch_builder *b, cg_batch *out);    /* out points into the builder */
+int64_t cgb_bytes(const cg_batch_builder *b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
