@@ -1,0 +1,386 @@
+"""ctypes binding of the C ABI in include/crumble_gpu.h (libcrumble_gpu.so).
+
+Host-side mirror of the reference interface for the hot path: the option block
+(cram_lossy_params, reference snp_score.c:185-226), the level presets (2380-2482) and
+``transcode`` (1336-2029) expressed as ``Crumble.process(batch)``.
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is
+usable, every compute call raises.  PyTorch is not needed by this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_DIR = _HERE / "lib"
+N_COUNTERS = 19
+COUNTER_NAMES = [
+    "diff", "indel_qual", "indel", "het_qual_A", "het_A", "hom_qual_A", "hom_A", "discrep_A",
+    "het_qual_B", "het_B", "hom_qual_B", "hom_B", "discrep_B", "columns", "low_mqual_perc",
+    "clip_perc", "ins_len_perc", "indel_ov_perc", "over_depth",
+]
+BED_TAGS = ["VDEEP", "DEEP", "CLIP", "INDEL_LEN", "INDEL_COVERAGE"]
+TIMERS = ["total", "tiles", "columns", "flagged", "depth", "chain", "rewrite", "pblock", "events", "h2d", "d2h"]
+
+
+class CrumbleError(RuntimeError):
+    pass
+
+
+class BedReg(C.Structure):
+    _fields_ = [("tid", C.c_int32), ("start", C.c_int32), ("end", C.c_int32)]
+
+
+class Params(C.Structure):
+    """cg_params: POD mirror of cram_lossy_params."""
+    _fields_ = [
+        ("reduce_qual", C.c_int32), ("binary_qual", C.c_int32),
+        ("iSTR_add", C.c_int32), ("sSTR_add", C.c_int32),
+        ("iSTR_mul", C.c_double), ("sSTR_mul", C.c_double),
+        ("qlow", C.c_int32), ("qcutoff", C.c_int32), ("qhigh", C.c_int32), ("qcap", C.c_int32),
+        ("min_mqual", C.c_int32),
+        ("indel_fract", C.c_double),
+        ("min_qual_A", C.c_int32), ("min_indel_A", C.c_int32), ("min_discrep_A", C.c_double),
+        ("min_qual_B", C.c_int32), ("min_indel_B", C.c_int32), ("min_discrep_B", C.c_double),
+        ("low_mqual_perc", C.c_double), ("clip_perc", C.c_double), ("ins_len_perc", C.c_double),
+        ("over_depth", C.c_double), ("indel_ov_perc", C.c_double),
+        ("pblock", C.c_int32), ("softclip", C.c_int32), ("perfect_col", C.c_int32),
+        ("verbose", C.c_int32), ("noPG", C.c_int32),
+        ("region_tid", C.c_int32), ("region_beg", C.c_int32), ("region_end", C.c_int32),
+        ("preserve_qual", C.c_uint8 * 256),
+        ("bed", C.POINTER(BedReg)), ("nbed", C.c_int32),
+    ]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("n_reads", C.c_int64),
+        ("tid", C.POINTER(C.c_int32)), ("pos", C.POINTER(C.c_int32)), ("flag", C.POINTER(C.c_uint16)),
+        ("mapq", C.POINTER(C.c_uint8)), ("l_qseq", C.POINTER(C.c_int32)), ("n_cigar", C.POINTER(C.c_uint16)),
+        ("off", C.POINTER(C.c_int64)), ("cigar_off", C.POINTER(C.c_int32)),
+        ("cigar", C.POINTER(C.c_uint32)), ("n_cigar_total", C.c_int64),
+        ("seq", C.POINTER(C.c_uint8)), ("seq_bytes", C.c_int64),
+        ("qual", C.POINTER(C.c_uint8)), ("qual_bytes", C.c_int64),
+    ]
+
+
+class BedEvent(C.Structure):
+    _fields_ = [("tid", C.c_int32), ("pos", C.c_int32), ("tag", C.c_int32)]
+
+
+class Column(C.Structure):
+    _fields_ = [("tid", C.c_int32), ("pos", C.c_int32), ("n_plp", C.c_int32), ("call", C.c_int32),
+                ("het_call", C.c_int32), ("het_phred", C.c_int32), ("phred", C.c_int32),
+                ("discrep", C.c_float), ("flags", C.c_uint32)]
+
+
+COLUMN_DTYPE = np.dtype([("tid", "<i4"), ("pos", "<i4"), ("n_plp", "<i4"), ("call", "<i4"), ("het_call", "<i4"),
+                         ("het_phred", "<i4"), ("phred", "<i4"), ("discrep", "<f4"), ("flags", "<u4")])
+EVENT_DTYPE = np.dtype([("tid", "<i4"), ("pos", "<i4"), ("tag", "<i4")])
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("qual_out", C.POINTER(C.c_uint8)),
+        ("events", C.POINTER(BedEvent)), ("events_cap", C.c_int64), ("n_events", C.c_int64),
+        ("counters", C.c_int64 * N_COUNTERS),
+        ("columns", C.POINTER(Column)), ("columns_cap", C.c_int64), ("n_columns", C.c_int64),
+    ]
+
+
+_lib = None
+_sim = None
+
+EXPORTS = [
+    "cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_set_params", "cg_strerror", "cg_last_error",
+    "cg_set_stream", "cg_process", "cg_upload", "cg_run", "cg_download", "cg_sync", "cg_last_ms", "cg_last_launches",
+    "cg_algorithmic_bytes", "cg_aligned_bases", "cg_n_columns", "cg_params_default", "cg_params_level",
+    "cgb_create", "cgb_destroy", "cgb_reset", "cgb_add", "cgb_add_bam_stream", "cgb_finish", "cgb_bytes",
+]
+
+
+def lib_path() -> Path:
+    return LIB_DIR / "libcrumble_gpu.so"
+
+
+def load_lib():
+    """Load libcrumble_gpu.so (built in-tree by ``__graft_entry__.build()``); raise loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not p.exists():
+        raise CrumbleError(f"{p} is missing: the CUDA extension is mandatory (run `python -c 'import __graft_entry__ as g; g.build()'`)")
+    lib = C.CDLL(str(p))
+    lib.cg_abi_version.restype = C.c_int
+    lib.cg_device_count.restype = C.c_int
+    lib.cg_create.restype = C.c_void_p
+    lib.cg_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(C.c_int)]
+    lib.cg_destroy.argtypes = [C.c_void_p]
+    lib.cg_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
+    lib.cg_strerror.restype = C.c_char_p
+    lib.cg_strerror.argtypes = [C.c_int]
+    lib.cg_last_error.restype = C.c_char_p
+    lib.cg_last_error.argtypes = [C.c_void_p]
+    lib.cg_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    for f in ("cg_process",):
+        getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Result)]
+    lib.cg_upload.argtypes = [C.c_void_p, C.POINTER(Batch)]
+    lib.cg_run.argtypes = [C.c_void_p]
+    lib.cg_sync.argtypes = [C.c_void_p]
+    lib.cg_download.argtypes = [C.c_void_p, C.POINTER(Result)]
+    lib.cg_last_ms.restype = C.c_float
+    lib.cg_last_ms.argtypes = [C.c_void_p, C.c_int]
+    lib.cg_last_launches.restype = C.c_int64
+    lib.cg_last_launches.argtypes = [C.c_void_p]
+    lib.cg_n_columns.restype = C.c_int64
+    lib.cg_n_columns.argtypes = [C.c_void_p]
+    lib.cg_algorithmic_bytes.restype = C.c_int64
+    lib.cg_algorithmic_bytes.argtypes = [C.POINTER(Batch)]
+    lib.cg_aligned_bases.restype = C.c_int64
+    lib.cg_aligned_bases.argtypes = [C.POINTER(Batch)]
+    lib.cg_params_default.argtypes = [C.POINTER(Params)]
+    lib.cg_params_level.argtypes = [C.POINTER(Params), C.c_int]
+    lib.cgb_create.restype = C.c_void_p
+    lib.cgb_create.argtypes = [C.c_int]
+    lib.cgb_destroy.argtypes = [C.c_void_p]
+    lib.cgb_reset.argtypes = [C.c_void_p]
+    lib.cgb_add_bam_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.cgb_add.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint16, C.c_uint8, C.c_int32, C.c_uint32,
+                            C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cgb_finish.argtypes = [C.c_void_p, C.POINTER(Batch)]
+    lib.cgb_bytes.restype = C.c_int64
+    lib.cgb_bytes.argtypes = [C.c_void_p]
+    lib.crumble_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    _lib = lib
+    return lib
+
+
+def _check(lib, code, ctx=None):
+    if code != 0:
+        detail = lib.cg_last_error(ctx).decode() if ctx else ""
+        raise CrumbleError(f"{lib.cg_strerror(code).decode()} [{code}] {detail}")
+
+
+def default_params(level: int | None = None, **overrides) -> Params:
+    """Reference defaults (snp_score.c:2152-2192), optionally a level preset, then field overrides."""
+    lib = load_lib()
+    p = Params()
+    lib.cg_params_default(C.byref(p))
+    if level is not None:
+        _check(lib, lib.cg_params_level(C.byref(p), level))
+    for k, v in overrides.items():
+        setattr(p, k, v)
+    return p
+
+
+class BatchBuilder:
+    """Host batcher: decoded records -> (pinned) structure-of-arrays."""
+
+    def __init__(self, pinned: bool = True):
+        self.lib = load_lib()
+        self.h = self.lib.cgb_create(1 if pinned else 0)
+        if not self.h:
+            raise CrumbleError("cgb_create failed")
+        self.batch = Batch()
+        self._keep = []
+
+    def add_bam_stream(self, buf: np.ndarray):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        _check(self.lib, self.lib.cgb_add_bam_stream(self.h, buf.ctypes.data, buf.size))
+
+    def add(self, tid, pos, flag, mapq, cigar, seq4, qual):
+        cigar = np.ascontiguousarray(cigar, dtype=np.uint32)
+        seq4 = np.ascontiguousarray(seq4, dtype=np.uint8)
+        qual = np.ascontiguousarray(qual, dtype=np.uint8)
+        _check(self.lib, self.lib.cgb_add(self.h, tid, pos, flag, mapq, qual.size, cigar.size,
+                                          cigar.ctypes.data, seq4.ctypes.data, qual.ctypes.data))
+
+    def finish(self) -> Batch:
+        _check(self.lib, self.lib.cgb_finish(self.h, C.byref(self.batch)))
+        return self.batch
+
+    def offsets(self) -> np.ndarray:
+        n = self.batch.n_reads
+        return np.ctypeslib.as_array(self.batch.off, shape=(n,)).copy() if n else np.zeros(0, np.int64)
+
+    def lengths(self) -> np.ndarray:
+        n = self.batch.n_reads
+        return np.ctypeslib.as_array(self.batch.l_qseq, shape=(n,)).copy() if n else np.zeros(0, np.int32)
+
+    def qual(self) -> np.ndarray:
+        return np.ctypeslib.as_array(self.batch.qual, shape=(self.batch.qual_bytes,))
+
+    def close(self):
+        if self.h:
+            self.lib.cgb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Crumble:
+    """One GPU context (one per device / process)."""
+
+    def __init__(self, params: Params | None = None, device: int = 0):
+        self.lib = load_lib()
+        if self.lib.cg_device_count() <= 0:
+            raise CrumbleError("no usable CUDA device: the GPU path is mandatory, there is no CPU fallback")
+        self.params = params if params is not None else default_params()
+        err = C.c_int(0)
+        self.h = self.lib.cg_create(C.byref(self.params), device, C.byref(err))
+        if not self.h:
+            raise CrumbleError(f"cg_create failed: {self.lib.cg_strerror(err.value).decode()}")
+        self._qout = None
+
+    def set_stream(self, cuda_stream_ptr: int):
+        _check(self.lib, self.lib.cg_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), self.h)
+
+    def _result(self, batch: Batch, want_columns: bool, events_cap: int, pinned_out=None):
+        res = Result()
+        if pinned_out is not None:
+            qout = pinned_out
+        else:
+            qout = np.empty(max(int(batch.qual_bytes), 1), dtype=np.uint8)
+        res.qual_out = qout.ctypes.data_as(C.POINTER(C.c_uint8))
+        ev = np.zeros(events_cap, dtype=EVENT_DTYPE)
+        res.events = ev.ctypes.data_as(C.POINTER(BedEvent))
+        res.events_cap = events_cap
+        cols = None
+        if want_columns:
+            cap = int(getattr(self, "_ncols_hint", 0)) or 1
+            cols = np.zeros(cap, dtype=COLUMN_DTYPE)
+            res.columns = cols.ctypes.data_as(C.POINTER(Column))
+            res.columns_cap = cap
+        return res, qout, ev, cols
+
+    def process(self, batch: Batch, want_columns: bool = False, events_cap: int = 1 << 16, pinned_out=None):
+        """End to end: host SoA in, host results out (upload + kernel chain + download)."""
+        if want_columns:
+            # first pass sizes the dump
+            self._ncols_hint = 1
+        while True:
+            res, qout, ev, cols = self._result(batch, want_columns, events_cap, pinned_out)
+            _check(self.lib, self.lib.cg_process(self.h, C.byref(batch), C.byref(res)), self.h)
+            redo = False
+            if res.n_events > events_cap:
+                events_cap = int(res.n_events); redo = True
+            if want_columns and res.n_columns > res.columns_cap:
+                self._ncols_hint = int(res.n_columns); redo = True
+            if not redo:
+                break
+        out = {
+            "qual": qout[: int(batch.qual_bytes)],
+            "events": ev[: int(res.n_events)],
+            "counters": {k: int(res.counters[i]) for i, k in enumerate(COUNTER_NAMES)},
+        }
+        if want_columns:
+            out["columns"] = cols[: int(res.n_columns)]
+        return out
+
+    # split phase (resident timing)
+    def upload(self, batch: Batch):
+        _check(self.lib, self.lib.cg_upload(self.h, C.byref(batch)), self.h)
+
+    def run(self):
+        _check(self.lib, self.lib.cg_run(self.h), self.h)
+
+    def download(self, batch: Batch, events_cap: int = 1 << 16, pinned_out=None):
+        res, qout, ev, _ = self._result(batch, False, events_cap, pinned_out)
+        _check(self.lib, self.lib.cg_download(self.h, C.byref(res)), self.h)
+        return {"qual": qout[: int(batch.qual_bytes)], "events": ev[: min(int(res.n_events), events_cap)],
+                "counters": {k: int(res.counters[i]) for i, k in enumerate(COUNTER_NAMES)}, "n_events": int(res.n_events)}
+
+    def ms(self, which: str = "total") -> float:
+        return float(self.lib.cg_last_ms(self.h, TIMERS.index(which)))
+
+    def timers(self) -> dict:
+        return {k: self.ms(k) for k in TIMERS}
+
+    def launches(self) -> int:
+        return int(self.lib.cg_last_launches(self.h))
+
+    def n_columns(self) -> int:
+        return int(self.lib.cg_n_columns(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def algorithmic_bytes(batch: Batch) -> int:
+    return int(load_lib().cg_algorithmic_bytes(C.byref(batch)))
+
+
+def aligned_bases(batch: Batch) -> int:
+    return int(load_lib().cg_aligned_bases(C.byref(batch)))
+
+
+def bed_text(events: np.ndarray, target_names) -> str:
+    """BED lines exactly as the reference prints them (snp_score.c:1496-1498 etc.)."""
+    return "".join(f"{target_names[e['tid']]}\t{max(int(e['pos']) - 50, 0)}\t{int(e['pos']) + 50}\t{BED_TAGS[e['tag']]}\n"
+                   for e in events)
+
+
+def crumble_cli(argv) -> int:
+    """Run the crumble command line (reference main(), snp_score.c:2144) in-process."""
+    lib = load_lib()
+    args = [b"crumble"] + [a.encode() if isinstance(a, str) else a for a in argv]
+    arr = (C.c_char_p * (len(args) + 1))(*args, None)
+    return int(lib.crumble_main(len(args), arr))
+
+
+# ---- synthetic data (libcrumble_sim.so) ------------------------------------------------------
+class SimCfg(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("n_contigs", C.c_int), ("contig_len", C.c_int64), ("depth", C.c_double),
+                ("read_len", C.c_int), ("qual_binned", C.c_int), ("features_per_mb", C.c_double), ("amplicon", C.c_int),
+                ("n_amplicons", C.c_int), ("amplicon_len", C.c_int), ("amplicon_depth", C.c_int),
+                ("n_unmapped_tail", C.c_int), ("threads", C.c_int)]
+
+
+def load_sim():
+    global _sim
+    if _sim is not None:
+        return _sim
+    p = LIB_DIR / "libcrumble_sim.so"
+    if not p.exists():
+        raise CrumbleError(f"{p} is missing (run __graft_entry__.build())")
+    s = C.CDLL(str(p))
+    s.simgen_preset.argtypes = [C.POINTER(SimCfg), C.c_char_p, C.c_double, C.c_uint64]
+    s.simgen_generate.argtypes = [C.POINTER(SimCfg), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                  C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    s.simgen_free.argtypes = [C.c_void_p]
+    _sim = s
+    return s
+
+
+def simulate(preset: str, scale: float = 1.0, seed: int = 1, threads: int = 0, **cfg_overrides):
+    """Synthetic aligned reads as an uncompressed BAM stream (numpy uint8)."""
+    s = load_sim()
+    cfg = SimCfg()
+    if s.simgen_preset(C.byref(cfg), preset.encode(), scale, seed) != 0:
+        raise ValueError(f"unknown preset {preset}")
+    cfg.threads = threads
+    for k, v in cfg_overrides.items():
+        setattr(cfg, k, v)
+    out = C.c_void_p(); n = C.c_size_t(); nr = C.c_int64(); nb = C.c_int64()
+    if s.simgen_generate(C.byref(cfg), C.byref(out), C.byref(n), C.byref(nr), C.byref(nb)) != 0:
+        raise CrumbleError("simgen failed")
+    arr = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(n.value,)).copy()
+    s.simgen_free(out)
+    return arr, int(nr.value), int(nb.value)

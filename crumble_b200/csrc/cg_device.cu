@@ -1,0 +1,658 @@
+/*
+ * cg_device.cu — sm_100a kernels and the C ABI of include/crumble_gpu.h.
+ *
+ * Kernel chain of one cg_run():
+ *   k_prep_read -> scan(pileup flag) -> k_prep_keys -> scan(prefix max of end keys)
+ *   -> k_gap -> scan(sum of zero-coverage gaps, + island compaction) -> k_finish_read
+ *   -> k_tile_index -> k_column (pileup + consensus + column heuristics; the hot kernel)
+ *   -> scan(flagged columns -> ordered list) -> k_flagged (indel spectrum, STR extents)
+ *   -> [depth scans -> k_epochs -> k_deep]   (only when the over-depth test can fire)
+ *   -> k_chain -> k_paint -> k_rewrite (per-read replay + P-block) -> scan(BED events)
+ *
+ * No tensor cores: the path is integer/byte work plus in-order FP64 sums.
+ * There is no CPU fallback in this file: without a device every entry point fails.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "cg_host.h"
+
+#define CG_CHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    snprintf(ctx->err, sizeof ctx->err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    return CG_ERR_CUDA; } } while (0)
+
+/* ============================== scan primitive ======================================== */
+#define SCAN_THREADS 256
+#define SCAN_ITEMS   16
+#define SCAN_CHUNK   (SCAN_THREADS * SCAN_ITEMS)
+
+struct OpSum { template <class T> __device__ static T apply(T a, T b) { return a + b; } };
+struct OpMax { template <class T> __device__ static T apply(T a, T b) { return a > b ? a : b; } };
+
+template <class T, class Op>
+__device__ __forceinline__ T block_scan_incl(T v, T ident, T *sh /* >= 32 */, T *block_total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = Op::apply(u, v);
+    }
+    if (lane == 31) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        T s = lane < (SCAN_THREADS / 32) ? sh[lane] : ident;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T u = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s = Op::apply(u, s);
+        }
+        sh[lane] = s;
+    }
+    __syncthreads();
+    if (w > 0) v = Op::apply(sh[w - 1], v);
+    *block_total = sh[SCAN_THREADS / 32 - 1];
+    __syncthreads();
+    return v;
+}
+
+template <class T, class Op, class Load>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(Load ld, int64_t n, T ident, T *aggr) {
+    __shared__ T sh[32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK;
+    T acc = ident;
+#pragma unroll 4
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        int64_t i = base + (int64_t)k * SCAN_THREADS + threadIdx.x;
+        if (i < n) acc = Op::apply(acc, ld(i));
+    }
+    T tot;
+    block_scan_incl<T, Op>(acc, ident, sh, &tot);
+    if (threadIdx.x == 0) aggr[blockIdx.x] = tot;
+}
+
+template <class T, class Op>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_aggr(T *aggr, int nb, T ident, T *total) {
+    __shared__ T sh[32];
+    T carry = ident;
+    for (int b0 = 0; b0 < nb; b0 += SCAN_THREADS) {
+        int b = b0 + threadIdx.x;
+        T v = b < nb ? aggr[b] : ident;
+        T tot;
+        T inc = block_scan_incl<T, Op>(v, ident, sh, &tot);
+        /* exclusive = carry (+) inclusive of the previous element */
+        T prev = __shfl_up_sync(0xffffffffu, inc, 1);
+        __shared__ T edge[SCAN_THREADS / 32];
+        if ((threadIdx.x & 31) == 31) edge[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        T ex;
+        if (threadIdx.x == 0) ex = ident;
+        else if ((threadIdx.x & 31) == 0) ex = edge[(threadIdx.x >> 5) - 1];
+        else ex = prev;
+        if (b < nb) aggr[b] = Op::apply(carry, ex);
+        carry = Op::apply(carry, tot);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
+/* st(i, inclusive, exclusive) */
+template <class T, class Op, class Load, class Store>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(Load ld, Store st, int64_t n, T ident, const T *aggr_excl) {
+    __shared__ T sh[32];
+    __shared__ T edge[SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK;
+    T carry = aggr_excl[blockIdx.x];
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        int64_t i = base + (int64_t)k * SCAN_THREADS + threadIdx.x;
+        T v = i < n ? ld(i) : ident;
+        T tot;
+        T inc = block_scan_incl<T, Op>(v, ident, sh, &tot);
+        T prev = __shfl_up_sync(0xffffffffu, inc, 1);
+        if ((threadIdx.x & 31) == 31) edge[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        T ex;
+        if (threadIdx.x == 0) ex = ident;
+        else if ((threadIdx.x & 31) == 0) ex = edge[(threadIdx.x >> 5) - 1];
+        else ex = prev;
+        if (i < n) st(i, Op::apply(carry, inc), Op::apply(carry, ex));
+        carry = Op::apply(carry, tot);
+        __syncthreads();
+    }
+}
+
+/* ============================== functors ============================================== */
+struct LdPileFlag { const int32_t *rspan; __device__ int32_t operator()(int64_t i) const { return rspan[i] != 0; } };
+struct StJmap { int32_t *jmap; __device__ void operator()(int64_t i, int32_t, int32_t ex) const { jmap[i] = ex; } };
+struct LdI64 { const int64_t *p; __device__ int64_t operator()(int64_t i) const { return p[i]; } };
+struct StI64Incl { int64_t *p; __device__ void operator()(int64_t i, int64_t inc, int64_t) const { p[i] = inc; } };
+struct LdIslandFlag { const int64_t *gapraw; __device__ int32_t operator()(int64_t j) const { return j == 0 || gapraw[j] > 0; } };
+struct StIsland {
+    CgIsland *isl; const int64_t *ks; const int64_t *gapsum; const int64_t *gapraw;
+    __device__ void operator()(int64_t j, int32_t, int32_t ex) const {
+        if (j == 0 || gapraw[j] > 0) {
+            CgIsland I; I.col_start = (int32_t)(ks[j] - ks[0] - gapsum[j]); I.tid = (int32_t)(ks[j] >> 32);
+            I.pos_start = (int32_t)(ks[j] & 0xffffffff); I.pad = 0; isl[ex] = I;
+        }
+    }
+};
+struct LdEvFlag { const uint16_t *ev; uint16_t mask; __device__ int32_t operator()(int64_t c) const { return (ev[c] & mask) != 0; } };
+struct StCompact { int32_t *out; const uint16_t *ev; uint16_t mask; __device__ void operator()(int64_t c, int32_t, int32_t ex) const { if (ev[c] & mask) out[ex] = (int32_t)c; } };
+struct LdDepthCounted { const uint32_t *depth; const uint16_t *ev; __device__ int64_t operator()(int64_t c) const { return (ev[c] & CG_EV_COUNTED) ? (int64_t)depth[c] : 0; } };
+struct LdCounted { const uint16_t *ev; __device__ int32_t operator()(int64_t c) const { return (ev[c] & CG_EV_COUNTED) != 0; } };
+struct StI32Incl { int32_t *p; __device__ void operator()(int64_t i, int32_t inc, int32_t) const { p[i] = inc; } };
+struct LdEvCount { const uint16_t *ev; __device__ int32_t operator()(int64_t c) const { return __popc(ev[c] & CG_EV_BEDMASK); } };
+struct StEvents {
+    cg_bed_event *out; const uint16_t *ev; CgDev D; int64_t cap;
+    __device__ void operator()(int64_t c, int32_t, int32_t ex) const {
+        int bits = ev[c] & CG_EV_BEDMASK;
+        if (!bits) return;
+        int is = cg_island_of(&D, (int)c);
+        int tid = D.isl[is].tid, pos = D.isl[is].pos_start + ((int)c - D.isl[is].col_start);
+        for (int t = 0; t < 5; t++) if (bits >> t & 1) { if (ex < cap) { cg_bed_event e; e.tid = tid; e.pos = pos; e.tag = t; out[ex] = e; } ex++; }
+    }
+};
+
+/* ============================== kernels ================================================ */
+__global__ void k_prep_read(const __grid_constant__ CgDev D) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < D.n_reads) cg_prep_read(&D, r);
+}
+__global__ void k_prep_keys(const __grid_constant__ CgDev D) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < D.n_reads) cg_prep_keys(&D, r);
+}
+/* raw gap per pileup read (needs the prefix max of end keys) */
+__global__ void k_gap(const __grid_constant__ CgDev D, const int32_t *n_pile, int64_t *gapraw) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < *n_pile) gapraw[j] = cg_gap_of(&D, j);
+}
+__global__ void k_finish_read(const __grid_constant__ CgDev D, const int32_t *n_pile, int32_t *dims) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int np = *n_pile;
+    if (j < np) {
+        cg_finish_read(&D, j, D.ks[0]);
+        if (j == np - 1) dims[1] = D.pmaxcol[j];     /* n_cols */
+    }
+    if (j == 0 && np == 0) dims[1] = 0;
+}
+__global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_tile_index(const __grid_constant__ CgDev D) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < D.n_pile) cg_tile_index(&D, j);
+}
+
+/* The hot kernel: one thread per dense reference column, one warp per 32-column tile;
+ * all lanes of a warp walk the same candidate read window, so read records are
+ * warp-uniform loads and base/quality bytes are adjacent across lanes. */
+__global__ void __launch_bounds__(128) k_column(const __grid_constant__ CgDev D) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    CgColOut o; o.cnt = 0; o.n_plp = 0;
+    if (c < D.n_cols) o = cg_column_body(&D, c);
+    /* counters: one atomic per warp and counter */
+    unsigned any = __ballot_sync(0xffffffffu, o.cnt != 0);
+    if (any) {
+        unsigned un = __reduce_or_sync(0xffffffffu, o.cnt);
+        while (un) {
+            int b = __ffs(un) - 1; un &= un - 1;
+            unsigned m = __ballot_sync(0xffffffffu, (o.cnt >> b) & 1);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&D.counters[b], (unsigned long long)__popc(m));
+        }
+    }
+    int mx = __reduce_max_sync(0xffffffffu, o.n_plp);
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(D.maxdepth, mx);
+}
+
+__global__ void __launch_bounds__(64) k_flagged(const __grid_constant__ CgDev D, CgFlagScratch *scratch) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    int stride = gridDim.x * blockDim.x;
+    CgFlagScratch *S = scratch + tid;
+    for (int k = tid; k < D.n_flagged; k += stride) {
+        uint32_t cnt = cg_flagged(&D, k, S);
+        while (cnt) { int b = __ffs(cnt) - 1; cnt &= cnt - 1; atomicAdd(&D.counters[b], 1ULL); }
+    }
+}
+
+/* depth-average epochs (snp_score.c:1478-1491,1684-1687): sequential over contigs and the
+ * ~n_cols/524289 halving points only; everything per-column is a prefix-sum lookup */
+struct CgEpoch { int32_t col_begin; int32_t pad; int64_t td_base, tc_base, d_off, c_off; };
+
+__global__ void k_epochs(const __grid_constant__ CgDev D, CgEpoch *ep, int32_t *n_ep, int cap) {
+    if (threadIdx.x || blockIdx.x) return;
+    int ne = 0;
+    int is = 0;
+    while (is < D.n_islands) {
+        int tid = D.isl[is].tid, is2 = is;
+        while (is2 + 1 < D.n_islands && D.isl[is2 + 1].tid == tid) is2++;
+        int c0 = D.isl[is].col_start, c1 = (is2 + 1 < D.n_islands) ? D.isl[is2 + 1].col_start : D.n_cols;
+        int64_t d_off = c0 ? D.dsum[c0 - 1] : 0, c_off = c0 ? D.csum[c0 - 1] : 0;
+        int64_t td = 0, tc = 0; int s = c0;
+        for (;;) {
+            if (ne < cap) { CgEpoch e; e.col_begin = s; e.pad = 0; e.td_base = td; e.tc_base = tc; e.d_off = d_off; e.c_off = c_off; ep[ne] = e; }
+            ne++;
+            /* first column in [s,c1) whose counted index makes total_col exceed 2^20 */
+            int64_t want = c_off + (1024 * 1024 + 1 - tc);
+            int lo = s, hi = c1;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if ((int64_t)D.csum[mid] < want) lo = mid + 1; else hi = mid; }
+            int c = lo;
+            while (c < c1 && !((D.ev[c] & CG_EV_PROCESSED) && (D.ev[c] & CG_EV_COUNTED))) c++;
+            if (c >= c1) break;
+            td = (td + (D.dsum[c] - d_off)) >> 1;
+            tc = (tc + ((int64_t)D.csum[c] - c_off)) >> 1;
+            d_off = D.dsum[c]; c_off = D.csum[c]; s = c + 1;
+            if (s >= c1) break;
+        }
+        is = is2 + 1;
+    }
+    *n_ep = ne;
+    if (ne > cap) *D.err = CG_ERR_OVERFLOW;
+}
+
+__global__ void k_deep(const __grid_constant__ CgDev D, const CgEpoch *ep, const int32_t *n_ep) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cnt = 0;
+    if (c < D.n_cols && (D.ev[c] & CG_EV_PROCESSED)) {
+        int lo = 0, hi = *n_ep - 1;
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (ep[mid].col_begin <= c) lo = mid; else hi = mid - 1; }
+        const CgEpoch e = ep[lo];
+        int64_t td = e.td_base + (D.dsum[c] - e.d_off), tc = e.tc_base + ((int64_t)D.csum[c] - e.c_off);
+        cnt = cg_deep_test(&D, c, td, tc);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, cnt != 0);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd(&D.counters[CG_CNT_OVER_DEPTH], (unsigned long long)__popc(m));
+}
+
+__global__ void k_chain(const __grid_constant__ CgDev D) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) cg_chain(&D, D.n_flagged);
+}
+__global__ void k_paint(const __grid_constant__ CgDev D) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < D.n_flagged) cg_paint(&D, k, D.n_flagged);
+}
+__global__ void __launch_bounds__(128) k_rewrite(const __grid_constant__ CgDev D) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < D.n_reads) cg_rewrite(&D, r, D.n_flagged);
+}
+__global__ void k_dump_flags(const __grid_constant__ CgDev D) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= D.n_cols) return;
+    cg_column z = D.coldump[c];
+    if (z.tid < 0) return;
+    uint8_t cb = D.cb[c]; uint16_t ev = D.ev[c];
+    if (cb & CG_CB_ACTIVE) z.flags |= 4;
+    if (cb & CG_CB_KEEP) z.flags |= 2;
+    if (ev & CG_EV_TRIGGER) z.flags |= 16;
+    if (ev & CG_EV_HADINDEL) z.flags |= 32;
+    z.flags |= (uint32_t)(ev & CG_EV_BEDMASK) << 8;
+    D.coldump[c] = z;
+}
+
+/* ============================== context ================================================ */
+struct dbuf { void *p; size_t cap; };
+
+struct cg_ctx {
+    int device; cudaStream_t stream; int own_stream;
+    cg_params params; CgTables *hT; CgTables *dT;
+    char err[512];
+    /* device buffers */
+    dbuf b_tid, b_pos, b_flag, b_mapq, b_lq, b_nc, b_off, b_coff, b_cigar, b_seq, b_qual, b_qout;
+    dbuf b_jmap, b_rspan, b_rd, b_ks, b_ke, b_gap, b_gapraw, b_pmax, b_orig, b_rbf;
+    dbuf b_tlo, b_tstart, b_isl, b_cb, b_ev, b_depth, b_dump, b_dsum, b_csum, b_fcol, b_trig, b_twin;
+    dbuf b_aggr, b_scal, b_scratch, b_epoch, b_events;
+    /* host mirrors */
+    int32_t *h_dims;              /* pinned: [0] n_pile [1] n_cols [2] n_islands [3] n_flagged [4] maxdepth [5] err [6] n_events [7] n_epochs */
+    unsigned long long *h_counters;
+    CgDev D;
+    int resident; int dump_columns;
+    int64_t qual_bytes, events_cap_dev;
+    cudaEvent_t ev[CG_N_TIMERS][2];
+    float ms[CG_N_TIMERS];
+    int64_t launches;
+};
+
+static int ensure(cg_ctx *ctx, dbuf *b, size_t bytes) {
+    if (bytes <= b->cap) return 0;
+    if (b->p) cudaFree(b->p);
+    size_t nc = bytes + (bytes >> 3) + 256;
+    b->p = NULL; b->cap = 0;
+    CG_CHECK(cudaMalloc(&b->p, nc));
+    b->cap = nc;
+    return 0;
+}
+
+static void *pinned_alloc(size_t n) { void *p = NULL; if (cudaHostAlloc(&p, n, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return NULL; } return p; }
+static void pinned_free(void *p) { cudaFreeHost(p); }
+
+extern "C" int cg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static void install_hooks(void) {
+    if (cg_device_count() > 0) { cg_pinned_alloc_hook = pinned_alloc; cg_pinned_free_hook = pinned_free; }
+}
+
+extern "C" int cg_enable_pinned(void) { install_hooks(); return cg_pinned_alloc_hook != NULL; }
+
+extern "C" int cg_set_params(cg_ctx *ctx, const cg_params *p) {
+    const char *why = NULL;
+    int e = cg_params_check(p, &why);
+    if (e) { snprintf(ctx->err, sizeof ctx->err, "not implemented on the device path: %s", why); return e; }
+    ctx->params = *p;
+    cg_tables_init(ctx->hT, p);
+    CG_CHECK(cudaMemcpyAsync(ctx->dT, ctx->hT, sizeof(CgTables), cudaMemcpyHostToDevice, ctx->stream));
+    CG_CHECK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" cg_ctx *cg_create(const cg_params *p, int device, int *err) {
+    int n = cg_device_count();
+    if (n <= 0 || device < 0 || device >= n) { if (err) *err = CG_ERR_NO_DEVICE; return NULL; }
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); if (err) *err = CG_ERR_NO_DEVICE; return NULL; }
+    install_hooks();
+    cg_ctx *ctx = (cg_ctx *)calloc(1, sizeof(cg_ctx));
+    if (!ctx) { if (err) *err = CG_ERR_NOMEM; return NULL; }
+    ctx->device = device;
+    int e = 0;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) e = CG_ERR_CUDA;
+    ctx->own_stream = 1;
+    ctx->hT = (CgTables *)malloc(sizeof(CgTables));
+    if (!e && cudaMalloc((void **)&ctx->dT, sizeof(CgTables)) != cudaSuccess) e = CG_ERR_CUDA;
+    if (!e && cudaHostAlloc((void **)&ctx->h_dims, 64, cudaHostAllocDefault) != cudaSuccess) e = CG_ERR_CUDA;
+    if (!e && cudaHostAlloc((void **)&ctx->h_counters, sizeof(unsigned long long) * 32, cudaHostAllocDefault) != cudaSuccess) e = CG_ERR_CUDA;
+    for (int i = 0; i < CG_N_TIMERS && !e; i++)
+        for (int k = 0; k < 2; k++) if (cudaEventCreate(&ctx->ev[i][k]) != cudaSuccess) e = CG_ERR_CUDA;
+    if (!e) e = cg_set_params(ctx, p);
+    if (e) { if (err) *err = e; cudaGetLastError(); cg_destroy(ctx); return NULL; }
+    if (err) *err = 0;
+    return ctx;
+}
+
+extern "C" void cg_destroy(cg_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    dbuf *all[] = { &ctx->b_tid, &ctx->b_pos, &ctx->b_flag, &ctx->b_mapq, &ctx->b_lq, &ctx->b_nc, &ctx->b_off, &ctx->b_coff, &ctx->b_cigar,
+        &ctx->b_seq, &ctx->b_qual, &ctx->b_qout, &ctx->b_jmap, &ctx->b_rspan, &ctx->b_rd, &ctx->b_ks, &ctx->b_ke, &ctx->b_gap, &ctx->b_gapraw,
+        &ctx->b_pmax, &ctx->b_orig, &ctx->b_rbf, &ctx->b_tlo, &ctx->b_tstart, &ctx->b_isl, &ctx->b_cb, &ctx->b_ev, &ctx->b_depth, &ctx->b_dump,
+        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events };
+    for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); i++) if (all[i]->p) cudaFree(all[i]->p);
+    if (ctx->dT) cudaFree(ctx->dT);
+    if (ctx->h_dims) cudaFreeHost(ctx->h_dims);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    for (int i = 0; i < CG_N_TIMERS; i++) for (int k = 0; k < 2; k++) if (ctx->ev[i][k]) cudaEventDestroy(ctx->ev[i][k]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    free(ctx->hT);
+    free(ctx);
+}
+
+extern "C" const char *cg_last_error(const cg_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+extern "C" int cg_set_stream(cg_ctx *ctx, void *s) {
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)s; ctx->own_stream = 0;
+    return 0;
+}
+extern "C" int cg_sync(cg_ctx *ctx) { CG_CHECK(cudaStreamSynchronize(ctx->stream)); return 0; }
+extern "C" float cg_last_ms(const cg_ctx *ctx, int which) { return (which >= 0 && which < CG_N_TIMERS) ? ctx->ms[which] : -1.f; }
+extern "C" int64_t cg_last_launches(const cg_ctx *ctx) { return ctx->launches; }
+extern "C" int64_t cg_n_columns(const cg_ctx *ctx) { return ctx->D.n_cols; }
+
+#define T0(i) cudaEventRecord(ctx->ev[i][0], st)
+#define T1(i) cudaEventRecord(ctx->ev[i][1], st)
+
+/* ---------------------------------------------------------------------------------------- */
+extern "C" int cg_upload(cg_ctx *ctx, const cg_batch *in) {
+    CG_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t n = in->n_reads;
+    if (n < 0 || in->qual_bytes < 0) return CG_ERR_BAD_ARG;
+    if (n > 0x7fffff00LL || in->n_cigar_total > 0x7fffff00LL) { snprintf(ctx->err, sizeof ctx->err, "batch too large: split it"); return CG_ERR_BAD_ARG; }
+    ctx->resident = 0;
+    size_t n1 = (size_t)n + 1;
+    int e;
+    if ((e = ensure(ctx, &ctx->b_tid, n1 * 4)) || (e = ensure(ctx, &ctx->b_pos, n1 * 4)) || (e = ensure(ctx, &ctx->b_flag, n1 * 2)) ||
+        (e = ensure(ctx, &ctx->b_mapq, n1)) || (e = ensure(ctx, &ctx->b_lq, n1 * 4)) || (e = ensure(ctx, &ctx->b_nc, n1 * 2)) ||
+        (e = ensure(ctx, &ctx->b_off, n1 * 8)) || (e = ensure(ctx, &ctx->b_coff, n1 * 4)) ||
+        (e = ensure(ctx, &ctx->b_cigar, ((size_t)in->n_cigar_total + 1) * 4)) || (e = ensure(ctx, &ctx->b_seq, (size_t)in->seq_bytes + 16)) ||
+        (e = ensure(ctx, &ctx->b_qual, (size_t)in->qual_bytes + 16)) || (e = ensure(ctx, &ctx->b_qout, (size_t)in->qual_bytes + 16))) return e;
+    T0(CG_T_H2D);
+    if (n) {
+        CG_CHECK(cudaMemcpyAsync(ctx->b_tid.p, in->tid, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_pos.p, in->pos, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_flag.p, in->flag, (size_t)n * 2, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_mapq.p, in->mapq, (size_t)n, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_lq.p, in->l_qseq, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_nc.p, in->n_cigar, (size_t)n * 2, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_off.p, in->off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_coff.p, in->cigar_off, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        if (in->n_cigar_total) CG_CHECK(cudaMemcpyAsync(ctx->b_cigar.p, in->cigar, (size_t)in->n_cigar_total * 4, cudaMemcpyHostToDevice, st));
+        if (in->seq_bytes) CG_CHECK(cudaMemcpyAsync(ctx->b_seq.p, in->seq, (size_t)in->seq_bytes, cudaMemcpyHostToDevice, st));
+        if (in->qual_bytes) CG_CHECK(cudaMemcpyAsync(ctx->b_qual.p, in->qual, (size_t)in->qual_bytes, cudaMemcpyHostToDevice, st));
+    }
+    T1(CG_T_H2D);
+    CgDev *D = &ctx->D;
+    memset(D, 0, sizeof(*D));
+    D->n_reads = n;
+    D->tid = (const int32_t *)ctx->b_tid.p; D->pos = (const int32_t *)ctx->b_pos.p; D->flag = (const uint16_t *)ctx->b_flag.p;
+    D->mapq = (const uint8_t *)ctx->b_mapq.p; D->l_qseq = (const int32_t *)ctx->b_lq.p; D->n_cigar = (const uint16_t *)ctx->b_nc.p;
+    D->off = (const int64_t *)ctx->b_off.p; D->cigar_off = (const int32_t *)ctx->b_coff.p; D->cigar = (const uint32_t *)ctx->b_cigar.p;
+    D->seq = (const uint8_t *)ctx->b_seq.p; D->qual = (const uint8_t *)ctx->b_qual.p; D->qual_out = (uint8_t *)ctx->b_qout.p;
+    ctx->qual_bytes = in->qual_bytes;
+    ctx->resident = 1;
+    return 0;
+}
+
+template <class T, class Op, class Load, class Store>
+static int run_scan(cg_ctx *ctx, Load ld, Store st_, int64_t n, T ident, T *total_dev) {
+    cudaStream_t st = ctx->stream;
+    int nb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    if (nb < 1) nb = 1;
+    int e = ensure(ctx, &ctx->b_aggr, (size_t)nb * sizeof(T) + 64);
+    if (e) return e;
+    T *aggr = (T *)ctx->b_aggr.p;
+    k_scan_reduce<T, Op, Load><<<nb, SCAN_THREADS, 0, st>>>(ld, n, ident, aggr);
+    k_scan_aggr<T, Op><<<1, SCAN_THREADS, 0, st>>>(aggr, nb, ident, total_dev);
+    k_scan_apply<T, Op, Load, Store><<<nb, SCAN_THREADS, 0, st>>>(ld, st_, n, ident, aggr);
+    ctx->launches += 3;
+    CG_CHECK(cudaGetLastError());
+    return 0;
+}
+
+static inline int nblk(int64_t n, int t) { int64_t b = (n + t - 1) / t; return (int)(b < 1 ? 1 : b); }
+
+extern "C" int cg_run(cg_ctx *ctx) {
+    if (!ctx->resident) return CG_ERR_STATE;
+    CG_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CgDev *D = &ctx->D;
+    const int64_t n = D->n_reads;
+    const size_t n1 = (size_t)n + 1;
+    int e;
+    ctx->launches = 0;
+    for (int i = 0; i < CG_N_TIMERS; i++) if (i != CG_T_H2D && i != CG_T_D2H) ctx->ms[i] = 0;
+    D->T = ctx->dT; cg_devparams_from(&D->P, &ctx->params);
+    if ((e = ensure(ctx, &ctx->b_scal, 1024))) return e;
+    /* scalars: [0] n_pile [1] n_cols [2] n_islands [3] n_flagged [4] maxdepth [5] err [6] n_events [7] n_epochs ; counters at +128 bytes */
+    int32_t *scal = (int32_t *)ctx->b_scal.p;
+    D->counters = (unsigned long long *)((char *)ctx->b_scal.p + 128);
+    D->maxdepth = scal + 4; D->err = scal + 5;
+    if ((e = ensure(ctx, &ctx->b_jmap, n1 * 4)) || (e = ensure(ctx, &ctx->b_rspan, n1 * 4)) || (e = ensure(ctx, &ctx->b_rd, n1 * sizeof(CgRead))) ||
+        (e = ensure(ctx, &ctx->b_ks, n1 * 8)) || (e = ensure(ctx, &ctx->b_ke, n1 * 8)) || (e = ensure(ctx, &ctx->b_gap, n1 * 8)) ||
+        (e = ensure(ctx, &ctx->b_gapraw, n1 * 8)) || (e = ensure(ctx, &ctx->b_pmax, n1 * 4)) || (e = ensure(ctx, &ctx->b_orig, n1 * 4)) ||
+        (e = ensure(ctx, &ctx->b_rbf, n1)) || (e = ensure(ctx, &ctx->b_isl, n1 * sizeof(CgIsland)))) return e;
+    D->jmap = (int32_t *)ctx->b_jmap.p; D->rspan = (int32_t *)ctx->b_rspan.p; D->rd = (CgRead *)ctx->b_rd.p;
+    D->ks = (int64_t *)ctx->b_ks.p; D->ke = (int64_t *)ctx->b_ke.p; D->gap = (int64_t *)ctx->b_gap.p;
+    D->pmaxcol = (int32_t *)ctx->b_pmax.p; D->orig = (int32_t *)ctx->b_orig.p; D->r_bf = (uint8_t *)ctx->b_rbf.p;
+    D->isl = (CgIsland *)ctx->b_isl.p;
+    int64_t *gapraw = (int64_t *)ctx->b_gapraw.p;
+
+    T0(CG_T_TOTAL);
+    T0(CG_T_TILES);
+    CG_CHECK(cudaMemsetAsync(ctx->b_scal.p, 0, 1024, st));
+    if (n > 0) {
+        k_prep_read<<<nblk(n, 256), 256, 0, st>>>(*D); ctx->launches++;
+        LdPileFlag lpf = { D->rspan }; StJmap sj = { D->jmap };
+        if ((e = run_scan<int32_t, OpSum>(ctx, lpf, sj, n, 0, scal + 0))) return e;
+        k_prep_keys<<<nblk(n, 256), 256, 0, st>>>(*D); ctx->launches++;
+        /* ke := inclusive prefix max (only the first n_pile entries are meaningful; the tail is never read) */
+        CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 4, cudaMemcpyDeviceToHost, st));
+        CG_CHECK(cudaStreamSynchronize(st));
+        D->n_pile = ctx->h_dims[0];
+    } else D->n_pile = 0;
+    const int np = D->n_pile;
+    if (np > 0) {
+        LdI64 lke = { D->ke }; StI64Incl ske = { D->ke };
+        if ((e = run_scan<int64_t, OpMax>(ctx, lke, ske, np, (int64_t)INT64_MIN, (int64_t *)NULL))) return e;
+        k_gap<<<nblk(np, 256), 256, 0, st>>>(*D, scal + 0, gapraw); ctx->launches++;
+        LdI64 lg = { gapraw }; StI64Incl sg = { D->gap };
+        if ((e = run_scan<int64_t, OpSum>(ctx, lg, sg, np, (int64_t)0, (int64_t *)NULL))) return e;
+        LdIslandFlag lif = { gapraw }; StIsland sis = { D->isl, D->ks, D->gap, gapraw };
+        if ((e = run_scan<int32_t, OpSum>(ctx, lif, sis, np, 0, scal + 2))) return e;
+        k_finish_read<<<nblk(np, 256), 256, 0, st>>>(*D, scal + 0, scal); ctx->launches++;
+    }
+    CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 32, cudaMemcpyDeviceToHost, st));
+    CG_CHECK(cudaStreamSynchronize(st));
+    if (ctx->h_dims[5]) { snprintf(ctx->err, sizeof ctx->err, "device reported error %d while building read records", ctx->h_dims[5]); return ctx->h_dims[5]; }
+    D->n_cols = np > 0 ? ctx->h_dims[1] : 0; D->n_islands = np > 0 ? ctx->h_dims[2] : 0;
+    D->n_tiles = (D->n_cols + 31) / 32;
+    const int nc = D->n_cols;
+    const size_t nc1 = (size_t)nc + 64;
+    D->want_dump = 0;
+    if ((e = ensure(ctx, &ctx->b_tlo, ((size_t)D->n_tiles + 2) * 4)) || (e = ensure(ctx, &ctx->b_tstart, ((size_t)D->n_tiles + 2) * 4)) ||
+        (e = ensure(ctx, &ctx->b_cb, nc1)) || (e = ensure(ctx, &ctx->b_ev, nc1 * 2)) || (e = ensure(ctx, &ctx->b_depth, nc1 * 4)) ||
+        (e = ensure(ctx, &ctx->b_fcol, nc1 * 4))) return e;
+    D->tile_lo = (int32_t *)ctx->b_tlo.p; D->tile_start = (int32_t *)ctx->b_tstart.p;
+    D->cb = (uint8_t *)ctx->b_cb.p; D->ev = (uint16_t *)ctx->b_ev.p; D->depth = (uint32_t *)ctx->b_depth.p; D->fcol = (int32_t *)ctx->b_fcol.p;
+    if (ctx->dump_columns || getenv("CG_COLUMN_DUMP")) {
+        if ((e = ensure(ctx, &ctx->b_dump, nc1 * sizeof(cg_column)))) return e;
+        D->coldump = (cg_column *)ctx->b_dump.p; D->want_dump = 1;
+    }
+    if (np > 0 && nc > 0) {
+        k_fill_i32<<<nblk(D->n_tiles + 2, 256), 256, 0, st>>>(D->tile_lo, D->n_tiles + 2, np);
+        k_fill_i32<<<nblk(D->n_tiles + 2, 256), 256, 0, st>>>(D->tile_start, D->n_tiles + 2, np);
+        k_tile_index<<<nblk(np, 256), 256, 0, st>>>(*D); ctx->launches += 3;
+    }
+    T1(CG_T_TILES);
+    T0(CG_T_COLUMNS);
+    if (nc > 0) { k_column<<<nblk(nc, 128), 128, 0, st>>>(*D); ctx->launches++; }
+    T1(CG_T_COLUMNS);
+    T0(CG_T_FLAGGED);
+    if (nc > 0) {
+        LdEvFlag lf = { D->ev, CG_EV_FLAGGED }; StCompact sc = { D->fcol, D->ev, CG_EV_FLAGGED };
+        if ((e = run_scan<int32_t, OpSum>(ctx, lf, sc, nc, 0, scal + 3))) return e;
+    }
+    CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 32, cudaMemcpyDeviceToHost, st));
+    CG_CHECK(cudaStreamSynchronize(st));
+    const int nf = D->n_flagged = ctx->h_dims[3];
+    const int maxdepth = ctx->h_dims[4];
+    if ((e = ensure(ctx, &ctx->b_trig, ((size_t)nf + 1) * sizeof(CgTrig))) || (e = ensure(ctx, &ctx->b_twin, ((size_t)nf + 1) * sizeof(CgWin)))) return e;
+    D->trig = (CgTrig *)ctx->b_trig.p; D->twin = (CgWin *)ctx->b_twin.p;
+    if (nf > 0) {
+        int threads = 64, blocks = nblk(nf, threads);
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        if ((e = ensure(ctx, &ctx->b_scratch, (size_t)blocks * threads * sizeof(CgFlagScratch)))) return e;
+        k_flagged<<<blocks, threads, 0, st>>>(*D, (CgFlagScratch *)ctx->b_scratch.p); ctx->launches++;
+    }
+    T1(CG_T_FLAGGED);
+    T0(CG_T_DEPTH);
+    /* over-depth can only fire when some column is deeper than -P (total_depth >= total_col), or -P < 1 */
+    if (nc > 0 && (ctx->params.over_depth < 1.0 || (double)maxdepth > ctx->params.over_depth)) {
+        if ((e = ensure(ctx, &ctx->b_dsum, nc1 * 8)) || (e = ensure(ctx, &ctx->b_csum, nc1 * 4))) return e;
+        D->dsum = (int64_t *)ctx->b_dsum.p; D->csum = (int32_t *)ctx->b_csum.p;
+        LdDepthCounted ld = { D->depth, D->ev }; StI64Incl sd = { D->dsum };
+        if ((e = run_scan<int64_t, OpSum>(ctx, ld, sd, nc, (int64_t)0, (int64_t *)NULL))) return e;
+        LdCounted lc = { D->ev }; StI32Incl sc2 = { D->csum };
+        if ((e = run_scan<int32_t, OpSum>(ctx, lc, sc2, nc, 0, (int32_t *)NULL))) return e;
+        int cap = D->n_islands + nc / 262144 + 16;
+        if ((e = ensure(ctx, &ctx->b_epoch, (size_t)cap * sizeof(CgEpoch)))) return e;
+        k_epochs<<<1, 32, 0, st>>>(*D, (CgEpoch *)ctx->b_epoch.p, scal + 7, cap);
+        k_deep<<<nblk(nc, 256), 256, 0, st>>>(*D, (const CgEpoch *)ctx->b_epoch.p, scal + 7); ctx->launches += 2;
+    }
+    T1(CG_T_DEPTH);
+    T0(CG_T_CHAIN);
+    if (nf > 0) {
+        k_chain<<<1, 32, 0, st>>>(*D);
+        k_paint<<<nblk(nf, 128), 128, 0, st>>>(*D); ctx->launches += 2;
+    }
+    T1(CG_T_CHAIN);
+    T0(CG_T_REWRITE);
+    if (n > 0) { k_rewrite<<<nblk(n, 128), 128, 0, st>>>(*D); ctx->launches++; }
+    T1(CG_T_REWRITE);
+    T0(CG_T_EVENTS);
+    if (nc > 0) {
+        /* BED events: ordered compaction; capacity grows on demand (cg_download re-runs the scatter if needed) */
+        if (!ctx->b_events.p) { if ((e = ensure(ctx, &ctx->b_events, sizeof(cg_bed_event) * 65536))) return e; }
+        ctx->events_cap_dev = (int64_t)(ctx->b_events.cap / sizeof(cg_bed_event));
+        LdEvCount le = { D->ev }; StEvents se = { (cg_bed_event *)ctx->b_events.p, D->ev, *D, ctx->events_cap_dev };
+        if ((e = run_scan<int32_t, OpSum>(ctx, le, se, nc, 0, scal + 6))) return e;
+        if (D->want_dump) { k_dump_flags<<<nblk(nc, 256), 256, 0, st>>>(*D); ctx->launches++; }
+    }
+    T1(CG_T_EVENTS);
+    T1(CG_T_TOTAL);
+    CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 32, cudaMemcpyDeviceToHost, st));
+    CG_CHECK(cudaMemcpyAsync(ctx->h_counters, D->counters, sizeof(unsigned long long) * CG_N_COUNTERS, cudaMemcpyDeviceToHost, st));
+    CG_CHECK(cudaStreamSynchronize(st));
+    CG_CHECK(cudaGetLastError());
+    for (int i = 0; i < CG_N_TIMERS; i++) {
+        if (i == CG_T_H2D || i == CG_T_D2H) continue;
+        float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev[i][0], ctx->ev[i][1]) == cudaSuccess) ctx->ms[i] = ms; else cudaGetLastError();
+    }
+    if (ctx->h_dims[5]) { snprintf(ctx->err, sizeof ctx->err, "device reported error %d", ctx->h_dims[5]); return ctx->h_dims[5]; }
+    if (ctx->h_dims[6] > ctx->events_cap_dev) {
+        /* more BED events than the device list holds: grow and redo the (cheap) ordered scatter */
+        if ((e = ensure(ctx, &ctx->b_events, sizeof(cg_bed_event) * ((size_t)ctx->h_dims[6] + 1024)))) return e;
+        ctx->events_cap_dev = (int64_t)(ctx->b_events.cap / sizeof(cg_bed_event));
+        LdEvCount le = { D->ev }; StEvents se = { (cg_bed_event *)ctx->b_events.p, D->ev, *D, ctx->events_cap_dev };
+        if ((e = run_scan<int32_t, OpSum>(ctx, le, se, nc, 0, scal + 6))) return e;
+        CG_CHECK(cudaStreamSynchronize(st));
+    }
+    ctx->resident = 2;
+    return 0;
+}
+
+extern "C" int cg_download(cg_ctx *ctx, cg_result *out) {
+    if (ctx->resident != 2) return CG_ERR_STATE;
+    CG_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    T0(CG_T_D2H);
+    if (out->qual_out && ctx->qual_bytes) CG_CHECK(cudaMemcpyAsync(out->qual_out, ctx->b_qout.p, (size_t)ctx->qual_bytes, cudaMemcpyDeviceToHost, st));
+    out->n_events = ctx->h_dims[6];
+    if (out->events && out->n_events) {
+        int64_t k = out->n_events < out->events_cap ? out->n_events : out->events_cap;
+        if (k) CG_CHECK(cudaMemcpyAsync(out->events, ctx->b_events.p, sizeof(cg_bed_event) * (size_t)k, cudaMemcpyDeviceToHost, st));
+    }
+    out->n_columns = 0;
+    cg_column *tmp = NULL;
+    if (out->columns && ctx->D.want_dump && ctx->D.n_cols) {
+        tmp = (cg_column *)malloc(sizeof(cg_column) * (size_t)ctx->D.n_cols);
+        if (!tmp) return CG_ERR_NOMEM;
+        CG_CHECK(cudaMemcpyAsync(tmp, ctx->b_dump.p, sizeof(cg_column) * (size_t)ctx->D.n_cols, cudaMemcpyDeviceToHost, st));
+    }
+    T1(CG_T_D2H);
+    CG_CHECK(cudaStreamSynchronize(st));
+    for (int i = 0; i < CG_N_COUNTERS; i++) out->counters[i] = (int64_t)ctx->h_counters[i];
+    if (tmp) {
+        for (int c = 0; c < ctx->D.n_cols; c++) {
+            if (tmp[c].tid < 0) continue;
+            if (out->n_columns < out->columns_cap) out->columns[out->n_columns] = tmp[c];
+            out->n_columns++;
+        }
+        free(tmp);
+    }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_D2H][0], ctx->ev[CG_T_D2H][1]) == cudaSuccess) ctx->ms[CG_T_D2H] = ms; else cudaGetLastError();
+    if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_H2D][0], ctx->ev[CG_T_H2D][1]) == cudaSuccess) ctx->ms[CG_T_H2D] = ms; else cudaGetLastError();
+    return 0;
+}
+
+extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
+    int e;
+    if ((e = cg_upload(ctx, in))) return e;
+    ctx->dump_columns = out->columns != NULL;
+    e = cg_run(ctx);
+    if (e) return e;
+    return cg_download(ctx, out);
+}

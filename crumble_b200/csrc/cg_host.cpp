@@ -204,6 +204,7 @@ struct cg_batch_builder {
 extern "C" cg_batch_builder *cgb_create(int pinned) {
     cg_batch_builder *b = (cg_batch_builder *)calloc(1, sizeof(*b));
     if (!b) return NULL;
+    if (pinned) cg_enable_pinned();
     int pin = pinned && cg_pinned_alloc_hook;
     b->tid.init(pin); b->pos.init(pin); b->l_qseq.init(pin); b->cigar_off.init(pin); b->flag.init(pin); b->n_cigar.init(pin);
     b->mapq.init(pin); b->off.init(pin); b->cigar.init(pin); b->seq.init(pin); b->qual.init(pin);

@@ -5,6 +5,7 @@
 int  cg_params_check(const cg_params *p, const char **why);
 void cg_devparams_from(CgDevParams *d, const cg_params *p);
 void cg_tables_init(CgTables *T, const cg_params *p);
+extern "C" int cg_enable_pinned(void);   /* installs the pinned-memory hooks when a device exists */
 extern void *(*cg_pinned_alloc_hook)(size_t);
 extern void (*cg_pinned_free_hook)(void *);
 #endif

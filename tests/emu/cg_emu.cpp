@@ -17,6 +17,7 @@
 struct cg_ctx { cg_params p; CgTables T; char err[256]; int64_t n_cols; };
 
 extern "C" int cg_device_count(void) { return 0; }
+extern "C" int cg_enable_pinned(void) { return 0; }
 extern "C" cg_ctx *cg_create(const cg_params *p, int device, int *err) {
     (void)device;
     const char *why = NULL;
