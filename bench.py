@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — aligned bases/s through the consensus + quality-rewrite hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C2] [--scale S]
+
+One "step" = one pass of the whole kernel chain (cg_run) over one resident batch of
+synthetic aligned reads (default: BASELINE.json configs[1] = crumble -9 on a 64 Mb,
+30x chr20-like contig, 2x150 bp; ~1.28e7 reads, ~1.9e9 aligned bases).  N>1: one process
+per GPU (torchrun), each rank owns one contig-sized shard (weak scaling, no data-path
+collective; torch.distributed only for the barrier and the max/sum of the results).
+
+Keys beyond the base contract: roofline (dominant kernel vs measured HBM peak),
+cpu_baseline (the reference's own code, oracle/_ref, on this box's host cores),
+e2e (host buffers in -> host buffers out through the C ABI), clocks, gpu_launches.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+WORKLOADS = {
+    # name: (preset, level args, description)
+    "C1": ("C1", ["-9"], "crumble -9, synthetic 1 Mb region, 30x 2x150bp"),
+    "C2": ("C2", ["-9"], "crumble -9, synthetic chr20 (64 Mb) 30x 2x150bp"),
+    "C3": ("C3", ["-1", "-B"], "crumble -1 -B, synthetic chr20 (64 Mb) 30x"),
+    "C4": ("C4", ["-9"], "crumble -9, 1000x amplicon panel (200 x 250 bp)"),
+}
+
+
+def level_params(cb, args):
+    import ctypes as C
+    p = cb.default_params()
+    for a in args:
+        if a[1] in "135789":
+            cb.load_lib().cg_params_level(C.byref(p), int(a[1]))
+        elif a == "-B":
+            p.binary_qual = 1
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="clocks", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index),
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm)); out["sm_max_mhz"] = float(max(mx)); out["reasons"] = sorted(reasons)
+            out["samples"] = len(sm)
+        return out
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ref_binary():
+    p = ROOT / "oracle" / "_ref" / "crumble_ref"
+    if p.exists():
+        return p, "reference"
+    p = ROOT / "oracle" / "bin" / "crumble_oracle"
+    if p.exists():
+        return p, "port"
+    return None, None
+
+
+def run_ref_once(binary, path, args):
+    env = dict(os.environ); env["CRUMBLE_REF_TIMING"] = "1"
+    r = subprocess.run([str(binary), "-z"] + args + ["-O", "bam,raw", path, "mem:discard"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, env=env)
+    if r.returncode != 0:
+        raise RuntimeError("reference run failed: " + r.stderr[-500:])
+    for line in r.stderr.splitlines():
+        if line.startswith("transcode_seconds="):
+            return float(line.split("=")[1])
+    return None
+
+
+def cpu_baseline(cb, workload, sample_mb=2.0):
+    """Reference transcode() (oracle/_ref, single thread as the reference is) on a bounded sample."""
+    binary, kind = ref_binary()
+    if binary is None:
+        return None
+    preset, args, _ = WORKLOADS[workload]
+    scale = sample_mb / 64.0 if preset in ("C2", "C3") else (sample_mb if preset == "C1" else 0.5)
+    data, nr, nb = cb.simulate(preset, scale, seed=4242)
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=tmpdir) as td:
+        path = os.path.join(td, "sample.ubam")
+        data.tofile(path)
+        secs = run_ref_once(binary, path, args)
+    return {"value": nb / secs, "unit": "aligned bases/s", "cores": 1, "kind": kind,
+            "sample": f"{preset} x{scale:.4g} seed 4242: {nr} reads, {nb} aligned bases, transcode() {secs:.2f} s (memory-backed reader, discarding writer)"}
+
+
+def bench_reference(a, rank, world):
+    """--impl reference: the reference's own CPU implementation on all host cores (one process per shard)."""
+    if rank != 0:
+        return
+    import crumble_b200 as cb
+    binary, kind = ref_binary()
+    if binary is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle binaries not built"}))
+        return
+    preset, args, desc = WORKLOADS[a.workload]
+    cores = os.cpu_count() or 1
+    nproc = max(1, min(cores, 64))
+    shard_mb = 0.5
+    scale = shard_mb / 64.0 if preset in ("C2", "C3") else (shard_mb if preset == "C1" else 0.1)
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=tmpdir) as td:
+        paths, bases = [], 0
+        for i in range(nproc):
+            data, nr, nb = cb.simulate(preset, scale, seed=9000 + i)
+            p = os.path.join(td, f"s{i}.ubam"); data.tofile(p); paths.append(p); bases += nb
+
+        def step():
+            t0 = time.perf_counter()
+            env = dict(os.environ)
+            procs = [subprocess.Popen([str(binary), "-z"] + args + ["-O", "bam,raw", p, "mem:discard"],
+                                      stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env) for p in paths]
+            for pr in procs:
+                if pr.wait() != 0:
+                    raise RuntimeError("reference shard failed")
+            return time.perf_counter() - t0
+        for _ in range(a.warmup):
+            step()
+        ts = [step() for _ in range(a.steps)]
+    tot = sum(ts)
+    v = bases * a.steps / tot
+    line = {"impl": "reference", "metric": "aligned bases/sec (consensus+qual rewrite)", "value": v, "unit": "aligned bases/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64+u8", "data": "synthetic",
+            "config": {"workload": desc, "sample": f"{nproc} shards x {shard_mb} Mb ({bases} aligned bases per step), one process per shard"},
+            "cpu_baseline": {"value": v, "unit": "aligned bases/s", "cores": nproc, "kind": kind,
+                             "sample": f"{nproc} concurrent single-threaded reference processes on disjoint {shard_mb} Mb shards (includes process start + file slurp)"},
+            "e2e": {"value": v, "unit": "aligned bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.warmup < 3 and a.impl != "reference":
+        a.warmup = 3
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        bench_reference(a, rank, world)
+        return
+
+    import torch
+    import crumble_b200 as cb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    preset, args, desc = WORKLOADS[a.workload]
+    t_gen = time.perf_counter()
+    data, n_reads, n_bases = cb.simulate(preset, a.scale, seed=100 + rank)
+    bb = cb.BatchBuilder(pinned=True)
+    bb.add_bam_stream(data)
+    del data
+    batch = bb.finish()
+    t_gen = time.perf_counter() - t_gen
+    algo_bytes = cb.algorithmic_bytes(batch)
+    bases = cb.aligned_bases(batch)
+    g = cb.Crumble(level_params(cb, args), device=local)
+    stream = torch.cuda.Stream(device=local)
+    g.set_stream(stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident: inputs already in HBM; K passes of the whole kernel chain ------------------
+    g.upload(batch)
+    for _ in range(a.warmup):
+        g.run()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    col_ms, rew_ms, stage = [], [], {}
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(a.steps):
+            g.run()
+            t = g.timers()
+            col_ms.append(t["columns"]); rew_ms.append(t["rewrite"])
+            for k, v in t.items():
+                stage[k] = stage.get(k, 0.0) + v / a.steps
+        ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = g.launches() * a.steps
+    clocks = sampler.stop()
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    tot_bases = torch.tensor([float(bases)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tot_bases, op=dist.ReduceOp.SUM)
+    dev_ms_max = float(tmax.item()); all_bases = float(tot_bases.item())
+    value = all_bases * a.steps / (dev_ms_max * 1e-3)
+
+    # ---- end to end: pinned host SoA -> C ABI -> host quality buffer, copies inside the timed region
+    qout = torch.empty(max(int(batch.qual_bytes), 1), dtype=torch.uint8, pin_memory=True).numpy()
+    g.process(batch, pinned_out=qout)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.e2e_steps):
+        out = g.process(batch, pinned_out=qout)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = all_bases * a.e2e_steps / float(te.item())
+    h2d = int(cb.load_lib().cgb_bytes(bb.h)); d2h = int(batch.qual_bytes) + 12 * len(out["events"]) + 8 * 19
+    e2e_timers = g.timers()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        col = float(np.mean(col_ms))
+        achieved = algo_bytes / (col * 1e-3) / 1e9
+        line = {
+            "metric": "aligned bases/sec (consensus+qual rewrite)", "value": value, "unit": "aligned bases/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dev_ms_max / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+u8", "data": "synthetic",
+            "config": {"workload": desc + (f" (scale {a.scale})" if a.scale != 1.0 else ""), "reads_per_gpu": int(batch.n_reads),
+                       "aligned_bases_per_gpu": int(bases), "columns_per_gpu": g.n_columns(), "sharding": "one contig shard per GPU, no collective",
+                       "l2": "inputs (>= 2.6 B/base resident) far exceed the 126 MB L2; no flush needed",
+                       "stage_ms": {k: round(v, 4) for k, v in stage.items()}, "datagen_s": round(t_gen, 2)},
+            "roofline": {"bound": "hbm", "kernel": "k_column", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": col, "peak_source": peak_src,
+                         "whole_chain_frac": algo_bytes / (dev_ms_max / a.steps * 1e-3) / 1e9 / peak},
+            "e2e": {"value": e2e_value, "unit": "aligned bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * float(te.item()) / a.e2e_steps, "h2d_ms": e2e_timers["h2d"], "d2h_ms": e2e_timers["d2h"],
+                    "steps": a.e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(cb, a.workload)
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"error": str(e)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

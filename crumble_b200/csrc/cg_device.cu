@@ -478,7 +478,7 @@ extern "C" int cg_run(cg_ctx *ctx) {
     /* scalars: [0] n_pile [1] n_cols [2] n_islands [3] n_flagged [4] maxdepth [5] err [6] n_events [7] n_epochs ; counters at +128 bytes */
     int32_t *scal = (int32_t *)ctx->b_scal.p;
     D->counters = (unsigned long long *)((char *)ctx->b_scal.p + 128);
-    D->maxdepth = scal + 4; D->err = scal + 5;
+    D->maxdepth = scal + 4; D->err = scal + 5; D->beyond = scal + 8;
     if ((e = ensure(ctx, &ctx->b_jmap, n1 * 4)) || (e = ensure(ctx, &ctx->b_rspan, n1 * 4)) || (e = ensure(ctx, &ctx->b_rd, n1 * sizeof(CgRead))) ||
         (e = ensure(ctx, &ctx->b_ks, n1 * 8)) || (e = ensure(ctx, &ctx->b_ke, n1 * 8)) || (e = ensure(ctx, &ctx->b_gap, n1 * 8)) ||
         (e = ensure(ctx, &ctx->b_gapraw, n1 * 8)) || (e = ensure(ctx, &ctx->b_pmax, n1 * 4)) || (e = ensure(ctx, &ctx->b_orig, n1 * 4)) ||
@@ -592,7 +592,7 @@ extern "C" int cg_run(cg_ctx *ctx) {
     }
     T1(CG_T_EVENTS);
     T1(CG_T_TOTAL);
-    CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 32, cudaMemcpyDeviceToHost, st));
+    CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 40, cudaMemcpyDeviceToHost, st));
     CG_CHECK(cudaMemcpyAsync(ctx->h_counters, D->counters, sizeof(unsigned long long) * CG_N_COUNTERS, cudaMemcpyDeviceToHost, st));
     CG_CHECK(cudaStreamSynchronize(st));
     CG_CHECK(cudaGetLastError());
@@ -634,6 +634,7 @@ extern "C" int cg_download(cg_ctx *ctx, cg_result *out) {
     T1(CG_T_D2H);
     CG_CHECK(cudaStreamSynchronize(st));
     for (int i = 0; i < CG_N_COUNTERS; i++) out->counters[i] = (int64_t)ctx->h_counters[i];
+    if (ctx->h_dims[8]) out->counters[CG_CNT_COLUMNS]++;   /* snp_score.c:1476 runs before the region break at 1516-1517 */
     if (tmp) {
         for (int c = 0; c < ctx->D.n_cols; c++) {
             if (tmp[c].tid < 0) continue;

@@ -11,65 +11,6 @@
 #include "cg_pipeline.h"
 #include "cg_host.h"
 
-/* ---- parameters ------------------------------------------------------------------------ */
-extern "C" void cg_params_default(cg_params *p) {          /* snp_score.c:91-147, 2152-2192 */
-    memset(p, 0, sizeof(*p));
-    p->reduce_qual = 1; p->binary_qual = 0;
-    p->iSTR_mul = 1.0; p->iSTR_add = 2; p->sSTR_mul = 0.0; p->sSTR_add = 0;
-    p->qlow = 5; p->qcutoff = 25; p->qhigh = 40; p->qcap = 60;
-    p->min_mqual = 0;
-    p->min_qual_A = 0; p->min_indel_A = 50; p->min_discrep_A = 2.0;
-    p->min_qual_B = 70; p->min_indel_B = 125; p->min_discrep_B = 1.5;
-    p->indel_fract = 0.0;
-    p->clip_perc = 0.2; p->low_mqual_perc = 1.0; p->ins_len_perc = 1.0; p->over_depth = 999.0; p->indel_ov_perc = 0.0;
-    p->pblock = 8;
-    p->region_tid = -1; p->region_beg = 0; p->region_end = INT_MAX;
-}
-
-extern "C" int cg_params_level(cg_params *p, int level) {  /* snp_score.c:2380-2482 */
-    switch (level) {
-    case 9: case 8:
-        p->pblock = level == 9 ? 8 : 0;
-        p->min_qual_B = 70; p->min_indel_B = 125; p->min_discrep_B = 1.5;
-        p->low_mqual_perc = 1.0; p->ins_len_perc = 1.0; p->indel_ov_perc = 0.0; p->over_depth = 999.0;
-        p->sSTR_mul = 0.0; p->sSTR_add = 0; p->iSTR_mul = 1.0; p->iSTR_add = 2; p->min_mqual = 0;
-        return 0;
-    case 7:
-        p->pblock = 0;
-        p->min_qual_B = 75; p->min_indel_B = 150; p->min_discrep_B = 1.0;
-        p->low_mqual_perc = 1.0; p->ins_len_perc = 1.0; p->indel_ov_perc = 0.0; p->over_depth = 999.0;
-        p->sSTR_mul = 0.0; p->sSTR_add = 0; p->iSTR_mul = 1.1; p->iSTR_add = 2; p->min_mqual = 0;
-        return 0;
-    case 5: case 3: case 1:
-        p->pblock = 0;
-        p->min_qual_B = 75; p->min_indel_B = 150; p->min_discrep_B = 1.0;
-        p->low_mqual_perc = 0.5; p->ins_len_perc = 0.1; p->indel_ov_perc = 0.5; p->over_depth = 3.0;
-        p->sSTR_mul = level == 5 ? 0.0 : 1.0; p->sSTR_add = level == 1 ? 5 : 0;
-        p->iSTR_mul = level == 1 ? 2.0 : 1.1; p->iSTR_add = level == 1 ? 1 : 2;
-        p->min_mqual = level == 1 ? 5 : 0;
-        return 0;
-    default:
-        return CG_ERR_BAD_ARG;
-    }
-}
-
-extern "C" const char *cg_strerror(int code) {
-    switch (code) {
-    case CG_OK: return "ok";
-    case CG_ERR_NO_DEVICE: return "no usable CUDA device (the GPU path is mandatory; there is no CPU fallback)";
-    case CG_ERR_CUDA: return "CUDA error";
-    case CG_ERR_NOMEM: return "out of memory";
-    case CG_ERR_BAD_ARG: return "bad argument";
-    case CG_ERR_UNSORTED: return "input is not coordinate sorted";
-    case CG_ERR_UNSUPPORTED: return "option not supported by the device path";
-    case CG_ERR_OVERFLOW: return "internal device list overflow";
-    case CG_ERR_STATE: return "calls made out of order";
-    default: return "unknown error";
-    }
-}
-
-extern "C" int cg_abi_version(void) { return CG_ABI_VERSION; }
-
 /* Which option combinations the device path implements today. */
 int cg_params_check(const cg_params *p, const char **why) {
     static const char *w_mul = "negative -i/-s STR multipliers";
@@ -179,8 +120,8 @@ template <class T> struct vec {
     }
     int reserve(size_t want) {
         if (want <= cap) return 0;
-        size_t nc = cap ? cap : 1024;
-        while (nc < want) nc += nc >> 1;
+        size_t nc = cap ? cap + (cap >> 1) : 1024;
+        if (nc < want) nc = want;
         T *np;
         if (pinned && cg_pinned_alloc_hook) {
             np = (T *)cg_pinned_alloc_hook(nc * sizeof(T));
@@ -258,6 +199,21 @@ extern "C" int cgb_add_bam_stream(cg_batch_builder *b, const uint8_t *buf, size_
     if (p + 4 > len) return CG_ERR_BAD_ARG;
     memcpy(&nref, buf + p, 4); p += 4;
     for (uint32_t i = 0; i < nref; i++) { uint32_t ln; if (p + 4 > len) return CG_ERR_BAD_ARG; memcpy(&ln, buf + p, 4); p += 4 + ln + 4; }
+    {   /* size everything once (pinned allocations are expensive to grow) */
+        size_t q = p, nrec = 0, qb = 0, nc = 0;
+        while (q + 4 <= len) {
+            uint32_t bs; memcpy(&bs, buf + q, 4);
+            if (bs < 32 || q + 4 + bs > len) return CG_ERR_BAD_ARG;
+            int32_t lseq; uint16_t ncig; memcpy(&lseq, buf + q + 4 + 16, 4); memcpy(&ncig, buf + q + 4 + 12, 2);
+            if (lseq < 0) return CG_ERR_BAD_ARG;
+            nrec++; qb += ((size_t)lseq + 7) & ~(size_t)7; nc += ncig;
+            q += 4 + bs;
+        }
+        size_t i = b->tid.n + nrec;
+        if (b->tid.reserve(i) || b->pos.reserve(i) || b->l_qseq.reserve(i) || b->cigar_off.reserve(i) || b->flag.reserve(i) ||
+            b->n_cigar.reserve(i) || b->mapq.reserve(i) || b->off.reserve(i) || b->qual.reserve(b->qual.n + qb + 16) ||
+            b->seq.reserve((b->qual.n + qb) / 2 + 16) || b->cigar.reserve(b->cigar.n + nc + 2)) return CG_ERR_NOMEM;
+    }
     while (p + 4 <= len) {
         uint32_t bs; memcpy(&bs, buf + p, 4);
         if (bs < 32 || p + 4 + bs > len) return CG_ERR_BAD_ARG;

@@ -75,6 +75,7 @@ typedef struct CgDev {
     /* scalars on the device */
     unsigned long long *counters;   /* CG_N_COUNTERS */
     int32_t *maxdepth; int32_t *err;
+    int32_t *beyond;          /* set when a counted column exists at/after the -r region end (the reference counts one, then breaks) */
     const CgTables *T;
     CgDevParams P;
     int32_t want_dump;
@@ -237,7 +238,7 @@ CG_HD CgColOut cg_column_body(const CgDev *D, int c) {
         tid = D->isl[is].tid; pos = D->isl[is].pos_start + (c - D->isl[is].col_start);
     }
     /* region end acts as a hard stop (the reference breaks out of the loop, 1516-1517) */
-    if (P->region_tid >= 0 && pos >= P->region_end) { D->cb[c] = cb; D->ev[c] = 0; if (D->want_dump) { cg_column z = {0}; z.tid = -1; D->coldump[c] = z; } return o; }
+    if (P->region_tid >= 0 && pos >= P->region_end) { *D->beyond = 1; D->cb[c] = cb; D->ev[c] = 0; if (D->want_dump) { cg_column z = {0}; z.tid = -1; D->coldump[c] = z; } return o; }
     ev |= CG_EV_COUNTED;
     o.cnt |= 1u << CG_CNT_COLUMNS;                                        /* 1476 */
     CgCons cB; cB.call = 5; cB.het_call = 0; cB.het_phred = 0; cB.phred = 0; cB.depth = 0; cB.discrep = 0;

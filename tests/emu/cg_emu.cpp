@@ -42,7 +42,7 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
     D.n_cigar = in->n_cigar; D.off = in->off; D.cigar_off = in->cigar_off; D.cigar = in->cigar; D.seq = in->seq; D.qual = in->qual;
     D.qual_out = out->qual_out;
     D.T = &ctx->T; cg_devparams_from(&D.P, &ctx->p);
-    int32_t err = 0, maxdepth = 0; D.err = &err; D.maxdepth = &maxdepth;
+    int32_t err = 0, maxdepth = 0, beyond = 0; D.err = &err; D.maxdepth = &maxdepth; D.beyond = &beyond;
     unsigned long long counters[CG_N_COUNTERS] = {0}; D.counters = counters;
     std::vector<int32_t> jmap(n + 1), rspan(n + 1);
     D.jmap = jmap.data(); D.rspan = rspan.data();
@@ -130,6 +130,7 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
             }
         }
     }
+    if (beyond) counters[CG_CNT_COLUMNS]++;      /* snp_score.c:1476 runs before the region break at 1516-1517 */
     for (int i = 0; i < CG_N_COUNTERS; i++) out->counters[i] = (int64_t)counters[i];
     out->n_columns = 0;
     if (out->columns) {

@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Regenerates the golden fixtures from oracle/_ref (the reference's own sources compiled
+verbatim; needs /root/reference at build time, so this only runs in the build container).
+
+    python tests/golden/make_golden.py
+
+Outputs (committed):
+  golden.json                      sha256 of the rewritten quality bytes, BED text and -v counters for
+                                   seeded synthetic data sets (crumble_b200.simulate) at several option sets
+  edge_cases.<tag>.qual.txt        rewritten quality strings of tests/golden/edge_cases.sam, one read per line
+  edge_cases.<tag>.bed             BED output for the same runs
+  ref_columns.tiny.-9.txt          the reference's own -DDEBUG per-column dump (call / score / preserve mark)
+"""
+import hashlib
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import numpy as np  # noqa: E402
+import crumble_b200 as cb  # noqa: E402
+from util import run_oracle, valid_mask  # noqa: E402
+
+SETS = {"tiny": ("tiny", 1.0, 3), "c1s": ("C1", 0.1, 11), "c2s": ("C2", 1 / 512, 5), "c4s": ("C4", 0.02, 4)}
+ARGS = [["-9"], ["-8"], ["-7"], ["-5"], ["-3"], ["-1"], ["-1", "-B"], ["-9", "-Y0.1"], ["-5", "-q30"], ["-9", "-U30"],
+        ["-1", "-m10", "-C0.05", "-Z0.01"], ["-9", "-p0", "-L0"], ["-9", "-X0.5", "-D200"], ["-3", "-i0.5,3", "-s2.0,1"]]
+EDGE = {"l9": ["-9"], "l1B": ["-1", "-B"], "l5q30": ["-5", "-q30"], "l3U35": ["-3", "-U35", "-Y0.2"],
+        "l9r": ["-9", "-r", "chrA:900-1600"], "l1r": ["-1", "-r", "chrA:1200-2100"]}
+
+
+def main():
+    ref = ROOT / "oracle" / "_ref" / "crumble_ref"
+    assert ref.exists(), "build oracle/_ref first (make -C oracle ref)"
+    gold = {}
+    for name, (preset, scale, seed) in SETS.items():
+        data, nr, nb = cb.simulate(preset, scale, seed, threads=1)
+        bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data); bb.finish()
+        m = valid_mask(bb)
+        gold[name] = {"preset": preset, "scale": scale, "seed": seed, "reads": nr, "aligned_bases": nb,
+                      "input_sha256": hashlib.sha256(data.tobytes()).hexdigest(), "runs": {}}
+        for a in ARGS:
+            r = run_oracle(data, a, kind="reference")
+            gold[name]["runs"][" ".join(a)] = {"qual_sha256": hashlib.sha256(r["qual"][m].tobytes()).hexdigest(),
+                                               "bed": r["bed"], "counters": r["counters"]}
+        bb.close()
+    json.dump(gold, open(HERE / "golden.json", "w"), indent=1, sort_keys=True)
+    sam = HERE / "edge_cases.sam"
+    for tag, a in EDGE.items():
+        out, bed = HERE / f"_tmp.{tag}.sam", HERE / f"edge_cases.{tag}.bed"
+        subprocess.run([str(ref), "-z"] + a + ["-b", str(bed), str(sam), str(out)], check=True)
+        with open(HERE / f"edge_cases.{tag}.qual.txt", "w") as f:
+            for line in open(out):
+                if not line.startswith("@"):
+                    c = line.rstrip("\n").split("\t"); f.write(c[0] + "\t" + c[10] + "\n")
+        out.unlink()
+    # the reference's own debug dump: "Depth tid pos n_plp \t call score \t[*]\t bases"
+    data, _, _ = cb.simulate(*SETS["tiny"], threads=1)
+    tmp = HERE / "_tmp.ubam"; data.tofile(tmp)
+    dbg = subprocess.run([str(ROOT / "oracle" / "_ref" / "crumble_ref_debug"), "-z", "-9", str(tmp), "mem:x"],
+                         stdout=subprocess.PIPE, text=True, check=True).stdout
+    tmp.unlink()
+    with open(HERE / "ref_columns.tiny.-9.txt", "w") as f:
+        n = 0
+        for line in dbg.splitlines():
+            if line.startswith("Depth 0"):           # first contig, first 20000 columns: pos(1-based) depth call+score mark
+                c = line.split("\t")
+                f.write("\t".join(c[1:5]).rstrip("\t") + "\n")
+                n += 1
+                if n == 20000:
+                    break
+    print("golden fixtures written")
+
+
+if __name__ == "__main__":
+    main()

@@ -76,3 +76,152 @@ def test_configs(name, args):
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+# ---- golden vectors (generated from the verbatim reference; no oracle run needed) --------------
+import hashlib
+import json
+import os
+import subprocess
+import tempfile
+
+from util import ROOT, PORT_BIN
+
+GOLD = json.load(open(ROOT / "tests" / "golden" / "golden.json"))
+GDIR = ROOT / "tests" / "golden"
+
+
+def params_from_args2(args):
+    out = []
+    for a in args:
+        if a.startswith("-i") or a.startswith("-s") or a.startswith("-X") or a.startswith("-D"):
+            out.append(a)
+        else:
+            out.append(a)
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_gpu_matches_golden(name):
+    g0 = GOLD[name]
+    data, nr, nb = cb.simulate(g0["preset"], g0["scale"], g0["seed"], threads=2)
+    assert hashlib.sha256(data.tobytes()).hexdigest() == g0["input_sha256"]
+    bb = cb.BatchBuilder(); bb.add_bam_stream(data); batch = bb.finish(); m = valid_mask(bb)
+    names = ["chr20"] if g0["preset"] != "tiny" else ["chr1", "chr2"]
+    for args, exp in g0["runs"].items():
+        p = cb.default_params()
+        import ctypes as C
+        for a in args.split():
+            k, v = a[1], a[2:]
+            if k in "135789": cb.load_lib().cg_params_level(C.byref(p), int(k))
+            elif k == "B": p.binary_qual = 1
+            elif k == "Y": p.indel_fract = float(v)
+            elif k == "q": p.min_qual_A = int(v)
+            elif k == "U": p.qcap = int(v)
+            elif k == "m": p.min_mqual = int(v)
+            elif k == "C": p.clip_perc = float(v)
+            elif k == "Z": p.ins_len_perc = float(v)
+            elif k == "p": p.pblock = int(v)
+            elif k == "L": p.reduce_qual = int(v)
+            elif k == "X": p.min_discrep_B = float(v)
+            elif k == "D": p.min_indel_B = int(v)
+            elif k == "i": p.iSTR_mul = float(v.split(",")[0]); p.iSTR_add = int(v.split(",")[1])
+            elif k == "s": p.sSTR_mul = float(v.split(",")[0]); p.sSTR_add = int(v.split(",")[1])
+            else: raise ValueError(a)
+        g = cb.Crumble(p, device=0)
+        out = g.process(batch)
+        assert hashlib.sha256(out["qual"][m].tobytes()).hexdigest() == exp["qual_sha256"], args
+        assert cb.bed_text(out["events"], names) == exp["bed"], args
+        assert out["counters"] == exp["counters"], args
+        g.close()
+
+
+EDGE = {"l9": ["-9"], "l1B": ["-1", "-B"], "l5q30": ["-5", "-q30"], "l3U35": ["-3", "-U35", "-Y0.2"],
+        "l9r": ["-9", "-r", "chrA:900-1600"], "l1r": ["-1", "-r", "chrA:1200-2100"]}
+
+
+@pytest.mark.parametrize("tag", sorted(EDGE))
+def test_gpu_cli_edge_cases(tag):
+    """the crumble_gpu command line (host driver + device path) on the odd-CIGAR SAM, against the reference's output"""
+    cli = ROOT / "crumble_b200" / "lib" / "crumble_gpu"
+    with tempfile.TemporaryDirectory() as td:
+        out, bed = os.path.join(td, "o.sam"), os.path.join(td, "o.bed")
+        r = subprocess.run([str(cli), "-z"] + EDGE[tag] + ["-b", bed, str(GDIR / "edge_cases.sam"), out], stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+        quals = [(l.rstrip("\n").split("\t")[0], l.rstrip("\n").split("\t")[10]) for l in open(out) if not l.startswith("@")]
+        exp = [tuple(l.rstrip("\n").split("\t")) for l in open(GDIR / f"edge_cases.{tag}.qual.txt")]
+        assert quals == exp
+        assert open(bed).read() == open(GDIR / f"edge_cases.{tag}.bed").read()
+        # aux tags and everything else pass through untouched; @PG is added without -z
+        r = subprocess.run([str(cli), "-9", str(GDIR / "edge_cases.sam"), out], stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0
+        txt = open(out).read()
+        assert "@PG\tID:crumble\tPN:crumble\tVN:0.9.1" in txt and "XX:Z:keepme" in txt
+
+
+def test_gpu_columns_bit_exact():
+    """per-column consensus (call, het_call, phred, het_phred, discrep) and column decisions against the CPU oracle:
+    the tolerance north_star allows is not needed — every field, including the float discrepancy, is identical."""
+    data, bb, batch, mask = dataset("c1s")
+    for args in (["-9"], ["-1"]):
+        g = cb.Crumble(params_from_args(args), device=0)
+        out = g.process(batch, want_columns=True)
+        cols = out["columns"]
+        with tempfile.TemporaryDirectory() as td:
+            fin, dump = os.path.join(td, "i.ubam"), os.path.join(td, "cols.bin")
+            data.tofile(fin)
+            subprocess.run([str(PORT_BIN), "-z"] + args + [fin, "mem:x"], check=True, env=dict(os.environ, ORACLE_COLUMN_DUMP=dump))
+            exp = np.fromfile(dump, dtype=cb.api.COLUMN_DTYPE)
+        assert len(cols) == len(exp)
+        for f in ("tid", "pos", "n_plp", "call", "het_call", "phred", "het_phred"):
+            assert np.array_equal(cols[f], exp[f]), f
+        assert np.array_equal(cols["discrep"].view(np.uint32), exp["discrep"].view(np.uint32)), "discrep differs bitwise"
+        for bit, nm in ((1, "preserve"), (2, "keep_qual"), (4, "window active"), (8, "processed")):
+            assert np.array_equal(cols["flags"] & bit, exp["flags"] & bit), nm
+        assert np.array_equal((cols["flags"] >> 8) & 31, (exp["flags"] >> 8) & 31), "BED tags"
+        g.close()
+
+
+def test_gpu_contig_sharding_invariance():
+    """size-independent property behind the multi-GPU split: contigs are independent, so processing a
+    two-contig batch equals processing each contig on its own (this is what one-shard-per-GPU relies on)."""
+    data, bb, batch, mask = dataset("tiny")
+    g = cb.Crumble(cb.default_params(1), device=0)
+    whole = g.process(batch)
+    n = int(batch.n_reads)
+    tid = np.ctypeslib.as_array(batch.tid, shape=(n,)); pos = np.ctypeslib.as_array(batch.pos, shape=(n,))
+    flag = np.ctypeslib.as_array(batch.flag, shape=(n,)); mapq = np.ctypeslib.as_array(batch.mapq, shape=(n,))
+    ln = bb.lengths(); off = bb.offsets(); nc = np.ctypeslib.as_array(batch.n_cigar, shape=(n,)); co = np.ctypeslib.as_array(batch.cigar_off, shape=(n,))
+    cig = np.ctypeslib.as_array(batch.cigar, shape=(int(batch.n_cigar_total),)); seq = np.ctypeslib.as_array(batch.seq, shape=(int(batch.seq_bytes),))
+    qual = bb.qual()
+    ev_parts, cnt = [], None
+    for t in (0, 1):
+        sb = cb.BatchBuilder()
+        idx = np.nonzero(tid == t)[0]
+        for i in idx:
+            sb.add(int(tid[i]), int(pos[i]), int(flag[i]), int(mapq[i]), cig[co[i]:co[i] + nc[i]], seq[off[i] // 2: off[i] // 2 + (ln[i] + 1) // 2], qual[off[i]: off[i] + ln[i]])
+        b2 = sb.finish()
+        o2 = g.process(b2)
+        so = sb.offsets()
+        for k, i in enumerate(idx):
+            assert np.array_equal(o2["qual"][so[k]: so[k] + ln[i]], whole["qual"][off[i]: off[i] + ln[i]])
+        ev_parts.append(o2["events"])
+        cnt = o2["counters"] if cnt is None else {k: cnt[k] + v for k, v in o2["counters"].items()}
+    assert np.array_equal(np.concatenate(ev_parts), whole["events"])
+    assert cnt == whole["counters"]
+    g.close()
+
+
+def test_gpu_empty_and_degenerate_batches():
+    g = cb.Crumble(cb.default_params(9), device=0)
+    e = cb.BatchBuilder(); out = g.process(e.finish())
+    assert len(out["events"]) == 0 and out["counters"]["columns"] == 0
+    # only unplaced / unmapped records: everything passes through, P-block still applied (snp_score.c:2004-2005)
+    u = cb.BatchBuilder()
+    q = np.array([30, 31, 32, 10, 11, 40, 40, 2], np.uint8)
+    u.add(-1, -1, 4, 0, np.zeros(0, np.uint32), np.zeros(4, np.uint8), q)
+    u.add(0, 10, 4, 0, np.zeros(0, np.uint32), np.zeros(4, np.uint8), q)
+    out = g.process(u.finish())
+    assert out["counters"]["columns"] == 0
+    assert list(out["qual"][:8]) == [31, 31, 31, 10, 10, 40, 40, 2] and list(out["qual"][8:16]) == [31, 31, 31, 10, 10, 40, 40, 2]
+    g.close()

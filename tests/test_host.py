@@ -1,0 +1,127 @@
+"""CPU tests of the host side: option surface, hts_lite I/O, the record batcher, and that the
+C-ABI library loads, exports every symbol include/crumble_gpu.h declares, and fails loudly
+(no CPU fallback) when no GPU is present."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import crumble_b200 as cb
+from util import EMU_BIN, PORT_BIN, REF_BIN, ROOT
+
+GDIR = ROOT / "tests" / "golden"
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(ROOT / "include" / "crumble_gpu.h").read()
+    declared = set(re.findall(r"\b(cgb?_[a-z_0-9]+)\s*\(", hdr)) - {"cg_ctx"}
+    lib = cb.load_lib()
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(cb.EXPORTS) <= declared
+    assert lib.cg_abi_version() == 1
+
+
+def test_no_device_fails_loudly():
+    lib = cb.load_lib()
+    if lib.cg_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(cb.CrumbleError, match="no usable CUDA device"):
+        cb.Crumble()
+    err = C.c_int(0)
+    p = cb.default_params()
+    assert not lib.cg_create(C.byref(p), 0, C.byref(err)) and err.value == -1
+    # the command line must fail too, not silently compute on the CPU
+    r = subprocess.run([str(ROOT / "crumble_b200" / "lib" / "crumble_gpu"), "-z", str(GDIR / "edge_cases.sam"), "/dev/null"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Error while reducing file" in r.stderr
+
+
+def test_product_does_not_reference_the_oracle():
+    """the shipped library must not link, call or embed anything under oracle/ or tests/emu/"""
+    out = subprocess.run(["nm", "-D", "--undefined-only", str(cb.lib_path())], stdout=subprocess.PIPE, text=True).stdout
+    assert "oracle" not in out and "emu" not in out
+    import re as _re
+    for f in (ROOT / "crumble_b200" / "csrc").rglob("*"):
+        if f.is_file() and f.suffix in (".c", ".cpp", ".cu", ".h", "") and "build" not in f.parts:
+            txt = f.read_text(errors="ignore")
+            incs = _re.findall(r'#include\s+[<"]([^>"]+)[>"]', txt)
+            assert not [i for i in incs if "oracle" in i or "emu" in i], f
+            if f.name == "Makefile":
+                assert "oracle" not in txt and "tests/" not in txt
+
+
+LEVEL_ARGS = [["-9"], ["-8"], ["-7"], ["-5"], ["-3"], ["-1"], ["-1", "-B", "-u45", "-l3", "-c20"], ["-9", "-Q60", "-D100", "-X1.2", "-m3"],
+              ["-i1.5,4", "-s0.5,2", "-q50", "-d60", "-x2.5"], ["-3", "-9"], ["-P5", "-C0.3", "-M0.4", "-Z0.2", "-V0.1", "-p4", "-L0"]]
+
+
+@pytest.mark.skipif(not REF_BIN.exists(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("args", LEVEL_ARGS, ids=lambda a: "".join(a))
+def test_option_parser_matches_reference_report(args):
+    """our getopt loop + presets print the same -v parameter block as the reference main() (option order matters)."""
+    sam = str(GDIR / "edge_cases.sam")
+    a = subprocess.run([str(REF_BIN), "-z", "-v"] + args + [sam, "mem:x"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    b = subprocess.run([str(PORT_BIN), "-z", "-v"] + args + [sam, "mem:x"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert a.returncode == 0 and b.returncode == 0
+    assert a.stdout == b.stdout
+    pa = [l for l in a.stderr.splitlines() if " = " in l and not l.startswith(("A", "B", "Col", "Low_", "Clip_", "Ins_", "indel_ov_perc", "count_"))]
+    pb = [l for l in b.stderr.splitlines() if " = " in l and not l.startswith(("A", "B", "Col", "Low_", "Clip_", "Ins_", "indel_ov_perc", "count_"))]
+    assert pa == pb and len(pa) == 5
+
+
+def test_python_level_presets_match_c():
+    p9, p1 = cb.default_params(9), cb.default_params(1)
+    assert (p9.pblock, p9.min_qual_B, p9.min_indel_B, p9.iSTR_add, p9.over_depth) == (8, 70, 125, 2, 999.0)
+    assert (p1.pblock, p1.min_qual_B, p1.min_mqual, p1.sSTR_add, p1.iSTR_mul, p1.over_depth) == (0, 75, 5, 5, 2.0, 3.0)
+    d = cb.default_params()
+    assert (d.qlow, d.qcutoff, d.qhigh, d.qcap, d.clip_perc, d.region_tid) == (5, 25, 40, 60, 0.2, -1)
+
+
+def test_hts_lite_sam_bam_roundtrip():
+    """SAM -> BGZF BAM -> SAM and SAM -> raw BAM -> SAM through the identity option set (-p0 -Q0 -L0)."""
+    sam = str(GDIR / "edge_cases.sam")
+    with tempfile.TemporaryDirectory() as td:
+        s1, bam, ubam, s2, s3 = (os.path.join(td, x) for x in ("a.sam", "a.bam", "a.ubam", "b.sam", "c.sam"))
+        ident = ["-z", "-p0", "-Q0", "-L0"]
+        for cmd in ([sam, s1], [sam, bam], [bam, s2], [sam, ubam], [ubam, s3]):
+            subprocess.run([str(PORT_BIN)] + ident + cmd, check=True)
+        body = lambda f: [l for l in open(f) if not l.startswith("@")]
+        orig = body(sam)
+        assert body(s1) == orig and body(s2) == orig and body(s3) == orig
+        import gzip
+        assert gzip.open(bam).read()[:4] == b"BAM\1" and open(ubam, "rb").read(4) == b"BAM\1"
+        # @PG line is added without -z
+        subprocess.run([str(PORT_BIN), "-p0", "-Q0", "-L0", sam, s1], check=True)
+        # (the oracle CLI does not add @PG; the product CLI does — checked on the GPU box)
+
+
+def test_batcher_layout_and_accounting():
+    data, nr, nb = cb.simulate("tiny", 0.2, 9, threads=1)
+    bb = cb.BatchBuilder(pinned=False)
+    bb.add_bam_stream(data)
+    b = bb.finish()
+    assert b.n_reads == nr
+    off, ln = bb.offsets(), bb.lengths()
+    assert (off % 8 == 0).all() and (np.diff(off) >= ln[:-1]).all()
+    assert cb.aligned_bases(b) == nb
+    ncig = np.ctypeslib.as_array(b.n_cigar, shape=(nr,)).astype(np.int64)
+    flag = np.ctypeslib.as_array(b.flag, shape=(nr,)); tid = np.ctypeslib.as_array(b.tid, shape=(nr,))
+    inp = (tid >= 0) & ((flag & 4) == 0) & (ncig > 0)
+    exp = int((((ln[inp] + 1) // 2) + 2 * ln[inp].astype(np.int64) + 4 * ncig[inp] + 16).sum())
+    assert cb.algorithmic_bytes(b) == exp          # 395 B per 150-bp single-op read
+    one = cb.BatchBuilder(pinned=False)
+    one.add(0, 5, 0, 60, np.array([150 << 4], np.uint32), np.zeros(75, np.uint8), np.full(150, 30, np.uint8))
+    assert cb.algorithmic_bytes(one.finish()) == 395
+
+
+def test_batcher_rejects_unsorted():
+    bb = cb.BatchBuilder(pinned=False)
+    c = np.array([10 << 4], np.uint32); s = np.zeros(5, np.uint8); q = np.full(10, 30, np.uint8)
+    bb.add(0, 100, 0, 60, c, s, q)
+    bb.add(0, 50, 0, 60, c, s, q)
+    with pytest.raises(cb.CrumbleError, match="sorted"):
+        bb.finish()
