@@ -185,22 +185,156 @@ __global__ void k_tile_index(const __grid_constant__ CgDev D) {
     if (j < D.n_pile) cg_tile_index(&D, j);
 }
 
-/* The hot kernel: one thread per dense reference column, one warp per 32-column tile;
- * all lanes of a warp walk the same candidate read window, so read records are
- * warp-uniform loads and base/quality bytes are adjacent across lanes. */
+/* The hot kernel: one thread per dense reference column, one warp per 32-column tile.
+ * All lanes of a warp walk the same candidate read window [tile_lo, tile_start[t+1]) in input order, so
+ * read records are warp-uniform 2x128-bit loads and base / quality bytes are adjacent across lanes.
+ * The loop is software-pipelined three deep (record j+2 | bytes j+1 | arithmetic j) to keep the
+ * record -> byte -> effective-quality -> table dependency chain off the critical path.  The 15 genotype
+ * sums and the discrepancy sums live in registers and are updated by predicated add.rn.f64 (no FMA, no
+ * select): per slot the sequence of IEEE additions is exactly the reference's (snp_score.c:656-683).
+ * Per-quality constants (MM, _M, q2p, 1-q2p) sit in shared memory as one 32-byte row per quality. */
+struct __align__(16) CgTabRow { double MM, hM, q2p, om; };
+
+struct ColBytes { uint32_t q, s; };
+
+__device__ __forceinline__ void col_load_rec(const CgDev &D, int j, int hi, uint4 &a, uint4 &b) {
+    if (j < hi) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(D.rd + j);
+        a = __ldg(p); b = __ldg(p + 1);
+    } else { a = make_uint4(0, 0, 0, 0); b = make_uint4(0, 0, 0, 0); }     /* span 0: covers nothing */
+}
+/* record fields from the two quads (layout of CgRead) */
+#define REC_OFF(a)    ((int64_t)(((uint64_t)(a).y << 32) | (a).x))
+#define REC_COL0(a)   ((int)(a).z)
+#define REC_SPAN(a)   ((int)(a).w)
+#define REC_POS(b)    ((int)(b).x)
+#define REC_CIGOFF(b) ((int)(b).y)
+#define REC_LQSEQ(b)  ((int)(b).z)
+#define REC_NCIG(b)   ((int)((b).w & 0xffff))
+#define REC_MAPQ(b)   ((int)(((b).w >> 16) & 0xff))
+#define REC_RF(b)     ((int)((b).w >> 24))
+
+__device__ __forceinline__ void col_load_bytes(const CgDev &D, int c, const uint4 &a, const uint4 &b, ColBytes &o) {
+    unsigned d = (unsigned)(c - REC_COL0(a));
+    o.q = 0; o.s = 0;
+    if (d < (unsigned)REC_SPAN(a) && (REC_RF(b) & CG_RF_SIMPLE)) {
+        const int64_t off = REC_OFF(a);
+        o.q = D.qual[off + d];
+        o.s = D.seq[(off >> 1) + (d >> 1)];
+    }
+}
+
+__device__ __noinline__ bool col_resolve_general(const CgDev &D, int c, int col0, int span, int cig_off, int n_cigar, int64_t off,
+                                                 CgCell *cell, uint32_t *q, uint32_t *sb) {
+    if (!cg_plp_resolve(D.cigar + cig_off, n_cigar, c - col0, span, cell)) return false;
+    *q = D.qual[off + cell->qpos];
+    *sb = D.seq[(off >> 1) + (cell->qpos >> 1)];
+    return true;
+}
+
+#define COL_ACC(base, MMv, HMv, OMv, QEv) \
+    asm volatile("{\n\t" \
+        ".reg .pred p0, p1, p2, p3, p4, pq, pv;\n\t" \
+        "setp.eq.s32 p0, %24, 0;\n\t setp.eq.s32 p1, %24, 1;\n\t setp.eq.s32 p2, %24, 2;\n\t setp.eq.s32 p3, %24, 3;\n\t setp.eq.s32 p4, %24, 4;\n\t" \
+        "setp.lt.u32 pv, %24, 5;\n\t" \
+        "@pv add.rn.f64 %20, %20, %23;\n\t" \
+        "@p0 add.rn.f64 %15, %15, %22;\n\t @p1 add.rn.f64 %16, %16, %22;\n\t @p2 add.rn.f64 %17, %17, %22;\n\t @p3 add.rn.f64 %18, %18, %22;\n\t @p4 add.rn.f64 %19, %19, %22;\n\t" \
+        "@p0 add.rn.f64 %0, %0, %21;\n\t" \
+        "or.pred pq, p0, p1;\n\t @pq add.rn.f64 %1, %1, %25;\n\t" \
+        "or.pred pq, p0, p2;\n\t @pq add.rn.f64 %2, %2, %25;\n\t" \
+        "or.pred pq, p0, p3;\n\t @pq add.rn.f64 %3, %3, %25;\n\t" \
+        "or.pred pq, p0, p4;\n\t @pq add.rn.f64 %4, %4, %25;\n\t" \
+        "@p1 add.rn.f64 %5, %5, %21;\n\t" \
+        "or.pred pq, p1, p2;\n\t @pq add.rn.f64 %6, %6, %25;\n\t" \
+        "or.pred pq, p1, p3;\n\t @pq add.rn.f64 %7, %7, %25;\n\t" \
+        "or.pred pq, p1, p4;\n\t @pq add.rn.f64 %8, %8, %25;\n\t" \
+        "@p2 add.rn.f64 %9, %9, %21;\n\t" \
+        "or.pred pq, p2, p3;\n\t @pq add.rn.f64 %10, %10, %25;\n\t" \
+        "or.pred pq, p2, p4;\n\t @pq add.rn.f64 %11, %11, %25;\n\t" \
+        "@p3 add.rn.f64 %12, %12, %21;\n\t" \
+        "or.pred pq, p3, p4;\n\t @pq add.rn.f64 %13, %13, %25;\n\t" \
+        "@p4 add.rn.f64 %14, %14, %21;\n\t" \
+        "}" \
+        : "+d"(A.S[0]), "+d"(A.S[1]), "+d"(A.S[2]), "+d"(A.S[3]), "+d"(A.S[4]), "+d"(A.S[5]), "+d"(A.S[6]), "+d"(A.S[7]), \
+          "+d"(A.S[8]), "+d"(A.S[9]), "+d"(A.S[10]), "+d"(A.S[11]), "+d"(A.S[12]), "+d"(A.S[13]), "+d"(A.S[14]), \
+          "+d"(A.sumsC[0]), "+d"(A.sumsC[1]), "+d"(A.sumsC[2]), "+d"(A.sumsC[3]), "+d"(A.sumsC[4]), "+d"(A.sumsE) \
+        : "d"(MMv), "d"(OMv), "d"(QEv), "r"(base), "d"(HMv))
+
 __global__ void __launch_bounds__(128) k_column(const __grid_constant__ CgDev D) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ CgTabRow tab[104];
+    const CgTables *T = D.T;
+    const CgDevParams *P = &D.P;
+    for (int i = threadIdx.x; i < 104; i += blockDim.x) {
+        int q = i > 100 ? 100 : i;
+        CgTabRow r; r.MM = T->MM[q]; r.hM = T->_M[q]; r.q2p = T->q2p[q]; r.om = T->omq2p[q];
+        tab[i] = r;
+    }
+    __syncthreads();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
     CgColOut o; o.cnt = 0; o.n_plp = 0;
-    if (c < D.n_cols) o = cg_column_body(&D, c);
-    /* counters: one atomic per warp and counter */
-    unsigned any = __ballot_sync(0xffffffffu, o.cnt != 0);
-    if (any) {
-        unsigned un = __reduce_or_sync(0xffffffffu, o.cnt);
-        while (un) {
-            int b = __ffs(un) - 1; un &= un - 1;
-            unsigned m = __ballot_sync(0xffffffffu, (o.cnt >> b) & 1);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&D.counters[b], (unsigned long long)__popc(m));
+    /* whole tiles beyond n_cols do not exist (grid is ceil(n_cols/128)); lanes beyond n_cols idle through the loop */
+    const int t = c >> 5;
+    int lo = 0, hi = 0;
+    if (t < D.n_tiles) { lo = D.tile_lo[t]; hi = D.tile_start[t + 1]; }
+    const bool live = c < D.n_cols;
+    CgConsAcc A; cg_cons_init(&A);
+    CgColStats st; st.n_plp = st.n_skip = st.low_mq = st.had_indel = st.indel_cnt = st.clipped = st.n_overlap = st.ins_seen = 0;
+    const int doB = P->min_qual_B != 0;
+    const int qcap = P->qcap, min_mqual = P->min_mqual;
+    const uint8_t *effB = T->effB;
+
+    uint4 a1, b1, a2, b2, a3, b3;
+    ColBytes y1, y2;
+    col_load_rec(D, lo, hi, a1, b1);
+    col_load_rec(D, lo + 1, hi, a2, b2);
+    col_load_bytes(D, c, a1, b1, y1);
+    for (int j = lo; j < hi; j++) {
+        col_load_rec(D, j + 2, hi, a3, b3);
+        col_load_bytes(D, c, a2, b2, y2);
+        /* ---- arithmetic for read j ---- */
+        const int col0 = REC_COL0(a1), span = REC_SPAN(a1);
+        const unsigned d = (unsigned)(c - col0);
+        if (live && d < (unsigned)span) {
+            const int rf = REC_RF(b1), lq = REC_LQSEQ(b1), mapq = REC_MAPQ(b1);
+            CgCell cell; uint32_t qv = y1.q, sb = y1.s;
+            bool ok = true;
+            if (rf & CG_RF_SIMPLE) {
+                cell.qpos = (int)d; cell.indel = 0; cell.is_del = 0; cell.is_refskip = 0;
+                cell.is_head = d == 0; cell.is_tail = (int)d == span - 1;
+            } else {
+                ok = col_resolve_general(D, c, col0, span, REC_CIGOFF(b1), REC_NCIG(b1), REC_OFF(a1), &cell, &qv, &sb);
+            }
+            if (ok) {
+                st.n_plp++;
+                st.low_mq += (mapq <= min_mqual);
+                if (cell.indel || cell.is_del) { st.had_indel = 1; st.indel_cnt++; }
+                if (cell.is_refskip) st.n_skip++;
+                else {
+                    if ((cell.is_head && cell.qpos > 0) || (cell.is_tail && cell.qpos + 1 < lq)) st.clipped++;
+                    if (!cell.is_tail && !cell.is_head) { st.n_overlap++; if (cell.indel > 0) st.ins_seen = 1; }
+                    if (lq && doB) {
+                        int nib = (sb >> ((~cell.qpos & 1) << 2)) & 0xf;
+                        int base = cell.is_del ? 4 : cg_nt16_to_base(nib);
+                        if (qv > (uint32_t)qcap && !T->preserve_qual[qv]) qv = qcap;
+                        const int eq = effB[(mapq << 8) | qv];
+                        const CgTabRow r = tab[eq];
+                        if (base < 5) {
+                            COL_ACC(base, r.MM, r.hM, r.om, r.q2p);
+                            A.depth++;
+                        } else cg_cons_add(T, &A, base, eq);
+                    }
+                }
+            }
         }
+        a1 = a2; b1 = b2; a2 = a3; b2 = b3; y1 = y2;
+    }
+    if (live) o = cg_column_finish(&D, c, lo, hi, &st, &A);
+    /* counters: one atomic per warp and counter */
+    unsigned un = __reduce_or_sync(0xffffffffu, o.cnt);
+    while (un) {
+        int b = __ffs(un) - 1; un &= un - 1;
+        unsigned m = __ballot_sync(0xffffffffu, (o.cnt >> b) & 1);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&D.counters[b], (unsigned long long)__popc(m));
     }
     int mx = __reduce_max_sync(0xffffffffu, o.n_plp);
     if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(D.maxdepth, mx);
@@ -272,9 +406,169 @@ __global__ void k_paint(const __grid_constant__ CgDev D) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < D.n_flagged) cg_paint(&D, k, D.n_flagged);
 }
-__global__ void __launch_bounds__(128) k_rewrite(const __grid_constant__ CgDev D) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < D.n_reads) cg_rewrite(&D, r, D.n_flagged);
+/* Per-read quality rewrite, warp per read, quality strings staged in shared memory:
+ *   phase A (warp per read, 32 reads per warp): replay of the rewrite loop into the read's slot.
+ *            single-M reads without back-fill take the register path: each lane owns 8 consecutive
+ *            bases (aligned 64-bit quality load, 32-bit sequence load, column bytes via aligned
+ *            load + neighbour shuffle); other reads are replayed op by op inside the slot;
+ *   phase B (thread per read): P-block, a sequential greedy scan, over the slot in shared memory;
+ *   phase C (warp per read): coalesced 64-bit stores of the slot.
+ * Reads longer than RW_MAXL fall back to the one-thread-per-read body (cg_rewrite). */
+#define RW_THREADS 128
+#define RW_READS   128
+#define RW_MAXL    256
+#define RW_STRIDE  260          /* bytes; 65 words: conflict-free when the threads of a warp walk their slots in step */
+
+__device__ __forceinline__ uint32_t rw_visit8(uint64_t q8, uint64_t cb8, uint32_t s4, int nvalid, uint8_t init_or, int keep,
+                                              const CgDevParams *P, const CgTables *T, uint32_t *hi_out) {
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint8_t qin = (uint8_t)(q8 >> (8 * k));
+        uint8_t v = qin;
+        if (k < nvalid) {
+            uint8_t cbv = (uint8_t)(cb8 >> (8 * k));
+            /* seq byte k>>1 of this lane's 4 sequence bytes; high nibble first */
+            int nib = (int)((s4 >> (8 * (k >> 1) + ((k & 1) ? 0 : 4))) & 0xf);
+            uint8_t oc = cg_cap_qual(qin, P, T);
+            v = keep ? oc : cg_visit((uint8_t)(qin | init_or), cbv, oc, nib, P, T);
+            v &= 0x7f;
+        }
+        if (k < 4) lo |= (uint32_t)v << (8 * k); else hi |= (uint32_t)v << (8 * (k - 4));
+    }
+    *hi_out = hi;
+    return lo;
+}
+
+__global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ CgDev D) {
+    __shared__ __align__(16) uint8_t sq[RW_READS * RW_STRIDE];
+    __shared__ int32_t sL[RW_READS];
+    const CgDevParams *P = &D.P;
+    const CgTables *T = D.T;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * RW_READS;
+    const int nf = D.n_flagged;
+
+    /* ---- phase A ---- */
+    for (int i = 0; i < RW_READS / (RW_THREADS / 32); i++) {
+        const int slot = w * (RW_READS / (RW_THREADS / 32)) + i;
+        const int64_t r = base + slot;
+        uint8_t *sl = sq + slot * RW_STRIDE;
+        int L = 0;
+        if (r < D.n_reads) L = D.l_qseq[r];
+        if (L <= 0) { if (lane == 0) sL[slot] = 0; continue; }
+        if (L > RW_MAXL) {
+            if (lane == 0) { cg_rewrite(&D, r, nf); sL[slot] = 0; }
+            continue;
+        }
+        const int64_t off = D.off[r];
+        const uint8_t *qin = D.qual + off;
+        const int x0 = lane * 8;
+        const int nvalid = L - x0;          /* <=0: lane idle */
+        if (!D.rspan[r]) {
+            /* never in the pileup: strip bit 7 only (P-block follows) */
+            if (nvalid > 0) {
+                uint64_t q8 = *(const uint64_t *)(qin + x0) & 0x7f7f7f7f7f7f7f7fULL;
+                *(uint32_t *)(sl + x0) = (uint32_t)q8; *(uint32_t *)(sl + x0 + 4) = (uint32_t)(q8 >> 32);
+            }
+            if (lane == 0) sL[slot] = L;
+            continue;
+        }
+        const int j = D.jmap[r];
+        const CgRead q = D.rd[j];
+        const int tail_unreached = (P->region_tid >= 0 && q.pos + q.span - 1 >= P->region_end);
+        const int head_proc = (D.cb[q.col0] & CG_CB_CODE_MASK) != CG_CB_UNPROC;
+        const uint8_t init_or = (head_proc && q.mapq <= P->min_mqual) ? 0x80 : 0;
+        if ((q.rf & CG_RF_SIMPLE) && q.span == L && !D.r_bf[j]) {
+            /* register path */
+            uint64_t q8 = 0, cb8 = 0; uint32_t s4 = 0;
+            /* column bytes [col0 + x0, +8): aligned word + neighbour's word */
+            const uint64_t cbase = (uint64_t)(uintptr_t)(D.cb + q.col0);
+            const int sh = (int)(cbase & 7) * 8;
+            const uint64_t *cw = (const uint64_t *)(cbase & ~(uint64_t)7);
+            uint64_t w0 = 0;
+            /* lane needs words lane and lane+1; the last needed word index is ((sh/8 + L - 1) >> 3) */
+            const int last_word = ((sh >> 3) + L - 1) >> 3;
+            if (lane <= last_word) w0 = cw[lane];
+            uint64_t w1 = __shfl_down_sync(0xffffffffu, w0, 1);
+            if (lane == 31) w1 = (last_word >= 32) ? cw[32] : 0;
+            cb8 = sh ? ((w0 >> sh) | (w1 << (64 - sh))) : w0;
+            if (nvalid > 0) {
+                q8 = *(const uint64_t *)(qin + x0);
+                s4 = *(const uint32_t *)(D.seq + (off >> 1) + lane * 4);
+                /* sequence bytes are little-endian in s4: byte b holds bases 2b (high nibble), 2b+1 (low nibble) */
+            }
+            /* whole-read keep: any covered column with keep_qual */
+            uint64_t m = cb8 & 0x8080808080808080ULL;
+            if (nvalid < 8) m = nvalid > 0 ? (m & ((1ULL << (8 * nvalid)) - 1)) : 0;
+            int keep = __any_sync(0xffffffffu, m != 0) && !tail_unreached;
+            if (nvalid > 0) {
+                uint32_t hi, lo = rw_visit8(q8, cb8, s4, nvalid < 8 ? nvalid : 8, init_or, keep, P, T, &hi);
+                *(uint32_t *)(sl + x0) = lo; *(uint32_t *)(sl + x0 + 4) = hi;
+            }
+        } else {
+            /* general path: replay inside the slot */
+            const uint32_t *cig = D.cigar + q.cig_off;
+            for (int x = lane; x < L; x += 32) sl[x] = qin[x] | init_or;
+            int keepbits = 0;
+            for (int c = q.col0 + lane; c < q.col0 + q.span; c += 32) keepbits |= D.cb[c];
+            int keep = __any_sync(0xffffffffu, keepbits & CG_CB_KEEP) && !tail_unreached;
+            __syncwarp();
+            int c = q.col0, y = 0;
+            for (int k = 0; k < q.n_cigar; k++) {
+                const int op = cg_cig_op(cig[k]), l = cg_cig_len(cig[k]);
+                if (cg_is_mop(op)) {
+                    for (int ii = lane; ii < l; ii += 32) {
+                        int x = y + ii;
+                        if (x < L) sl[x] = cg_visit(sl[x], D.cb[c + ii], cg_cap_qual(qin[x], P, T), cg_seq_nib(&D, &q, x), P, T);
+                    }
+                    c += l; y += l;
+                } else if (op == 2 || op == 3) {
+                    if (lane == 0 && y < L) {
+                        uint8_t oc = cg_cap_qual(qin[y], P, T); int nib = cg_seq_nib(&D, &q, y); uint8_t v = sl[y];
+                        for (int ii = 0; ii < l; ii++) v = cg_visit(v, D.cb[c + ii], oc, nib, P, T);
+                        sl[y] = v;
+                    }
+                    c += l;
+                } else if (op == 1 || op == 4) y += l;
+                __syncwarp();
+            }
+            if (D.r_bf[j]) {
+                for (int k = cg_trig_lower_bound(&D, nf, q.col0); k < nf && D.fcol[k] < q.col0 + q.span; k++) {
+                    const CgTrig *t = &D.trig[k];
+                    if (!(t->hasI || t->hasS)) continue;
+                    CgCell cell;
+                    if (!cg_cell(&D, &q, t->col, &cell)) continue;
+                    int xs = cg_ref2query_pos(cig, q.n_cigar, q.pos, D.twin[k].min_pos2);
+                    for (int x = xs + lane; x <= cell.qpos && x < L; x += 32) sl[x] = (uint8_t)(cg_cap_qual(qin[x], P, T) | 0x80);
+                }
+                __syncwarp();
+            }
+            for (int x = lane; x < L; x += 32) sl[x] = (keep ? cg_cap_qual(qin[x], P, T) : sl[x]) & 0x7f;
+        }
+        if (lane == 0) sL[slot] = L;
+    }
+    __syncthreads();
+    /* ---- phase B: P-block, thread per read ---- */
+    if (P->pblock) {
+        const int L = sL[threadIdx.x];
+        if (L > 0) cg_pblock(sq + threadIdx.x * RW_STRIDE, L, P->pblock, P->qcap, T);
+    }
+    __syncthreads();
+    /* ---- phase C: coalesced store ---- */
+    for (int i = 0; i < RW_READS / (RW_THREADS / 32); i++) {
+        const int slot = w * (RW_READS / (RW_THREADS / 32)) + i;
+        const int L = sL[slot];
+        if (L <= 0) continue;
+        const int64_t r = base + slot;
+        const uint8_t *sl = sq + slot * RW_STRIDE;
+        uint8_t *out = D.qual_out + D.off[r];
+        const int x0 = lane * 8;
+        if (x0 < L) {
+            uint64_t v = (uint64_t)*(const uint32_t *)(sl + x0) | ((uint64_t)*(const uint32_t *)(sl + x0 + 4) << 32);
+            *(uint64_t *)(out + x0) = v;
+        }
+    }
 }
 __global__ void k_dump_flags(const __grid_constant__ CgDev D) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -579,7 +873,7 @@ extern "C" int cg_run(cg_ctx *ctx) {
     }
     T1(CG_T_CHAIN);
     T0(CG_T_REWRITE);
-    if (n > 0) { k_rewrite<<<nblk(n, 128), 128, 0, st>>>(*D); ctx->launches++; }
+    if (n > 0) { k_rewrite<<<nblk(n, RW_READS), RW_THREADS, 0, st>>>(*D); ctx->launches++; }
     T1(CG_T_REWRITE);
     T0(CG_T_EVENTS);
     if (nc > 0) {

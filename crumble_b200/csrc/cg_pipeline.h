@@ -197,32 +197,17 @@ CG_HD void cg_column_cons(const CgDev *D, int c, int lo, int hi, CgCons *out) {
     cg_cons_finalize(T, &a, out);
 }
 
-CG_HD CgColOut cg_column_body(const CgDev *D, int c) {
+typedef struct CgColStats { int n_plp, n_skip, low_mq, had_indel, indel_cnt, clipped, n_overlap, ins_seen; } CgColStats;
+
+/* everything after the per-read loop: consensus finalisation and the column decisions */
+CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgColStats *st, CgConsAcc *acc) {
     const CgDevParams *P = &D->P;
     const CgTables *T = D->T;
     CgColOut o; o.cnt = 0; o.n_plp = 0;
-    const int t = c >> 5;
-    const int lo = D->tile_lo[t], hi = D->tile_start[t + 1];
-    int n_plp = 0, n_skip = 0, low_mq = 0, had_indel = 0, indel_cnt = 0, clipped = 0, n_overlap = 0;
-    int ins_seen = 0;
-    CgConsAcc a; cg_cons_init(&a);
+    const int n_plp = st->n_plp, n_skip = st->n_skip, low_mq = st->low_mq, had_indel = st->had_indel;
+    const int clipped = st->clipped, n_overlap = st->n_overlap, ins_seen = st->ins_seen;
     const int doB = P->min_qual_B != 0;
-    for (int j = lo; j < hi; j++) {
-        const CgRead q = D->rd[j];
-        CgCell cell;
-        if (!cg_cell(D, &q, c, &cell)) continue;
-        n_plp++;
-        low_mq += (q.mapq <= P->min_mqual);                               /* 1663 */
-        if (cell.indel || cell.is_del) { had_indel = 1; indel_cnt++; }    /* 1664-1665 */
-        if (cell.is_refskip) { n_skip++; continue; }
-        if ((cell.is_head && cell.qpos > 0) || (cell.is_tail && cell.qpos + 1 < q.l_qseq)) clipped++;   /* 1701-1703 */
-        if (!cell.is_tail && !cell.is_head) { n_overlap++; if (cell.indel > 0) ins_seen = 1; }       /* 1705-1708 */
-        if (!q.l_qseq || !doB) continue;
-        int nib = cg_seq_nib(D, &q, cell.qpos);
-        int base = cell.is_del ? 4 : cg_nt16_to_base(nib);
-        uint8_t qv = cg_cap_qual(D->qual[q.off + cell.qpos], P, T);
-        cg_cons_add(T, &a, base, T->effB[((int)q.mapq << 8) | qv]);
-    }
+    CgConsAcc &a = *acc;
     o.n_plp = n_plp;
     uint16_t ev = 0; uint8_t cb = CG_CB_UNPROC;
     D->depth[c] = (uint32_t)n_plp;
@@ -309,6 +294,38 @@ CG_HD CgColOut cg_column_body(const CgDev *D, int c) {
         D->coldump[c] = z;
     }
     return o;
+}
+
+CG_HD CgColOut cg_column_body(const CgDev *D, int c) {
+    const CgDevParams *P = &D->P;
+    const CgTables *T = D->T;
+    CgColOut o; o.cnt = 0; o.n_plp = 0;
+    const int t = c >> 5;
+    const int lo = D->tile_lo[t], hi = D->tile_start[t + 1];
+    int n_plp = 0, n_skip = 0, low_mq = 0, had_indel = 0, indel_cnt = 0, clipped = 0, n_overlap = 0;
+    int ins_seen = 0;
+    CgConsAcc a; cg_cons_init(&a);
+    const int doB = P->min_qual_B != 0;
+    for (int j = lo; j < hi; j++) {
+        const CgRead q = D->rd[j];
+        CgCell cell;
+        if (!cg_cell(D, &q, c, &cell)) continue;
+        n_plp++;
+        low_mq += (q.mapq <= P->min_mqual);                               /* 1663 */
+        if (cell.indel || cell.is_del) { had_indel = 1; indel_cnt++; }    /* 1664-1665 */
+        if (cell.is_refskip) { n_skip++; continue; }
+        if ((cell.is_head && cell.qpos > 0) || (cell.is_tail && cell.qpos + 1 < q.l_qseq)) clipped++;   /* 1701-1703 */
+        if (!cell.is_tail && !cell.is_head) { n_overlap++; if (cell.indel > 0) ins_seen = 1; }       /* 1705-1708 */
+        if (!q.l_qseq || !doB) continue;
+        int nib = cg_seq_nib(D, &q, cell.qpos);
+        int base = cell.is_del ? 4 : cg_nt16_to_base(nib);
+        uint8_t qv = cg_cap_qual(D->qual[q.off + cell.qpos], P, T);
+        cg_cons_add(T, &a, base, T->effB[((int)q.mapq << 8) | qv]);
+    }
+    CgColStats st; st.n_plp = n_plp; st.n_skip = n_skip; st.low_mq = low_mq; st.had_indel = had_indel; st.indel_cnt = indel_cnt;
+    st.clipped = clipped; st.n_overlap = n_overlap; st.ins_seen = ins_seen;
+    (void)o;
+    return cg_column_finish(D, c, lo, hi, &st, &a);
 }
 
 /* ---- stage: flagged (one per flagged column): indel-size spectrum tests and the STR
