@@ -44,7 +44,7 @@ typedef struct CgTables {
     double  e_tab2[1002];     /* exp(i/10.)                              (snp_score.c:383-384) */
     double  min_e_exp;        /* DBL_MIN_EXP*log(2)+1       (snp_score.c:540) */
     double  log_c1, log_c2;   /* (double)(-1.0f/3), (double)(2.0f/3)    (snp_score.c:515) */
-    uint8_t effB[65536];      /* [mapq<<8|qual] -> max(1, (uint8_t)ph_log(1-(_m*_p+(1-_m)/4))) (632-642) */
+    uint8_t effB[65536];      /* [mapq<<8|qual] -> max(1, (uint8_t)ph_log(1-(_m*_p+(1-_m)/4))) (632-642), qual capped first (1325-1332) */
     uint8_t effA[256];        /* mode A: max(1,qual), clamped to the table size */
     uint8_t bin2[256];        /* snp_score.c:234-247 (values are < 256 for sane -l/-u) */
     uint8_t preserve_qual[256];

@@ -186,79 +186,113 @@ __global__ void k_tile_index(const __grid_constant__ CgDev D) {
 }
 
 /* The hot kernel: one thread per dense reference column, one warp per 32-column tile.
- * All lanes of a warp walk the same candidate read window [tile_lo, tile_start[t+1]) in input order, so
- * read records are warp-uniform 2x128-bit loads and base / quality bytes are adjacent across lanes.
- * The loop is software-pipelined three deep (record j+2 | bytes j+1 | arithmetic j) to keep the
- * record -> byte -> effective-quality -> table dependency chain off the critical path.  The 15 genotype
- * sums and the discrepancy sums live in registers and are updated by predicated add.rn.f64 (no FMA, no
- * select): per slot the sequence of IEEE additions is exactly the reference's (snp_score.c:656-683).
- * Per-quality constants (MM, _M, q2p, 1-q2p) sit in shared memory as one 32-byte row per quality. */
-struct __align__(16) CgTabRow { double MM, hM, q2p, om; };
+ * All lanes of a warp walk the same candidate read window [tile_lo, tile_start[t+1]) in input order, so the
+ * 16-byte hot half of each read record is one warp-uniform 128-bit load and base / quality bytes are adjacent
+ * across lanes.  The loop is software-pipelined three deep (record j+2 | bytes j+1 | arithmetic j) and unrolled by
+ * three so the pipeline registers rotate by renaming.  The 15 genotype sums and 5 discrepancy sums live in
+ * registers; each read adds to the 6 of them its base selects, through a real branch per base present in the
+ * warp (a switch, as the reference's own code at snp_score.c:656-683) — cheaper than masking all 20 because the
+ * masks would cost two ALU ops per accumulator.  Per slot the IEEE add sequence equals the reference's.
+ * Per-quality constants (MM, _M, 1-q2p) sit in shared memory; the cap (-U) is folded into the effective-quality
+ * table.  sumsE of the reference is dead (never read after the loop) and is not computed. */
+struct __align__(8) CgTabRow { double MM, hM, om; };
 
-struct ColBytes { uint32_t q, s; };
-
-__device__ __forceinline__ void col_load_rec(const CgDev &D, int j, int hi, uint4 &a, uint4 &b) {
-    if (j < hi) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(D.rd + j);
-        a = __ldg(p); b = __ldg(p + 1);
-    } else { a = make_uint4(0, 0, 0, 0); b = make_uint4(0, 0, 0, 0); }     /* span 0: covers nothing */
+__device__ __forceinline__ uint4 col_load_rec(const CgDev &D, int j, int hi) {
+    int jj = j < hi ? j : hi - 1;                                  /* clamp: always a valid record ... */
+    uint4 a = __ldg(reinterpret_cast<const uint4 *>(D.rd + jj));
+    if (j >= hi) a.z = 0;                                          /* ... with span 0 past the window: covers nothing */
+    return a;
 }
-/* record fields from the two quads (layout of CgRead) */
-#define REC_OFF(a)    ((int64_t)(((uint64_t)(a).y << 32) | (a).x))
-#define REC_COL0(a)   ((int)(a).z)
-#define REC_SPAN(a)   ((int)(a).w)
-#define REC_POS(b)    ((int)(b).x)
-#define REC_CIGOFF(b) ((int)(b).y)
-#define REC_LQSEQ(b)  ((int)(b).z)
-#define REC_NCIG(b)   ((int)((b).w & 0xffff))
-#define REC_MAPQ(b)   ((int)(((b).w >> 16) & 0xff))
-#define REC_RF(b)     ((int)((b).w >> 24))
+__device__ __forceinline__ uint32_t col_load_bytes(const CgDev &D, int c, const uint4 &a) {
+    unsigned d = (unsigned)(c - (int)a.y);
+    uint32_t r = 0;
+    if (d < a.z) {                                                 /* covering lanes only; non-simple reads reload below */
+        const uint8_t *q = D.qual + ((size_t)a.x << 3) + d;
+        const uint8_t *s = D.seq + ((size_t)a.x << 2) + (d >> 1);
+        r = (uint32_t)*q | ((uint32_t)*s << 8);
+    }
+    return r;
+}
 
-__device__ __forceinline__ void col_load_bytes(const CgDev &D, int c, const uint4 &a, const uint4 &b, ColBytes &o) {
-    unsigned d = (unsigned)(c - REC_COL0(a));
-    o.q = 0; o.s = 0;
-    if (d < (unsigned)REC_SPAN(a) && (REC_RF(b) & CG_RF_SIMPLE)) {
-        const int64_t off = REC_OFF(a);
-        o.q = D.qual[off + d];
-        o.s = D.seq[(off >> 1) + (d >> 1)];
+/* non-simple CIGARs (a few percent of reads): out of line, result packed into registers
+ * bits 0..23 qpos | 24 is_del | 25 is_refskip | 26 is_head | 27 is_tail | 28 ok ; high word = indel */
+__device__ __noinline__ uint64_t col_resolve_general(const uint32_t *cig, int n_cigar, int d, int span) {
+    CgCell cell;
+    if (!cg_plp_resolve(cig, n_cigar, d, span, &cell)) return 0;
+    uint32_t lo = (uint32_t)(cell.qpos & 0xffffff) | ((uint32_t)cell.is_del << 24) | ((uint32_t)cell.is_refskip << 25) |
+                  ((uint32_t)cell.is_head << 26) | ((uint32_t)cell.is_tail << 27) | (1u << 28);
+    return ((uint64_t)(uint32_t)cell.indel << 32) | lo;
+}
+
+/* exact recomputation of a column's accumulators with the generic code: used for the rare columns holding an N base */
+__device__ __noinline__ void col_gather_generic(const CgDev *D, int c, int lo, int hi, CgConsAcc *A) {
+    const CgTables *T = D->T;
+    cg_cons_init(A);
+    for (int j = lo; j < hi; j++) {
+        const CgRead q = D->rd[j];
+        CgCell cell;
+        if (!cg_cell(D, &q, c, &cell)) continue;
+        if (cell.is_refskip || !q.l_qseq) continue;
+        int nib = cg_seq_nib(D, &q, cell.qpos);
+        int base = cell.is_del ? 4 : cg_nt16_to_base(nib);
+        uint8_t qv = cg_cap_qual(D->qual[CG_OFF(&q) + cell.qpos], &D->P, T);
+        cg_cons_add(T, A, base, T->effB[((int)q.mapq << 8) | qv]);
     }
 }
 
-__device__ __noinline__ bool col_resolve_general(const CgDev &D, int c, int col0, int span, int cig_off, int n_cigar, int64_t off,
-                                                 CgCell *cell, uint32_t *q, uint32_t *sb) {
-    if (!cg_plp_resolve(D.cigar + cig_off, n_cigar, c - col0, span, cell)) return false;
-    *q = D.qual[off + cell->qpos];
-    *sb = D.seq[(off >> 1) + (cell->qpos >> 1)];
-    return true;
-}
-
-#define COL_ACC(base, MMv, HMv, OMv, QEv) \
-    asm volatile("{\n\t" \
-        ".reg .pred p0, p1, p2, p3, p4, pq, pv;\n\t" \
-        "setp.eq.s32 p0, %24, 0;\n\t setp.eq.s32 p1, %24, 1;\n\t setp.eq.s32 p2, %24, 2;\n\t setp.eq.s32 p3, %24, 3;\n\t setp.eq.s32 p4, %24, 4;\n\t" \
-        "setp.lt.u32 pv, %24, 5;\n\t" \
-        "@pv add.rn.f64 %20, %20, %23;\n\t" \
-        "@p0 add.rn.f64 %15, %15, %22;\n\t @p1 add.rn.f64 %16, %16, %22;\n\t @p2 add.rn.f64 %17, %17, %22;\n\t @p3 add.rn.f64 %18, %18, %22;\n\t @p4 add.rn.f64 %19, %19, %22;\n\t" \
-        "@p0 add.rn.f64 %0, %0, %21;\n\t" \
-        "or.pred pq, p0, p1;\n\t @pq add.rn.f64 %1, %1, %25;\n\t" \
-        "or.pred pq, p0, p2;\n\t @pq add.rn.f64 %2, %2, %25;\n\t" \
-        "or.pred pq, p0, p3;\n\t @pq add.rn.f64 %3, %3, %25;\n\t" \
-        "or.pred pq, p0, p4;\n\t @pq add.rn.f64 %4, %4, %25;\n\t" \
-        "@p1 add.rn.f64 %5, %5, %21;\n\t" \
-        "or.pred pq, p1, p2;\n\t @pq add.rn.f64 %6, %6, %25;\n\t" \
-        "or.pred pq, p1, p3;\n\t @pq add.rn.f64 %7, %7, %25;\n\t" \
-        "or.pred pq, p1, p4;\n\t @pq add.rn.f64 %8, %8, %25;\n\t" \
-        "@p2 add.rn.f64 %9, %9, %21;\n\t" \
-        "or.pred pq, p2, p3;\n\t @pq add.rn.f64 %10, %10, %25;\n\t" \
-        "or.pred pq, p2, p4;\n\t @pq add.rn.f64 %11, %11, %25;\n\t" \
-        "@p3 add.rn.f64 %12, %12, %21;\n\t" \
-        "or.pred pq, p3, p4;\n\t @pq add.rn.f64 %13, %13, %25;\n\t" \
-        "@p4 add.rn.f64 %14, %14, %21;\n\t" \
-        "}" \
-        : "+d"(A.S[0]), "+d"(A.S[1]), "+d"(A.S[2]), "+d"(A.S[3]), "+d"(A.S[4]), "+d"(A.S[5]), "+d"(A.S[6]), "+d"(A.S[7]), \
-          "+d"(A.S[8]), "+d"(A.S[9]), "+d"(A.S[10]), "+d"(A.S[11]), "+d"(A.S[12]), "+d"(A.S[13]), "+d"(A.S[14]), \
-          "+d"(A.sumsC[0]), "+d"(A.sumsC[1]), "+d"(A.sumsC[2]), "+d"(A.sumsC[3]), "+d"(A.sumsC[4]), "+d"(A.sumsE) \
-        : "d"(MMv), "d"(OMv), "d"(QEv), "r"(base), "d"(HMv))
+/* one pipeline step: issue the record load for read JJ+2 and the byte loads for read JJ+1, then the arithmetic of read JJ */
+#define COL_STEP(r1, y1, r2, y2, r3, JJ) do { \
+    r3 = col_load_rec(D, (JJ) + 2, hi); \
+    y2 = col_load_bytes(D, c, r2); \
+    const unsigned d_ = (unsigned)(c - (int)r1.y); \
+    const int span_ = (int)r1.z; \
+    if (d_ < (unsigned)span_) { \
+        const uint32_t pk_ = r1.w; \
+        const int mapq_ = (pk_ >> 16) & 0xff; \
+        uint32_t qv_ = y1 & 0xff, sb_ = y1 >> 8; \
+        int qpos_ = (int)d_, contrib_ = doB; \
+        int base_; \
+        n_plp++; \
+        low_mq += (mapq_ <= min_mqual); \
+        if (pk_ & ((uint32_t)CG_RF_SIMPLE << 24)) { \
+            n_overlap += (d_ != 0) & ((int)d_ != span_ - 1); \
+        } else { \
+            const CgRead *rq_ = D.rd + ((JJ) < hi ? (JJ) : hi - 1); \
+            const int lq_ = rq_->l_qseq; \
+            uint64_t pkc_ = col_resolve_general(D.cigar + rq_->cig_off, rq_->n_cigar, (int)d_, span_); \
+            uint32_t lo_ = (uint32_t)pkc_; \
+            const int indel_ = (int)(uint32_t)(pkc_ >> 32); \
+            const int isdel_ = (lo_ >> 24) & 1, skip_ = (lo_ >> 25) & 1, head_ = (lo_ >> 26) & 1, tail_ = (lo_ >> 27) & 1; \
+            qpos_ = lo_ & 0xffffff; \
+            if (!((lo_ >> 28) & 1)) { n_plp--; low_mq -= (mapq_ <= min_mqual); contrib_ = 0; } \
+            else { \
+                if (indel_ | isdel_) { had_indel = 1; indel_cnt++; } \
+                if (skip_) { n_skip++; contrib_ = 0; } \
+                else { \
+                    clipped += (head_ & (qpos_ > 0)) | (tail_ & (qpos_ + 1 < lq_)); \
+                    const int mid_ = !tail_ & !head_; \
+                    n_overlap += mid_; ins_seen |= mid_ & (indel_ > 0); \
+                    if (!lq_) contrib_ = 0; \
+                    else { const size_t off_ = (size_t)r1.x << 3; qv_ = D.qual[off_ + qpos_]; sb_ = D.seq[(off_ >> 1) + (qpos_ >> 1)]; } \
+                    if (isdel_) sb_ = 0x100; /* marks a deletion: base 4 */ \
+                } \
+            } \
+        } \
+        if (contrib_) { \
+            const int nib_ = (sb_ >> ((~qpos_ & 1) << 2)) & 0xf; \
+            base_ = (sb_ & 0x100) ? 4 : cg_nt16_to_base(nib_); \
+            const CgTabRow w_ = tab[effB[(mapq_ << 8) | qv_]]; \
+            switch (base_) { \
+            case 0: A.S[0] += w_.MM; A.S[1] += w_.hM; A.S[2] += w_.hM; A.S[3] += w_.hM; A.S[4] += w_.hM; A.sumsC[0] += w_.om; depth++; break; \
+            case 1: A.S[1] += w_.hM; A.S[5] += w_.MM; A.S[6] += w_.hM; A.S[7] += w_.hM; A.S[8] += w_.hM; A.sumsC[1] += w_.om; depth++; break; \
+            case 2: A.S[2] += w_.hM; A.S[6] += w_.hM; A.S[9] += w_.MM; A.S[10] += w_.hM; A.S[11] += w_.hM; A.sumsC[2] += w_.om; depth++; break; \
+            case 3: A.S[3] += w_.hM; A.S[7] += w_.hM; A.S[10] += w_.hM; A.S[12] += w_.MM; A.S[13] += w_.hM; A.sumsC[3] += w_.om; depth++; break; \
+            case 4: A.S[4] += w_.hM; A.S[8] += w_.hM; A.S[11] += w_.hM; A.S[13] += w_.hM; A.S[14] += w_.MM; A.sumsC[4] += w_.om; depth++; break; \
+            default: nN++; break; \
+            } \
+        } \
+    } \
+} while (0)
 
 __global__ void __launch_bounds__(128) k_column(const __grid_constant__ CgDev D) {
     __shared__ CgTabRow tab[104];
@@ -266,69 +300,41 @@ __global__ void __launch_bounds__(128) k_column(const __grid_constant__ CgDev D)
     const CgDevParams *P = &D.P;
     for (int i = threadIdx.x; i < 104; i += blockDim.x) {
         int q = i > 100 ? 100 : i;
-        CgTabRow r; r.MM = T->MM[q]; r.hM = T->_M[q]; r.q2p = T->q2p[q]; r.om = T->omq2p[q];
+        CgTabRow r; r.MM = T->MM[q]; r.hM = T->_M[q]; r.om = T->omq2p[q];
         tab[i] = r;
     }
     __syncthreads();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     CgColOut o; o.cnt = 0; o.n_plp = 0;
-    /* whole tiles beyond n_cols do not exist (grid is ceil(n_cols/128)); lanes beyond n_cols idle through the loop */
     const int t = c >> 5;
     int lo = 0, hi = 0;
-    if (t < D.n_tiles) { lo = D.tile_lo[t]; hi = D.tile_start[t + 1]; }
-    const bool live = c < D.n_cols;
+    if (t < D.n_tiles && c < D.n_cols) { lo = D.tile_lo[t]; hi = D.tile_start[t + 1]; }   /* lanes past n_cols: empty window */
     CgConsAcc A; cg_cons_init(&A);
-    CgColStats st; st.n_plp = st.n_skip = st.low_mq = st.had_indel = st.indel_cnt = st.clipped = st.n_overlap = st.ins_seen = 0;
+    int n_plp = 0, n_skip = 0, low_mq = 0, had_indel = 0, indel_cnt = 0, clipped = 0, n_overlap = 0, ins_seen = 0, nN = 0, depth = 0;
     const int doB = P->min_qual_B != 0;
-    const int qcap = P->qcap, min_mqual = P->min_mqual;
+    const int min_mqual = P->min_mqual;
     const uint8_t *effB = T->effB;
 
-    uint4 a1, b1, a2, b2, a3, b3;
-    ColBytes y1, y2;
-    col_load_rec(D, lo, hi, a1, b1);
-    col_load_rec(D, lo + 1, hi, a2, b2);
-    col_load_bytes(D, c, a1, b1, y1);
-    for (int j = lo; j < hi; j++) {
-        col_load_rec(D, j + 2, hi, a3, b3);
-        col_load_bytes(D, c, a2, b2, y2);
-        /* ---- arithmetic for read j ---- */
-        const int col0 = REC_COL0(a1), span = REC_SPAN(a1);
-        const unsigned d = (unsigned)(c - col0);
-        if (live && d < (unsigned)span) {
-            const int rf = REC_RF(b1), lq = REC_LQSEQ(b1), mapq = REC_MAPQ(b1);
-            CgCell cell; uint32_t qv = y1.q, sb = y1.s;
-            bool ok = true;
-            if (rf & CG_RF_SIMPLE) {
-                cell.qpos = (int)d; cell.indel = 0; cell.is_del = 0; cell.is_refskip = 0;
-                cell.is_head = d == 0; cell.is_tail = (int)d == span - 1;
-            } else {
-                ok = col_resolve_general(D, c, col0, span, REC_CIGOFF(b1), REC_NCIG(b1), REC_OFF(a1), &cell, &qv, &sb);
-            }
-            if (ok) {
-                st.n_plp++;
-                st.low_mq += (mapq <= min_mqual);
-                if (cell.indel || cell.is_del) { st.had_indel = 1; st.indel_cnt++; }
-                if (cell.is_refskip) st.n_skip++;
-                else {
-                    if ((cell.is_head && cell.qpos > 0) || (cell.is_tail && cell.qpos + 1 < lq)) st.clipped++;
-                    if (!cell.is_tail && !cell.is_head) { st.n_overlap++; if (cell.indel > 0) st.ins_seen = 1; }
-                    if (lq && doB) {
-                        int nib = (sb >> ((~cell.qpos & 1) << 2)) & 0xf;
-                        int base = cell.is_del ? 4 : cg_nt16_to_base(nib);
-                        if (qv > (uint32_t)qcap && !T->preserve_qual[qv]) qv = qcap;
-                        const int eq = effB[(mapq << 8) | qv];
-                        const CgTabRow r = tab[eq];
-                        if (base < 5) {
-                            COL_ACC(base, r.MM, r.hM, r.om, r.q2p);
-                            A.depth++;
-                        } else cg_cons_add(T, &A, base, eq);
-                    }
-                }
-            }
+    if (lo < hi) {
+        uint4 r1, r2, r3;
+        uint32_t y1, y2, y3;
+        r1 = col_load_rec(D, lo, hi);
+        r2 = col_load_rec(D, lo + 1, hi);
+        y1 = col_load_bytes(D, c, r1);
+        /* three steps per trip so the pipeline registers rotate by renaming, not by moves; steps past hi see span 0 */
+        for (int j = lo; j < hi; j += 3) {
+            COL_STEP(r1, y1, r2, y2, r3, j);
+            COL_STEP(r2, y2, r3, y3, r1, j + 1);
+            COL_STEP(r3, y3, r1, y1, r2, j + 2);
         }
-        a1 = a2; b1 = b2; a2 = a3; b2 = b3; y1 = y2;
     }
-    if (live) o = cg_column_finish(&D, c, lo, hi, &st, &A);
+    if (c < D.n_cols) {
+        CgColStats st; st.n_plp = n_plp; st.n_skip = n_skip; st.low_mq = low_mq; st.had_indel = had_indel; st.indel_cnt = indel_cnt;
+        st.clipped = clipped; st.n_overlap = n_overlap; st.ins_seen = ins_seen;
+        A.depth = depth; A.nN = 0; A.sumsE = 0;
+        if (nN) col_gather_generic(&D, c, lo, hi, &A);      /* N bases add to 14 slots: exact slow path */
+        o = cg_column_finish(&D, c, lo, hi, &st, &A);
+    }
     /* counters: one atomic per warp and counter */
     unsigned un = __reduce_or_sync(0xffffffffu, o.cnt);
     while (un) {
@@ -703,7 +709,7 @@ extern "C" int cg_upload(cg_ctx *ctx, const cg_batch *in) {
     cudaStream_t st = ctx->stream;
     const int64_t n = in->n_reads;
     if (n < 0 || in->qual_bytes < 0) return CG_ERR_BAD_ARG;
-    if (n > 0x7fffff00LL || in->n_cigar_total > 0x7fffff00LL) { snprintf(ctx->err, sizeof ctx->err, "batch too large: split it"); return CG_ERR_BAD_ARG; }
+    if (n > 0x7fffff00LL || in->n_cigar_total > 0x7fffff00LL || in->qual_bytes >= (1LL << 35)) { snprintf(ctx->err, sizeof ctx->err, "batch too large: split it"); return CG_ERR_BAD_ARG; }
     ctx->resident = 0;
     size_t n1 = (size_t)n + 1;
     int e;

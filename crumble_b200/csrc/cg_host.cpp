@@ -91,13 +91,17 @@ void cg_tables_init(CgTables *T, const cg_params *p) {
     T->log_c2 = (double)(2.0f / 3);
     for (int mq = 0; mq < 256; mq++)
         for (int q = 0; q < 256; q++) {                                              /* 632-642 */
-            double _p = mqual_pow[q], _m = mqual_pow[mq];
+            /* the pileup copy is capped before the consensus sees it (cap_quality, 1325-1332): fold it into the table */
+            int qc = (q > p->qcap && !p->preserve_qual[q]) ? p->qcap : q;
+            if (qc < 0) qc = 0;
+            if (qc > 255) qc = 255;
+            double _p = mqual_pow[qc], _m = mqual_pow[mq];
             uint8_t e = (uint8_t)(-3.0103 * host_fast_log2(1 - (_m * _p + (1 - _m) / 4), T->log_c1, T->log_c2));
             if (e < 1) e = 1;
             if (e > 100) e = 100;          /* the reference would index past its 101-entry tables here */
             T->effB[(mq << 8) | q] = e;
         }
-    for (int q = 0; q < 256; q++) { int e = q < 1 ? 1 : (q > 100 ? 100 : q); T->effA[q] = (uint8_t)e; }
+    for (int q = 0; q < 256; q++) { int qc = (q > p->qcap && !p->preserve_qual[q]) ? p->qcap : q; int e = qc < 1 ? 1 : (qc > 100 ? 100 : qc); T->effA[q] = (uint8_t)e; }
     for (int i = 0; i < 256; i++) {                                                  /* init_bins 234-247 */
         int v = i < p->qcutoff ? p->qlow : p->qhigh;
         if (p->preserve_qual[i] > 1) v = i;

@@ -19,12 +19,15 @@
 #include "../../include/crumble_gpu.h"
 
 #define CG_RF_PILEUP  1
-#define CG_RF_SIMPLE  2       /* single M/=/X op */
+#define CG_RF_SIMPLE  2       /* single M/=/X op with l_qseq == span (0 < l_qseq < 65535): qpos = column offset, never clipped */
 
 typedef struct CgRead {       /* 32 bytes, one per pileup read (compacted, input order) */
-    int64_t  off;             /* qual byte offset (seq at off/2) */
+    /* hot half: everything the column kernel needs for a single-M read */
+    uint32_t off8;            /* qual byte offset / 8 (seq at off/2) */
     int32_t  col0;            /* dense column of the first reference base */
     int32_t  span;            /* reference span */
+    uint32_t pk;              /* min(l_qseq,0xffff) | mapq << 16 | rf << 24 */
+    /* cold half */
     int32_t  pos;             /* reference position */
     int32_t  cig_off;
     int32_t  l_qseq;
@@ -32,6 +35,7 @@ typedef struct CgRead {       /* 32 bytes, one per pileup read (compacted, input
     uint8_t  mapq;
     uint8_t  rf;
 } CgRead;
+#define CG_OFF(q) ((int64_t)(q)->off8 << 3)
 
 typedef struct CgIsland { int32_t col_start, tid, pos_start, pad; } CgIsland;
 
@@ -122,7 +126,7 @@ CG_HD void cg_finish_read(const CgDev *D, int j, int64_t K0) {
     int64_t r = D->orig[j];
     CgRead q;
     int span = D->rspan[r];
-    q.off = D->off[r];
+    q.off8 = (uint32_t)(D->off[r] >> 3);
     q.col0 = (int32_t)(D->ks[j] - K0 - D->gap[j]);
     q.span = span;
     q.pos = D->pos[r];
@@ -131,8 +135,9 @@ CG_HD void cg_finish_read(const CgDev *D, int j, int64_t K0) {
     q.n_cigar = D->n_cigar[r];
     q.mapq = D->mapq[r];
     uint8_t rf = CG_RF_PILEUP;
-    if (q.n_cigar == 1 && cg_is_mop(cg_cig_op(D->cigar[q.cig_off]))) rf |= CG_RF_SIMPLE;
+    if (q.n_cigar == 1 && cg_is_mop(cg_cig_op(D->cigar[q.cig_off])) && q.l_qseq == span && span < 65535) rf |= CG_RF_SIMPLE;
     q.rf = rf;
+    q.pk = (uint32_t)(q.l_qseq > 0xffff ? 0xffff : q.l_qseq) | ((uint32_t)q.mapq << 16) | ((uint32_t)rf << 24);
     D->rd[j] = q;
     D->pmaxcol[j] = (int32_t)(D->ke[j] - K0 - D->gap[j]);
     D->r_bf[j] = 0;
@@ -170,7 +175,7 @@ CG_HD bool cg_cell(const CgDev *D, const CgRead *q, int c, CgCell *cell) {
 }
 
 CG_HD int cg_seq_nib(const CgDev *D, const CgRead *q, int x) {
-    return (D->seq[(q->off >> 1) + (x >> 1)] >> ((~x & 1) << 2)) & 0xf;
+    return (D->seq[(CG_OFF(q) >> 1) + (x >> 1)] >> ((~x & 1) << 2)) & 0xf;
 }
 
 /* ---- stage: column (one per dense column) --------------------------------------------
@@ -190,7 +195,7 @@ CG_HD void cg_column_cons(const CgDev *D, int c, int lo, int hi, CgCons *out) {
         if (cell.is_refskip || !q.l_qseq) continue;                       /* 589-595 */
         int nib = cg_seq_nib(D, &q, cell.qpos);
         int base = cell.is_del ? 4 : cg_nt16_to_base(nib);                /* 603-609 */
-        uint8_t qv = cg_cap_qual(D->qual[q.off + cell.qpos], &D->P, T);   /* pileup copy is capped (1325-1332) */
+        uint8_t qv = cg_cap_qual(D->qual[CG_OFF(&q) + cell.qpos], &D->P, T);   /* pileup copy is capped (1325-1332) */
         int eq = MODE_B ? T->effB[((int)q.mapq << 8) | qv] : T->effA[qv];
         cg_cons_add(T, &a, base, eq);
     }
@@ -319,7 +324,7 @@ CG_HD CgColOut cg_column_body(const CgDev *D, int c) {
         if (!q.l_qseq || !doB) continue;
         int nib = cg_seq_nib(D, &q, cell.qpos);
         int base = cell.is_del ? 4 : cg_nt16_to_base(nib);
-        uint8_t qv = cg_cap_qual(D->qual[q.off + cell.qpos], P, T);
+        uint8_t qv = cg_cap_qual(D->qual[CG_OFF(&q) + cell.qpos], P, T);
         cg_cons_add(T, &a, base, T->effB[((int)q.mapq << 8) | qv]);
     }
     CgColStats st; st.n_plp = n_plp; st.n_skip = n_skip; st.low_mq = low_mq; st.had_indel = had_indel; st.indel_cnt = indel_cnt;
@@ -368,10 +373,10 @@ CG_HDN uint32_t cg_flagged(const CgDev *D, int k, CgFlagScratch *S) {
             if (is_indel) { int v = (cell.indel < 0 ? -cell.indel : cell.indel) + cell.is_del; if (indel < v) indel = v; }
             else indel = 1;                                                /* 1725-1730 */
             if (gate && q.l_qseq > 0) {                                    /* 1732-1739: the two calls are identical in effect */
-                int phantom = (q.l_qseq & 1) ? (D->seq[(q.off >> 1) + (q.l_qseq >> 1)] & 0xf)
-                                             : (cg_cap_qual(D->qual[q.off], P, D->T) >> 4);
+                int phantom = (q.l_qseq & 1) ? (D->seq[(CG_OFF(&q) >> 1) + (q.l_qseq >> 1)] & 0xf)
+                                             : (cg_cap_qual(D->qual[CG_OFF(&q)], P, D->T) >> 4);
                 int lo_r = m_run, hi_r = M_run;
-                cg_mask_lc(D->seq + (q.off >> 1), q.l_qseq, phantom, D->cigar + q.cig_off, q.n_cigar, q.pos,
+                cg_mask_lc(D->seq + (CG_OFF(&q) >> 1), q.l_qseq, phantom, D->cigar + q.cig_off, q.n_cigar, q.pos,
                            cell.qpos + 1, is_indel ? P->iSTR_add : P->sSTR_add, S->win, &S->reps, &lo_r, &hi_r);
                 if (S->reps.overflow) *D->err = CG_ERR_OVERFLOW;
                 m_run = lo_r; M_run = hi_r;
