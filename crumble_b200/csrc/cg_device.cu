@@ -197,23 +197,6 @@ __global__ void k_tile_index(const __grid_constant__ CgDev D) {
  * table.  sumsE of the reference is dead (never read after the loop) and is not computed. */
 struct __align__(8) CgTabRow { double MM, hM, om; };
 
-__device__ __forceinline__ uint4 col_load_rec(const CgDev &D, int j, int hi) {
-    int jj = j < hi ? j : hi - 1;                                  /* clamp: always a valid record ... */
-    uint4 a = __ldg(reinterpret_cast<const uint4 *>(D.rd + jj));
-    if (j >= hi) a.z = 0;                                          /* ... with span 0 past the window: covers nothing */
-    return a;
-}
-__device__ __forceinline__ uint32_t col_load_bytes(const CgDev &D, int c, const uint4 &a) {
-    unsigned d = (unsigned)(c - (int)a.y);
-    uint32_t r = 0;
-    if (d < a.z) {                                                 /* covering lanes only; non-simple reads reload below */
-        const uint8_t *q = D.qual + ((size_t)a.x << 3) + d;
-        const uint8_t *s = D.seq + ((size_t)a.x << 2) + (d >> 1);
-        r = (uint32_t)*q | ((uint32_t)*s << 8);
-    }
-    return r;
-}
-
 /* non-simple CIGARs (a few percent of reads): out of line, result packed into registers
  * bits 0..23 qpos | 24 is_del | 25 is_refskip | 26 is_head | 27 is_tail | 28 ok ; high word = indel */
 __device__ __noinline__ uint64_t col_resolve_general(const uint32_t *cig, int n_cigar, int d, int span) {
@@ -240,62 +223,56 @@ __device__ __noinline__ void col_gather_generic(const CgDev *D, int c, int lo, i
     }
 }
 
-/* one pipeline step: issue the record load for read JJ+2 and the byte loads for read JJ+1, then the arithmetic of read JJ */
-#define COL_STEP(r1, y1, r2, y2, r3, JJ) do { \
-    r3 = col_load_rec(D, (JJ) + 2, hi); \
-    y2 = col_load_bytes(D, c, r2); \
-    const unsigned d_ = (unsigned)(c - (int)r1.y); \
-    const int span_ = (int)r1.z; \
-    if (d_ < (unsigned)span_) { \
-        const uint32_t pk_ = r1.w; \
-        const int mapq_ = (pk_ >> 16) & 0xff; \
-        uint32_t qv_ = y1 & 0xff, sb_ = y1 >> 8; \
-        int qpos_ = (int)d_, contrib_ = doB; \
-        int base_; \
-        n_plp++; \
-        low_mq += (mapq_ <= min_mqual); \
-        if (pk_ & ((uint32_t)CG_RF_SIMPLE << 24)) { \
-            n_overlap += (d_ != 0) & ((int)d_ != span_ - 1); \
-        } else { \
-            const CgRead *rq_ = D.rd + ((JJ) < hi ? (JJ) : hi - 1); \
-            const int lq_ = rq_->l_qseq; \
-            uint64_t pkc_ = col_resolve_general(D.cigar + rq_->cig_off, rq_->n_cigar, (int)d_, span_); \
-            uint32_t lo_ = (uint32_t)pkc_; \
-            const int indel_ = (int)(uint32_t)(pkc_ >> 32); \
-            const int isdel_ = (lo_ >> 24) & 1, skip_ = (lo_ >> 25) & 1, head_ = (lo_ >> 26) & 1, tail_ = (lo_ >> 27) & 1; \
-            qpos_ = lo_ & 0xffffff; \
-            if (!((lo_ >> 28) & 1)) { n_plp--; low_mq -= (mapq_ <= min_mqual); contrib_ = 0; } \
-            else { \
-                if (indel_ | isdel_) { had_indel = 1; indel_cnt++; } \
-                if (skip_) { n_skip++; contrib_ = 0; } \
-                else { \
-                    clipped += (head_ & (qpos_ > 0)) | (tail_ & (qpos_ + 1 < lq_)); \
-                    const int mid_ = !tail_ & !head_; \
-                    n_overlap += mid_; ins_seen |= mid_ & (indel_ > 0); \
-                    if (!lq_) contrib_ = 0; \
-                    else { const size_t off_ = (size_t)r1.x << 3; qv_ = D.qual[off_ + qpos_]; sb_ = D.seq[(off_ >> 1) + (qpos_ >> 1)]; } \
-                    if (isdel_) sb_ = 0x100; /* marks a deletion: base 4 */ \
-                } \
-            } \
-        } \
-        if (contrib_) { \
-            const int nib_ = (sb_ >> ((~qpos_ & 1) << 2)) & 0xf; \
-            base_ = (sb_ & 0x100) ? 4 : cg_nt16_to_base(nib_); \
-            const CgTabRow w_ = tab[effB[(mapq_ << 8) | qv_]]; \
-            switch (base_) { \
-            case 0: A.S[0] += w_.MM; A.S[1] += w_.hM; A.S[2] += w_.hM; A.S[3] += w_.hM; A.S[4] += w_.hM; A.sumsC[0] += w_.om; depth++; break; \
-            case 1: A.S[1] += w_.hM; A.S[5] += w_.MM; A.S[6] += w_.hM; A.S[7] += w_.hM; A.S[8] += w_.hM; A.sumsC[1] += w_.om; depth++; break; \
-            case 2: A.S[2] += w_.hM; A.S[6] += w_.hM; A.S[9] += w_.MM; A.S[10] += w_.hM; A.S[11] += w_.hM; A.sumsC[2] += w_.om; depth++; break; \
-            case 3: A.S[3] += w_.hM; A.S[7] += w_.hM; A.S[10] += w_.hM; A.S[12] += w_.MM; A.S[13] += w_.hM; A.sumsC[3] += w_.om; depth++; break; \
-            case 4: A.S[4] += w_.hM; A.S[8] += w_.hM; A.S[11] += w_.hM; A.S[13] += w_.hM; A.S[14] += w_.MM; A.sumsC[4] += w_.om; depth++; break; \
-            default: nN++; break; \
-            } \
-        } \
-    } \
-} while (0)
+/* ---- shared-memory staging of a 128-column tile ------------------------------------------------------------
+ * A block owns 128 consecutive dense columns.  The candidate reads of the tile are processed in chunks of
+ * COL_CH reads: for every read of a chunk the block copies, with 16-byte cp.async (LDGSTS, no register staging,
+ * all copies in flight together), the 144-byte window of its quality string and the 80-byte window of its packed
+ * sequence that face the tile, keeping the source misalignment, plus the 16-byte hot record.  The arithmetic then
+ * runs out of shared memory: the record is a broadcast LDS, base/quality bytes are conflict-free byte LDS.
+ * Chunks are double-buffered (copy of chunk k+1 overlaps the arithmetic of chunk k). */
+#define COL_CH      64
+#define COL_QROW    144
+#define COL_SROW    80
+struct __align__(16) ColStage {
+    uint8_t  q[COL_CH][COL_QROW];
+    uint8_t  s[COL_CH][COL_SROW];
+    uint4    rec[COL_CH];            /* off8, col0, span, pk */
+    uint32_t meta[COL_CH];           /* qual misalignment | seq misalignment << 8 | (d0 & 1) << 16 */
+};
 
-__global__ void __launch_bounds__(128) k_column(const __grid_constant__ CgDev D) {
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
+
+/* copy chunk [j0, j0+n) of the block's read window into stage S; two threads per read, 7 x 16 B each */
+__device__ __forceinline__ void col_stage_issue(const CgDev &D, ColStage *S, int j0, int n, int tile_c0, int64_t qlim, int64_t slim) {
+    const int r = threadIdx.x >> 1, h = threadIdx.x & 1;
+    if (r < n) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(D.rd + j0 + r));
+        const int d0 = tile_c0 - (int)a.y;
+        const int64_t off = (int64_t)a.x << 3;
+        const int64_t qs = off + d0, qa = qs & ~(int64_t)15;
+        const int64_t ss = (off >> 1) + (d0 >> 1), sa = ss & ~(int64_t)15;
+        if (h == 0) {
+            S->rec[r] = a;
+            S->meta[r] = (uint32_t)(qs - qa) | ((uint32_t)(ss - sa) << 8) | ((uint32_t)(d0 & 1) << 16);
+#pragma unroll
+            for (int i = 0; i < 7; i++) { int64_t src = qa + 16 * i; if (src >= 0 && src + 16 <= qlim) cp_async16(&S->q[r][16 * i], D.qual + src); }
+        } else {
+#pragma unroll
+            for (int i = 7; i < 9; i++) { int64_t src = qa + 16 * i; if (src >= 0 && src + 16 <= qlim) cp_async16(&S->q[r][16 * i], D.qual + src); }
+#pragma unroll
+            for (int i = 0; i < 5; i++) { int64_t src = sa + 16 * i; if (src >= 0 && src + 16 <= slim) cp_async16(&S->s[r][16 * i], D.seq + src); }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_column(const __grid_constant__ CgDev D, int64_t qlim, int64_t slim) {
     __shared__ CgTabRow tab[104];
+    __shared__ ColStage stage[2];
     const CgTables *T = D.T;
     const CgDevParams *P = &D.P;
     for (int i = threadIdx.x; i < 104; i += blockDim.x) {
@@ -303,32 +280,95 @@ __global__ void __launch_bounds__(128) k_column(const __grid_constant__ CgDev D)
         CgTabRow r; r.MM = T->MM[q]; r.hM = T->_M[q]; r.om = T->omq2p[q];
         tab[i] = r;
     }
-    __syncthreads();
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tile_c0 = blockIdx.x * 128;
+    const int x = threadIdx.x;                       /* column within the tile */
+    const int c = tile_c0 + x;
+    const int w = threadIdx.x >> 5;
     CgColOut o; o.cnt = 0; o.n_plp = 0;
-    const int t = c >> 5;
+    /* block window = union of its four 32-column tiles; each warp walks only the rows of its own tile */
+    const int t0 = blockIdx.x * 4;
+    const int tl = (D.n_tiles - 1 < t0 + 3) ? D.n_tiles - 1 : t0 + 3;
+    const int blo = D.tile_lo[t0], bhi = D.tile_start[tl + 1];
     int lo = 0, hi = 0;
-    if (t < D.n_tiles && c < D.n_cols) { lo = D.tile_lo[t]; hi = D.tile_start[t + 1]; }   /* lanes past n_cols: empty window */
+    if (t0 + w < D.n_tiles) { lo = D.tile_lo[t0 + w]; hi = D.tile_start[t0 + w + 1]; }
+    const bool live = c < D.n_cols;
     CgConsAcc A; cg_cons_init(&A);
     int n_plp = 0, n_skip = 0, low_mq = 0, had_indel = 0, indel_cnt = 0, clipped = 0, n_overlap = 0, ins_seen = 0, nN = 0, depth = 0;
     const int doB = P->min_qual_B != 0;
     const int min_mqual = P->min_mqual;
     const uint8_t *effB = T->effB;
 
-    if (lo < hi) {
-        uint4 r1, r2, r3;
-        uint32_t y1, y2, y3;
-        r1 = col_load_rec(D, lo, hi);
-        r2 = col_load_rec(D, lo + 1, hi);
-        y1 = col_load_bytes(D, c, r1);
-        /* three steps per trip so the pipeline registers rotate by renaming, not by moves; steps past hi see span 0 */
-        for (int j = lo; j < hi; j += 3) {
-            COL_STEP(r1, y1, r2, y2, r3, j);
-            COL_STEP(r2, y2, r3, y3, r1, j + 1);
-            COL_STEP(r3, y3, r1, y1, r2, j + 2);
+    const int nchunk = (bhi - blo + COL_CH - 1) / COL_CH;
+    if (nchunk > 0) { int n = bhi - blo < COL_CH ? bhi - blo : COL_CH; col_stage_issue(D, &stage[0], blo, n, tile_c0, qlim, slim); }
+    cp_async_commit();
+    for (int k = 0; k < nchunk; k++) {
+        const int j0 = blo + k * COL_CH;
+        if (k + 1 < nchunk) {
+            int n = bhi - (j0 + COL_CH); if (n > COL_CH) n = COL_CH;
+            col_stage_issue(D, &stage[(k + 1) & 1], j0 + COL_CH, n, tile_c0, qlim, slim);
         }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const ColStage *S = &stage[k & 1];
+        int r0 = lo - j0, r1 = hi - j0;
+        if (r0 < 0) r0 = 0;
+        if (r1 > COL_CH) r1 = COL_CH;
+        if (live) for (int r = r0; r < r1; r++) {
+            const uint4 rec = S->rec[r];
+            const unsigned d_ = (unsigned)(c - (int)rec.y);
+            const int span_ = (int)rec.z;
+            if (d_ < (unsigned)span_) {
+                const uint32_t pk_ = rec.w;
+                const int mapq_ = (pk_ >> 16) & 0xff;
+                const uint32_t meta = S->meta[r];
+                uint32_t qv_ = S->q[r][(meta & 0xff) + x];
+                uint32_t sb_ = S->s[r][((meta >> 8) & 0xff) + ((((meta >> 16) & 1) + x) >> 1)];
+                int qpos_ = (int)d_, contrib_ = doB;
+                n_plp++;
+                low_mq += (mapq_ <= min_mqual);
+                if (pk_ & ((uint32_t)CG_RF_SIMPLE << 24)) {
+                    n_overlap += (d_ != 0) & ((int)d_ != span_ - 1);
+                } else {
+                    const CgRead *rq_ = D.rd + j0 + r;
+                    const int lq_ = rq_->l_qseq;
+                    uint64_t pkc_ = col_resolve_general(D.cigar + rq_->cig_off, rq_->n_cigar, (int)d_, span_);
+                    uint32_t lo_ = (uint32_t)pkc_;
+                    const int indel_ = (int)(uint32_t)(pkc_ >> 32);
+                    const int isdel_ = (lo_ >> 24) & 1, skip_ = (lo_ >> 25) & 1, head_ = (lo_ >> 26) & 1, tail_ = (lo_ >> 27) & 1;
+                    qpos_ = lo_ & 0xffffff;
+                    if (!((lo_ >> 28) & 1)) { n_plp--; low_mq -= (mapq_ <= min_mqual); contrib_ = 0; }
+                    else {
+                        if (indel_ | isdel_) { had_indel = 1; indel_cnt++; }
+                        if (skip_) { n_skip++; contrib_ = 0; }
+                        else {
+                            clipped += (head_ & (qpos_ > 0)) | (tail_ & (qpos_ + 1 < lq_));
+                            const int mid_ = !tail_ & !head_;
+                            n_overlap += mid_; ins_seen |= mid_ & (indel_ > 0);
+                            if (!lq_) contrib_ = 0;
+                            else { const size_t off_ = (size_t)rec.x << 3; qv_ = D.qual[off_ + qpos_]; sb_ = D.seq[(off_ >> 1) + (qpos_ >> 1)]; }
+                            if (isdel_) sb_ = 0x100;      /* marks a deletion: base 4 */
+                        }
+                    }
+                }
+                if (contrib_) {
+                    const int nib_ = (sb_ >> ((~qpos_ & 1) << 2)) & 0xf;
+                    const int base_ = (sb_ & 0x100) ? 4 : cg_nt16_to_base(nib_);
+                    const CgTabRow w_ = tab[effB[(mapq_ << 8) | qv_]];
+                    switch (base_) {
+                    case 0: A.S[0] += w_.MM; A.S[1] += w_.hM; A.S[2] += w_.hM; A.S[3] += w_.hM; A.S[4] += w_.hM; A.sumsC[0] += w_.om; depth++; break;
+                    case 1: A.S[1] += w_.hM; A.S[5] += w_.MM; A.S[6] += w_.hM; A.S[7] += w_.hM; A.S[8] += w_.hM; A.sumsC[1] += w_.om; depth++; break;
+                    case 2: A.S[2] += w_.hM; A.S[6] += w_.hM; A.S[9] += w_.MM; A.S[10] += w_.hM; A.S[11] += w_.hM; A.sumsC[2] += w_.om; depth++; break;
+                    case 3: A.S[3] += w_.hM; A.S[7] += w_.hM; A.S[10] += w_.hM; A.S[12] += w_.MM; A.S[13] += w_.hM; A.sumsC[3] += w_.om; depth++; break;
+                    case 4: A.S[4] += w_.hM; A.S[8] += w_.hM; A.S[11] += w_.hM; A.S[13] += w_.hM; A.S[14] += w_.MM; A.sumsC[4] += w_.om; depth++; break;
+                    default: nN++; break;
+                    }
+                }
+            }
+        }
+        __syncthreads();
     }
-    if (c < D.n_cols) {
+    if (live) {
         CgColStats st; st.n_plp = n_plp; st.n_skip = n_skip; st.low_mq = low_mq; st.had_indel = had_indel; st.indel_cnt = indel_cnt;
         st.clipped = clipped; st.n_overlap = n_overlap; st.ins_seen = ins_seen;
         A.depth = depth; A.nN = 0; A.sumsE = 0;
@@ -716,8 +756,8 @@ extern "C" int cg_upload(cg_ctx *ctx, const cg_batch *in) {
     if ((e = ensure(ctx, &ctx->b_tid, n1 * 4)) || (e = ensure(ctx, &ctx->b_pos, n1 * 4)) || (e = ensure(ctx, &ctx->b_flag, n1 * 2)) ||
         (e = ensure(ctx, &ctx->b_mapq, n1)) || (e = ensure(ctx, &ctx->b_lq, n1 * 4)) || (e = ensure(ctx, &ctx->b_nc, n1 * 2)) ||
         (e = ensure(ctx, &ctx->b_off, n1 * 8)) || (e = ensure(ctx, &ctx->b_coff, n1 * 4)) ||
-        (e = ensure(ctx, &ctx->b_cigar, ((size_t)in->n_cigar_total + 1) * 4)) || (e = ensure(ctx, &ctx->b_seq, (size_t)in->seq_bytes + 16)) ||
-        (e = ensure(ctx, &ctx->b_qual, (size_t)in->qual_bytes + 16)) || (e = ensure(ctx, &ctx->b_qout, (size_t)in->qual_bytes + 16))) return e;
+        (e = ensure(ctx, &ctx->b_cigar, ((size_t)in->n_cigar_total + 1) * 4)) || (e = ensure(ctx, &ctx->b_seq, (size_t)in->seq_bytes + 128)) ||
+        (e = ensure(ctx, &ctx->b_qual, (size_t)in->qual_bytes + 128)) || (e = ensure(ctx, &ctx->b_qout, (size_t)in->qual_bytes + 16))) return e;
     T0(CG_T_H2D);
     if (n) {
         CG_CHECK(cudaMemcpyAsync(ctx->b_tid.p, in->tid, (size_t)n * 4, cudaMemcpyHostToDevice, st));
@@ -837,7 +877,7 @@ extern "C" int cg_run(cg_ctx *ctx) {
     }
     T1(CG_T_TILES);
     T0(CG_T_COLUMNS);
-    if (nc > 0) { k_column<<<nblk(nc, 128), 128, 0, st>>>(*D); ctx->launches++; }
+    if (nc > 0) { k_column<<<nblk(nc, 128), 128, 0, st>>>(*D, (int64_t)ctx->qual_bytes + 64, (int64_t)(ctx->qual_bytes / 2) + 64); ctx->launches++; }
     T1(CG_T_COLUMNS);
     T0(CG_T_FLAGGED);
     if (nc > 0) {
