@@ -104,7 +104,8 @@ EXPORTS = [
 
 
 def lib_path() -> Path:
-    return LIB_DIR / "libcrumble_gpu.so"
+    # CRUMBLE_GPU_LIB: A/B runs of differently tuned builds of the same library (tools/build_variant.sh)
+    return Path(os.environ["CRUMBLE_GPU_LIB"]) if os.environ.get("CRUMBLE_GPU_LIB") else LIB_DIR / "libcrumble_gpu.so"
 
 
 def load_lib():

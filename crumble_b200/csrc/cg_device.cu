@@ -185,27 +185,49 @@ __global__ void k_tile_index(const __grid_constant__ CgDev D) {
     if (j < D.n_pile) cg_tile_index(&D, j);
 }
 
-/* The hot kernel: one thread per dense reference column, one warp per 32-column tile.
- * All lanes of a warp walk the same candidate read window [tile_lo, tile_start[t+1]) in input order, so the
- * 16-byte hot half of each read record is one warp-uniform 128-bit load and base / quality bytes are adjacent
- * across lanes.  The loop is software-pipelined three deep (record j+2 | bytes j+1 | arithmetic j) and unrolled by
- * three so the pipeline registers rotate by renaming.  The 15 genotype sums and 5 discrepancy sums live in
- * registers; each read adds to the 6 of them its base selects, through a real branch per base present in the
- * warp (a switch, as the reference's own code at snp_score.c:656-683) — cheaper than masking all 20 because the
- * masks would cost two ALU ops per accumulator.  Per slot the IEEE add sequence equals the reference's.
- * Per-quality constants (MM, _M, 1-q2p) sit in shared memory; the cap (-U) is folded into the effective-quality
- * table.  sumsE of the reference is dead (never read after the loop) and is not computed. */
-struct __align__(8) CgTabRow { double MM, hM, om; };
+/* The hot kernel: one thread per dense reference column, one warp per 32-column tile; warps are independent
+ * (no block barrier inside the loop).  Per chunk of COL_ROWS candidate reads a warp runs two phases:
+ *
+ *  stage   every read of the chunk is decoded ONCE into a row of 32 16-bit pileup cells in the warp's shared
+ *          memory (4 lanes per read, 8 adjacent columns per lane: two aligned 64-bit quality loads and two 32-bit
+ *          sequence loads are funnel-shifted into place, the eight nt16 codes are mapped to bases in one
+ *          SIMD-within-register pass, quality x mapq goes through the effective-quality table; the ragged ends of
+ *          a read are cut with mask rows from a small shared table; reads with a non-trivial CIGAR walk it once
+ *          per lane, out of line).  A cell carries everything the column loop needs: valid | base | effective
+ *          quality | ins | clip | indel | mid | low-mapq.  Uncovered cells are zero.
+ *  column  each lane walks its column down the rows: one 16-bit LDS per cell, flag counters kept as four packed
+ *          8-bit fields, the per-quality constants (MM, _M, 1-q2p) from a 32-byte shared-memory row addressed by
+ *          the cell's own bits, and the in-order FP64 accumulation.
+ *
+ * Accumulators live in RANK space: the bases of a column are numbered in order of first appearance and the 15
+ * genotype sums + 5 discrepancy sums are kept as H[rank], C[rank], P[rank pair].  A read of rank k adds to H[k], C[k]
+ * and the four pairs holding k, exactly the six adds of the reference's switch (snp_score.c:656-683), in the same
+ * order per slot, so every slot sees the same IEEE add sequence.  Because nearly all cells of a column carry its
+ * first base, the fast path (cell's base == first base) is taken by whole warps whatever the reference base under
+ * each lane is; a switch on the base itself diverged ~4 ways per row.  The permutation is undone once per column.
+ * sumsE of the reference is dead (never read after the loop) and is not computed. */
+#define COL_WARPS    4
+#ifndef COL_MINB
+#define COL_MINB     5          /* resident blocks per SM the register allocation is sized for */
+#endif
+#define COL_ROWS     80         /* rows per chunk: 80 x 64 B = 20 x 32 doubles, the un-permute scratch */
+#define CELL_VALID   0x8000u
+#define CELL_BASE_SH 12         /* bits 14..12: base 0..4 = ACGT*, 5 = N, 6 = ref-skip, 7 = no contribution */
+#define CELL_BASE_M  0x7000u
+#define CELL_E_SH    5          /* bits 11..5: effective quality (1..100) == byte offset / 32 of its table row */
+#define CELL_E_M     0x0fe0u
+#define CELL_INS     0x0010u
+#define CELL_CLIP    0x0008u
+#define CELL_INDEL   0x0004u
+#define CELL_MID     0x0002u
+#define CELL_LOWMQ   0x0001u
 
-/* non-simple CIGARs (a few percent of reads): out of line, result packed into registers
- * bits 0..23 qpos | 24 is_del | 25 is_refskip | 26 is_head | 27 is_tail | 28 ok ; high word = indel */
-__device__ __noinline__ uint64_t col_resolve_general(const uint32_t *cig, int n_cigar, int d, int span) {
-    CgCell cell;
-    if (!cg_plp_resolve(cig, n_cigar, d, span, &cell)) return 0;
-    uint32_t lo = (uint32_t)(cell.qpos & 0xffffff) | ((uint32_t)cell.is_del << 24) | ((uint32_t)cell.is_refskip << 25) |
-                  ((uint32_t)cell.is_head << 26) | ((uint32_t)cell.is_tail << 27) | (1u << 28);
-    return ((uint64_t)(uint32_t)cell.indel << 32) | lo;
-}
+struct __align__(16) ColTabRow { double MM, hM, om, pad; };
+struct __align__(16) ColSmem {
+    union { uint16_t cell[COL_ROWS][32]; double dump[20][32]; } w[COL_WARPS];
+    ColTabRow tab[104];
+    uint4 mask[9][9];            /* [a][b]: 0xffff in the 16-bit lanes k with a <= k < b */
+};
 
 /* exact recomputation of a column's accumulators with the generic code: used for the rare columns holding an N base */
 __device__ __noinline__ void col_gather_generic(const CgDev *D, int c, int lo, int hi, CgConsAcc *A) {
@@ -223,155 +245,237 @@ __device__ __noinline__ void col_gather_generic(const CgDev *D, int c, int lo, i
     }
 }
 
-/* ---- shared-memory staging of a 128-column tile ------------------------------------------------------------
- * A block owns 128 consecutive dense columns.  The candidate reads of the tile are processed in chunks of
- * COL_CH reads: for every read of a chunk the block copies, with 16-byte cp.async (LDGSTS, no register staging,
- * all copies in flight together), the 144-byte window of its quality string and the 80-byte window of its packed
- * sequence that face the tile, keeping the source misalignment, plus the 16-byte hot record.  The arithmetic then
- * runs out of shared memory: the record is a broadcast LDS, base/quality bytes are conflict-free byte LDS.
- * Chunks are double-buffered (copy of chunk k+1 overlaps the arithmetic of chunk k). */
-#define COL_CH      64
-#define COL_QROW    144
-#define COL_SROW    80
-struct __align__(16) ColStage {
-    uint8_t  q[COL_CH][COL_QROW];
-    uint8_t  s[COL_CH][COL_SROW];
-    uint4    rec[COL_CH];            /* off8, col0, span, pk */
-    uint32_t meta[COL_CH];           /* qual misalignment | seq misalignment << 8 | (d0 & 1) << 16 */
-};
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sa), "l"(gmem));
+/* cells d_first+[ka,kb) of a read with a non-trivial CIGAR (a few percent of reads): ONE walk of the CIGAR
+ * (same state machine as cg_plp_resolve), out of line */
+__device__ __noinline__ uint4 col_stage_general(const CgDev *D, int j, int d_first, int ka, int kb, uint32_t rowf, int doB) {
+    const CgRead q = D->rd[j];
+    const uint32_t *cig = D->cigar + q.cig_off;
+    const uint8_t *er = D->T->effB + ((int)q.mapq << 8);
+    const int64_t off = CG_OFF(&q);
+    const int n_cigar = q.n_cigar, span = q.span, lq = q.l_qseq;
+    uint32_t c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = 0;
+    int x = 0, y = 0, k = ka;
+    for (int i = 0; i < n_cigar && k < kb; i++) {
+        const int op = cg_cig_op(cig[i]), l = cg_cig_len(cig[i]);
+        if (cg_is_refop(op)) {
+            if (d_first + k < x + l) {
+                /* indel reported on the last column of this op (cg_plp_resolve) */
+                int indel_last = 0;
+                if (i + 1 < n_cigar) {
+                    const int op2 = cg_cig_op(cig[i + 1]), l2 = cg_cig_len(cig[i + 1]);
+                    if (op2 == 2) indel_last = -l2;
+                    else if (op2 == 1) indel_last = l2;
+                    else if (op2 == 6 && i + 2 < n_cigar) {
+                        int l3 = 0;
+                        for (int jj = i + 2; jj < n_cigar; jj++) {
+                            const int o3 = cg_cig_op(cig[jj]);
+                            if (o3 == 1) l3 += cg_cig_len(cig[jj]);
+                            else if (cg_is_refop(o3)) break;
+                        }
+                        if (l3 > 0) indel_last = l3;
+                    }
+                }
+                const bool mop = cg_is_mop(op);
+                for (; k < kb && d_first + k < x + l; k++) {
+                    const int d = d_first + k;
+                    const int indel = (d == x + l - 1) ? indel_last : 0;
+                    const int is_del = !mop, qpos = mop ? y + (d - x) : y;
+                    const bool head = d == 0, tail = d == span - 1;
+                    uint32_t f = rowf, base = 7, e = 1;
+                    if (indel | is_del) f |= CELL_INDEL;
+                    if (op == 3) base = 6;
+                    else {
+                        if ((head && qpos > 0) || (tail && qpos + 1 < lq)) f |= CELL_CLIP;
+                        if (!tail && !head) { f |= CELL_MID; if (indel > 0) f |= CELL_INS; }
+                        if (lq && doB) {
+                            e = er[D->qual[off + qpos]];
+                            base = is_del ? 4 : cg_nt16_to_base((D->seq[(off >> 1) + (qpos >> 1)] >> ((~qpos & 1) << 2)) & 0xf);
+                        }
+                    }
+                    const uint32_t cv = f | (e << CELL_E_SH) | (base << CELL_BASE_SH);
+#pragma unroll
+                    for (int kk = 0; kk < 8; kk++) if (kk == k) c[kk] = cv;
+                }
+            }
+            x += l;
+            if (cg_is_mop(op)) y += l;
+        } else if (op == 1 || op == 4) y += l;
+    }
+    return make_uint4(c[0] | c[1] << 16, c[2] | c[3] << 16, c[4] | c[5] << 16, c[6] | c[7] << 16);
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
 
-/* copy chunk [j0, j0+n) of the block's read window into stage S; two threads per read, 7 x 16 B each */
-__device__ __forceinline__ void col_stage_issue(const CgDev &D, ColStage *S, int j0, int n, int tile_c0, int64_t qlim, int64_t slim) {
-    const int r = threadIdx.x >> 1, h = threadIdx.x & 1;
-    if (r < n) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(D.rd + j0 + r));
-        const int d0 = tile_c0 - (int)a.y;
-        const int64_t off = (int64_t)a.x << 3;
-        const int64_t qs = off + d0, qa = qs & ~(int64_t)15;
-        const int64_t ss = (off >> 1) + (d0 >> 1), sa = ss & ~(int64_t)15;
-        if (h == 0) {
-            S->rec[r] = a;
-            S->meta[r] = (uint32_t)(qs - qa) | ((uint32_t)(ss - sa) << 8) | ((uint32_t)(d0 & 1) << 16);
+/* eight nt16 codes (one per nibble) -> eight base codes (A0 C1 G2 T3, anything else 5) */
+__device__ __forceinline__ uint32_t col_bases8(uint32_t X) {
+    const uint32_t M = 0x11111111u;
+    const uint32_t p0 = X & M, p1 = (X >> 1) & M, p2 = (X >> 2) & M, p3 = (X >> 3) & M;
+    const uint32_t t = (p0 + p1 + p2 + p3) ^ M;                       /* nibble == 0 iff exactly one bit set */
+    const uint32_t one = ((t | (t >> 1) | (t >> 2)) & M) ^ M;
+    const uint32_t m = one * 15u;
+    return ((p1 + p2 * 2u + p3 * 3u) & m) | (0x55555555u & ~m);
+}
+
+/* decode rows [j0, j0+n) of the warp's read window into its cell matrix: 4 lanes per row, 8 columns per lane */
+__device__ __forceinline__ void col_stage(const CgDev &D, ColSmem *S, uint16_t (*cells)[32], int j0, int n, int tile_c0, int doB, int min_mqual) {
+    const int lane = threadIdx.x & 31, x0 = (lane & 3) * 8;
+    const uint8_t *effB = D.T->effB;
+    for (int r = lane >> 2; r < n; r += 8) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(D.rd + j0 + r));      /* off8, col0, span, pk */
+        const int d_first = x0 + tile_c0 - (int)a.y;       /* column offset inside the read of this lane's first cell */
+        const int span = (int)a.z;
+        int ka = -d_first, kb = span - d_first;            /* cells k in [ka, kb) lie on the read */
+        uint4 out = make_uint4(0, 0, 0, 0);
+        if (ka < 8 && kb > 0) {
+            const uint32_t pk = a.w;
+            const int mapq = (pk >> 16) & 0xff;
+            const uint32_t rowf = CELL_VALID | (mapq <= min_mqual ? CELL_LOWMQ : 0u);
+            if (pk & ((uint32_t)CG_RF_SIMPLE << 24)) {
+                /* single-M read: query offset == column offset */
+                const int64_t A = ((int64_t)a.x << 3) + d_first;                    /* byte address of the first quality */
+                const uint2 *qa = reinterpret_cast<const uint2 *>(D.qual + (A & ~(int64_t)7));
+                const uint2 w0 = __ldg(qa), w1 = __ldg(qa + 1);
+                const int64_t Bb = (A >> 1) & ~(int64_t)3;                          /* aligned byte address of the sequence word */
+                const uint32_t *sa = reinterpret_cast<const uint32_t *>(D.seq + Bb);
+                uint32_t v0 = __ldg(sa), v1 = __ldg(sa + 1);
+                const int s = (int)(A & 7);
+                const uint32_t Wa = (s & 4) ? w0.y : w0.x, Wb = (s & 4) ? w1.x : w0.y, Wc = (s & 4) ? w1.y : w1.x;
+                const uint32_t qlo = __funnelshift_r(Wa, Wb, (s & 3) * 8), qhi = __funnelshift_r(Wb, Wc, (s & 3) * 8);
+                const int m0 = (int)(A - (Bb << 1));                                /* first nibble inside the 64-bit word, 0..7 */
+                v0 = ((v0 & 0x0f0f0f0fu) << 4) | ((v0 >> 4) & 0x0f0f0f0fu);         /* high nibble first -> little-endian nibbles */
+                v1 = ((v1 & 0x0f0f0f0fu) << 4) | ((v1 >> 4) & 0x0f0f0f0fu);
+                const uint32_t Bs = doB ? col_bases8(__funnelshift_r(v0, v1, 4 * m0)) : 0x77777777u;
+                const uint8_t *er = effB + (mapq << 8);
+                uint32_t c[8];
 #pragma unroll
-            for (int i = 0; i < 7; i++) { int64_t src = qa + 16 * i; if (src >= 0 && src + 16 <= qlim) cp_async16(&S->q[r][16 * i], D.qual + src); }
-        } else {
-#pragma unroll
-            for (int i = 7; i < 9; i++) { int64_t src = qa + 16 * i; if (src >= 0 && src + 16 <= qlim) cp_async16(&S->q[r][16 * i], D.qual + src); }
-#pragma unroll
-            for (int i = 0; i < 5; i++) { int64_t src = sa + 16 * i; if (src >= 0 && src + 16 <= slim) cp_async16(&S->s[r][16 * i], D.seq + src); }
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t qv = ((k < 4 ? qlo >> (8 * k) : qhi >> (8 * (k - 4)))) & 0xff;
+                    const uint32_t e = __ldg(er + qv);
+                    const uint32_t b = (4 * k <= CELL_BASE_SH) ? (Bs << (CELL_BASE_SH - 4 * k)) : (Bs >> (4 * k - CELL_BASE_SH));
+                    c[k] = (b & CELL_BASE_M) | (e << CELL_E_SH) | rowf;
+                }
+                /* ragged ends: valid cells [ka,kb), of which the read's first and last column are not "mid" */
+                const int va = ka < 0 ? 0 : ka, vb = kb > 8 ? 8 : kb;
+                const int ma = ka + 1 < 0 ? 0 : ka + 1, mb = kb - 1 > 8 ? 8 : (kb - 1 < 0 ? 0 : kb - 1);
+                const uint4 vm = S->mask[va][vb], mm = S->mask[ma > 8 ? 8 : ma][mb];
+                const uint32_t MIDW = CELL_MID | (CELL_MID << 16);
+                out.x = ((c[0] | c[1] << 16) & vm.x) | (mm.x & MIDW);
+                out.y = ((c[2] | c[3] << 16) & vm.y) | (mm.y & MIDW);
+                out.z = ((c[4] | c[5] << 16) & vm.z) | (mm.z & MIDW);
+                out.w = ((c[6] | c[7] << 16) & vm.w) | (mm.w & MIDW);
+            } else {
+                out = col_stage_general(&D, j0 + r, d_first, ka < 0 ? 0 : ka, kb > 8 ? 8 : kb, rowf, doB);
+            }
         }
+        *reinterpret_cast<uint4 *>(&cells[r][x0]) = out;
     }
 }
 
-__global__ void __launch_bounds__(128) k_column(const __grid_constant__ CgDev D, int64_t qlim, int64_t slim) {
-    __shared__ CgTabRow tab[104];
-    __shared__ ColStage stage[2];
+__global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __grid_constant__ CgDev D) {
+    __shared__ ColSmem S;
     const CgTables *T = D.T;
     const CgDevParams *P = &D.P;
     for (int i = threadIdx.x; i < 104; i += blockDim.x) {
         int q = i > 100 ? 100 : i;
-        CgTabRow r; r.MM = T->MM[q]; r.hM = T->_M[q]; r.om = T->omq2p[q];
-        tab[i] = r;
+        ColTabRow r; r.MM = T->MM[q]; r.hM = T->_M[q]; r.om = T->omq2p[q]; r.pad = 0;
+        S.tab[i] = r;
     }
-    const int tile_c0 = blockIdx.x * 128;
-    const int x = threadIdx.x;                       /* column within the tile */
-    const int c = tile_c0 + x;
-    const int w = threadIdx.x >> 5;
+    if (threadIdx.x < 81) {
+        const int a = threadIdx.x / 9, b = threadIdx.x % 9;
+        uint32_t m[4];
+        for (int i = 0; i < 4; i++) m[i] = ((2 * i >= a && 2 * i < b) ? 0xffffu : 0u) | ((2 * i + 1 >= a && 2 * i + 1 < b) ? 0xffff0000u : 0u);
+        S.mask[a][b] = make_uint4(m[0], m[1], m[2], m[3]);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int t = blockIdx.x * COL_WARPS + w;        /* this warp's 32-column tile */
+    const int tile_c0 = t * 32;
+    const int c = tile_c0 + lane;
     CgColOut o; o.cnt = 0; o.n_plp = 0;
-    /* block window = union of its four 32-column tiles; each warp walks only the rows of its own tile */
-    const int t0 = blockIdx.x * 4;
-    const int tl = (D.n_tiles - 1 < t0 + 3) ? D.n_tiles - 1 : t0 + 3;
-    const int blo = D.tile_lo[t0], bhi = D.tile_start[tl + 1];
     int lo = 0, hi = 0;
-    if (t0 + w < D.n_tiles) { lo = D.tile_lo[t0 + w]; hi = D.tile_start[t0 + w + 1]; }
+    if (t < D.n_tiles) { lo = D.tile_lo[t]; hi = D.tile_start[t + 1]; }
     const bool live = c < D.n_cols;
-    CgConsAcc A; cg_cons_init(&A);
-    int n_plp = 0, n_skip = 0, low_mq = 0, had_indel = 0, indel_cnt = 0, clipped = 0, n_overlap = 0, ins_seen = 0, nN = 0, depth = 0;
     const int doB = P->min_qual_B != 0;
     const int min_mqual = P->min_mqual;
-    const uint8_t *effB = T->effB;
+    uint16_t (*cells)[32] = S.w[w].cell;
 
-    const int nchunk = (bhi - blo + COL_CH - 1) / COL_CH;
-    if (nchunk > 0) { int n = bhi - blo < COL_CH ? bhi - blo : COL_CH; col_stage_issue(D, &stage[0], blo, n, tile_c0, qlim, slim); }
-    cp_async_commit();
-    for (int k = 0; k < nchunk; k++) {
-        const int j0 = blo + k * COL_CH;
-        if (k + 1 < nchunk) {
-            int n = bhi - (j0 + COL_CH); if (n > COL_CH) n = COL_CH;
-            col_stage_issue(D, &stage[(k + 1) & 1], j0 + COL_CH, n, tile_c0, qlim, slim);
-        }
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-        const ColStage *S = &stage[k & 1];
-        int r0 = lo - j0, r1 = hi - j0;
-        if (r0 < 0) r0 = 0;
-        if (r1 > COL_CH) r1 = COL_CH;
-        if (live) for (int r = r0; r < r1; r++) {
-            const uint4 rec = S->rec[r];
-            const unsigned d_ = (unsigned)(c - (int)rec.y);
-            const int span_ = (int)rec.z;
-            if (d_ < (unsigned)span_) {
-                const uint32_t pk_ = rec.w;
-                const int mapq_ = (pk_ >> 16) & 0xff;
-                const uint32_t meta = S->meta[r];
-                uint32_t qv_ = S->q[r][(meta & 0xff) + x];
-                uint32_t sb_ = S->s[r][((meta >> 8) & 0xff) + ((((meta >> 16) & 1) + x) >> 1)];
-                int qpos_ = (int)d_, contrib_ = doB;
+    double H0 = 0, H1 = 0, H2 = 0, H3 = 0, H4 = 0, C0 = 0, C1 = 0, C2 = 0, C3 = 0, C4 = 0;
+    double P01 = 0, P02 = 0, P03 = 0, P04 = 0, P12 = 0, P13 = 0, P14 = 0, P23 = 0, P24 = 0, P34 = 0;
+    uint32_t pi = 0xfffffu, nseen = 0;               /* base -> rank, 4 bits per base, 15 = not seen yet */
+    uint32_t b0s = 0xffffffffu;                      /* first base of the column, in cell position */
+    int n_plp = 0, n_skip = 0, n_none = 0, nN = 0, low_mq = 0, n_overlap = 0, indel_cnt = 0, clipped = 0;
+    uint32_t orc = 0;
+    const char *tab = reinterpret_cast<const char *>(S.tab);
+
+    for (int j0 = lo; j0 < hi; j0 += COL_ROWS) {
+        const int n = hi - j0 < COL_ROWS ? hi - j0 : COL_ROWS;
+        __syncwarp();
+        col_stage(D, &S, cells, j0, n, tile_c0, doB, min_mqual);
+        __syncwarp();
+        uint32_t pk = 0;
+        const uint16_t *col = &cells[0][lane];
+#pragma unroll 2
+        for (int r = 0; r < n; r++) {
+            const uint32_t cell = col[r * 32];
+            if (cell & CELL_VALID) {
                 n_plp++;
-                low_mq += (mapq_ <= min_mqual);
-                if (pk_ & ((uint32_t)CG_RF_SIMPLE << 24)) {
-                    n_overlap += (d_ != 0) & ((int)d_ != span_ - 1);
+                pk += ((cell & 0xfu) * 0x00204081u) & 0x01010101u;             /* lowmq | mid | indel | clip -> 4 byte counters */
+                orc |= cell;
+                const char *row = tab + (cell & CELL_E_M);
+                if ((cell & CELL_BASE_M) == b0s) {
+                    const double2 mh = *reinterpret_cast<const double2 *>(row);
+                    const double om = *reinterpret_cast<const double *>(row + 16);
+                    H0 += mh.x; P01 += mh.y; P02 += mh.y; P03 += mh.y; P04 += mh.y; C0 += om;
                 } else {
-                    const CgRead *rq_ = D.rd + j0 + r;
-                    const int lq_ = rq_->l_qseq;
-                    uint64_t pkc_ = col_resolve_general(D.cigar + rq_->cig_off, rq_->n_cigar, (int)d_, span_);
-                    uint32_t lo_ = (uint32_t)pkc_;
-                    const int indel_ = (int)(uint32_t)(pkc_ >> 32);
-                    const int isdel_ = (lo_ >> 24) & 1, skip_ = (lo_ >> 25) & 1, head_ = (lo_ >> 26) & 1, tail_ = (lo_ >> 27) & 1;
-                    qpos_ = lo_ & 0xffffff;
-                    if (!((lo_ >> 28) & 1)) { n_plp--; low_mq -= (mapq_ <= min_mqual); contrib_ = 0; }
-                    else {
-                        if (indel_ | isdel_) { had_indel = 1; indel_cnt++; }
-                        if (skip_) { n_skip++; contrib_ = 0; }
-                        else {
-                            clipped += (head_ & (qpos_ > 0)) | (tail_ & (qpos_ + 1 < lq_));
-                            const int mid_ = !tail_ & !head_;
-                            n_overlap += mid_; ins_seen |= mid_ & (indel_ > 0);
-                            if (!lq_) contrib_ = 0;
-                            else { const size_t off_ = (size_t)rec.x << 3; qv_ = D.qual[off_ + qpos_]; sb_ = D.seq[(off_ >> 1) + (qpos_ >> 1)]; }
-                            if (isdel_) sb_ = 0x100;      /* marks a deletion: base 4 */
+                    const uint32_t base = (cell >> CELL_BASE_SH) & 7u;
+                    if (base < 5u) {
+                        const double2 mh = *reinterpret_cast<const double2 *>(row);
+                        const double om = *reinterpret_cast<const double *>(row + 16);
+                        uint32_t rank = (pi >> (base << 2)) & 0xfu;
+                        if (rank == 15u) {
+                            rank = nseen++; pi = (pi & ~(0xfu << (base << 2))) | (rank << (base << 2));
+                            if (rank == 0) b0s = cell & CELL_BASE_M;
                         }
-                    }
-                }
-                if (contrib_) {
-                    const int nib_ = (sb_ >> ((~qpos_ & 1) << 2)) & 0xf;
-                    const int base_ = (sb_ & 0x100) ? 4 : cg_nt16_to_base(nib_);
-                    const CgTabRow w_ = tab[effB[(mapq_ << 8) | qv_]];
-                    switch (base_) {
-                    case 0: A.S[0] += w_.MM; A.S[1] += w_.hM; A.S[2] += w_.hM; A.S[3] += w_.hM; A.S[4] += w_.hM; A.sumsC[0] += w_.om; depth++; break;
-                    case 1: A.S[1] += w_.hM; A.S[5] += w_.MM; A.S[6] += w_.hM; A.S[7] += w_.hM; A.S[8] += w_.hM; A.sumsC[1] += w_.om; depth++; break;
-                    case 2: A.S[2] += w_.hM; A.S[6] += w_.hM; A.S[9] += w_.MM; A.S[10] += w_.hM; A.S[11] += w_.hM; A.sumsC[2] += w_.om; depth++; break;
-                    case 3: A.S[3] += w_.hM; A.S[7] += w_.hM; A.S[10] += w_.hM; A.S[12] += w_.MM; A.S[13] += w_.hM; A.sumsC[3] += w_.om; depth++; break;
-                    case 4: A.S[4] += w_.hM; A.S[8] += w_.hM; A.S[11] += w_.hM; A.S[13] += w_.hM; A.S[14] += w_.MM; A.sumsC[4] += w_.om; depth++; break;
-                    default: nN++; break;
-                    }
+                        if (rank == 0)      { H0 += mh.x; P01 += mh.y; P02 += mh.y; P03 += mh.y; P04 += mh.y; C0 += om; }
+                        else if (rank == 1) { P01 += mh.y; H1 += mh.x; P12 += mh.y; P13 += mh.y; P14 += mh.y; C1 += om; }
+                        else if (rank == 2) { P02 += mh.y; P12 += mh.y; H2 += mh.x; P23 += mh.y; P24 += mh.y; C2 += om; }
+                        else if (rank == 3) { P03 += mh.y; P13 += mh.y; P23 += mh.y; H3 += mh.x; P34 += mh.y; C3 += om; }
+                        else                { P04 += mh.y; P14 += mh.y; P24 += mh.y; P34 += mh.y; H4 += mh.x; C4 += om; }
+                    } else if (base == 5u) nN++;
+                    else if (base == 6u) n_skip++;
+                    else n_none++;
                 }
             }
         }
-        __syncthreads();
+        low_mq += pk & 0xff; n_overlap += (pk >> 8) & 0xff; indel_cnt += (pk >> 16) & 0xff; clipped += pk >> 24;
     }
+    __syncwarp();                                    /* the cell matrix is dead: reuse it to undo the rank permutation */
     if (live) {
-        CgColStats st; st.n_plp = n_plp; st.n_skip = n_skip; st.low_mq = low_mq; st.had_indel = had_indel; st.indel_cnt = indel_cnt;
-        st.clipped = clipped; st.n_overlap = n_overlap; st.ins_seen = ins_seen;
-        A.depth = depth; A.nN = 0; A.sumsE = 0;
+        double *dump = &S.w[w].dump[0][lane];
+        dump[0 * 32] = H0; dump[1 * 32] = H1; dump[2 * 32] = H2; dump[3 * 32] = H3; dump[4 * 32] = H4;
+        dump[5 * 32] = C0; dump[6 * 32] = C1; dump[7 * 32] = C2; dump[8 * 32] = C3; dump[9 * 32] = C4;
+        dump[10 * 32] = P01; dump[11 * 32] = P02; dump[12 * 32] = P03; dump[13 * 32] = P04; dump[14 * 32] = P12;
+        dump[15 * 32] = P13; dump[16 * 32] = P14; dump[17 * 32] = P23; dump[18 * 32] = P24; dump[19 * 32] = P34;
+        int rk[5];
+#pragma unroll
+        for (int b = 0; b < 5; b++) { uint32_t r = (pi >> (4 * b)) & 0xfu; if (r == 15u) r = nseen++; rk[b] = (int)r; }   /* unseen bases take the unused ranks: their sums are 0 / pure */
+        CgConsAcc A;
+        int s = 0;
+#pragma unroll
+        for (int a = 0; a < 5; a++) {
+            A.sumsC[a] = dump[(5 + rk[a]) * 32];
+#pragma unroll
+            for (int b = a; b < 5; b++, s++) {
+                if (a == b) A.S[s] = dump[rk[a] * 32];
+                else {
+                    const int u = rk[a] < rk[b] ? rk[a] : rk[b], v = rk[a] < rk[b] ? rk[b] : rk[a];
+                    A.S[s] = dump[(10 + ((u * (9 - u)) >> 1) + (v - u - 1)) * 32];
+                }
+            }
+        }
+        CgColStats st; st.n_plp = n_plp; st.n_skip = n_skip; st.low_mq = low_mq; st.had_indel = indel_cnt > 0; st.indel_cnt = indel_cnt;
+        st.clipped = clipped; st.n_overlap = n_overlap; st.ins_seen = (orc & CELL_INS) != 0;
+        A.depth = n_plp - n_skip - n_none - nN; A.nN = 0; A.sumsE = 0;
         if (nN) col_gather_generic(&D, c, lo, hi, &A);      /* N bases add to 14 slots: exact slow path */
         o = cg_column_finish(&D, c, lo, hi, &st, &A);
     }
@@ -380,10 +484,10 @@ __global__ void __launch_bounds__(128) k_column(const __grid_constant__ CgDev D,
     while (un) {
         int b = __ffs(un) - 1; un &= un - 1;
         unsigned m = __ballot_sync(0xffffffffu, (o.cnt >> b) & 1);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&D.counters[b], (unsigned long long)__popc(m));
+        if (lane == 0) atomicAdd(&D.counters[b], (unsigned long long)__popc(m));
     }
     int mx = __reduce_max_sync(0xffffffffu, o.n_plp);
-    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(D.maxdepth, mx);
+    if (lane == 0 && mx > 0) atomicMax(D.maxdepth, mx);
 }
 
 __global__ void __launch_bounds__(64) k_flagged(const __grid_constant__ CgDev D, CgFlagScratch *scratch) {
@@ -631,6 +735,8 @@ __global__ void k_dump_flags(const __grid_constant__ CgDev D) {
 }
 
 /* ============================== context ================================================ */
+/* the staging loads of k_column / k_rewrite read whole aligned words around a read: pad both ends of seq and qual */
+#define CG_FRONT_PAD 256
 struct dbuf { void *p; size_t cap; };
 
 struct cg_ctx {
@@ -756,8 +862,8 @@ extern "C" int cg_upload(cg_ctx *ctx, const cg_batch *in) {
     if ((e = ensure(ctx, &ctx->b_tid, n1 * 4)) || (e = ensure(ctx, &ctx->b_pos, n1 * 4)) || (e = ensure(ctx, &ctx->b_flag, n1 * 2)) ||
         (e = ensure(ctx, &ctx->b_mapq, n1)) || (e = ensure(ctx, &ctx->b_lq, n1 * 4)) || (e = ensure(ctx, &ctx->b_nc, n1 * 2)) ||
         (e = ensure(ctx, &ctx->b_off, n1 * 8)) || (e = ensure(ctx, &ctx->b_coff, n1 * 4)) ||
-        (e = ensure(ctx, &ctx->b_cigar, ((size_t)in->n_cigar_total + 1) * 4)) || (e = ensure(ctx, &ctx->b_seq, (size_t)in->seq_bytes + 128)) ||
-        (e = ensure(ctx, &ctx->b_qual, (size_t)in->qual_bytes + 128)) || (e = ensure(ctx, &ctx->b_qout, (size_t)in->qual_bytes + 16))) return e;
+        (e = ensure(ctx, &ctx->b_cigar, ((size_t)in->n_cigar_total + 1) * 4)) || (e = ensure(ctx, &ctx->b_seq, (size_t)in->seq_bytes + 128 + CG_FRONT_PAD)) ||
+        (e = ensure(ctx, &ctx->b_qual, (size_t)in->qual_bytes + 128 + CG_FRONT_PAD)) || (e = ensure(ctx, &ctx->b_qout, (size_t)in->qual_bytes + 16))) return e;
     T0(CG_T_H2D);
     if (n) {
         CG_CHECK(cudaMemcpyAsync(ctx->b_tid.p, in->tid, (size_t)n * 4, cudaMemcpyHostToDevice, st));
@@ -769,8 +875,8 @@ extern "C" int cg_upload(cg_ctx *ctx, const cg_batch *in) {
         CG_CHECK(cudaMemcpyAsync(ctx->b_off.p, in->off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
         CG_CHECK(cudaMemcpyAsync(ctx->b_coff.p, in->cigar_off, (size_t)n * 4, cudaMemcpyHostToDevice, st));
         if (in->n_cigar_total) CG_CHECK(cudaMemcpyAsync(ctx->b_cigar.p, in->cigar, (size_t)in->n_cigar_total * 4, cudaMemcpyHostToDevice, st));
-        if (in->seq_bytes) CG_CHECK(cudaMemcpyAsync(ctx->b_seq.p, in->seq, (size_t)in->seq_bytes, cudaMemcpyHostToDevice, st));
-        if (in->qual_bytes) CG_CHECK(cudaMemcpyAsync(ctx->b_qual.p, in->qual, (size_t)in->qual_bytes, cudaMemcpyHostToDevice, st));
+        if (in->seq_bytes) CG_CHECK(cudaMemcpyAsync((char *)ctx->b_seq.p + CG_FRONT_PAD, in->seq, (size_t)in->seq_bytes, cudaMemcpyHostToDevice, st));
+        if (in->qual_bytes) CG_CHECK(cudaMemcpyAsync((char *)ctx->b_qual.p + CG_FRONT_PAD, in->qual, (size_t)in->qual_bytes, cudaMemcpyHostToDevice, st));
     }
     T1(CG_T_H2D);
     CgDev *D = &ctx->D;
@@ -779,7 +885,7 @@ extern "C" int cg_upload(cg_ctx *ctx, const cg_batch *in) {
     D->tid = (const int32_t *)ctx->b_tid.p; D->pos = (const int32_t *)ctx->b_pos.p; D->flag = (const uint16_t *)ctx->b_flag.p;
     D->mapq = (const uint8_t *)ctx->b_mapq.p; D->l_qseq = (const int32_t *)ctx->b_lq.p; D->n_cigar = (const uint16_t *)ctx->b_nc.p;
     D->off = (const int64_t *)ctx->b_off.p; D->cigar_off = (const int32_t *)ctx->b_coff.p; D->cigar = (const uint32_t *)ctx->b_cigar.p;
-    D->seq = (const uint8_t *)ctx->b_seq.p; D->qual = (const uint8_t *)ctx->b_qual.p; D->qual_out = (uint8_t *)ctx->b_qout.p;
+    D->seq = (const uint8_t *)ctx->b_seq.p + CG_FRONT_PAD; D->qual = (const uint8_t *)ctx->b_qual.p + CG_FRONT_PAD; D->qual_out = (uint8_t *)ctx->b_qout.p;
     ctx->qual_bytes = in->qual_bytes;
     ctx->resident = 1;
     return 0;
@@ -877,7 +983,7 @@ extern "C" int cg_run(cg_ctx *ctx) {
     }
     T1(CG_T_TILES);
     T0(CG_T_COLUMNS);
-    if (nc > 0) { k_column<<<nblk(nc, 128), 128, 0, st>>>(*D, (int64_t)ctx->qual_bytes + 64, (int64_t)(ctx->qual_bytes / 2) + 64); ctx->launches++; }
+    if (nc > 0) { k_column<<<nblk(D->n_tiles, COL_WARPS), COL_WARPS * 32, 0, st>>>(*D); ctx->launches++; }
     T1(CG_T_COLUMNS);
     T0(CG_T_FLAGGED);
     if (nc > 0) {
