@@ -55,7 +55,7 @@ typedef struct CgDevParams {
     int32_t reduce_qual, binary_qual;
     int32_t iSTR_add, sSTR_add;
     double  iSTR_mul, sSTR_mul;
-    int32_t qlow, qhigh, qcap;
+    int32_t qlow, qhigh, qcap, qcutoff;
     int32_t min_mqual;
     double  indel_fract;
     int32_t min_qual_A, min_indel_A; double min_discrep_A;
@@ -321,8 +321,8 @@ CG_HD void cg_cons_finalize(const CgTables *T, CgConsAcc *a, CgCons *o) {
 
 /* ---- column record encodings shared by the kernels ------------------------------------ */
 /* cb[c] (u8): what the per-read rewrite needs from a column */
-#define CG_CB_CODE_MASK   0x1f      /* call1idx*5+call2idx (idx 4 = matches nothing); 31 = column not processed */
-#define CG_CB_UNPROC      31
+#define CG_CB_CALL_MASK   0x0f      /* nt16 codes of call1 | call2 (A=1 C=2 G=4 T=8; '*' and N match no base) */
+#define CG_CB_UNPROC      0x10      /* column not processed (all ref-skip, VDEEP, outside -r) */
 #define CG_CB_PRESERVE    0x20      /* snp_score.c:1624-1628,1648-1649 */
 #define CG_CB_ACTIVE      0x40      /* min_pos != INT_MAX at this column (snp_score.c:1880) */
 #define CG_CB_KEEP        0x80      /* keep_qual (snp_score.c:1668,1679,1771,1805,1816) */
@@ -341,26 +341,24 @@ CG_HD void cg_cons_finalize(const CgTables *T, CgConsAcc *a, CgCons *o) {
 #define CG_EV_HADINDEL    0x0400
 #define CG_EV_PROCESSED   0x0800
 
-/* call masks -> 0..4 index codes; call index 4 ('*' = 16) and 5 (N = 32) never equal an nt16 base code */
+/* call1 | call2 as the set of nt16 codes a base must equal to agree with the call (snp_score.c:1526-1542, 1906-1910):
+ * calls 0..3 are A C G T; call 4 ('*' = 16) and 5 (N = 32) never equal an nt16 base code */
 CG_HD int cg_call_code(const CgCons *c) {
     int c1, c2;
     if (c->het_phred > 0) { c1 = c->het_call / 5; c2 = c->het_call % 5; }
     else { c1 = c2 = c->call; }
-    if (c1 > 4) c1 = 4;
-    if (c2 > 4) c2 = 4;
-    return c1 * 5 + c2;
+    return ((c1 < 4) ? (1 << c1) : 0) | ((c2 < 4) ? (1 << c2) : 0);
 }
 
 /* ---- per-byte visit of the rewrite loop (snp_score.c:1880-1919), see SURVEY.md §9.7 ---- */
 CG_HD uint8_t cg_visit(uint8_t val, uint8_t cbv, uint8_t orig_capped, int nib,
                        const CgDevParams *P, const CgTables *T) {
-    int code = cbv & CG_CB_CODE_MASK;
-    if (code == CG_CB_UNPROC) return val;
+    if (cbv & CG_CB_UNPROC) return val;
     if (cbv & CG_CB_ACTIVE) val = (uint8_t)(orig_capped | 0x80);
     if (cbv & CG_CB_PRESERVE) val |= 0x80;
     if (!(val & 0x80)) {
-        int c1 = code / 5, c2 = code % 5;
-        bool match = (c1 < 4 && nib == (1 << c1)) || (c2 < 4 && nib == (1 << c2));
+        /* base == call1 || base == call2: an nt16 code equals a one-hot call mask iff it is one-hot and inside the set */
+        bool match = nib && !(nib & (nib - 1)) && (nib & cbv & CG_CB_CALL_MASK);
         if (match) val = (uint8_t)P->qhigh;
         else if (P->reduce_qual) val = P->binary_qual ? T->bin2[val] : (uint8_t)P->qlow;
     }
@@ -371,27 +369,31 @@ CG_HD uint8_t cg_cap_qual(uint8_t q, const CgDevParams *P, const CgTables *T) { 
     return (q > P->qcap && !T->preserve_qual[q]) ? (uint8_t)P->qcap : q;
 }
 
-/* ---- P-block (pblock, snp_score.c:803-834), in place on qual[0..len) -------------------- */
-CG_HD void cg_pblock(uint8_t *qual, int len, int level, int qcap, const CgTables *T) {
+/* ---- P-block (pblock, snp_score.c:803-834), in place on qual[0..len) --------------------
+ * A run whose bytes all equal the value it would be filled with is left alone (same result, no stores);
+ * HASP = 0 when the preserve_qual table is all zero (no -k/-K), which removes the per-byte table lookups. */
+template <int HASP>
+CG_HD void cg_pblock_t(uint8_t *qual, int len, int level, int qcap, const CgTables *T) {
     int i, j, qmin = INT_MAX, qmax = INT_MIN, last_qmin = 0, last_qmax = 0, mid;
     level *= 2;
     for (i = j = 0; i < len; i++) {
         int q = qual[i];
         if (qmin > q) qmin = q;
         if (qmax < q) qmax = q;
-        if (qmax - qmin > level || T->preserve_qual[q]) {
+        if (qmax - qmin > level || (HASP && T->preserve_qual[q])) {
             mid = (last_qmin + last_qmax) / 2;
             if (mid > qcap) mid = qcap;
-            for (int k = j; k < i; k++) qual[k] = (uint8_t)mid;
-            while (i < len && T->preserve_qual[qual[i]]) i++;
+            if (last_qmin != last_qmax || mid != last_qmin) for (int k = j; k < i; k++) qual[k] = (uint8_t)mid;
+            if (HASP) while (i < len && T->preserve_qual[qual[i]]) i++;
             if (i < len) qmin = qmax = qual[i];        /* the reference reads qual[len] here; value unused when i==len */
             j = i;
         }
         last_qmin = qmin; last_qmax = qmax;
     }
     mid = (last_qmin + last_qmax) / 2;
-    for (int k = j; k < i && k < len; k++) qual[k] = (uint8_t)mid;
+    if (last_qmin != last_qmax) for (int k = j; k < i && k < len; k++) qual[k] = (uint8_t)mid;
 }
+CG_HD void cg_pblock(uint8_t *qual, int len, int level, int qcap, const CgTables *T) { cg_pblock_t<1>(qual, len, level, qcap, T); }
 
 /* ---- STR finder (find_STR / add_rep, str_finder.c:34-189) on 2-bit codes ---------------- */
 typedef struct CgRepList { int n; int overflow; int start[CG_REP_CAP]; int end[CG_REP_CAP]; } CgRepList;

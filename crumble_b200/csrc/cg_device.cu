@@ -402,9 +402,9 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
     double H0 = 0, H1 = 0, H2 = 0, H3 = 0, H4 = 0, C0 = 0, C1 = 0, C2 = 0, C3 = 0, C4 = 0;
     double P01 = 0, P02 = 0, P03 = 0, P04 = 0, P12 = 0, P13 = 0, P14 = 0, P23 = 0, P24 = 0, P34 = 0;
     uint32_t pi = 0xfffffu, nseen = 0;               /* base -> rank, 4 bits per base, 15 = not seen yet */
-    uint32_t b0s = 0xffffffffu;                      /* first base of the column, in cell position */
+    uint32_t b0s = 0xffffffffu, b1s = 0xffffffffu;   /* first and second base of the column, in cell position */
     int n_plp = 0, n_skip = 0, n_none = 0, nN = 0, low_mq = 0, n_overlap = 0, indel_cnt = 0, clipped = 0;
-    uint32_t orc = 0;
+    uint32_t ins_seen = 0;
     const char *tab = reinterpret_cast<const char *>(S.tab);
 
     for (int j0 = lo; j0 < hi; j0 += COL_ROWS) {
@@ -412,42 +412,56 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
         __syncwarp();
         col_stage(D, &S, cells, j0, n, tile_c0, doB, min_mqual);
         __syncwarp();
-        uint32_t pk = 0;
         const uint16_t *col = &cells[0][lane];
-#pragma unroll 2
-        for (int r = 0; r < n; r++) {
-            const uint32_t cell = col[r * 32];
-            if (cell & CELL_VALID) {
-                n_plp++;
-                pk += ((cell & 0xfu) * 0x00204081u) & 0x01010101u;             /* lowmq | mid | indel | clip -> 4 byte counters */
-                orc |= cell;
-                const char *row = tab + (cell & CELL_E_M);
-                if ((cell & CELL_BASE_M) == b0s) {
-                    const double2 mh = *reinterpret_cast<const double2 *>(row);
-                    const double om = *reinterpret_cast<const double *>(row + 16);
-                    H0 += mh.x; P01 += mh.y; P02 += mh.y; P03 += mh.y; P04 += mh.y; C0 += om;
-                } else {
-                    const uint32_t base = (cell >> CELL_BASE_SH) & 7u;
-                    if (base < 5u) {
-                        const double2 mh = *reinterpret_cast<const double2 *>(row);
-                        const double om = *reinterpret_cast<const double *>(row + 16);
-                        uint32_t rank = (pi >> (base << 2)) & 0xfu;
-                        if (rank == 15u) {
-                            rank = nseen++; pi = (pi & ~(0xfu << (base << 2))) | (rank << (base << 2));
-                            if (rank == 0) b0s = cell & CELL_BASE_M;
-                        }
-                        if (rank == 0)      { H0 += mh.x; P01 += mh.y; P02 += mh.y; P03 += mh.y; P04 += mh.y; C0 += om; }
-                        else if (rank == 1) { P01 += mh.y; H1 += mh.x; P12 += mh.y; P13 += mh.y; P14 += mh.y; C1 += om; }
-                        else if (rank == 2) { P02 += mh.y; P12 += mh.y; H2 += mh.x; P23 += mh.y; P24 += mh.y; C2 += om; }
-                        else if (rank == 3) { P03 += mh.y; P13 += mh.y; P23 += mh.y; H3 += mh.x; P34 += mh.y; C3 += om; }
-                        else                { P04 += mh.y; P14 += mh.y; P24 += mh.y; P34 += mh.y; H4 += mh.x; C4 += om; }
-                    } else if (base == 5u) nN++;
-                    else if (base == 6u) n_skip++;
-                    else n_none++;
-                }
+        /* flag counters: five 6-bit fields in one word (ins | clip | indel | mid | lowmq), flushed every 32 rows */
+#define COL_CELL(cell_) do { const uint32_t cell = (cell_); \
+            if (cell & CELL_VALID) { \
+                n_plp++; \
+                pk += ((cell & 0x1fu) * 0x00108421u) & 0x01041041u; \
+                const char *row = tab + (cell & CELL_E_M); \
+                if ((cell & CELL_BASE_M) == b0s) { \
+                    const double2 mh = *reinterpret_cast<const double2 *>(row); \
+                    const double om = *reinterpret_cast<const double *>(row + 16); \
+                    H0 += mh.x; P01 += mh.y; P02 += mh.y; P03 += mh.y; P04 += mh.y; C0 += om; \
+                } else if ((cell & CELL_BASE_M) == b1s) { \
+                    const double2 mh = *reinterpret_cast<const double2 *>(row); \
+                    const double om = *reinterpret_cast<const double *>(row + 16); \
+                    P01 += mh.y; H1 += mh.x; P12 += mh.y; P13 += mh.y; P14 += mh.y; C1 += om; \
+                } else { \
+                    const uint32_t base = (cell >> CELL_BASE_SH) & 7u; \
+                    if (base < 5u) { \
+                        const double2 mh = *reinterpret_cast<const double2 *>(row); \
+                        const double om = *reinterpret_cast<const double *>(row + 16); \
+                        uint32_t rank = (pi >> (base << 2)) & 0xfu; \
+                        if (rank == 15u) { \
+                            rank = nseen++; pi = (pi & ~(0xfu << (base << 2))) | (rank << (base << 2)); \
+                            if (rank == 0) b0s = cell & CELL_BASE_M; \
+                            if (rank == 1) b1s = cell & CELL_BASE_M; \
+                        } \
+                        if (rank == 0)      { H0 += mh.x; P01 += mh.y; P02 += mh.y; P03 += mh.y; P04 += mh.y; C0 += om; } \
+                        else if (rank == 1) { P01 += mh.y; H1 += mh.x; P12 += mh.y; P13 += mh.y; P14 += mh.y; C1 += om; } \
+                        else if (rank == 2) { P02 += mh.y; P12 += mh.y; H2 += mh.x; P23 += mh.y; P24 += mh.y; C2 += om; } \
+                        else if (rank == 3) { P03 += mh.y; P13 += mh.y; P23 += mh.y; H3 += mh.x; P34 += mh.y; C3 += om; } \
+                        else                { P04 += mh.y; P14 += mh.y; P24 += mh.y; P34 += mh.y; H4 += mh.x; C4 += om; } \
+                    } else if (base == 5u) nN++; \
+                    else if (base == 6u) n_skip++; \
+                    else n_none++; \
+                } \
+            } } while (0)
+        for (int rb = 0; rb < n; rb += 32) {
+            const int re = n - rb < 32 ? n - rb : 32;
+            uint32_t pk = 0;
+            const uint16_t *cp = col + rb * 32;
+            int r = 0;
+            for (; r + 4 <= re; r += 4) {
+                /* the four cell loads are independent: their latency overlaps the arithmetic of the previous rows */
+                const uint32_t c0 = cp[(r + 0) * 32], c1 = cp[(r + 1) * 32], c2 = cp[(r + 2) * 32], c3 = cp[(r + 3) * 32];
+                COL_CELL(c0); COL_CELL(c1); COL_CELL(c2); COL_CELL(c3);
             }
+            for (; r < re; r++) COL_CELL(cp[r * 32]);
+            low_mq += pk & 0x3f; n_overlap += (pk >> 6) & 0x3f; indel_cnt += (pk >> 12) & 0x3f; clipped += (pk >> 18) & 0x3f; ins_seen |= pk >> 24;
         }
-        low_mq += pk & 0xff; n_overlap += (pk >> 8) & 0xff; indel_cnt += (pk >> 16) & 0xff; clipped += pk >> 24;
+#undef COL_CELL
     }
     __syncwarp();                                    /* the cell matrix is dead: reuse it to undo the rank permutation */
     if (live) {
@@ -474,7 +488,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
             }
         }
         CgColStats st; st.n_plp = n_plp; st.n_skip = n_skip; st.low_mq = low_mq; st.had_indel = indel_cnt > 0; st.indel_cnt = indel_cnt;
-        st.clipped = clipped; st.n_overlap = n_overlap; st.ins_seen = (orc & CELL_INS) != 0;
+        st.clipped = clipped; st.n_overlap = n_overlap; st.ins_seen = ins_seen != 0;
         A.depth = n_plp - n_skip - n_none - nN; A.nN = 0; A.sumsE = 0;
         if (nN) col_gather_generic(&D, c, lo, hi, &A);      /* N bases add to 14 slots: exact slow path */
         o = cg_column_finish(&D, c, lo, hi, &st, &A);
@@ -556,113 +570,222 @@ __global__ void k_paint(const __grid_constant__ CgDev D) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < D.n_flagged) cg_paint(&D, k, D.n_flagged);
 }
-/* Per-read quality rewrite, warp per read, quality strings staged in shared memory:
- *   phase A (warp per read, 32 reads per warp): replay of the rewrite loop into the read's slot.
- *            single-M reads without back-fill take the register path: each lane owns 8 consecutive
- *            bases (aligned 64-bit quality load, 32-bit sequence load, column bytes via aligned
- *            load + neighbour shuffle); other reads are replayed op by op inside the slot;
- *   phase B (thread per read): P-block, a sequential greedy scan, over the slot in shared memory;
- *   phase C (warp per read): coalesced 64-bit stores of the slot.
- * Reads longer than RW_MAXL fall back to the one-thread-per-read body (cg_rewrite). */
+/* Per-read quality rewrite.  A block owns RW_READS consecutive records; their quality strings, packed sequences
+ * and the column bytes under them are three CONTIGUOUS ranges, fetched with three bulk async copies (TMA,
+ * cp.async.bulk + mbarrier) into shared memory.  Then
+ *   phase A (warp per read): replay of the rewrite loop in place in shared memory.  Single-M reads without
+ *            back-fill run SIMD-within-register, 8 bases per lane: kept / match / binning are byte-parallel
+ *            mask arithmetic on the 64-bit quality word, the 64-bit column word and the 8 expanded nt16 codes.
+ *            Other reads (indels, clips, back-fill) are replayed op by op;
+ *   phase B (thread per read): P-block, a sequential greedy scan, in place; runs of one value are not refilled;
+ *   phase C: one bulk async store of the block's output range (8-byte edges by the owning threads).
+ * Blocks whose ranges do not fit the staging buffers (long reads) run the one-thread-per-read body (cg_rewrite). */
 #define RW_THREADS 128
 #define RW_READS   128
-#define RW_MAXL    256
-#define RW_STRIDE  260          /* bytes; 65 words: conflict-free when the threads of a warp walk their slots in step */
+#define RW_QCAP    (RW_READS * 168)     /* staged quality bytes (152 per padded 150-base read) */
+#define RW_CCAP    3072                 /* staged column bytes */
 
-__device__ __forceinline__ uint32_t rw_visit8(uint64_t q8, uint64_t cb8, uint32_t s4, int nvalid, uint8_t init_or, int keep,
-                                              const CgDevParams *P, const CgTables *T, uint32_t *hi_out) {
-    uint32_t lo = 0, hi = 0;
-#pragma unroll
+struct RwMeta { int32_t qoff, L, coff, kind; int32_t j; uint8_t init_or, tail_unreached, pad0, pad1; };   /* offsets inside the staging buffers */
+struct __align__(128) RwSmem {
+    uint8_t q[RW_QCAP + 32];
+    uint8_t s[RW_QCAP / 2 + 32];
+    uint8_t c[RW_CCAP + 32];
+    RwMeta  m[RW_READS];
+    unsigned long long bar;
+    long long red[4][4];
+    long long rng[6];                   /* qa, qbytes, sa, sbytes, ca, cbytes (cbytes < 0: fallback) */
+};
+
+struct RwK { uint32_t QH, QL, cut, capadd; int mode; };   /* mode 0: mismatches keep their value, 1: -> qlow, 2: binary */
+
+/* four quality bytes: byte-parallel form of cg_visit for reads whose bytes are < 0x80 and <= qcap */
+__device__ __forceinline__ uint32_t rw_swar4(uint32_t q, uint32_t cb, uint32_t nib, uint32_t init80, const RwK &K) {
+    const uint32_t kept = (((cb & 0x70707070u) + 0x70707070u) | init80) & 0x80808080u;     /* unproc | preserve | active | low mapq */
+    const uint32_t m = nib & cb & 0x0f0f0f0fu;
+    const uint32_t nzm = (m + 0x0f0f0f0fu) & 0x10101010u;                                    /* base inside the call set */
+    const uint32_t h = nib & ((nib | 0x10101010u) - 0x01010101u) & 0x0f0f0f0fu;
+    const uint32_t nzh = (h + 0x0f0f0f0fu) & 0x10101010u;                                    /* ambiguity code: never equal to a call */
+    const uint32_t M = ((nzm & ~nzh) >> 4) * 0xffu;
+    const uint32_t Kp = (kept >> 7) * 0xffu;
+    uint32_t low = q;
+    if (K.mode == 1) low = K.QL;
+    else if (K.mode == 2) { const uint32_t G = (((q + K.cut) & 0x80808080u) >> 7) * 0xffu; low = (K.QH & G) | (K.QL & ~G); }
+    return ((q & Kp) | (~Kp & ((K.QH & M) | (~M & low)))) & 0x7f7f7f7fu;
+}
+
+/* scalar form for the same 8 bytes (any byte >= 0x80 or above -U) */
+__device__ __noinline__ uint64_t rw_visit8_scalar(uint64_t q8, uint64_t cb8, uint32_t s4, uint8_t init_or, int keep, const CgDevParams *P, const CgTables *T) {
+    uint64_t out = 0;
     for (int k = 0; k < 8; k++) {
-        uint8_t qin = (uint8_t)(q8 >> (8 * k));
-        uint8_t v = qin;
-        if (k < nvalid) {
-            uint8_t cbv = (uint8_t)(cb8 >> (8 * k));
-            /* seq byte k>>1 of this lane's 4 sequence bytes; high nibble first */
-            int nib = (int)((s4 >> (8 * (k >> 1) + ((k & 1) ? 0 : 4))) & 0xf);
-            uint8_t oc = cg_cap_qual(qin, P, T);
-            v = keep ? oc : cg_visit((uint8_t)(qin | init_or), cbv, oc, nib, P, T);
-            v &= 0x7f;
-        }
-        if (k < 4) lo |= (uint32_t)v << (8 * k); else hi |= (uint32_t)v << (8 * (k - 4));
+        const uint8_t qin = (uint8_t)(q8 >> (8 * k)), cbv = (uint8_t)(cb8 >> (8 * k));
+        const int nib = (int)((s4 >> (8 * (k >> 1) + ((k & 1) ? 0 : 4))) & 0xf);
+        const uint8_t oc = cg_cap_qual(qin, P, T);
+        const uint8_t v = keep ? oc : cg_visit((uint8_t)(qin | init_or), cbv, oc, nib, P, T);
+        out |= (uint64_t)(v & 0x7f) << (8 * k);
     }
-    *hi_out = hi;
-    return lo;
+    return out;
+}
+
+__device__ __forceinline__ void rw_mbar_init(unsigned long long *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void rw_bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void rw_mbar_expect(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rw_mbar_wait(unsigned long long *bar, uint32_t phase) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n"
+                 :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(phase) : "memory");
 }
 
 __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ CgDev D) {
-    __shared__ __align__(16) uint8_t sq[RW_READS * RW_STRIDE];
-    __shared__ int32_t sL[RW_READS];
+    __shared__ RwSmem S;
     const CgDevParams *P = &D.P;
     const CgTables *T = D.T;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t base = (int64_t)blockIdx.x * RW_READS;
     const int nf = D.n_flagged;
 
+    /* ---- phase 0: per-read facts, block ranges, bulk loads ---- */
+    if (threadIdx.x == 0) rw_mbar_init(&S.bar);
+    int64_t off = 0; int L = 0, kind = 0, col0 = 0, span = 0, j = -1; uint8_t init_mq = 0, tail_unreached = 0;
+    {
+        const int64_t r = base + threadIdx.x;
+        if (r < D.n_reads) { L = D.l_qseq[r]; off = D.off[r]; }
+        if (L > 0) {
+            kind = 1;
+            if (D.rspan[r]) {
+                j = D.jmap[r];
+                const CgRead q = D.rd[j];
+                col0 = q.col0; span = q.span;
+                tail_unreached = (P->region_tid >= 0 && q.pos + q.span - 1 >= P->region_end);
+                init_mq = q.mapq <= P->min_mqual;
+                kind = ((q.rf & CG_RF_SIMPLE) && q.span == L && L <= 256 && !D.r_bf[j]) ? 2 : 3;
+            }
+        }
+        long long v0 = L > 0 ? off : LLONG_MAX, v1 = L > 0 ? off + L : LLONG_MIN;
+        long long v2 = kind >= 2 ? col0 : LLONG_MAX, v3 = kind >= 2 ? (long long)col0 + span : LLONG_MIN;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            long long u0 = __shfl_xor_sync(0xffffffffu, v0, o), u1 = __shfl_xor_sync(0xffffffffu, v1, o);
+            long long u2 = __shfl_xor_sync(0xffffffffu, v2, o), u3 = __shfl_xor_sync(0xffffffffu, v3, o);
+            v0 = u0 < v0 ? u0 : v0; v1 = u1 > v1 ? u1 : v1; v2 = u2 < v2 ? u2 : v2; v3 = u3 > v3 ? u3 : v3;
+        }
+        if (lane == 0) { S.red[w][0] = v0; S.red[w][1] = v1; S.red[w][2] = v2; S.red[w][3] = v3; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long lo = LLONG_MAX, hi = LLONG_MIN, clo = LLONG_MAX, chi = LLONG_MIN;
+        for (int i = 0; i < RW_THREADS / 32; i++) {
+            lo = S.red[i][0] < lo ? S.red[i][0] : lo; hi = S.red[i][1] > hi ? S.red[i][1] : hi;
+            clo = S.red[i][2] < clo ? S.red[i][2] : clo; chi = S.red[i][3] > chi ? S.red[i][3] : chi;
+        }
+        long long qa = 0, qb = 0, sa = 0, sb = 0, ca = 0, cbn = 0;
+        if (hi > lo) {
+            qa = lo & ~15LL; qb = ((hi + 15) & ~15LL) - qa;
+            sa = (lo >> 1) & ~15LL; sb = ((((hi + 1) >> 1) + 15) & ~15LL) - sa;
+            if (chi > clo) { ca = clo & ~15LL; cbn = ((chi + 15) & ~15LL) - ca; }
+            if (qb > RW_QCAP + 16 || sb > RW_QCAP / 2 + 16 || cbn > RW_CCAP + 16) cbn = -1;
+            else {
+                rw_mbar_expect(&S.bar, (uint32_t)(qb + sb + cbn));
+                rw_bulk_g2s(S.q, D.qual + qa, (uint32_t)qb, &S.bar);
+                rw_bulk_g2s(S.s, D.seq + sa, (uint32_t)sb, &S.bar);
+                if (cbn > 0) rw_bulk_g2s(S.c, D.cb + ca, (uint32_t)cbn, &S.bar);
+            }
+        }
+        S.rng[0] = qa; S.rng[1] = qb; S.rng[2] = sa; S.rng[3] = sb; S.rng[4] = ca; S.rng[5] = cbn;
+        S.red[0][0] = lo; S.red[0][1] = hi;
+    }
+    __syncthreads();
+    const long long qa = S.rng[0], qbytes = S.rng[1], sa = S.rng[2], ca = S.rng[4], cbytes = S.rng[5];
+    if (qbytes == 0) return;                                   /* nothing but empty records */
+    if (cbytes < 0) {                                          /* ranges too long for the staging buffers */
+        const int64_t r = base + threadIdx.x;
+        if (r < D.n_reads) cg_rewrite(&D, r, nf);
+        return;
+    }
+    {
+        RwMeta m; m.qoff = (int32_t)(off - qa); m.L = L; m.coff = (int32_t)(col0 - ca); m.kind = kind; m.j = j;
+        m.init_or = init_mq; m.tail_unreached = tail_unreached; m.pad0 = m.pad1 = 0;
+        S.m[threadIdx.x] = m;
+    }
+    __syncthreads();
+    rw_mbar_wait(&S.bar, 0);
+
     /* ---- phase A ---- */
+    RwK K;
+    K.QH = (uint32_t)(P->qhigh & 0xff) * 0x01010101u; K.QL = (uint32_t)(P->qlow & 0xff) * 0x01010101u;
+    K.mode = !P->reduce_qual ? 0 : (P->binary_qual ? 2 : 1);
+    { int cq = P->qcutoff < 0 ? 0 : (P->qcutoff > 128 ? 128 : P->qcutoff); K.cut = (uint32_t)((128 - cq) & 0xff) * 0x01010101u; }
+    K.capadd = P->qcap >= 127 ? 0u : (uint32_t)(127 - (P->qcap < 0 ? 0 : P->qcap)) * 0x01010101u;
+    const bool swar_ok = !P->any_preserve_qual;
     for (int i = 0; i < RW_READS / (RW_THREADS / 32); i++) {
         const int slot = w * (RW_READS / (RW_THREADS / 32)) + i;
-        const int64_t r = base + slot;
-        uint8_t *sl = sq + slot * RW_STRIDE;
-        int L = 0;
-        if (r < D.n_reads) L = D.l_qseq[r];
-        if (L <= 0) { if (lane == 0) sL[slot] = 0; continue; }
-        if (L > RW_MAXL) {
-            if (lane == 0) { cg_rewrite(&D, r, nf); sL[slot] = 0; }
-            continue;
-        }
-        const int64_t off = D.off[r];
-        const uint8_t *qin = D.qual + off;
-        const int x0 = lane * 8;
-        const int nvalid = L - x0;          /* <=0: lane idle */
-        if (!D.rspan[r]) {
+        const RwMeta m = S.m[slot];
+        if (m.kind == 0) continue;
+        uint8_t *sl = S.q + m.qoff;
+        const int Lr = m.L;
+        if (m.kind == 1) {
             /* never in the pileup: strip bit 7 only (P-block follows) */
-            if (nvalid > 0) {
-                uint64_t q8 = *(const uint64_t *)(qin + x0) & 0x7f7f7f7f7f7f7f7fULL;
-                *(uint32_t *)(sl + x0) = (uint32_t)q8; *(uint32_t *)(sl + x0 + 4) = (uint32_t)(q8 >> 32);
+            for (int x0 = lane * 8; x0 < Lr; x0 += 256) {
+                uint64_t q8 = *(const uint64_t *)(sl + x0);
+                const int nv = Lr - x0;
+                const uint64_t vm = nv >= 8 ? ~0ULL : ((1ULL << (8 * nv)) - 1);
+                *(uint64_t *)(sl + x0) = (q8 & 0x7f7f7f7f7f7f7f7fULL & vm) | (q8 & ~vm);
             }
-            if (lane == 0) sL[slot] = L;
             continue;
         }
-        const int j = D.jmap[r];
-        const CgRead q = D.rd[j];
-        const int tail_unreached = (P->region_tid >= 0 && q.pos + q.span - 1 >= P->region_end);
-        const int head_proc = (D.cb[q.col0] & CG_CB_CODE_MASK) != CG_CB_UNPROC;
-        const uint8_t init_or = (head_proc && q.mapq <= P->min_mqual) ? 0x80 : 0;
-        if ((q.rf & CG_RF_SIMPLE) && q.span == L && !D.r_bf[j]) {
-            /* register path */
-            uint64_t q8 = 0, cb8 = 0; uint32_t s4 = 0;
-            /* column bytes [col0 + x0, +8): aligned word + neighbour's word */
-            const uint64_t cbase = (uint64_t)(uintptr_t)(D.cb + q.col0);
-            const int sh = (int)(cbase & 7) * 8;
-            const uint64_t *cw = (const uint64_t *)(cbase & ~(uint64_t)7);
-            uint64_t w0 = 0;
-            /* lane needs words lane and lane+1; the last needed word index is ((sh/8 + L - 1) >> 3) */
-            const int last_word = ((sh >> 3) + L - 1) >> 3;
-            if (lane <= last_word) w0 = cw[lane];
-            uint64_t w1 = __shfl_down_sync(0xffffffffu, w0, 1);
-            if (lane == 31) w1 = (last_word >= 32) ? cw[32] : 0;
-            cb8 = sh ? ((w0 >> sh) | (w1 << (64 - sh))) : w0;
-            if (nvalid > 0) {
-                q8 = *(const uint64_t *)(qin + x0);
-                s4 = *(const uint32_t *)(D.seq + (off >> 1) + lane * 4);
-                /* sequence bytes are little-endian in s4: byte b holds bases 2b (high nibble), 2b+1 (low nibble) */
+        const uint8_t *cbp = S.c + m.coff;
+        const uint8_t init_or = (m.init_or && !(cbp[0] & CG_CB_UNPROC)) ? 0x80 : 0;      /* head column processed and mapq <= -m */
+        if (m.kind == 2) {
+            /* L <= 256: lane owns bases [8*lane, 8*lane+8) */
+            const uint8_t *sp = S.s + (((qa + m.qoff) >> 1) - sa);
+            const int x0 = lane * 8, nv = Lr - x0;                  /* nv <= 0: idle lane */
+            const uint64_t vm = nv >= 8 ? ~0ULL : (nv > 0 ? ((1ULL << (8 * nv)) - 1) : 0ULL);
+            uint64_t q8 = 0; uint32_t s4 = 0, clo = 0, chi = 0;
+            if (nv > 0) {
+                q8 = *(const uint64_t *)(sl + x0);
+                s4 = *(const uint32_t *)(sp + (x0 >> 1));
+                /* column bytes [coff + x0, +8): two aligned words, funnel-shifted */
+                const uintptr_t ca_ = (uintptr_t)(cbp + x0);
+                const uint2 *cw = (const uint2 *)(ca_ & ~(uintptr_t)7);
+                const uint2 w0 = cw[0], w1 = cw[1];
+                const int sh = (int)(ca_ & 7);
+                const uint32_t Wa = (sh & 4) ? w0.y : w0.x, Wb = (sh & 4) ? w1.x : w0.y, Wc = (sh & 4) ? w1.y : w1.x;
+                clo = __funnelshift_r(Wa, Wb, (sh & 3) * 8) & (uint32_t)vm; chi = __funnelshift_r(Wb, Wc, (sh & 3) * 8) & (uint32_t)(vm >> 32);
             }
             /* whole-read keep: any covered column with keep_qual */
-            uint64_t m = cb8 & 0x8080808080808080ULL;
-            if (nvalid < 8) m = nvalid > 0 ? (m & ((1ULL << (8 * nvalid)) - 1)) : 0;
-            int keep = __any_sync(0xffffffffu, m != 0) && !tail_unreached;
-            if (nvalid > 0) {
-                uint32_t hi, lo = rw_visit8(q8, cb8, s4, nvalid < 8 ? nvalid : 8, init_or, keep, P, T, &hi);
-                *(uint32_t *)(sl + x0) = lo; *(uint32_t *)(sl + x0 + 4) = hi;
+            const int keep = __any_sync(0xffffffffu, (clo | chi) & 0x80808080u) && !m.tail_unreached;
+            if (nv > 0) {
+                const uint32_t init80 = init_or ? 0x80808080u : 0u;
+                const uint32_t qlo = (uint32_t)q8, qhi = (uint32_t)(q8 >> 32);
+                uint64_t res;
+                const uint32_t bad = ((((qlo & 0x7f7f7f7fu) + K.capadd) | qlo) | (((qhi & 0x7f7f7f7fu) + K.capadd) | qhi)) & 0x80808080u;
+                if (swar_ok && !bad) {
+                    if (keep) res = q8;                             /* memcpy of the (uncapped: <= -U) originals, snp_score.c:1939-1940 */
+                    else {
+                        const uint32_t t0 = __byte_perm(s4, 0, 0x1100), t1 = __byte_perm(s4, 0, 0x3322);
+                        const uint32_t n0 = ((t0 >> 4) & 0x000f000fu) | (t0 & 0x0f000f00u), n1 = ((t1 >> 4) & 0x000f000fu) | (t1 & 0x0f000f00u);
+                        res = (uint64_t)rw_swar4(qlo, clo, n0, init80, K) | ((uint64_t)rw_swar4(qhi, chi, n1, init80, K) << 32);
+                    }
+                } else {
+                    res = rw_visit8_scalar(q8, (uint64_t)clo | ((uint64_t)chi << 32), s4, init_or, keep, P, T);
+                }
+                *(uint64_t *)(sl + x0) = (res & vm) | (q8 & ~vm);
             }
         } else {
-            /* general path: replay inside the slot */
+            /* general path: replay inside the slot; originals and column bytes from global memory */
+            const CgRead q = D.rd[m.j];
+            const uint8_t *qin = D.qual + (qa + m.qoff);
             const uint32_t *cig = D.cigar + q.cig_off;
-            for (int x = lane; x < L; x += 32) sl[x] = qin[x] | init_or;
+            for (int x = lane; x < Lr; x += 32) sl[x] = qin[x] | init_or;
             int keepbits = 0;
             for (int c = q.col0 + lane; c < q.col0 + q.span; c += 32) keepbits |= D.cb[c];
-            int keep = __any_sync(0xffffffffu, keepbits & CG_CB_KEEP) && !tail_unreached;
+            int keep = __any_sync(0xffffffffu, keepbits & CG_CB_KEEP) && !m.tail_unreached;
             __syncwarp();
             int c = q.col0, y = 0;
             for (int k = 0; k < q.n_cigar; k++) {
@@ -670,11 +793,11 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
                 if (cg_is_mop(op)) {
                     for (int ii = lane; ii < l; ii += 32) {
                         int x = y + ii;
-                        if (x < L) sl[x] = cg_visit(sl[x], D.cb[c + ii], cg_cap_qual(qin[x], P, T), cg_seq_nib(&D, &q, x), P, T);
+                        if (x < Lr) sl[x] = cg_visit(sl[x], D.cb[c + ii], cg_cap_qual(qin[x], P, T), cg_seq_nib(&D, &q, x), P, T);
                     }
                     c += l; y += l;
                 } else if (op == 2 || op == 3) {
-                    if (lane == 0 && y < L) {
+                    if (lane == 0 && y < Lr) {
                         uint8_t oc = cg_cap_qual(qin[y], P, T); int nib = cg_seq_nib(&D, &q, y); uint8_t v = sl[y];
                         for (int ii = 0; ii < l; ii++) v = cg_visit(v, D.cb[c + ii], oc, nib, P, T);
                         sl[y] = v;
@@ -683,41 +806,40 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
                 } else if (op == 1 || op == 4) y += l;
                 __syncwarp();
             }
-            if (D.r_bf[j]) {
+            if (D.r_bf[m.j]) {
                 for (int k = cg_trig_lower_bound(&D, nf, q.col0); k < nf && D.fcol[k] < q.col0 + q.span; k++) {
                     const CgTrig *t = &D.trig[k];
                     if (!(t->hasI || t->hasS)) continue;
                     CgCell cell;
                     if (!cg_cell(&D, &q, t->col, &cell)) continue;
                     int xs = cg_ref2query_pos(cig, q.n_cigar, q.pos, D.twin[k].min_pos2);
-                    for (int x = xs + lane; x <= cell.qpos && x < L; x += 32) sl[x] = (uint8_t)(cg_cap_qual(qin[x], P, T) | 0x80);
+                    for (int x = xs + lane; x <= cell.qpos && x < Lr; x += 32) sl[x] = (uint8_t)(cg_cap_qual(qin[x], P, T) | 0x80);
                 }
                 __syncwarp();
             }
-            for (int x = lane; x < L; x += 32) sl[x] = (keep ? cg_cap_qual(qin[x], P, T) : sl[x]) & 0x7f;
+            for (int x = lane; x < Lr; x += 32) sl[x] = (keep ? cg_cap_qual(qin[x], P, T) : sl[x]) & 0x7f;
         }
-        if (lane == 0) sL[slot] = L;
     }
     __syncthreads();
     /* ---- phase B: P-block, thread per read ---- */
     if (P->pblock) {
-        const int L = sL[threadIdx.x];
-        if (L > 0) cg_pblock(sq + threadIdx.x * RW_STRIDE, L, P->pblock, P->qcap, T);
+        const RwMeta m = S.m[threadIdx.x];
+        if (m.kind) { if (P->any_preserve_qual) cg_pblock_t<1>(S.q + m.qoff, m.L, P->pblock, P->qcap, T); else cg_pblock_t<0>(S.q + m.qoff, m.L, P->pblock, P->qcap, T); }
     }
+    /* ---- phase C: the block's output range ---- */
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
-    /* ---- phase C: coalesced store ---- */
-    for (int i = 0; i < RW_READS / (RW_THREADS / 32); i++) {
-        const int slot = w * (RW_READS / (RW_THREADS / 32)) + i;
-        const int L = sL[slot];
-        if (L <= 0) continue;
-        const int64_t r = base + slot;
-        const uint8_t *sl = sq + slot * RW_STRIDE;
-        uint8_t *out = D.qual_out + D.off[r];
-        const int x0 = lane * 8;
-        if (x0 < L) {
-            uint64_t v = (uint64_t)*(const uint32_t *)(sl + x0) | ((uint64_t)*(const uint32_t *)(sl + x0 + 4) << 32);
-            *(uint64_t *)(out + x0) = v;
+    {
+        const long long lo = S.red[0][0], hi8 = (S.red[0][1] + 7) & ~7LL;            /* 8-aligned: record offsets are */
+        const long long ilo = (lo + 15) & ~15LL, ihi = hi8 & ~15LL;
+        if (threadIdx.x == 0 && ihi > ilo) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                         :: "l"(D.qual_out + ilo), "r"((unsigned)__cvta_generic_to_shared(S.q + (ilo - qa))), "r"((uint32_t)(ihi - ilo)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
+        if (threadIdx.x == 1 && lo < ilo && lo < hi8) *(uint64_t *)(D.qual_out + lo) = *(const uint64_t *)(S.q + (lo - qa));
+        if (threadIdx.x == 2 && ihi < hi8 && ihi >= ilo) *(uint64_t *)(D.qual_out + ihi) = *(const uint64_t *)(S.q + (ihi - qa));
+        if (threadIdx.x == 0 && ihi > ilo) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
     }
 }
 __global__ void k_dump_flags(const __grid_constant__ CgDev D) {

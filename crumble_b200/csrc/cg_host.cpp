@@ -29,7 +29,7 @@ void cg_devparams_from(CgDevParams *d, const cg_params *p) {
     memset(d, 0, sizeof(*d));
     d->reduce_qual = p->reduce_qual; d->binary_qual = p->binary_qual;
     d->iSTR_add = p->iSTR_add; d->sSTR_add = p->sSTR_add; d->iSTR_mul = p->iSTR_mul; d->sSTR_mul = p->sSTR_mul;
-    d->qlow = p->qlow; d->qhigh = p->qhigh; d->qcap = p->qcap;
+    d->qlow = p->qlow; d->qhigh = p->qhigh; d->qcap = p->qcap; d->qcutoff = p->qcutoff;
     d->min_mqual = p->min_mqual; d->indel_fract = p->indel_fract;
     d->min_qual_A = p->min_qual_A; d->min_indel_A = p->min_indel_A; d->min_discrep_A = p->min_discrep_A;
     d->min_qual_B = p->min_qual_B; d->min_indel_B = p->min_indel_B; d->min_discrep_B = p->min_discrep_B;

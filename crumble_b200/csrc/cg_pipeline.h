@@ -245,7 +245,7 @@ CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgC
         if (P->min_qual_A != 0) cg_column_cons<0>(D, c, lo, hi, &cA);
         int hA = 0, sA = 0, hB = 0, sB = 0;
         const CgCons *cc = doB ? &cB : &cA;                                /* B's calls overwrite A's (1534-1543) */
-        int code = (doB || P->min_qual_A) ? cg_call_code(cc) : 24;         /* call1=call2=0 matches nothing */
+        int code = (doB || P->min_qual_A) ? cg_call_code(cc) : 0;          /* call1=call2=0 matches nothing */
         if (P->min_qual_A) {                                               /* 1576-1583 */
             hA = cA.het_phred > 0 ? cA.het_call : cA.call * 5 + cA.call;
             sA = cA.het_phred > 0 ? cA.het_phred : cA.phred;
@@ -480,7 +480,7 @@ CG_HDN void cg_rewrite(const CgDev *D, int64_t r, int n_flagged) {
     for (int c = q.col0; c < q.col0 + q.span; c++) keep |= D->cb[c];
     keep = (keep & CG_CB_KEEP) != 0;
     if (P->region_tid >= 0 && q.pos + q.span - 1 >= P->region_end) keep = 0;      /* tail column never reached */
-    const int head_proc = (D->cb[q.col0] & CG_CB_CODE_MASK) != CG_CB_UNPROC;
+    const int head_proc = !(D->cb[q.col0] & CG_CB_UNPROC);
     const uint8_t init_or = (head_proc && q.mapq <= P->min_mqual) ? 0x80 : 0;     /* 1852-1859 */
     for (int x = 0; x < L; x++) out[x] = qin[x] | init_or;
     /* visits in column order */
