@@ -504,13 +504,116 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
     if (lane == 0 && mx > 0) atomicMax(D.maxdepth, mx);
 }
 
-__global__ void __launch_bounds__(64) k_flagged(const __grid_constant__ CgDev D, CgFlagScratch *scratch) {
-    int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    int stride = gridDim.x * blockDim.x;
-    CgFlagScratch *S = scratch + tid;
-    for (int k = tid; k < D.n_flagged; k += stride) {
-        uint32_t cnt = cg_flagged(&D, k, S);
-        while (cnt) { int b = __ffs(cnt) - 1; cnt &= cnt - 1; atomicAdd(&D.counters[b], 1ULL); }
+/* Flagged columns (had an indel / may open a keep window), one WARP per column, lanes over the column's reads:
+ * the same decisions as cg_flagged (cg_pipeline.h; snp_score.c:1690-1762, 1775-1819) with the per-read work —
+ * pileup cell, mask_LC_regions + find_STR of every triggering read — spread over the lanes.  What the reference
+ * computes read by read is order-free except for two things, both recovered from the index of the LAST
+ * triggering read of each type: the running STR extents as seen by that read (PI/QI, PS/QS = min/max over the
+ * triggering reads up to it) and the column variable `indel`. */
+#define FL_WARPS 4
+__global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant__ CgDev D, CgFlagScratch *scratch) {
+    __shared__ int hist[FL_WARPS][104];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int gw = blockIdx.x * FL_WARPS + w, nw = gridDim.x * FL_WARPS;
+    CgFlagScratch *S = scratch + (size_t)gw * 32 + lane;
+    const CgDevParams *P = &D.P;
+    const unsigned FULL = 0xffffffffu;
+    for (int k = gw; k < D.n_flagged; k += nw) {
+        const int c = D.fcol[k];
+        const int t = c >> 5;
+        const int lo = D.tile_lo[t], hi = D.tile_start[t + 1];
+        const uint16_t ev = D.ev[c];
+        const int n_plp = (int)D.depth[c];
+        const int had_indel = (ev & CG_EV_HADINDEL) != 0, lowscore = (ev & CG_EV_LOWSCORE) != 0, strall = (ev & CG_EV_STRALL) != 0;
+        const int is = cg_island_of(&D, c);
+        const int tid = D.isl[is].tid, pos = D.isl[is].pos_start + (c - D.isl[is].col_start);
+        for (int i = lane; i < 104; i += 32) hist[w][i] = 0;
+        __syncwarp();
+        /* pass 1: indel count, insertion-size spectrum, last triggering read of each type */
+        int indel_cnt = 0, jI = -1, jS = -1, maxsz = 0, nIq = 0;
+        for (int j = lo + lane; j < hi; j += 32) {
+            const CgRead q = D.rd[j]; CgCell cell;
+            if (!cg_cell(&D, &q, c, &cell)) continue;
+            if (cell.indel || cell.is_del) indel_cnt++;
+            if (cell.is_refskip) continue;                                     /* 1696-1697 */
+            const int is_indel = (cell.indel || cell.is_del);
+            if (!cell.is_head && !cell.is_tail && (cell.indel > 0 || had_indel)) {     /* 1708-1713 */
+                if (cell.indel > maxsz) maxsz = cell.indel;
+                if (cell.indel >= 0) atomicAdd(&hist[w][cell.indel < 99 ? cell.indel : 99], 1);
+            }
+            if ((is_indel || strall) && lowscore) {                            /* 1718-1720 */
+                if (is_indel) { jI = j; nIq++; } else jS = j;
+            }
+        }
+        indel_cnt = __reduce_add_sync(FULL, indel_cnt); nIq = __reduce_add_sync(FULL, nIq);
+        jI = __reduce_max_sync(FULL, jI); jS = __reduce_max_sync(FULL, jS); maxsz = __reduce_max_sync(FULL, maxsz);
+        const int gate = indel_cnt >= n_plp * P->indel_fract;                  /* 1732 */
+        /* pass 2: STR extents of the triggering reads */
+        int mA = pos, MA = pos, mI = pos, MI = pos, mS = pos, MS = pos, vall = 0, vafter = 0;
+        if (jI >= 0 || jS >= 0) {
+            for (int j = lo + lane; j < hi; j += 32) {
+                const CgRead q = D.rd[j]; CgCell cell;
+                if (!cg_cell(&D, &q, c, &cell)) continue;
+                if (cell.is_refskip) continue;
+                const int is_indel = (cell.indel || cell.is_del);
+                if (!(is_indel || strall)) continue;
+                if (is_indel) {
+                    const int v = (cell.indel < 0 ? -cell.indel : cell.indel) + cell.is_del;
+                    if (v > vall) vall = v;
+                    if (j > jS && v > vafter) vafter = v;
+                }
+                if (gate && q.l_qseq > 0) {                                    /* 1732-1739: the two calls are identical in effect */
+                    const int phantom = (q.l_qseq & 1) ? (D.seq[(CG_OFF(&q) >> 1) + (q.l_qseq >> 1)] & 0xf)
+                                                       : (cg_cap_qual(D.qual[CG_OFF(&q)], P, D.T) >> 4);
+                    int lo_r = pos, hi_r = pos;
+                    cg_mask_lc(D.seq + (CG_OFF(&q) >> 1), q.l_qseq, phantom, D.cigar + q.cig_off, q.n_cigar, q.pos,
+                               cell.qpos + 1, is_indel ? P->iSTR_add : P->sSTR_add, S->win, &S->reps, &lo_r, &hi_r);
+                    if (S->reps.overflow) *D.err = CG_ERR_OVERFLOW;
+                    if (lo_r < mA) mA = lo_r;
+                    if (hi_r > MA) MA = hi_r;
+                    if (j <= jI) { if (lo_r < mI) mI = lo_r; if (hi_r > MI) MI = hi_r; }
+                    if (j <= jS) { if (lo_r < mS) mS = lo_r; if (hi_r > MS) MS = hi_r; }
+                }
+            }
+            mA = __reduce_min_sync(FULL, mA); MA = __reduce_max_sync(FULL, MA);
+            mI = __reduce_min_sync(FULL, mI); MI = __reduce_max_sync(FULL, MI);
+            mS = __reduce_min_sync(FULL, mS); MS = __reduce_max_sync(FULL, MS);
+            vall = __reduce_max_sync(FULL, vall); vafter = __reduce_max_sync(FULL, vafter);
+            /* every read of a trigger column is back-filled (1870-1879) */
+            for (int j = lo + lane; j < hi; j += 32) {
+                const CgRead q = D.rd[j];
+                if ((unsigned)(c - q.col0) < (unsigned)q.span) D.r_bf[j] = 1;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            CgTrig tr; tr.tid = tid; tr.pos = pos; tr.col = c;
+            tr.hasI = jI >= 0; tr.hasS = jS >= 0;
+            tr.PI = tr.hasI ? mI : pos; tr.QI = tr.hasI ? MI : pos; tr.PS = tr.hasS ? mS : pos; tr.QS = tr.hasS ? MS : pos;
+            tr.A = mA; tr.B = MA;
+            tr.indel = tr.hasS ? (vafter > 1 ? vafter : 1) : vall;             /* 1725-1730: a SNP-type trigger resets it to 1 */
+            D.trig[k] = tr;
+            uint32_t cnt = 0;
+            if (nIq) cnt |= 1u << CG_CNT_INDEL_QUAL;                           /* 1762 */
+            uint16_t ev_add = 0; int keep = 0;
+            const int indel_sz = maxsz < 100 ? maxsz : 100;
+            if (indel_sz) {                                                    /* 1777-1819 */
+                int qd1 = 0, qd2 = 0, ov = 0;
+                for (int i = 0; i <= indel_sz && i < 100; i++) {
+                    int d = hist[w][i];
+                    if (!d) continue;
+                    ov += d;
+                    if (qd1 < d) { qd2 = qd1; qd1 = d; } else if (qd2 < d) qd2 = d;
+                }
+                if ((ov - qd1 - qd2) > P->ins_len_perc * (ov + .1)) { ev_add |= CG_EV_INDEL_LEN; keep = 1; cnt |= 1u << CG_CNT_INS_LEN_PERC; }
+                if ((double)ov < P->indel_ov_perc * n_plp) { ev_add |= CG_EV_INDEL_COV; keep = 1; cnt |= 1u << CG_CNT_INDEL_OV_PERC; }
+            }
+            if (tr.hasI || tr.hasS) ev_add |= CG_EV_TRIGGER;
+            if (ev_add) D.ev[c] = (uint16_t)(ev | ev_add);
+            if (keep) D.cb[c] |= CG_CB_KEEP;
+            while (cnt) { int b = __ffs(cnt) - 1; cnt &= cnt - 1; atomicAdd(&D.counters[b], 1ULL); }
+        }
+        __syncwarp();
     }
 }
 
@@ -563,8 +666,44 @@ __global__ void k_deep(const __grid_constant__ CgDev D, const CgEpoch *ep, const
     if (m && (threadIdx.x & 31) == 0) atomicAdd(&D.counters[CG_CNT_OVER_DEPTH], (unsigned long long)__popc(m));
 }
 
-__global__ void k_chain(const __grid_constant__ CgDev D) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) cg_chain(&D, D.n_flagged);
+/* Keep-window chain (snp_score.c:1508-1511,1741-1755) in parallel.  The state (min_pos..max_pos2) is reset whenever
+ * a trigger lies beyond max_pos2, so the chain falls into independent segments; a segment head is recognised without
+ * knowing the state from an UPPER BOUND of max_pos2: windows only grow with the running STR maximum, so
+ *   max_pos2 after trigger i  <=  U_i = max_{i' <= i} ceil( pos_i' + (Bmax_i' - pos_i') * mul + add ),  Bmax = prefix max of B
+ * (both prefix maxima restricted to the contig by packing tid into the high word).  pos_k > U_{k-1} proves a reset at k;
+ * each proven head then replays its segment sequentially (unproven resets inside are found by the replay itself). */
+struct LdTrigB { const CgTrig *t; __device__ int64_t operator()(int64_t k) const { const CgTrig x = t[k]; return ((int64_t)x.tid << 32) | (uint32_t)((x.hasI || x.hasS) ? (x.B > 0 ? x.B : 0) : 0); } };
+struct LdTrigU {
+    const CgTrig *t; const int64_t *bmax; double mul, add;
+    __device__ int64_t operator()(int64_t k) const {
+        const CgTrig x = t[k];
+        uint32_t u = 0;
+        if (x.hasI || x.hasS) {
+            const double M = (double)(uint32_t)bmax[k];
+            double f = (double)x.pos + (M - x.pos) * mul + add + 2.0;
+            if (f < 0) f = 0;
+            u = f >= 2147483647.0 ? 0x7fffffffu : (uint32_t)f;
+        }
+        return ((int64_t)x.tid << 32) | u;
+    }
+};
+__device__ __forceinline__ bool chain_is_head(const CgTrig &x, int k, const int64_t *umax) {
+    if (k == 0) return true;
+    const int64_t u = umax[k - 1];
+    return (int32_t)(u >> 32) != x.tid || (uint32_t)x.pos > (uint32_t)u;
+}
+__global__ void k_chain(const __grid_constant__ CgDev D, const int64_t *umax) {
+    const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k0 >= D.n_flagged) return;
+    CgTrig t = D.trig[k0];
+    if (!(t.hasI || t.hasS) || !chain_is_head(t, k0, umax)) return;
+    CgWin w; cg_win_reset(&w);
+    for (int k = k0;;) {
+        cg_win_step(&w, &t, &D.P);
+        D.twin[k] = w;
+        for (k++; k < D.n_flagged; k++) { t = D.trig[k]; if (t.hasI || t.hasS) break; }
+        if (k >= D.n_flagged || chain_is_head(t, k, umax)) break;
+    }
 }
 __global__ void k_paint(const __grid_constant__ CgDev D) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -869,7 +1008,7 @@ struct cg_ctx {
     dbuf b_tid, b_pos, b_flag, b_mapq, b_lq, b_nc, b_off, b_coff, b_cigar, b_seq, b_qual, b_qout;
     dbuf b_jmap, b_rspan, b_rd, b_ks, b_ke, b_gap, b_gapraw, b_pmax, b_orig, b_rbf;
     dbuf b_tlo, b_tstart, b_isl, b_cb, b_ev, b_depth, b_dump, b_dsum, b_csum, b_fcol, b_trig, b_twin;
-    dbuf b_aggr, b_scal, b_scratch, b_epoch, b_events;
+    dbuf b_aggr, b_scal, b_scratch, b_epoch, b_events, b_chain;
     /* host mirrors */
     int32_t *h_dims;              /* pinned: [0] n_pile [1] n_cols [2] n_islands [3] n_flagged [4] maxdepth [5] err [6] n_events [7] n_epochs */
     unsigned long long *h_counters;
@@ -946,7 +1085,7 @@ extern "C" void cg_destroy(cg_ctx *ctx) {
     dbuf *all[] = { &ctx->b_tid, &ctx->b_pos, &ctx->b_flag, &ctx->b_mapq, &ctx->b_lq, &ctx->b_nc, &ctx->b_off, &ctx->b_coff, &ctx->b_cigar,
         &ctx->b_seq, &ctx->b_qual, &ctx->b_qout, &ctx->b_jmap, &ctx->b_rspan, &ctx->b_rd, &ctx->b_ks, &ctx->b_ke, &ctx->b_gap, &ctx->b_gapraw,
         &ctx->b_pmax, &ctx->b_orig, &ctx->b_rbf, &ctx->b_tlo, &ctx->b_tstart, &ctx->b_isl, &ctx->b_cb, &ctx->b_ev, &ctx->b_depth, &ctx->b_dump,
-        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events };
+        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain };
     for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); i++) if (all[i]->p) cudaFree(all[i]->p);
     if (ctx->dT) cudaFree(ctx->dT);
     if (ctx->h_dims) cudaFreeHost(ctx->h_dims);
@@ -1119,7 +1258,7 @@ extern "C" int cg_run(cg_ctx *ctx) {
     if ((e = ensure(ctx, &ctx->b_trig, ((size_t)nf + 1) * sizeof(CgTrig))) || (e = ensure(ctx, &ctx->b_twin, ((size_t)nf + 1) * sizeof(CgWin)))) return e;
     D->trig = (CgTrig *)ctx->b_trig.p; D->twin = (CgWin *)ctx->b_twin.p;
     if (nf > 0) {
-        int threads = 64, blocks = nblk(nf, threads);
+        int threads = FL_WARPS * 32, blocks = nblk(nf, FL_WARPS);
         if (blocks > 148 * 4) blocks = 148 * 4;
         if ((e = ensure(ctx, &ctx->b_scratch, (size_t)blocks * threads * sizeof(CgFlagScratch)))) return e;
         k_flagged<<<blocks, threads, 0, st>>>(*D, (CgFlagScratch *)ctx->b_scratch.p); ctx->launches++;
@@ -1142,7 +1281,16 @@ extern "C" int cg_run(cg_ctx *ctx) {
     T1(CG_T_DEPTH);
     T0(CG_T_CHAIN);
     if (nf > 0) {
-        k_chain<<<1, 32, 0, st>>>(*D);
+        if ((e = ensure(ctx, &ctx->b_chain, ((size_t)nf + 1) * 16))) return e;
+        int64_t *bmax = (int64_t *)ctx->b_chain.p, *umax = bmax + nf;
+        double mul = ctx->params.iSTR_mul > ctx->params.sSTR_mul ? ctx->params.iSTR_mul : ctx->params.sSTR_mul;
+        double add = ctx->params.iSTR_add > ctx->params.sSTR_add ? ctx->params.iSTR_add : ctx->params.sSTR_add;
+        if (mul < 0) mul = 0;
+        LdTrigB lb = { D->trig }; StI64Incl sb = { bmax };
+        if ((e = run_scan<int64_t, OpMax>(ctx, lb, sb, nf, (int64_t)INT64_MIN, (int64_t *)NULL))) return e;
+        LdTrigU lu = { D->trig, bmax, mul, add }; StI64Incl su = { umax };
+        if ((e = run_scan<int64_t, OpMax>(ctx, lu, su, nf, (int64_t)INT64_MIN, (int64_t *)NULL))) return e;
+        k_chain<<<nblk(nf, 128), 128, 0, st>>>(*D, umax);
         k_paint<<<nblk(nf, 128), 128, 0, st>>>(*D); ctx->launches += 2;
     }
     T1(CG_T_CHAIN);
