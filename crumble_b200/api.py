@@ -133,6 +133,7 @@ def load_lib():
     lib.cg_upload.argtypes = [C.c_void_p, C.POINTER(Batch)]
     lib.cg_run.argtypes = [C.c_void_p]
     lib.cg_sync.argtypes = [C.c_void_p]
+    lib.cg_set_chunk_bytes.argtypes = [C.c_void_p, C.c_int64]
     lib.cg_download.argtypes = [C.c_void_p, C.POINTER(Result)]
     lib.cg_last_ms.restype = C.c_float
     lib.cg_last_ms.argtypes = [C.c_void_p, C.c_int]
@@ -288,6 +289,10 @@ class Crumble:
         return out
 
     # split phase (resident timing)
+    def set_chunk_bytes(self, nbytes: int):
+        """Upload-chunk size of the streamed ``process`` (results do not depend on it)."""
+        _check(self.lib, self.lib.cg_set_chunk_bytes(self.h, int(nbytes)), self.h)
+
     def upload(self, batch: Batch):
         _check(self.lib, self.lib.cg_upload(self.h, C.byref(batch)), self.h)
 

@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "cg_host.h"
 
 #define CG_CHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -371,7 +372,7 @@ __device__ __forceinline__ void col_stage(const CgDev &D, ColSmem *S, uint16_t (
     }
 }
 
-__global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __grid_constant__ CgDev D) {
+__global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __grid_constant__ CgDev D, int t_begin, int t_end) {
     __shared__ ColSmem S;
     const CgTables *T = D.T;
     const CgDevParams *P = &D.P;
@@ -388,13 +389,13 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int t = blockIdx.x * COL_WARPS + w;        /* this warp's 32-column tile */
+    const int t = t_begin + blockIdx.x * COL_WARPS + w;   /* this warp's 32-column tile */
     const int tile_c0 = t * 32;
     const int c = tile_c0 + lane;
     CgColOut o; o.cnt = 0; o.n_plp = 0;
     int lo = 0, hi = 0;
-    if (t < D.n_tiles) { lo = D.tile_lo[t]; hi = D.tile_start[t + 1]; }
-    const bool live = c < D.n_cols;
+    if (t < t_end) { lo = D.tile_lo[t]; hi = D.tile_start[t + 1]; }
+    const bool live = t < t_end && c < D.n_cols;
     const int doB = P->min_qual_B != 0;
     const int min_mqual = P->min_mqual;
     uint16_t (*cells)[32] = S.w[w].cell;
@@ -511,14 +512,14 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
  * triggering read of each type: the running STR extents as seen by that read (PI/QI, PS/QS = min/max over the
  * triggering reads up to it) and the column variable `indel`. */
 #define FL_WARPS 4
-__global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant__ CgDev D, CgFlagScratch *scratch) {
+__global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant__ CgDev D, CgFlagScratch *scratch, int k_begin, int k_end) {
     __shared__ int hist[FL_WARPS][104];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int gw = blockIdx.x * FL_WARPS + w, nw = gridDim.x * FL_WARPS;
     CgFlagScratch *S = scratch + (size_t)gw * 32 + lane;
     const CgDevParams *P = &D.P;
     const unsigned FULL = 0xffffffffu;
-    for (int k = gw; k < D.n_flagged; k += nw) {
+    for (int k = k_begin + gw; k < k_end; k += nw) {
         const int c = D.fcol[k];
         const int t = c >> 5;
         const int lo = D.tile_lo[t], hi = D.tile_start[t + 1];
@@ -620,20 +621,27 @@ __global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant
 /* depth-average epochs (snp_score.c:1478-1491,1684-1687): sequential over contigs and the
  * ~n_cols/524289 halving points only; everything per-column is a prefix-sum lookup */
 struct CgEpoch { int32_t col_begin; int32_t pad; int64_t td_base, tc_base, d_off, c_off; };
+/* what a slice of columns hands to the next one: the contig whose running sums are open, and the prefix sums so far */
+struct CgEpochCarry { int32_t tid, valid; int64_t td, tc, d_off, c_off; int64_t dsum_last; int32_t csum_last, n_ep; };
 
-__global__ void k_epochs(const __grid_constant__ CgDev D, CgEpoch *ep, int32_t *n_ep, int cap) {
+__global__ void k_epochs(const __grid_constant__ CgDev D, CgEpoch *ep, CgEpochCarry *carry, int cap, int cb, int ce) {
     if (threadIdx.x || blockIdx.x) return;
-    int ne = 0;
-    int is = 0;
-    while (is < D.n_islands) {
-        int tid = D.isl[is].tid, is2 = is;
+    int ne = carry->n_ep;
+    int is = cg_island_of(&D, cb);
+    while (is < D.n_islands && D.isl[is].col_start < ce) {
+        const int tid = D.isl[is].tid; int is2 = is;
         while (is2 + 1 < D.n_islands && D.isl[is2 + 1].tid == tid) is2++;
-        int c0 = D.isl[is].col_start, c1 = (is2 + 1 < D.n_islands) ? D.isl[is2 + 1].col_start : D.n_cols;
-        int64_t d_off = c0 ? D.dsum[c0 - 1] : 0, c_off = c0 ? D.csum[c0 - 1] : 0;
-        int64_t td = 0, tc = 0; int s = c0;
-        for (;;) {
+        const int c0 = D.isl[is].col_start > cb ? D.isl[is].col_start : cb;
+        const int c1_true = (is2 + 1 < D.n_islands) ? D.isl[is2 + 1].col_start : D.n_cols;
+        const int c1 = c1_true < ce ? c1_true : ce;
+        int64_t d_off, c_off, td, tc; int s = c0;
+        if (carry->valid && carry->tid == tid) { td = carry->td; tc = carry->tc; d_off = carry->d_off; c_off = carry->c_off; }
+        else {
+            d_off = c0 ? D.dsum[c0 - 1] : 0; c_off = c0 ? D.csum[c0 - 1] : 0; td = tc = 0;
             if (ne < cap) { CgEpoch e; e.col_begin = s; e.pad = 0; e.td_base = td; e.tc_base = tc; e.d_off = d_off; e.c_off = c_off; ep[ne] = e; }
             ne++;
+        }
+        for (;;) {
             /* first column in [s,c1) whose counted index makes total_col exceed 2^20 */
             int64_t want = c_off + (1024 * 1024 + 1 - tc);
             int lo = s, hi = c1;
@@ -644,19 +652,24 @@ __global__ void k_epochs(const __grid_constant__ CgDev D, CgEpoch *ep, int32_t *
             td = (td + (D.dsum[c] - d_off)) >> 1;
             tc = (tc + ((int64_t)D.csum[c] - c_off)) >> 1;
             d_off = D.dsum[c]; c_off = D.csum[c]; s = c + 1;
+            if (s >= c1_true) break;
+            if (ne < cap) { CgEpoch e; e.col_begin = s; e.pad = 0; e.td_base = td; e.tc_base = tc; e.d_off = d_off; e.c_off = c_off; ep[ne] = e; }
+            ne++;
             if (s >= c1) break;
         }
+        carry->tid = tid; carry->valid = 1; carry->td = td; carry->tc = tc; carry->d_off = d_off; carry->c_off = c_off;
         is = is2 + 1;
     }
-    *n_ep = ne;
+    carry->n_ep = ne;
+    if (ce > cb) { carry->dsum_last = D.dsum[ce - 1]; carry->csum_last = D.csum[ce - 1]; }
     if (ne > cap) *D.err = CG_ERR_OVERFLOW;
 }
 
-__global__ void k_deep(const __grid_constant__ CgDev D, const CgEpoch *ep, const int32_t *n_ep) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_deep(const __grid_constant__ CgDev D, const CgEpoch *ep, const CgEpochCarry *carry, int cb, int ce) {
+    int c = cb + blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t cnt = 0;
-    if (c < D.n_cols && (D.ev[c] & CG_EV_PROCESSED)) {
-        int lo = 0, hi = *n_ep - 1;
+    if (c < ce && (D.ev[c] & CG_EV_PROCESSED)) {
+        int lo = 0, hi = carry->n_ep - 1;
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (ep[mid].col_begin <= c) lo = mid; else hi = mid - 1; }
         const CgEpoch e = ep[lo];
         int64_t td = e.td_base + (D.dsum[c] - e.d_off), tc = e.tc_base + ((int64_t)D.csum[c] - e.c_off);
@@ -672,9 +685,17 @@ __global__ void k_deep(const __grid_constant__ CgDev D, const CgEpoch *ep, const
  *   max_pos2 after trigger i  <=  U_i = max_{i' <= i} ceil( pos_i' + (Bmax_i' - pos_i') * mul + add ),  Bmax = prefix max of B
  * (both prefix maxima restricted to the contig by packing tid into the high word).  pos_k > U_{k-1} proves a reset at k;
  * each proven head then replays its segment sequentially (unproven resets inside are found by the replay itself). */
-struct LdTrigB { const CgTrig *t; __device__ int64_t operator()(int64_t k) const { const CgTrig x = t[k]; return ((int64_t)x.tid << 32) | (uint32_t)((x.hasI || x.hasS) ? (x.B > 0 ? x.B : 0) : 0); } };
+struct CgChainCarry { int64_t bkey, ukey; CgWin w; int32_t has, pad; };    /* state after the last trigger of the previous slice */
+struct LdTrigB {
+    const CgTrig *t; const CgChainCarry *cy;
+    __device__ int64_t operator()(int64_t k) const {
+        const CgTrig x = t[k];
+        const int64_t v = ((int64_t)x.tid << 32) | (uint32_t)((x.hasI || x.hasS) ? (x.B > 0 ? x.B : 0) : 0);
+        return v > cy->bkey ? v : cy->bkey;
+    }
+};
 struct LdTrigU {
-    const CgTrig *t; const int64_t *bmax; double mul, add;
+    const CgTrig *t; const int64_t *bmax; const CgChainCarry *cy; double mul, add;
     __device__ int64_t operator()(int64_t k) const {
         const CgTrig x = t[k];
         uint32_t u = 0;
@@ -684,30 +705,42 @@ struct LdTrigU {
             if (f < 0) f = 0;
             u = f >= 2147483647.0 ? 0x7fffffffu : (uint32_t)f;
         }
-        return ((int64_t)x.tid << 32) | u;
+        const int64_t v = ((int64_t)x.tid << 32) | u;
+        return v > cy->ukey ? v : cy->ukey;
     }
 };
-__device__ __forceinline__ bool chain_is_head(const CgTrig &x, int k, const int64_t *umax) {
-    if (k == 0) return true;
-    const int64_t u = umax[k - 1];
+__device__ __forceinline__ bool chain_is_head(const CgTrig &x, int k, int k_begin, const int64_t *umax, const CgChainCarry *cy) {
+    const int64_t u = k == k_begin ? cy->ukey : umax[k - 1];
     return (int32_t)(u >> 32) != x.tid || (uint32_t)x.pos > (uint32_t)u;
 }
-__global__ void k_chain(const __grid_constant__ CgDev D, const int64_t *umax) {
-    const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k0 >= D.n_flagged) return;
+/* umax is indexed by flagged entry (global); the thread of the slice's first entry also continues an open segment */
+__global__ void k_chain(const __grid_constant__ CgDev D, const int64_t *umax, const CgChainCarry *cy, int k_begin, int k_end) {
+    int k0 = k_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k0 >= k_end) return;
     CgTrig t = D.trig[k0];
-    if (!(t.hasI || t.hasS) || !chain_is_head(t, k0, umax)) return;
     CgWin w; cg_win_reset(&w);
+    if (k0 == k_begin) {
+        while (!(t.hasI || t.hasS)) { if (++k0 >= k_end) return; t = D.trig[k0]; }
+        if (!chain_is_head(t, k0, k_begin, umax, cy) && cy->has) w = cy->w;
+    } else if (!(t.hasI || t.hasS) || !chain_is_head(t, k0, k_begin, umax, cy)) return;
     for (int k = k0;;) {
         cg_win_step(&w, &t, &D.P);
         D.twin[k] = w;
-        for (k++; k < D.n_flagged; k++) { t = D.trig[k]; if (t.hasI || t.hasS) break; }
-        if (k >= D.n_flagged || chain_is_head(t, k, umax)) break;
+        for (k++; k < k_end; k++) { t = D.trig[k]; if (t.hasI || t.hasS) break; }
+        if (k >= k_end || chain_is_head(t, k, k_begin, umax, cy)) break;
     }
 }
-__global__ void k_paint(const __grid_constant__ CgDev D) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < D.n_flagged) cg_paint(&D, k, D.n_flagged);
+__global__ void k_chain_carry(const __grid_constant__ CgDev D, const int64_t *bmax, const int64_t *umax, CgChainCarry *cy, int k_begin, int k_end) {
+    if (threadIdx.x || blockIdx.x || k_end <= k_begin) return;
+    cy->bkey = bmax[k_end - 1]; cy->ukey = umax[k_end - 1];
+    for (int k = k_end - 1; k >= k_begin; k--) {
+        const CgTrig *t = &D.trig[k];
+        if (t->hasI || t->hasS) { cy->w = D.twin[k]; cy->has = 1; break; }
+    }
+}
+__global__ void k_paint(const __grid_constant__ CgDev D, int k_begin, int k_end) {
+    int k = k_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < k_end) cg_paint(&D, k, k_end);
 }
 /* Per-read quality rewrite.  A block owns RW_READS consecutive records; their quality strings, packed sequences
  * and the column bytes under them are three CONTIGUOUS ranges, fetched with three bulk async copies (TMA,
@@ -781,12 +814,12 @@ __device__ __forceinline__ void rw_mbar_wait(unsigned long long *bar, uint32_t p
                  :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(phase) : "memory");
 }
 
-__global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ CgDev D) {
+__global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ CgDev D, int64_t rec_begin, int64_t rec_end) {
     __shared__ RwSmem S;
     const CgDevParams *P = &D.P;
     const CgTables *T = D.T;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t base = (int64_t)blockIdx.x * RW_READS;
+    const int64_t base = rec_begin + (int64_t)blockIdx.x * RW_READS;
     const int nf = D.n_flagged;
 
     /* ---- phase 0: per-read facts, block ranges, bulk loads ---- */
@@ -794,7 +827,7 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
     int64_t off = 0; int L = 0, kind = 0, col0 = 0, span = 0, j = -1; uint8_t init_mq = 0, tail_unreached = 0;
     {
         const int64_t r = base + threadIdx.x;
-        if (r < D.n_reads) { L = D.l_qseq[r]; off = D.off[r]; }
+        if (r < rec_end) { L = D.l_qseq[r]; off = D.off[r]; }
         if (L > 0) {
             kind = 1;
             if (D.rspan[r]) {
@@ -844,7 +877,7 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
     if (qbytes == 0) return;                                   /* nothing but empty records */
     if (cbytes < 0) {                                          /* ranges too long for the staging buffers */
         const int64_t r = base + threadIdx.x;
-        if (r < D.n_reads) cg_rewrite(&D, r, nf);
+        if (r < rec_end) cg_rewrite(&D, r, nf);
         return;
     }
     {
@@ -1015,6 +1048,10 @@ struct cg_ctx {
     CgDev D;
     int resident; int dump_columns;
     int64_t qual_bytes, events_cap_dev;
+    int need_depth, epoch_cap, nf_total;
+    int64_t chunk_bytes;
+    cudaStream_t s_h2d, s_d2h; cudaEvent_t ev_up[32], ev_done[32], ev_misc;
+    char h_carry_init[64];
     cudaEvent_t ev[CG_N_TIMERS][2];
     float ms[CG_N_TIMERS];
     int64_t launches;
@@ -1027,6 +1064,21 @@ static int ensure(cg_ctx *ctx, dbuf *b, size_t bytes) {
     b->p = NULL; b->cap = 0;
     CG_CHECK(cudaMalloc(&b->p, nc));
     b->cap = nc;
+    return 0;
+}
+
+/* grow a buffer whose contents must survive (lists appended to slice after slice) */
+static int ensure_keep(cg_ctx *ctx, dbuf *b, size_t bytes) {
+    if (bytes <= b->cap) return 0;
+    size_t nc = bytes * 2 + 4096;
+    void *np_ = NULL;
+    CG_CHECK(cudaMalloc(&np_, nc));
+    if (b->p) {
+        CG_CHECK(cudaMemcpyAsync(np_, b->p, b->cap, cudaMemcpyDeviceToDevice, ctx->stream));
+        CG_CHECK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(b->p);
+    }
+    b->p = np_; b->cap = nc;
     return 0;
 }
 
@@ -1091,6 +1143,7 @@ extern "C" void cg_destroy(cg_ctx *ctx) {
     if (ctx->h_dims) cudaFreeHost(ctx->h_dims);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (int i = 0; i < CG_N_TIMERS; i++) for (int k = 0; k < 2; k++) if (ctx->ev[i][k]) cudaEventDestroy(ctx->ev[i][k]);
+    if (ctx->s_h2d) { cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h); for (int i = 0; i < 32; i++) { cudaEventDestroy(ctx->ev_up[i]); cudaEventDestroy(ctx->ev_done[i]); } cudaEventDestroy(ctx->ev_misc); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx->hT);
     free(ctx);
@@ -1102,6 +1155,7 @@ extern "C" int cg_set_stream(cg_ctx *ctx, void *s) {
     ctx->stream = (cudaStream_t)s; ctx->own_stream = 0;
     return 0;
 }
+extern "C" int cg_set_chunk_bytes(cg_ctx *ctx, int64_t bytes) { ctx->chunk_bytes = bytes; return 0; }
 extern "C" int cg_sync(cg_ctx *ctx) { CG_CHECK(cudaStreamSynchronize(ctx->stream)); return 0; }
 extern "C" float cg_last_ms(const cg_ctx *ctx, int which) { return (which >= 0 && which < CG_N_TIMERS) ? ctx->ms[which] : -1.f; }
 extern "C" int64_t cg_last_launches(const cg_ctx *ctx) { return ctx->launches; }
@@ -1111,13 +1165,10 @@ extern "C" int64_t cg_n_columns(const cg_ctx *ctx) { return ctx->D.n_cols; }
 #define T1(i) cudaEventRecord(ctx->ev[i][1], st)
 
 /* ---------------------------------------------------------------------------------------- */
-extern "C" int cg_upload(cg_ctx *ctx, const cg_batch *in) {
-    CG_CHECK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
+static int alloc_inputs(cg_ctx *ctx, const cg_batch *in) {
     const int64_t n = in->n_reads;
     if (n < 0 || in->qual_bytes < 0) return CG_ERR_BAD_ARG;
     if (n > 0x7fffff00LL || in->n_cigar_total > 0x7fffff00LL || in->qual_bytes >= (1LL << 35)) { snprintf(ctx->err, sizeof ctx->err, "batch too large: split it"); return CG_ERR_BAD_ARG; }
-    ctx->resident = 0;
     size_t n1 = (size_t)n + 1;
     int e;
     if ((e = ensure(ctx, &ctx->b_tid, n1 * 4)) || (e = ensure(ctx, &ctx->b_pos, n1 * 4)) || (e = ensure(ctx, &ctx->b_flag, n1 * 2)) ||
@@ -1125,21 +1176,6 @@ extern "C" int cg_upload(cg_ctx *ctx, const cg_batch *in) {
         (e = ensure(ctx, &ctx->b_off, n1 * 8)) || (e = ensure(ctx, &ctx->b_coff, n1 * 4)) ||
         (e = ensure(ctx, &ctx->b_cigar, ((size_t)in->n_cigar_total + 1) * 4)) || (e = ensure(ctx, &ctx->b_seq, (size_t)in->seq_bytes + 128 + CG_FRONT_PAD)) ||
         (e = ensure(ctx, &ctx->b_qual, (size_t)in->qual_bytes + 128 + CG_FRONT_PAD)) || (e = ensure(ctx, &ctx->b_qout, (size_t)in->qual_bytes + 16))) return e;
-    T0(CG_T_H2D);
-    if (n) {
-        CG_CHECK(cudaMemcpyAsync(ctx->b_tid.p, in->tid, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        CG_CHECK(cudaMemcpyAsync(ctx->b_pos.p, in->pos, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        CG_CHECK(cudaMemcpyAsync(ctx->b_flag.p, in->flag, (size_t)n * 2, cudaMemcpyHostToDevice, st));
-        CG_CHECK(cudaMemcpyAsync(ctx->b_mapq.p, in->mapq, (size_t)n, cudaMemcpyHostToDevice, st));
-        CG_CHECK(cudaMemcpyAsync(ctx->b_lq.p, in->l_qseq, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        CG_CHECK(cudaMemcpyAsync(ctx->b_nc.p, in->n_cigar, (size_t)n * 2, cudaMemcpyHostToDevice, st));
-        CG_CHECK(cudaMemcpyAsync(ctx->b_off.p, in->off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        CG_CHECK(cudaMemcpyAsync(ctx->b_coff.p, in->cigar_off, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        if (in->n_cigar_total) CG_CHECK(cudaMemcpyAsync(ctx->b_cigar.p, in->cigar, (size_t)in->n_cigar_total * 4, cudaMemcpyHostToDevice, st));
-        if (in->seq_bytes) CG_CHECK(cudaMemcpyAsync((char *)ctx->b_seq.p + CG_FRONT_PAD, in->seq, (size_t)in->seq_bytes, cudaMemcpyHostToDevice, st));
-        if (in->qual_bytes) CG_CHECK(cudaMemcpyAsync((char *)ctx->b_qual.p + CG_FRONT_PAD, in->qual, (size_t)in->qual_bytes, cudaMemcpyHostToDevice, st));
-    }
-    T1(CG_T_H2D);
     CgDev *D = &ctx->D;
     memset(D, 0, sizeof(*D));
     D->n_reads = n;
@@ -1148,6 +1184,44 @@ extern "C" int cg_upload(cg_ctx *ctx, const cg_batch *in) {
     D->off = (const int64_t *)ctx->b_off.p; D->cigar_off = (const int32_t *)ctx->b_coff.p; D->cigar = (const uint32_t *)ctx->b_cigar.p;
     D->seq = (const uint8_t *)ctx->b_seq.p + CG_FRONT_PAD; D->qual = (const uint8_t *)ctx->b_qual.p + CG_FRONT_PAD; D->qual_out = (uint8_t *)ctx->b_qout.p;
     ctx->qual_bytes = in->qual_bytes;
+    return 0;
+}
+
+/* the small per-record arrays and the CIGARs: everything the read/tile preparation needs */
+static int upload_meta(cg_ctx *ctx, const cg_batch *in, cudaStream_t st) {
+    const int64_t n = in->n_reads;
+    if (!n) return 0;
+    CG_CHECK(cudaMemcpyAsync(ctx->b_tid.p, in->tid, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CG_CHECK(cudaMemcpyAsync(ctx->b_pos.p, in->pos, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CG_CHECK(cudaMemcpyAsync(ctx->b_flag.p, in->flag, (size_t)n * 2, cudaMemcpyHostToDevice, st));
+    CG_CHECK(cudaMemcpyAsync(ctx->b_mapq.p, in->mapq, (size_t)n, cudaMemcpyHostToDevice, st));
+    CG_CHECK(cudaMemcpyAsync(ctx->b_lq.p, in->l_qseq, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CG_CHECK(cudaMemcpyAsync(ctx->b_nc.p, in->n_cigar, (size_t)n * 2, cudaMemcpyHostToDevice, st));
+    CG_CHECK(cudaMemcpyAsync(ctx->b_off.p, in->off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CG_CHECK(cudaMemcpyAsync(ctx->b_coff.p, in->cigar_off, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    if (in->n_cigar_total) CG_CHECK(cudaMemcpyAsync(ctx->b_cigar.p, in->cigar, (size_t)in->n_cigar_total * 4, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+/* bytes [b0, b1) of the quality buffer and the matching half of the packed sequences */
+static int upload_bases(cg_ctx *ctx, const cg_batch *in, int64_t b0, int64_t b1, cudaStream_t st) {
+    if (b1 <= b0) return 0;
+    CG_CHECK(cudaMemcpyAsync((char *)ctx->b_qual.p + CG_FRONT_PAD + b0, in->qual + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+    int64_t s0 = b0 >> 1, s1 = (b1 + 1) >> 1;
+    if (s1 > in->seq_bytes) s1 = in->seq_bytes;
+    if (s1 > s0) CG_CHECK(cudaMemcpyAsync((char *)ctx->b_seq.p + CG_FRONT_PAD + s0, in->seq + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+extern "C" int cg_upload(cg_ctx *ctx, const cg_batch *in) {
+    CG_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->resident = 0;
+    int e;
+    if ((e = alloc_inputs(ctx, in))) return e;
+    T0(CG_T_H2D);
+    if ((e = upload_meta(ctx, in, st)) || (e = upload_bases(ctx, in, 0, in->qual_bytes, st))) return e;
+    T1(CG_T_H2D);
     ctx->resident = 1;
     return 0;
 }
@@ -1170,9 +1244,43 @@ static int run_scan(cg_ctx *ctx, Load ld, Store st_, int64_t n, T ident, T *tota
 
 static inline int nblk(int64_t n, int t) { int64_t b = (n + t - 1) / t; return (int)(b < 1 ? 1 : b); }
 
-extern "C" int cg_run(cg_ctx *ctx) {
-    if (!ctx->resident) return CG_ERR_STATE;
-    CG_CHECK(cudaSetDevice(ctx->device));
+/* ---- slices ------------------------------------------------------------------------------
+ * The chain runs over SLICES of the batch in position order: columns of tiles [t0,t1), then the sparse passes of
+ * those columns with the cross-column state (keep-window chain, depth average) carried from slice to slice on the
+ * device, then the rewrite of every record whose last column lies below the slice end.  A resident batch is one
+ * slice; cg_process cuts the batch so that slice i starts as soon as upload chunk i has landed and its qualities
+ * travel back while later chunks are still arriving (H2D, kernels and D2H overlap, PCIe is full duplex). */
+#define CG_MAX_CHUNKS 32
+struct CgBounds { int64_t rb[CG_MAX_CHUNKS]; int32_t n; };
+/* upload chunk i ends before record rb[i]; out[2i] = tiles complete once it has landed, out[2i+1] = records final then */
+__global__ void k_bounds(const __grid_constant__ CgDev D, const __grid_constant__ CgBounds B, int64_t *out) {
+    const int i = threadIdx.x;
+    if (i >= B.n) return;
+    const int64_t r = B.rb[i];
+    const int j = r < D.n_reads ? D.jmap[r] : D.n_pile;            /* first pileup read at/after record r */
+    int64_t T = D.n_tiles, rec = D.n_reads;
+    if (j < D.n_pile) {
+        T = D.rd[j].col0 >> 5;                                      /* columns < 32T only see reads before j */
+        const int R = D.tile_lo[T];                                 /* reads before R end at or below column 32T */
+        rec = R < D.n_pile ? (int64_t)D.orig[R] : D.n_reads;
+        if (rec > r) rec = r;
+    }
+    out[2 * i] = T; out[2 * i + 1] = rec;
+}
+__global__ void k_window_max(const __grid_constant__ CgDev D, int32_t *out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int v = t < D.n_tiles ? D.tile_start[t + 1] - D.tile_lo[t] : 0;
+    v = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+}
+struct LdEvFlagOff { const uint16_t *ev; uint16_t mask; __device__ int32_t operator()(int64_t c) const { return (ev[c] & mask) != 0; } };
+struct StCompactOff { int32_t *out; const uint16_t *ev; uint16_t mask; int32_t c0; __device__ void operator()(int64_t c, int32_t, int32_t ex) const { if (ev[c] & mask) out[ex] = (int32_t)c + c0; } };
+struct StI64Carry { int64_t *p; const CgEpochCarry *cy; __device__ void operator()(int64_t i, int64_t inc, int64_t) const { p[i] = inc + cy->dsum_last; } };
+struct StI32Carry { int32_t *p; const CgEpochCarry *cy; __device__ void operator()(int64_t i, int32_t inc, int32_t) const { p[i] = inc + cy->csum_last; } };
+
+/* scalars on the device (b_scal): int32 [0] n_pile [1] n_cols [2] n_islands [3] n_flagged of the slice [4] maxdepth [5] err
+ * [6] n_events [7] - [8] beyond [9] window max; counters at +128 B; chain carry at +512 B; epoch carry at +640 B; bounds at +768 B */
+static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
     cudaStream_t st = ctx->stream;
     CgDev *D = &ctx->D;
     const int64_t n = D->n_reads;
@@ -1181,8 +1289,7 @@ extern "C" int cg_run(cg_ctx *ctx) {
     ctx->launches = 0;
     for (int i = 0; i < CG_N_TIMERS; i++) if (i != CG_T_H2D && i != CG_T_D2H) ctx->ms[i] = 0;
     D->T = ctx->dT; cg_devparams_from(&D->P, &ctx->params);
-    if ((e = ensure(ctx, &ctx->b_scal, 1024))) return e;
-    /* scalars: [0] n_pile [1] n_cols [2] n_islands [3] n_flagged [4] maxdepth [5] err [6] n_events [7] n_epochs ; counters at +128 bytes */
+    if ((e = ensure(ctx, &ctx->b_scal, 2048))) return e;
     int32_t *scal = (int32_t *)ctx->b_scal.p;
     D->counters = (unsigned long long *)((char *)ctx->b_scal.p + 128);
     D->maxdepth = scal + 4; D->err = scal + 5; D->beyond = scal + 8;
@@ -1196,9 +1303,13 @@ extern "C" int cg_run(cg_ctx *ctx) {
     D->isl = (CgIsland *)ctx->b_isl.p;
     int64_t *gapraw = (int64_t *)ctx->b_gapraw.p;
 
-    T0(CG_T_TOTAL);
     T0(CG_T_TILES);
-    CG_CHECK(cudaMemsetAsync(ctx->b_scal.p, 0, 1024, st));
+    CG_CHECK(cudaMemsetAsync(ctx->b_scal.p, 0, 2048, st));
+    {
+        CgChainCarry cc; memset(&cc, 0, sizeof cc); cc.bkey = INT64_MIN; cc.ukey = INT64_MIN; cg_win_reset(&cc.w);
+        memcpy(ctx->h_carry_init, &cc, sizeof cc);
+        CG_CHECK(cudaMemcpyAsync((char *)ctx->b_scal.p + 512, ctx->h_carry_init, sizeof cc, cudaMemcpyHostToDevice, st));
+    }
     if (n > 0) {
         k_prep_read<<<nblk(n, 256), 256, 0, st>>>(*D); ctx->launches++;
         LdPileFlag lpf = { D->rspan }; StJmap sj = { D->jmap };
@@ -1225,6 +1336,7 @@ extern "C" int cg_run(cg_ctx *ctx) {
     if (ctx->h_dims[5]) { snprintf(ctx->err, sizeof ctx->err, "device reported error %d while building read records", ctx->h_dims[5]); return ctx->h_dims[5]; }
     D->n_cols = np > 0 ? ctx->h_dims[1] : 0; D->n_islands = np > 0 ? ctx->h_dims[2] : 0;
     D->n_tiles = (D->n_cols + 31) / 32;
+    D->n_flagged = 0;
     const int nc = D->n_cols;
     const size_t nc1 = (size_t)nc + 64;
     D->want_dump = 0;
@@ -1237,76 +1349,114 @@ extern "C" int cg_run(cg_ctx *ctx) {
         if ((e = ensure(ctx, &ctx->b_dump, nc1 * sizeof(cg_column)))) return e;
         D->coldump = (cg_column *)ctx->b_dump.p; D->want_dump = 1;
     }
+    ctx->need_depth = 0;
+    for (int i = 0; i < 2 * CG_MAX_CHUNKS; i++) h_bounds[i] = 0;
     if (np > 0 && nc > 0) {
+        CG_CHECK(cudaMemsetAsync(D->cb, 0, nc1, st));              /* k_paint may mark columns of a later slice before k_column fills them */
         k_fill_i32<<<nblk(D->n_tiles + 2, 256), 256, 0, st>>>(D->tile_lo, D->n_tiles + 2, np);
         k_fill_i32<<<nblk(D->n_tiles + 2, 256), 256, 0, st>>>(D->tile_start, D->n_tiles + 2, np);
-        k_tile_index<<<nblk(np, 256), 256, 0, st>>>(*D); ctx->launches += 3;
+        k_tile_index<<<nblk(np, 256), 256, 0, st>>>(*D);
+        k_window_max<<<nblk(D->n_tiles, 256), 256, 0, st>>>(*D, scal + 9);
+        k_bounds<<<1, CG_MAX_CHUNKS, 0, st>>>(*D, *bounds, (int64_t *)((char *)ctx->b_scal.p + 768)); ctx->launches += 5;
+        CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 48, cudaMemcpyDeviceToHost, st));
+        CG_CHECK(cudaMemcpyAsync(h_bounds, (char *)ctx->b_scal.p + 768, sizeof(int64_t) * 2 * CG_MAX_CHUNKS, cudaMemcpyDeviceToHost, st));
+        CG_CHECK(cudaStreamSynchronize(st));
+        /* over-depth (snp_score.c:1673) needs n_plp > -P * mean depth >= -P: impossible when no tile has more than -P candidates */
+        ctx->need_depth = ctx->params.over_depth < 1.0 || (double)ctx->h_dims[9] > ctx->params.over_depth;
+        if (ctx->need_depth) {
+            if ((e = ensure(ctx, &ctx->b_dsum, nc1 * 8)) || (e = ensure(ctx, &ctx->b_csum, nc1 * 4))) return e;
+            D->dsum = (int64_t *)ctx->b_dsum.p; D->csum = (int32_t *)ctx->b_csum.p;
+            ctx->epoch_cap = D->n_islands + nc / 262144 + 16 + 2 * CG_MAX_CHUNKS;
+            if ((e = ensure(ctx, &ctx->b_epoch, (size_t)ctx->epoch_cap * sizeof(CgEpoch)))) return e;
+        }
     }
     T1(CG_T_TILES);
-    T0(CG_T_COLUMNS);
-    if (nc > 0) { k_column<<<nblk(D->n_tiles, COL_WARPS), COL_WARPS * 32, 0, st>>>(*D); ctx->launches++; }
-    T1(CG_T_COLUMNS);
-    T0(CG_T_FLAGGED);
-    if (nc > 0) {
-        LdEvFlag lf = { D->ev, CG_EV_FLAGGED }; StCompact sc = { D->fcol, D->ev, CG_EV_FLAGGED };
-        if ((e = run_scan<int32_t, OpSum>(ctx, lf, sc, nc, 0, scal + 3))) return e;
+    ctx->nf_total = 0;
+    return 0;
+}
+
+/* one slice: tiles [t0,t1) -> their columns -> sparse passes -> records [r0,r1) */
+static int run_slice(cg_ctx *ctx, int t0, int t1, int64_t r0, int64_t r1, int timed) {
+    cudaStream_t st = ctx->stream;
+    CgDev *D = &ctx->D;
+    int32_t *scal = (int32_t *)ctx->b_scal.p;
+    CgChainCarry *ccarry = (CgChainCarry *)((char *)ctx->b_scal.p + 512);
+    CgEpochCarry *ecarry = (CgEpochCarry *)((char *)ctx->b_scal.p + 640);
+    int e;
+    const int c0 = t0 * 32, c1 = t1 * 32 < D->n_cols ? t1 * 32 : D->n_cols;
+    const int ncs = c1 - c0;
+    int nfs = 0;
+    const int kb = ctx->nf_total;
+    if (timed) T0(CG_T_COLUMNS);
+    if (t1 > t0) { k_column<<<nblk(t1 - t0, COL_WARPS), COL_WARPS * 32, 0, st>>>(*D, t0, t1); ctx->launches++; }
+    if (timed) { T1(CG_T_COLUMNS); T0(CG_T_FLAGGED); }
+    if (ncs > 0) {
+        LdEvFlagOff lf = { D->ev + c0, CG_EV_FLAGGED }; StCompactOff sc = { D->fcol + kb, D->ev + c0, CG_EV_FLAGGED, c0 };
+        if ((e = run_scan<int32_t, OpSum>(ctx, lf, sc, ncs, 0, scal + 3))) return e;
+        CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 32, cudaMemcpyDeviceToHost, st));
+        CG_CHECK(cudaStreamSynchronize(st));
+        nfs = ctx->h_dims[3];
     }
-    CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 32, cudaMemcpyDeviceToHost, st));
-    CG_CHECK(cudaStreamSynchronize(st));
-    const int nf = D->n_flagged = ctx->h_dims[3];
-    const int maxdepth = ctx->h_dims[4];
-    if ((e = ensure(ctx, &ctx->b_trig, ((size_t)nf + 1) * sizeof(CgTrig))) || (e = ensure(ctx, &ctx->b_twin, ((size_t)nf + 1) * sizeof(CgWin)))) return e;
+    const int ke = kb + nfs;
+    if ((e = ensure_keep(ctx, &ctx->b_trig, ((size_t)ke + 1) * sizeof(CgTrig))) || (e = ensure_keep(ctx, &ctx->b_twin, ((size_t)ke + 1) * sizeof(CgWin))) ||
+        (e = ensure_keep(ctx, &ctx->b_chain, ((size_t)ke + 1) * 16))) return e;
     D->trig = (CgTrig *)ctx->b_trig.p; D->twin = (CgWin *)ctx->b_twin.p;
-    if (nf > 0) {
-        int threads = FL_WARPS * 32, blocks = nblk(nf, FL_WARPS);
+    D->n_flagged = ke;
+    if (nfs > 0) {
+        int threads = FL_WARPS * 32, blocks = nblk(nfs, FL_WARPS);
         if (blocks > 148 * 4) blocks = 148 * 4;
         if ((e = ensure(ctx, &ctx->b_scratch, (size_t)blocks * threads * sizeof(CgFlagScratch)))) return e;
-        k_flagged<<<blocks, threads, 0, st>>>(*D, (CgFlagScratch *)ctx->b_scratch.p); ctx->launches++;
+        k_flagged<<<blocks, threads, 0, st>>>(*D, (CgFlagScratch *)ctx->b_scratch.p, kb, ke); ctx->launches++;
     }
-    T1(CG_T_FLAGGED);
-    T0(CG_T_DEPTH);
-    /* over-depth can only fire when some column is deeper than -P (total_depth >= total_col), or -P < 1 */
-    if (nc > 0 && (ctx->params.over_depth < 1.0 || (double)maxdepth > ctx->params.over_depth)) {
-        if ((e = ensure(ctx, &ctx->b_dsum, nc1 * 8)) || (e = ensure(ctx, &ctx->b_csum, nc1 * 4))) return e;
-        D->dsum = (int64_t *)ctx->b_dsum.p; D->csum = (int32_t *)ctx->b_csum.p;
-        LdDepthCounted ld = { D->depth, D->ev }; StI64Incl sd = { D->dsum };
-        if ((e = run_scan<int64_t, OpSum>(ctx, ld, sd, nc, (int64_t)0, (int64_t *)NULL))) return e;
-        LdCounted lc = { D->ev }; StI32Incl sc2 = { D->csum };
-        if ((e = run_scan<int32_t, OpSum>(ctx, lc, sc2, nc, 0, (int32_t *)NULL))) return e;
-        int cap = D->n_islands + nc / 262144 + 16;
-        if ((e = ensure(ctx, &ctx->b_epoch, (size_t)cap * sizeof(CgEpoch)))) return e;
-        k_epochs<<<1, 32, 0, st>>>(*D, (CgEpoch *)ctx->b_epoch.p, scal + 7, cap);
-        k_deep<<<nblk(nc, 256), 256, 0, st>>>(*D, (const CgEpoch *)ctx->b_epoch.p, scal + 7); ctx->launches += 2;
+    if (timed) { T1(CG_T_FLAGGED); T0(CG_T_DEPTH); }
+    if (ctx->need_depth && ncs > 0) {
+        LdDepthCounted ld = { D->depth + c0, D->ev + c0 }; StI64Carry sd = { D->dsum + c0, ecarry };
+        if ((e = run_scan<int64_t, OpSum>(ctx, ld, sd, ncs, (int64_t)0, (int64_t *)NULL))) return e;
+        LdCounted lc = { D->ev + c0 }; StI32Carry sc2 = { D->csum + c0, ecarry };
+        if ((e = run_scan<int32_t, OpSum>(ctx, lc, sc2, ncs, 0, (int32_t *)NULL))) return e;
+        k_epochs<<<1, 32, 0, st>>>(*D, (CgEpoch *)ctx->b_epoch.p, ecarry, ctx->epoch_cap, c0, c1);
+        k_deep<<<nblk(ncs, 256), 256, 0, st>>>(*D, (const CgEpoch *)ctx->b_epoch.p, ecarry, c0, c1); ctx->launches += 2;
     }
-    T1(CG_T_DEPTH);
-    T0(CG_T_CHAIN);
-    if (nf > 0) {
-        if ((e = ensure(ctx, &ctx->b_chain, ((size_t)nf + 1) * 16))) return e;
-        int64_t *bmax = (int64_t *)ctx->b_chain.p, *umax = bmax + nf;
+    if (timed) { T1(CG_T_DEPTH); T0(CG_T_CHAIN); }
+    if (nfs > 0) {
+        /* b_chain holds bmax (first half) and umax (second half) per flagged entry, indexed by slice-local position */
+        int64_t *bmax = (int64_t *)ctx->b_chain.p, *umax = bmax + nfs;
         double mul = ctx->params.iSTR_mul > ctx->params.sSTR_mul ? ctx->params.iSTR_mul : ctx->params.sSTR_mul;
         double add = ctx->params.iSTR_add > ctx->params.sSTR_add ? ctx->params.iSTR_add : ctx->params.sSTR_add;
         if (mul < 0) mul = 0;
-        LdTrigB lb = { D->trig }; StI64Incl sb = { bmax };
-        if ((e = run_scan<int64_t, OpMax>(ctx, lb, sb, nf, (int64_t)INT64_MIN, (int64_t *)NULL))) return e;
-        LdTrigU lu = { D->trig, bmax, mul, add }; StI64Incl su = { umax };
-        if ((e = run_scan<int64_t, OpMax>(ctx, lu, su, nf, (int64_t)INT64_MIN, (int64_t *)NULL))) return e;
-        k_chain<<<nblk(nf, 128), 128, 0, st>>>(*D, umax);
-        k_paint<<<nblk(nf, 128), 128, 0, st>>>(*D); ctx->launches += 2;
+        LdTrigB lb = { D->trig + kb, ccarry }; StI64Incl sb = { bmax };
+        if ((e = run_scan<int64_t, OpMax>(ctx, lb, sb, nfs, (int64_t)INT64_MIN, (int64_t *)NULL))) return e;
+        LdTrigU lu = { D->trig + kb, bmax, ccarry, mul, add }; StI64Incl su = { umax };
+        if ((e = run_scan<int64_t, OpMax>(ctx, lu, su, nfs, (int64_t)INT64_MIN, (int64_t *)NULL))) return e;
+        k_chain<<<nblk(nfs, 128), 128, 0, st>>>(*D, umax - kb, ccarry, kb, ke);
+        k_paint<<<nblk(nfs, 128), 128, 0, st>>>(*D, kb, ke);
+        k_chain_carry<<<1, 32, 0, st>>>(*D, bmax - kb, umax - kb, ccarry, kb, ke); ctx->launches += 3;
     }
-    T1(CG_T_CHAIN);
-    T0(CG_T_REWRITE);
-    if (n > 0) { k_rewrite<<<nblk(n, RW_READS), RW_THREADS, 0, st>>>(*D); ctx->launches++; }
-    T1(CG_T_REWRITE);
-    T0(CG_T_EVENTS);
+    if (timed) { T1(CG_T_CHAIN); T0(CG_T_REWRITE); }
+    if (r1 > r0) { k_rewrite<<<nblk(r1 - r0, RW_READS), RW_THREADS, 0, st>>>(*D, r0, r1); ctx->launches++; }
+    if (timed) T1(CG_T_REWRITE);
+    ctx->nf_total = ke;
+    CG_CHECK(cudaGetLastError());
+    return 0;
+}
+
+/* ordered BED event list, counters, dump flags; leaves everything small on the host side of the context */
+static int run_finish(cg_ctx *ctx, int timed) {
+    cudaStream_t st = ctx->stream;
+    CgDev *D = &ctx->D;
+    int32_t *scal = (int32_t *)ctx->b_scal.p;
+    const int nc = D->n_cols;
+    int e;
+    if (timed) T0(CG_T_EVENTS);
     if (nc > 0) {
-        /* BED events: ordered compaction; capacity grows on demand (cg_download re-runs the scatter if needed) */
+        /* BED events: ordered compaction; capacity grows on demand */
         if (!ctx->b_events.p) { if ((e = ensure(ctx, &ctx->b_events, sizeof(cg_bed_event) * 65536))) return e; }
         ctx->events_cap_dev = (int64_t)(ctx->b_events.cap / sizeof(cg_bed_event));
         LdEvCount le = { D->ev }; StEvents se = { (cg_bed_event *)ctx->b_events.p, D->ev, *D, ctx->events_cap_dev };
         if ((e = run_scan<int32_t, OpSum>(ctx, le, se, nc, 0, scal + 6))) return e;
         if (D->want_dump) { k_dump_flags<<<nblk(nc, 256), 256, 0, st>>>(*D); ctx->launches++; }
     }
-    T1(CG_T_EVENTS);
+    if (timed) T1(CG_T_EVENTS);
     T1(CG_T_TOTAL);
     CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 40, cudaMemcpyDeviceToHost, st));
     CG_CHECK(cudaMemcpyAsync(ctx->h_counters, D->counters, sizeof(unsigned long long) * CG_N_COUNTERS, cudaMemcpyDeviceToHost, st));
@@ -1314,6 +1464,7 @@ extern "C" int cg_run(cg_ctx *ctx) {
     CG_CHECK(cudaGetLastError());
     for (int i = 0; i < CG_N_TIMERS; i++) {
         if (i == CG_T_H2D || i == CG_T_D2H) continue;
+        if (!timed && i != CG_T_TOTAL && i != CG_T_TILES) continue;
         float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev[i][0], ctx->ev[i][1]) == cudaSuccess) ctx->ms[i] = ms; else cudaGetLastError();
     }
     if (ctx->h_dims[5]) { snprintf(ctx->err, sizeof ctx->err, "device reported error %d", ctx->h_dims[5]); return ctx->h_dims[5]; }
@@ -1329,12 +1480,24 @@ extern "C" int cg_run(cg_ctx *ctx) {
     return 0;
 }
 
-extern "C" int cg_download(cg_ctx *ctx, cg_result *out) {
-    if (ctx->resident != 2) return CG_ERR_STATE;
+extern "C" int cg_run(cg_ctx *ctx) {
+    if (!ctx->resident) return CG_ERR_STATE;
     CG_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    T0(CG_T_D2H);
-    if (out->qual_out && ctx->qual_bytes) CG_CHECK(cudaMemcpyAsync(out->qual_out, ctx->b_qout.p, (size_t)ctx->qual_bytes, cudaMemcpyDeviceToHost, st));
+    CgBounds B; memset(&B, 0, sizeof B); B.n = 1; B.rb[0] = ctx->D.n_reads;
+    int64_t hb[2 * CG_MAX_CHUNKS];
+    int e;
+    T0(CG_T_TOTAL);
+    if ((e = run_prep(ctx, &B, hb))) return e;
+    if ((e = run_slice(ctx, 0, ctx->D.n_tiles, 0, ctx->D.n_reads, 1))) return e;
+    return run_finish(ctx, 1);
+}
+
+/* events, counters, column dump (small); the qualities only when q_too */
+static int download_results(cg_ctx *ctx, cg_result *out, int q_too) {
+    cudaStream_t st = ctx->stream;
+    if (q_too) T0(CG_T_D2H);
+    if (q_too && out->qual_out && ctx->qual_bytes) CG_CHECK(cudaMemcpyAsync(out->qual_out, ctx->b_qout.p, (size_t)ctx->qual_bytes, cudaMemcpyDeviceToHost, st));
     out->n_events = ctx->h_dims[6];
     if (out->events && out->n_events) {
         int64_t k = out->n_events < out->events_cap ? out->n_events : out->events_cap;
@@ -1347,7 +1510,7 @@ extern "C" int cg_download(cg_ctx *ctx, cg_result *out) {
         if (!tmp) return CG_ERR_NOMEM;
         CG_CHECK(cudaMemcpyAsync(tmp, ctx->b_dump.p, sizeof(cg_column) * (size_t)ctx->D.n_cols, cudaMemcpyDeviceToHost, st));
     }
-    T1(CG_T_D2H);
+    if (q_too) T1(CG_T_D2H);
     CG_CHECK(cudaStreamSynchronize(st));
     for (int i = 0; i < CG_N_COUNTERS; i++) out->counters[i] = (int64_t)ctx->h_counters[i];
     if (ctx->h_dims[8]) out->counters[CG_CNT_COLUMNS]++;   /* snp_score.c:1476 runs before the region break at 1516-1517 */
@@ -1359,17 +1522,102 @@ extern "C" int cg_download(cg_ctx *ctx, cg_result *out) {
         }
         free(tmp);
     }
+    return 0;
+}
+
+extern "C" int cg_download(cg_ctx *ctx, cg_result *out) {
+    if (ctx->resident != 2) return CG_ERR_STATE;
+    CG_CHECK(cudaSetDevice(ctx->device));
+    int e = download_results(ctx, out, 1);
+    if (e) return e;
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_D2H][0], ctx->ev[CG_T_D2H][1]) == cudaSuccess) ctx->ms[CG_T_D2H] = ms; else cudaGetLastError();
     if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_H2D][0], ctx->ev[CG_T_H2D][1]) == cudaSuccess) ctx->ms[CG_T_H2D] = ms; else cudaGetLastError();
     return 0;
 }
 
+/* End to end, streamed: the base data goes up in chunks on a copy stream; slice i of the chain starts when chunk i has
+ * landed; the qualities of the records it finalises go down on a second copy stream while later chunks still arrive. */
 extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
+    CG_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
     int e;
-    if ((e = cg_upload(ctx, in))) return e;
+    ctx->resident = 0;
     ctx->dump_columns = out->columns != NULL;
-    e = cg_run(ctx);
-    if (e) return e;
-    return cg_download(ctx, out);
+    if ((e = alloc_inputs(ctx, in))) return e;
+    if (!ctx->s_h2d) {
+        CG_CHECK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        CG_CHECK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < CG_MAX_CHUNKS; i++) {
+            CG_CHECK(cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming));
+            CG_CHECK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+        }
+        CG_CHECK(cudaEventCreateWithFlags(&ctx->ev_misc, cudaEventDisableTiming));
+    }
+    /* chunk the records by quality bytes (about 96 MB per chunk, at most CG_MAX_CHUNKS) */
+    const int64_t n = in->n_reads;
+    int nch = (int)(in->qual_bytes / (ctx->chunk_bytes > 0 ? ctx->chunk_bytes : (96LL << 20))) + 1;
+    if (nch > CG_MAX_CHUNKS) nch = CG_MAX_CHUNKS;
+    if (n < nch) nch = n > 0 ? (int)n : 1;
+    CgBounds B; memset(&B, 0, sizeof B); B.n = nch;
+    int64_t boff[CG_MAX_CHUNKS + 1]; boff[0] = 0;
+    for (int i = 0; i < nch; i++) {
+        int64_t r = n;
+        if (i + 1 < nch) {
+            const int64_t target = in->qual_bytes / nch * (i + 1);
+            int64_t lo = i ? B.rb[i - 1] : 0, hi = n;
+            while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (in->off[mid] < target) lo = mid + 1; else hi = mid; }
+            r = lo;
+        }
+        B.rb[i] = r;
+        boff[i + 1] = r < n ? in->off[r] : in->qual_bytes;
+    }
+    T0(CG_T_TOTAL);
+    cudaEventRecord(ctx->ev[CG_T_H2D][0], st);
+    if ((e = upload_meta(ctx, in, st))) return e;
+    /* the copy stream must not run ahead of buffer (re)allocation or of earlier users of the buffers: order it after st */
+    CG_CHECK(cudaEventRecord(ctx->ev_misc, st));
+    CG_CHECK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_misc, 0));
+    CG_CHECK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_misc, 0));
+    for (int i = 0; i < nch; i++) {
+        if ((e = upload_bases(ctx, in, boff[i], boff[i + 1], ctx->s_h2d))) return e;
+        CG_CHECK(cudaEventRecord(ctx->ev_up[i], ctx->s_h2d));
+    }
+    cudaEventRecord(ctx->ev[CG_T_H2D][1], ctx->s_h2d);
+    int64_t hb[2 * CG_MAX_CHUNKS];
+    const int trace = getenv("CG_TRACE") != NULL;
+    struct timespec ts0, ts1; clock_gettime(CLOCK_MONOTONIC, &ts0);
+#define CG_TRACE_AT(what, i) do { if (trace) { clock_gettime(CLOCK_MONOTONIC, &ts1); \
+        fprintf(stderr, "[cg_process] %8.3f ms  %s %d\n", (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6, what, i); } } while (0)
+    if ((e = run_prep(ctx, &B, hb))) return e;
+    CG_TRACE_AT("prep done, chunks", nch);
+    int tprev = 0; int64_t rprev = 0;
+    cudaEventRecord(ctx->ev[CG_T_D2H][0], ctx->s_d2h);
+    for (int i = 0; i < nch; i++) {
+        int t1 = (i + 1 == nch) ? ctx->D.n_tiles : (int)hb[2 * i];
+        int64_t r1 = (i + 1 == nch) ? n : hb[2 * i + 1];
+        if (t1 < tprev) t1 = tprev;
+        if (r1 < rprev) r1 = rprev;
+        CG_CHECK(cudaStreamWaitEvent(st, ctx->ev_up[i], 0));
+        if ((e = run_slice(ctx, tprev, t1, rprev, r1, 0))) return e;
+        if (r1 > rprev && out->qual_out) {
+            const int64_t b0 = in->off[rprev], b1 = r1 < n ? in->off[r1] : in->qual_bytes;
+            CG_CHECK(cudaEventRecord(ctx->ev_done[i], st));
+            CG_CHECK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[i], 0));
+            if (b1 > b0) CG_CHECK(cudaMemcpyAsync(out->qual_out + b0, (char *)ctx->b_qout.p + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        }
+        tprev = t1; rprev = r1;
+        CG_TRACE_AT("slice enqueued (host passed its column sync)", i);
+    }
+    cudaEventRecord(ctx->ev[CG_T_D2H][1], ctx->s_d2h);
+    if ((e = run_finish(ctx, 0))) return e;
+    CG_TRACE_AT("finish done", 0);
+    if ((e = download_results(ctx, out, 0))) return e;
+    CG_CHECK(cudaStreamSynchronize(ctx->s_d2h));
+    CG_TRACE_AT("d2h drained", 0);
+    CG_CHECK(cudaStreamSynchronize(ctx->s_h2d));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_D2H][0], ctx->ev[CG_T_D2H][1]) == cudaSuccess) ctx->ms[CG_T_D2H] = ms; else cudaGetLastError();
+    if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_H2D][0], ctx->ev[CG_T_H2D][1]) == cudaSuccess) ctx->ms[CG_T_H2D] = ms; else cudaGetLastError();
+    return 0;
 }

@@ -217,7 +217,7 @@ CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgC
     uint16_t ev = 0; uint8_t cb = CG_CB_UNPROC;
     D->depth[c] = (uint32_t)n_plp;
     if (n_plp == 0 || n_skip == n_plp) {                                  /* 1466-1472 (n_plp==0 cannot happen on a dense column) */
-        D->cb[c] = cb; D->ev[c] = 0;
+        D->cb[c] = (uint8_t)(cb | (D->cb[c] & CG_CB_ACTIVE)); D->ev[c] = 0;
         if (D->want_dump) { cg_column z = {0}; z.tid = -1; D->coldump[c] = z; }
         return o;
     }
@@ -228,7 +228,7 @@ CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgC
         tid = D->isl[is].tid; pos = D->isl[is].pos_start + (c - D->isl[is].col_start);
     }
     /* region end acts as a hard stop (the reference breaks out of the loop, 1516-1517) */
-    if (P->region_tid >= 0 && pos >= P->region_end) { *D->beyond = 1; D->cb[c] = cb; D->ev[c] = 0; if (D->want_dump) { cg_column z = {0}; z.tid = -1; D->coldump[c] = z; } return o; }
+    if (P->region_tid >= 0 && pos >= P->region_end) { *D->beyond = 1; D->cb[c] = (uint8_t)(cb | (D->cb[c] & CG_CB_ACTIVE)); D->ev[c] = 0; if (D->want_dump) { cg_column z = {0}; z.tid = -1; D->coldump[c] = z; } return o; }
     ev |= CG_EV_COUNTED;
     o.cnt |= 1u << CG_CNT_COLUMNS;                                        /* 1476 */
     CgCons cB; cB.call = 5; cB.het_call = 0; cB.het_phred = 0; cB.phred = 0; cB.depth = 0; cB.discrep = 0;
@@ -289,7 +289,7 @@ CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgC
         if (preserve) dflags |= 1;
         if (keep) dflags |= 2;
     }
-    D->cb[c] = cb; D->ev[c] = ev;
+    D->cb[c] = (uint8_t)(cb | (D->cb[c] & CG_CB_ACTIVE)); D->ev[c] = ev;
     if (D->want_dump) {
         cg_column z;
         const CgCons *cc = doB ? &cB : &cA;

@@ -150,6 +150,9 @@ int cg_upload(cg_ctx *ctx, const cg_batch *in);
 int cg_run(cg_ctx *ctx);
 int cg_download(cg_ctx *ctx, cg_result *out);
 int cg_sync(cg_ctx *ctx);
+/* cg_process streams the batch in upload chunks of about this many quality bytes (default 96 MiB, at most 32 chunks);
+ * slice i of the kernel chain starts when chunk i has landed.  Results do not depend on it. */
+int cg_set_chunk_bytes(cg_ctx *ctx, int64_t bytes);
 
 /* measurement helpers */
 enum { CG_T_TOTAL = 0, CG_T_TILES, CG_T_COLUMNS, CG_T_FLAGGED, CG_T_DEPTH, CG_T_CHAIN, CG_T_REWRITE, CG_T_PBLOCK, CG_T_EVENTS, CG_T_H2D, CG_T_D2H, CG_N_TIMERS };
