@@ -209,7 +209,7 @@ __global__ void k_tile_index(const __grid_constant__ CgDev D) {
  * sumsE of the reference is dead (never read after the loop) and is not computed. */
 #define COL_WARPS    4
 #ifndef COL_MINB
-#define COL_MINB     5          /* resident blocks per SM the register allocation is sized for */
+#define COL_MINB     6          /* resident blocks per SM the register allocation is sized for */
 #endif
 #define COL_ROWS     80         /* rows per chunk: 80 x 64 B = 20 x 32 doubles, the un-permute scratch */
 #define CELL_VALID   0x8000u
@@ -225,7 +225,8 @@ __global__ void k_tile_index(const __grid_constant__ CgDev D) {
 
 struct __align__(16) ColTabRow { double MM, hM, om, pad; };
 struct __align__(16) ColSmem {
-    union { uint16_t cell[COL_ROWS][32]; double dump[20][32]; } w[COL_WARPS];
+    union { uint16_t cell[COL_ROWS + 4][32]; double dump[20][32]; } w[COL_WARPS];   /* + padding rows for the look-ahead load */
+    double rare[COL_WARPS][9][32];
     ColTabRow tab[104];
     uint4 mask[9][9];            /* [a][b]: 0xffff in the 16-bit lanes k with a <= k < b */
 };
@@ -246,65 +247,26 @@ __device__ __noinline__ void col_gather_generic(const CgDev *D, int c, int lo, i
     }
 }
 
-/* cells d_first+[ka,kb) of a read with a non-trivial CIGAR (a few percent of reads): ONE walk of the CIGAR
- * (same state machine as cg_plp_resolve), out of line */
-__device__ __noinline__ uint4 col_stage_general(const CgDev *D, int j, int d_first, int ka, int kb, uint32_t rowf, int doB) {
+/* one cell of a read with a non-trivial CIGAR (a few percent of reads): the whole warp resolves one such read at a
+ * time, lane = column, each lane walking the CIGAR to its own column (cg_plp_resolve) */
+__device__ __noinline__ uint32_t col_cell_general(const CgDev *D, int j, int d, uint32_t rowf, int doB) {
     const CgRead q = D->rd[j];
-    const uint32_t *cig = D->cigar + q.cig_off;
-    const uint8_t *er = D->T->effB + ((int)q.mapq << 8);
-    const int64_t off = CG_OFF(&q);
-    const int n_cigar = q.n_cigar, span = q.span, lq = q.l_qseq;
-    uint32_t c[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) c[k] = 0;
-    int x = 0, y = 0, k = ka;
-    for (int i = 0; i < n_cigar && k < kb; i++) {
-        const int op = cg_cig_op(cig[i]), l = cg_cig_len(cig[i]);
-        if (cg_is_refop(op)) {
-            if (d_first + k < x + l) {
-                /* indel reported on the last column of this op (cg_plp_resolve) */
-                int indel_last = 0;
-                if (i + 1 < n_cigar) {
-                    const int op2 = cg_cig_op(cig[i + 1]), l2 = cg_cig_len(cig[i + 1]);
-                    if (op2 == 2) indel_last = -l2;
-                    else if (op2 == 1) indel_last = l2;
-                    else if (op2 == 6 && i + 2 < n_cigar) {
-                        int l3 = 0;
-                        for (int jj = i + 2; jj < n_cigar; jj++) {
-                            const int o3 = cg_cig_op(cig[jj]);
-                            if (o3 == 1) l3 += cg_cig_len(cig[jj]);
-                            else if (cg_is_refop(o3)) break;
-                        }
-                        if (l3 > 0) indel_last = l3;
-                    }
-                }
-                const bool mop = cg_is_mop(op);
-                for (; k < kb && d_first + k < x + l; k++) {
-                    const int d = d_first + k;
-                    const int indel = (d == x + l - 1) ? indel_last : 0;
-                    const int is_del = !mop, qpos = mop ? y + (d - x) : y;
-                    const bool head = d == 0, tail = d == span - 1;
-                    uint32_t f = rowf, base = 7, e = 1;
-                    if (indel | is_del) f |= CELL_INDEL;
-                    if (op == 3) base = 6;
-                    else {
-                        if ((head && qpos > 0) || (tail && qpos + 1 < lq)) f |= CELL_CLIP;
-                        if (!tail && !head) { f |= CELL_MID; if (indel > 0) f |= CELL_INS; }
-                        if (lq && doB) {
-                            e = er[D->qual[off + qpos]];
-                            base = is_del ? 4 : cg_nt16_to_base((D->seq[(off >> 1) + (qpos >> 1)] >> ((~qpos & 1) << 2)) & 0xf);
-                        }
-                    }
-                    const uint32_t cv = f | (e << CELL_E_SH) | (base << CELL_BASE_SH);
-#pragma unroll
-                    for (int kk = 0; kk < 8; kk++) if (kk == k) c[kk] = cv;
-                }
-            }
-            x += l;
-            if (cg_is_mop(op)) y += l;
-        } else if (op == 1 || op == 4) y += l;
+    if ((unsigned)d >= (unsigned)q.span) return 0;
+    CgCell cell;
+    if (!cg_plp_resolve(D->cigar + q.cig_off, q.n_cigar, d, q.span, &cell)) return 0;
+    uint32_t f = rowf, base = 7, e = 1;
+    if (cell.indel | cell.is_del) f |= CELL_INDEL;
+    if (cell.is_refskip) base = 6;
+    else {
+        if ((cell.is_head && cell.qpos > 0) || (cell.is_tail && cell.qpos + 1 < q.l_qseq)) f |= CELL_CLIP;
+        if (!cell.is_tail && !cell.is_head) { f |= CELL_MID; if (cell.indel > 0) f |= CELL_INS; }
+        if (q.l_qseq && doB) {
+            const int64_t off = CG_OFF(&q);
+            e = D->T->effB[((int)q.mapq << 8) | D->qual[off + cell.qpos]];
+            base = cell.is_del ? 4 : cg_nt16_to_base((D->seq[(off >> 1) + (cell.qpos >> 1)] >> ((~cell.qpos & 1) << 2)) & 0xf);
+        }
     }
-    return make_uint4(c[0] | c[1] << 16, c[2] | c[3] << 16, c[4] | c[5] << 16, c[6] | c[7] << 16);
+    return f | (e << CELL_E_SH) | (base << CELL_BASE_SH);
 }
 
 /* eight nt16 codes (one per nibble) -> eight base codes (A0 C1 G2 T3, anything else 5) */
@@ -321,12 +283,15 @@ __device__ __forceinline__ uint32_t col_bases8(uint32_t X) {
 __device__ __forceinline__ void col_stage(const CgDev &D, ColSmem *S, uint16_t (*cells)[32], int j0, int n, int tile_c0, int doB, int min_mqual) {
     const int lane = threadIdx.x & 31, x0 = (lane & 3) * 8;
     const uint8_t *effB = D.T->effB;
-    for (int r = lane >> 2; r < n; r += 8) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(D.rd + j0 + r));      /* off8, col0, span, pk */
+    for (int rb = 0; rb < n; rb += 8) {
+        const int r = rb + (lane >> 2);
+        uint4 a = make_uint4(0, 0, 0, 0);
+        if (r < n) a = __ldg(reinterpret_cast<const uint4 *>(D.rd + j0 + r));       /* off8, col0, span, pk */
         const int d_first = x0 + tile_c0 - (int)a.y;       /* column offset inside the read of this lane's first cell */
-        const int span = (int)a.z;
+        const int span = (int)a.z;                         /* 0 beyond the chunk: no cell */
         int ka = -d_first, kb = span - d_first;            /* cells k in [ka, kb) lie on the read */
         uint4 out = make_uint4(0, 0, 0, 0);
+        int general = 0;
         if (ka < 8 && kb > 0) {
             const uint32_t pk = a.w;
             const int mapq = (pk >> 16) & 0xff;
@@ -364,11 +329,22 @@ __device__ __forceinline__ void col_stage(const CgDev &D, ColSmem *S, uint16_t (
                 out.y = ((c[2] | c[3] << 16) & vm.y) | (mm.y & MIDW);
                 out.z = ((c[4] | c[5] << 16) & vm.z) | (mm.z & MIDW);
                 out.w = ((c[6] | c[7] << 16) & vm.w) | (mm.w & MIDW);
-            } else {
-                out = col_stage_general(&D, j0 + r, d_first, ka < 0 ? 0 : ka, kb > 8 ? 8 : kb, rowf, doB);
+            } else general = 1;
+        }
+        if (r < n) *reinterpret_cast<uint4 *>(&cells[r][x0]) = out;
+        /* rows with a non-trivial CIGAR: one at a time, lane = column */
+        unsigned gm = __ballot_sync(0xffffffffu, general);
+        gm = (gm | (gm >> 1) | (gm >> 2) | (gm >> 3)) & 0x11111111u;            /* one bit per lane group = row */
+        if (gm) {
+            __syncwarp();
+            while (gm) {
+                const int gl = __ffs(gm) - 1; gm &= gm - 1;
+                const int gr = (r - (lane >> 2)) + (gl >> 2);              /* row of that lane group in this pass */
+                const uint4 ga = __ldg(reinterpret_cast<const uint4 *>(D.rd + j0 + gr));
+                const uint32_t grow = CELL_VALID | ((int)((ga.w >> 16) & 0xff) <= min_mqual ? CELL_LOWMQ : 0u);
+                cells[gr][lane] = (uint16_t)col_cell_general(&D, j0 + gr, tile_c0 + lane - (int)ga.y, grow, doB);
             }
         }
-        *reinterpret_cast<uint4 *>(&cells[r][x0]) = out;
     }
 }
 
@@ -400,8 +376,12 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
     const int min_mqual = P->min_mqual;
     uint16_t (*cells)[32] = S.w[w].cell;
 
-    double H0 = 0, H1 = 0, H2 = 0, H3 = 0, H4 = 0, C0 = 0, C1 = 0, C2 = 0, C3 = 0, C4 = 0;
-    double P01 = 0, P02 = 0, P03 = 0, P04 = 0, P12 = 0, P13 = 0, P14 = 0, P23 = 0, P24 = 0, P34 = 0;
+    /* ranks 0 and 1 (and their pairs) in registers; H2 H3 H4 C2 C3 C4 P23 P24 P34 in shared memory */
+    double H0 = 0, H1 = 0, C0 = 0, C1 = 0;
+    double P01 = 0, P02 = 0, P03 = 0, P04 = 0, P12 = 0, P13 = 0, P14 = 0;
+    double *rare = &S.rare[w][0][lane];
+#pragma unroll
+    for (int i = 0; i < 9; i++) rare[i * 32] = 0;
     uint32_t pi = 0xfffffu, nseen = 0;               /* base -> rank, 4 bits per base, 15 = not seen yet */
     uint32_t b0s = 0xffffffffu, b1s = 0xffffffffu;   /* first and second base of the column, in cell position */
     int n_plp = 0, n_skip = 0, n_none = 0, nN = 0, low_mq = 0, n_overlap = 0, indel_cnt = 0, clipped = 0;
@@ -415,62 +395,60 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
         __syncwarp();
         const uint16_t *col = &cells[0][lane];
         /* flag counters: five 6-bit fields in one word (ins | clip | indel | mid | lowmq), flushed every 32 rows */
-#define COL_CELL(cell_) do { const uint32_t cell = (cell_); \
-            if (cell & CELL_VALID) { \
-                n_plp++; \
-                pk += ((cell & 0x1fu) * 0x00108421u) & 0x01041041u; \
-                const char *row = tab + (cell & CELL_E_M); \
-                if ((cell & CELL_BASE_M) == b0s) { \
-                    const double2 mh = *reinterpret_cast<const double2 *>(row); \
-                    const double om = *reinterpret_cast<const double *>(row + 16); \
-                    H0 += mh.x; P01 += mh.y; P02 += mh.y; P03 += mh.y; P04 += mh.y; C0 += om; \
-                } else if ((cell & CELL_BASE_M) == b1s) { \
-                    const double2 mh = *reinterpret_cast<const double2 *>(row); \
-                    const double om = *reinterpret_cast<const double *>(row + 16); \
-                    P01 += mh.y; H1 += mh.x; P12 += mh.y; P13 += mh.y; P14 += mh.y; C1 += om; \
-                } else { \
-                    const uint32_t base = (cell >> CELL_BASE_SH) & 7u; \
-                    if (base < 5u) { \
-                        const double2 mh = *reinterpret_cast<const double2 *>(row); \
-                        const double om = *reinterpret_cast<const double *>(row + 16); \
-                        uint32_t rank = (pi >> (base << 2)) & 0xfu; \
-                        if (rank == 15u) { \
-                            rank = nseen++; pi = (pi & ~(0xfu << (base << 2))) | (rank << (base << 2)); \
-                            if (rank == 0) b0s = cell & CELL_BASE_M; \
-                            if (rank == 1) b1s = cell & CELL_BASE_M; \
-                        } \
-                        if (rank == 0)      { H0 += mh.x; P01 += mh.y; P02 += mh.y; P03 += mh.y; P04 += mh.y; C0 += om; } \
-                        else if (rank == 1) { P01 += mh.y; H1 += mh.x; P12 += mh.y; P13 += mh.y; P14 += mh.y; C1 += om; } \
-                        else if (rank == 2) { P02 += mh.y; P12 += mh.y; H2 += mh.x; P23 += mh.y; P24 += mh.y; C2 += om; } \
-                        else if (rank == 3) { P03 += mh.y; P13 += mh.y; P23 += mh.y; H3 += mh.x; P34 += mh.y; C3 += om; } \
-                        else                { P04 += mh.y; P14 += mh.y; P24 += mh.y; P34 += mh.y; H4 += mh.x; C4 += om; } \
-                    } else if (base == 5u) nN++; \
-                    else if (base == 6u) n_skip++; \
-                    else n_none++; \
-                } \
-            } } while (0)
         for (int rb = 0; rb < n; rb += 32) {
             const int re = n - rb < 32 ? n - rb : 32;
             uint32_t pk = 0;
             const uint16_t *cp = col + rb * 32;
-            int r = 0;
-            for (; r + 4 <= re; r += 4) {
-                /* the four cell loads are independent: their latency overlaps the arithmetic of the previous rows */
-                const uint32_t c0 = cp[(r + 0) * 32], c1 = cp[(r + 1) * 32], c2 = cp[(r + 2) * 32], c3 = cp[(r + 3) * 32];
-                COL_CELL(c0); COL_CELL(c1); COL_CELL(c2); COL_CELL(c3);
+            uint32_t nxt = cp[0];
+#pragma unroll 1
+            for (int r = 0; r < re; r++) {
+                const uint32_t cell = nxt;
+                nxt = cp[(r + 1) * 32];                      /* next row's cell: its latency overlaps this row's arithmetic (row COL_ROWS exists as padding) */
+                if (cell & CELL_VALID) {
+                    n_plp++;
+                    pk += ((cell & 0x1fu) * 0x00108421u) & 0x01041041u;
+                    const char *row = tab + (cell & CELL_E_M);
+                    const double2 mh = *reinterpret_cast<const double2 *>(row);
+                    const double om = *reinterpret_cast<const double *>(row + 16);
+                    if ((cell & CELL_BASE_M) == b0s) {
+                        H0 += mh.x; P01 += mh.y; P02 += mh.y; P03 += mh.y; P04 += mh.y; C0 += om;
+                    } else if ((cell & CELL_BASE_M) == b1s) {
+                        P01 += mh.y; H1 += mh.x; P12 += mh.y; P13 += mh.y; P14 += mh.y; C1 += om;
+                    } else {
+                        const uint32_t base = (cell >> CELL_BASE_SH) & 7u;
+                        if (base < 5u) {
+                            uint32_t rank = (pi >> (base << 2)) & 0xfu;
+                            if (rank == 15u) {
+                                rank = nseen++; pi = (pi & ~(0xfu << (base << 2))) | (rank << (base << 2));
+                                if (rank == 0) b0s = cell & CELL_BASE_M;
+                                if (rank == 1) b1s = cell & CELL_BASE_M;
+                            }
+                            if (rank == 0)      { H0 += mh.x; P01 += mh.y; P02 += mh.y; P03 += mh.y; P04 += mh.y; C0 += om; }
+                            else if (rank == 1) { P01 += mh.y; H1 += mh.x; P12 += mh.y; P13 += mh.y; P14 += mh.y; C1 += om; }
+                            else {
+                                /* third and later bases of a column: their own sums live in shared memory */
+                                rare[(rank - 2) * 32] += mh.x; rare[(rank + 1) * 32] += om;
+                                rare[(rank == 4 ? 7 : 6) * 32] += mh.y; rare[(rank == 2 ? 7 : 8) * 32] += mh.y;
+                                if (rank == 2)      { P02 += mh.y; P12 += mh.y; }
+                                else if (rank == 3) { P03 += mh.y; P13 += mh.y; }
+                                else                { P04 += mh.y; P14 += mh.y; }
+                            }
+                        } else if (base == 5u) nN++;
+                        else if (base == 6u) n_skip++;
+                        else n_none++;
+                    }
+                }
             }
-            for (; r < re; r++) COL_CELL(cp[r * 32]);
             low_mq += pk & 0x3f; n_overlap += (pk >> 6) & 0x3f; indel_cnt += (pk >> 12) & 0x3f; clipped += (pk >> 18) & 0x3f; ins_seen |= pk >> 24;
         }
-#undef COL_CELL
     }
     __syncwarp();                                    /* the cell matrix is dead: reuse it to undo the rank permutation */
     if (live) {
         double *dump = &S.w[w].dump[0][lane];
-        dump[0 * 32] = H0; dump[1 * 32] = H1; dump[2 * 32] = H2; dump[3 * 32] = H3; dump[4 * 32] = H4;
-        dump[5 * 32] = C0; dump[6 * 32] = C1; dump[7 * 32] = C2; dump[8 * 32] = C3; dump[9 * 32] = C4;
+        dump[0 * 32] = H0; dump[1 * 32] = H1; dump[2 * 32] = rare[0 * 32]; dump[3 * 32] = rare[1 * 32]; dump[4 * 32] = rare[2 * 32];
+        dump[5 * 32] = C0; dump[6 * 32] = C1; dump[7 * 32] = rare[3 * 32]; dump[8 * 32] = rare[4 * 32]; dump[9 * 32] = rare[5 * 32];
         dump[10 * 32] = P01; dump[11 * 32] = P02; dump[12 * 32] = P03; dump[13 * 32] = P04; dump[14 * 32] = P12;
-        dump[15 * 32] = P13; dump[16 * 32] = P14; dump[17 * 32] = P23; dump[18 * 32] = P24; dump[19 * 32] = P34;
+        dump[15 * 32] = P13; dump[16 * 32] = P14; dump[17 * 32] = rare[6 * 32]; dump[18 * 32] = rare[7 * 32]; dump[19 * 32] = rare[8 * 32];
         int rk[5];
 #pragma unroll
         for (int b = 0; b < 5; b++) { uint32_t r = (pi >> (4 * b)) & 0xfu; if (r == 15u) r = nseen++; rk[b] = (int)r; }   /* unseen bases take the unused ranks: their sums are 0 / pure */
