@@ -211,6 +211,18 @@ __global__ void k_tile_index(const __grid_constant__ CgDev D) {
 #ifndef COL_MINB
 #define COL_MINB     6          /* resident blocks per SM the register allocation is sized for */
 #endif
+#ifndef COL_PIPE
+#define COL_PIPE     1
+#endif
+#ifndef COL_RECUP
+#define COL_RECUP    0
+#endif
+#ifndef COL_LOOK
+#define COL_LOOK     1
+#endif
+#ifndef COL_PEEK
+#define COL_PEEK     1
+#endif
 #define COL_ROWS     80         /* rows per chunk: 80 x 64 B = 20 x 32 doubles, the un-permute scratch */
 #define CELL_VALID   0x8000u
 #define CELL_BASE_SH 12         /* bits 14..12: base 0..4 = ACGT*, 5 = N, 6 = ref-skip, 7 = no contribution */
@@ -279,14 +291,63 @@ __device__ __forceinline__ uint32_t col_bases8(uint32_t X) {
     return ((p1 + p2 * 2u + p3 * 3u) & m) | (0x55555555u & ~m);
 }
 
-/* decode rows [j0, j0+n) of the warp's read window into its cell matrix: 4 lanes per row, 8 columns per lane */
+/* decode rows [j0, j0+n) of the warp's read window into its cell matrix: 4 lanes per row, 8 columns per lane.
+ * Global-memory latency is taken off the critical path twice: the 16-byte hot records of the whole chunk are
+ * loaded up front (one per lane, three rounds) and handed out by shuffles, and the quality / sequence words of
+ * pass i+1 are requested before pass i is decoded. */
+struct ColRaw { uint2 w0, w1; uint32_t v0, v1; };
+
+__device__ __forceinline__ uint4 col_rec_of(const uint4 (&rc)[3], int rb, int n, int lane) {
+    const int r = rb + (lane >> 2);
+    const int slot = rb >> 5;                                /* warp-uniform: rb is a multiple of 8 */
+    uint4 p = slot == 0 ? rc[0] : (slot == 1 ? rc[1] : rc[2]);
+    uint4 a;
+    a.x = __shfl_sync(0xffffffffu, p.x, r & 31); a.y = __shfl_sync(0xffffffffu, p.y, r & 31);
+    a.z = __shfl_sync(0xffffffffu, p.z, r & 31); a.w = __shfl_sync(0xffffffffu, p.w, r & 31);
+    if (r >= n) a.z = 0;                                     /* span 0: no cell */
+    return a;
+}
+__device__ __forceinline__ bool col_lane_simple(const uint4 &a, int d_first) {
+    return -d_first < 8 && (int)a.z - d_first > 0 && (a.w & ((uint32_t)CG_RF_SIMPLE << 24));
+}
+__device__ __forceinline__ ColRaw col_raw_load(const CgDev &D, const uint4 &a, int d_first) {
+    ColRaw R; R.w0 = make_uint2(0, 0); R.w1 = make_uint2(0, 0); R.v0 = R.v1 = 0;
+    if (col_lane_simple(a, d_first)) {
+        const int64_t A = ((int64_t)a.x << 3) + d_first;                    /* byte address of the first quality */
+        const uint2 *qa = reinterpret_cast<const uint2 *>(D.qual + (A & ~(int64_t)7));
+        R.w0 = __ldg(qa); R.w1 = __ldg(qa + 1);
+        const uint32_t *sa = reinterpret_cast<const uint32_t *>(D.seq + ((A >> 1) & ~(int64_t)3));
+        R.v0 = __ldg(sa); R.v1 = __ldg(sa + 1);
+    }
+    return R;
+}
+
 __device__ __forceinline__ void col_stage(const CgDev &D, ColSmem *S, uint16_t (*cells)[32], int j0, int n, int tile_c0, int doB, int min_mqual) {
     const int lane = threadIdx.x & 31, x0 = (lane & 3) * 8;
     const uint8_t *effB = D.T->effB;
+#if COL_RECUP
+    uint4 rc[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        rc[i] = make_uint4(0, 0, 0, 0);
+        if (i * 32 + lane < n) rc[i] = __ldg(reinterpret_cast<const uint4 *>(D.rd + j0 + i * 32 + lane));     /* off8, col0, span, pk */
+    }
+#define COL_REC(rb_) col_rec_of(rc, (rb_), n, lane)
+#else
+    const CgRead *rdp = D.rd + j0 + (lane >> 2);
+#define COL_REC(rb_) (((rb_) + (lane >> 2) < n) ? __ldg(reinterpret_cast<const uint4 *>(rdp + (rb_))) : make_uint4(0, 0, 0, 0))
+#endif
+    uint4 a = COL_REC(0);
+    ColRaw raw = col_raw_load(D, a, x0 + tile_c0 - (int)a.y);
     for (int rb = 0; rb < n; rb += 8) {
         const int r = rb + (lane >> 2);
-        uint4 a = make_uint4(0, 0, 0, 0);
-        if (r < n) a = __ldg(reinterpret_cast<const uint4 *>(D.rd + j0 + r));       /* off8, col0, span, pk */
+        /* request the next pass's words before decoding this one */
+        uint4 a_nx = make_uint4(0, 0, 0, 0); ColRaw raw_nx = raw;
+#if COL_PIPE
+        if (rb + 8 < n) { a_nx = COL_REC(rb + 8); raw_nx = col_raw_load(D, a_nx, x0 + tile_c0 - (int)a_nx.y); }
+#else
+        if (rb) { a = COL_REC(rb); raw = col_raw_load(D, a, x0 + tile_c0 - (int)a.y); }
+#endif
         const int d_first = x0 + tile_c0 - (int)a.y;       /* column offset inside the read of this lane's first cell */
         const int span = (int)a.z;                         /* 0 beyond the chunk: no cell */
         int ka = -d_first, kb = span - d_first;            /* cells k in [ka, kb) lie on the read */
@@ -298,12 +359,10 @@ __device__ __forceinline__ void col_stage(const CgDev &D, ColSmem *S, uint16_t (
             const uint32_t rowf = CELL_VALID | (mapq <= min_mqual ? CELL_LOWMQ : 0u);
             if (pk & ((uint32_t)CG_RF_SIMPLE << 24)) {
                 /* single-M read: query offset == column offset */
-                const int64_t A = ((int64_t)a.x << 3) + d_first;                    /* byte address of the first quality */
-                const uint2 *qa = reinterpret_cast<const uint2 *>(D.qual + (A & ~(int64_t)7));
-                const uint2 w0 = __ldg(qa), w1 = __ldg(qa + 1);
-                const int64_t Bb = (A >> 1) & ~(int64_t)3;                          /* aligned byte address of the sequence word */
-                const uint32_t *sa = reinterpret_cast<const uint32_t *>(D.seq + Bb);
-                uint32_t v0 = __ldg(sa), v1 = __ldg(sa + 1);
+                const int64_t A = ((int64_t)a.x << 3) + d_first;
+                const int64_t Bb = (A >> 1) & ~(int64_t)3;
+                const uint2 w0 = raw.w0, w1 = raw.w1;
+                uint32_t v0 = raw.v0, v1 = raw.v1;
                 const int s = (int)(A & 7);
                 const uint32_t Wa = (s & 4) ? w0.y : w0.x, Wb = (s & 4) ? w1.x : w0.y, Wc = (s & 4) ? w1.y : w1.x;
                 const uint32_t qlo = __funnelshift_r(Wa, Wb, (s & 3) * 8), qhi = __funnelshift_r(Wb, Wc, (s & 3) * 8);
@@ -339,12 +398,15 @@ __device__ __forceinline__ void col_stage(const CgDev &D, ColSmem *S, uint16_t (
             __syncwarp();
             while (gm) {
                 const int gl = __ffs(gm) - 1; gm &= gm - 1;
-                const int gr = (r - (lane >> 2)) + (gl >> 2);              /* row of that lane group in this pass */
+                const int gr = rb + (gl >> 2);                             /* row of that lane group in this pass */
                 const uint4 ga = __ldg(reinterpret_cast<const uint4 *>(D.rd + j0 + gr));
                 const uint32_t grow = CELL_VALID | ((int)((ga.w >> 16) & 0xff) <= min_mqual ? CELL_LOWMQ : 0u);
                 cells[gr][lane] = (uint16_t)col_cell_general(&D, j0 + gr, tile_c0 + lane - (int)ga.y, grow, doB);
             }
         }
+#if COL_PIPE
+        a = a_nx; raw = raw_nx;
+#endif
     }
 }
 
@@ -394,16 +456,35 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
         col_stage(D, &S, cells, j0, n, tile_c0, doB, min_mqual);
         __syncwarp();
         const uint16_t *col = &cells[0][lane];
+        if (COL_PEEK && nseen == 0) {
+            /* the column's first base is (nearly always) the base of its first covering read: look it up before the
+             * loop so that the first cell of every column does not take the rank-assignment path */
+            int r = 0; uint32_t cell = 0;
+            while (r < n && !((cell = col[r * 32]) & CELL_VALID)) r++;
+            if (r < n && ((cell >> CELL_BASE_SH) & 7u) < 5u) {
+                const uint32_t base = (cell >> CELL_BASE_SH) & 7u;
+                b0s = cell & CELL_BASE_M; nseen = 1; pi = (pi & ~(0xfu << (base << 2)));
+            }
+        }
         /* flag counters: five 6-bit fields in one word (ins | clip | indel | mid | lowmq), flushed every 32 rows */
         for (int rb = 0; rb < n; rb += 32) {
             const int re = n - rb < 32 ? n - rb : 32;
             uint32_t pk = 0;
             const uint16_t *cp = col + rb * 32;
+#if COL_LOOK == 2
+            uint32_t nxt = cp[0], nxt2 = cp[32];
+#else
             uint32_t nxt = cp[0];
+#endif
 #pragma unroll 1
             for (int r = 0; r < re; r++) {
                 const uint32_t cell = nxt;
-                nxt = cp[(r + 1) * 32];                      /* next row's cell: its latency overlaps this row's arithmetic (row COL_ROWS exists as padding) */
+#if COL_LOOK == 2
+                nxt = nxt2;
+                nxt2 = cp[(r + 2) * 32];                     /* two rows ahead: the load's latency overlaps two rows of arithmetic (padding rows exist) */
+#else
+                nxt = cp[(r + 1) * 32];                      /* next row's cell: its latency overlaps this row's arithmetic (padding rows exist) */
+#endif
                 if (cell & CELL_VALID) {
                     n_plp++;
                     pk += ((cell & 0x1fu) * 0x00108421u) & 0x01041041u;
