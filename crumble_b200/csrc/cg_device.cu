@@ -869,8 +869,12 @@ __device__ __forceinline__ void rw_mbar_expect(unsigned long long *bar, uint32_t
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void rw_mbar_wait(unsigned long long *bar, uint32_t phase) {
-    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n"
-                 :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(phase) : "memory");
+    /* bounded: a bulk copy that never completes must end in a reported fault, not in a hung device */
+    unsigned ok = 0;
+    for (int spin = 0; spin < (1 << 22) && !ok; spin++)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(phase) : "memory");
+    if (!ok) __trap();
 }
 
 __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ CgDev D, int64_t rec_begin, int64_t rec_end) {
