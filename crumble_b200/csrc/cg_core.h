@@ -396,7 +396,7 @@ CG_HD void cg_pblock_t(uint8_t *qual, int len, int level, int qcap, const CgTabl
 CG_HD void cg_pblock(uint8_t *qual, int len, int level, int qcap, const CgTables *T) { cg_pblock_t<1>(qual, len, level, qcap, T); }
 
 /* ---- STR finder (find_STR / add_rep, str_finder.c:34-189) on 2-bit codes ---------------- */
-typedef struct CgRepList { int n; int overflow; int start[CG_REP_CAP]; int end[CG_REP_CAP]; } CgRepList;
+typedef struct CgRepList { int n; int overflow; int16_t start[CG_REP_CAP]; int16_t end[CG_REP_CAP]; } CgRepList;   /* window positions: 0..500 */
 
 /* seq_nt16_str char -> L[] of str_finder.c:15-32: C->1, G->2, T->3, everything else 0 */
 CG_HD uint8_t cg_nt16_to_2bit(int nib) { return nib == 2 ? 1 : nib == 4 ? 2 : nib == 8 ? 3 : 0; }
@@ -417,7 +417,7 @@ CG_HD void cg_add_rep(CgRepList *L, const uint8_t *s, int clen, int pos, int rle
     for (int i = k + 1; i < L->n; i++)
         if (L->start[i] < el_start) { L->start[w] = L->start[i]; L->end[w] = L->end[i]; w++; }
     if (w >= CG_REP_CAP) { L->overflow = 1; L->n = w; return; }
-    L->start[w] = el_start; L->end[w] = el_end;
+    L->start[w] = (int16_t)el_start; L->end[w] = (int16_t)el_end;
     L->n = w + 1;
 }
 
@@ -484,6 +484,7 @@ typedef struct CgTrig {
     int32_t hasI, hasS;
     int32_t indel;            /* column variable `indel` (snp_score.c:1725-1730) */
     int32_t col;              /* dense column */
+    int32_t jI, jS;           /* device path: last indel-type / SNP-type triggering read (pileup index), -1 if none */
 } CgTrig;
 
 typedef struct CgWin { int32_t min_pos, max_pos, min_pos2, max_pos2; } CgWin;

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(Load ld, Store st, 
 /* ============================== functors ============================================== */
 struct LdPileFlag { const int32_t *rspan; __device__ int32_t operator()(int64_t i) const { return rspan[i] != 0; } };
 struct StJmap { int32_t *jmap; __device__ void operator()(int64_t i, int32_t, int32_t ex) const { jmap[i] = ex; } };
+struct LdI32 { const int32_t *p; __device__ int32_t operator()(int64_t i) const { return p[i]; } };
 struct LdI64 { const int64_t *p; __device__ int64_t operator()(int64_t i) const { return p[i]; } };
 struct StI64Incl { int64_t *p; __device__ void operator()(int64_t i, int64_t inc, int64_t) const { p[i] = inc; } };
 struct LdIslandFlag { const int64_t *gapraw; __device__ int32_t operator()(int64_t j) const { return j == 0 || gapraw[j] > 0; } };
@@ -564,18 +565,21 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
     if (lane == 0 && mx > 0) atomicMax(D.maxdepth, mx);
 }
 
-/* Flagged columns (had an indel / may open a keep window), one WARP per column, lanes over the column's reads:
- * the same decisions as cg_flagged (cg_pipeline.h; snp_score.c:1690-1762, 1775-1819) with the per-read work —
- * pileup cell, mask_LC_regions + find_STR of every triggering read — spread over the lanes.  What the reference
- * computes read by read is order-free except for two things, both recovered from the index of the LAST
- * triggering read of each type: the running STR extents as seen by that read (PI/QI, PS/QS = min/max over the
- * triggering reads up to it) and the column variable `indel`. */
+/* Flagged columns (had an indel / may open a keep window): the decisions of cg_flagged (cg_pipeline.h;
+ * snp_score.c:1690-1762, 1775-1819) in two kernels.
+ *  k_flagged    one WARP per column, lanes over the column's reads: indel count, insertion-size spectrum tests, and
+ *               which reads trigger.  What the reference computes read by read is order-free except for two things,
+ *               both recovered from the index of the LAST triggering read of each type (jI, jS): the running STR
+ *               extents as seen by that read (PI/QI, PS/QS = min/max over the triggering reads up to it) and the
+ *               column variable `indel`.  The column's number of (column, read) STR work items goes to items[k].
+ *  k_str_items  one THREAD per work item (after an exclusive scan of items[]): mask_LC_regions + find_STR of one
+ *               read at one column — the expensive, strictly sequential part — with every lane busy whatever the
+ *               number of triggering reads per column; extents are folded into the trigger record with atomics. */
 #define FL_WARPS 4
-__global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant__ CgDev D, CgFlagScratch *scratch, int k_begin, int k_end) {
+__global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant__ CgDev D, int32_t *items, int k_begin, int k_end) {
     __shared__ int hist[FL_WARPS][104];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int gw = blockIdx.x * FL_WARPS + w, nw = gridDim.x * FL_WARPS;
-    CgFlagScratch *S = scratch + (size_t)gw * 32 + lane;
     const CgDevParams *P = &D.P;
     const unsigned FULL = 0xffffffffu;
     for (int k = k_begin + gw; k < k_end; k += nw) {
@@ -589,8 +593,8 @@ __global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant
         const int tid = D.isl[is].tid, pos = D.isl[is].pos_start + (c - D.isl[is].col_start);
         for (int i = lane; i < 104; i += 32) hist[w][i] = 0;
         __syncwarp();
-        /* pass 1: indel count, insertion-size spectrum, last triggering read of each type */
-        int indel_cnt = 0, jI = -1, jS = -1, maxsz = 0, nIq = 0;
+        /* indel count, insertion-size spectrum, last triggering read of each type, `indel` */
+        int indel_cnt = 0, jI = -1, jS = -1, maxsz = 0, nIq = 0, nitem = 0;
         for (int j = lo + lane; j < hi; j += 32) {
             const CgRead q = D.rd[j]; CgCell cell;
             if (!cg_cell(&D, &q, c, &cell)) continue;
@@ -603,56 +607,33 @@ __global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant
             }
             if ((is_indel || strall) && lowscore) {                            /* 1718-1720 */
                 if (is_indel) { jI = j; nIq++; } else jS = j;
+                if (q.l_qseq > 0) nitem++;
             }
         }
-        indel_cnt = __reduce_add_sync(FULL, indel_cnt); nIq = __reduce_add_sync(FULL, nIq);
+        indel_cnt = __reduce_add_sync(FULL, indel_cnt); nIq = __reduce_add_sync(FULL, nIq); nitem = __reduce_add_sync(FULL, nitem);
         jI = __reduce_max_sync(FULL, jI); jS = __reduce_max_sync(FULL, jS); maxsz = __reduce_max_sync(FULL, maxsz);
         const int gate = indel_cnt >= n_plp * P->indel_fract;                  /* 1732 */
-        /* pass 2: STR extents of the triggering reads */
-        int mA = pos, MA = pos, mI = pos, MI = pos, mS = pos, MS = pos, vall = 0, vafter = 0;
+        int vall = 0, vafter = 0;
         if (jI >= 0 || jS >= 0) {
             for (int j = lo + lane; j < hi; j += 32) {
                 const CgRead q = D.rd[j]; CgCell cell;
+                if ((unsigned)(c - q.col0) < (unsigned)q.span) D.r_bf[j] = 1;  /* every read of a trigger column is back-filled (1870-1879) */
                 if (!cg_cell(&D, &q, c, &cell)) continue;
-                if (cell.is_refskip) continue;
-                const int is_indel = (cell.indel || cell.is_del);
-                if (!(is_indel || strall)) continue;
-                if (is_indel) {
-                    const int v = (cell.indel < 0 ? -cell.indel : cell.indel) + cell.is_del;
-                    if (v > vall) vall = v;
-                    if (j > jS && v > vafter) vafter = v;
-                }
-                if (gate && q.l_qseq > 0) {                                    /* 1732-1739: the two calls are identical in effect */
-                    const int phantom = (q.l_qseq & 1) ? (D.seq[(CG_OFF(&q) >> 1) + (q.l_qseq >> 1)] & 0xf)
-                                                       : (cg_cap_qual(D.qual[CG_OFF(&q)], P, D.T) >> 4);
-                    int lo_r = pos, hi_r = pos;
-                    cg_mask_lc(D.seq + (CG_OFF(&q) >> 1), q.l_qseq, phantom, D.cigar + q.cig_off, q.n_cigar, q.pos,
-                               cell.qpos + 1, is_indel ? P->iSTR_add : P->sSTR_add, S->win, &S->reps, &lo_r, &hi_r);
-                    if (S->reps.overflow) *D.err = CG_ERR_OVERFLOW;
-                    if (lo_r < mA) mA = lo_r;
-                    if (hi_r > MA) MA = hi_r;
-                    if (j <= jI) { if (lo_r < mI) mI = lo_r; if (hi_r > MI) MI = hi_r; }
-                    if (j <= jS) { if (lo_r < mS) mS = lo_r; if (hi_r > MS) MS = hi_r; }
-                }
+                if (cell.is_refskip || !(cell.indel || cell.is_del)) continue;
+                const int v = (cell.indel < 0 ? -cell.indel : cell.indel) + cell.is_del;
+                if (v > vall) vall = v;
+                if (j > jS && v > vafter) vafter = v;
             }
-            mA = __reduce_min_sync(FULL, mA); MA = __reduce_max_sync(FULL, MA);
-            mI = __reduce_min_sync(FULL, mI); MI = __reduce_max_sync(FULL, MI);
-            mS = __reduce_min_sync(FULL, mS); MS = __reduce_max_sync(FULL, MS);
             vall = __reduce_max_sync(FULL, vall); vafter = __reduce_max_sync(FULL, vafter);
-            /* every read of a trigger column is back-filled (1870-1879) */
-            for (int j = lo + lane; j < hi; j += 32) {
-                const CgRead q = D.rd[j];
-                if ((unsigned)(c - q.col0) < (unsigned)q.span) D.r_bf[j] = 1;
-            }
         }
         __syncwarp();
         if (lane == 0) {
             CgTrig tr; tr.tid = tid; tr.pos = pos; tr.col = c;
-            tr.hasI = jI >= 0; tr.hasS = jS >= 0;
-            tr.PI = tr.hasI ? mI : pos; tr.QI = tr.hasI ? MI : pos; tr.PS = tr.hasS ? mS : pos; tr.QS = tr.hasS ? MS : pos;
-            tr.A = mA; tr.B = MA;
+            tr.hasI = jI >= 0; tr.hasS = jS >= 0; tr.jI = jI; tr.jS = jS;
+            tr.PI = tr.QI = tr.PS = tr.QS = tr.A = tr.B = pos;                /* k_str_items widens them */
             tr.indel = tr.hasS ? (vafter > 1 ? vafter : 1) : vall;             /* 1725-1730: a SNP-type trigger resets it to 1 */
             D.trig[k] = tr;
+            items[k - k_begin] = ((tr.hasI || tr.hasS) && gate) ? nitem : 0;   /* 1732: no STR search below the indel fraction */
             uint32_t cnt = 0;
             if (nIq) cnt |= 1u << CG_CNT_INDEL_QUAL;                           /* 1762 */
             uint16_t ev_add = 0; int keep = 0;
@@ -674,6 +655,43 @@ __global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant
             while (cnt) { int b = __ffs(cnt) - 1; cnt &= cnt - 1; atomicAdd(&D.counters[b], 1ULL); }
         }
         __syncwarp();
+    }
+}
+
+/* item_off = inclusive scan of items[] over the slice's flagged entries; *n_items = total */
+__global__ void __launch_bounds__(64) k_str_items(const __grid_constant__ CgDev D, CgFlagScratch *scratch, const int32_t *item_off, const int32_t *n_items, int k_begin, int k_end) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    CgFlagScratch *S = scratch + gt;
+    const CgDevParams *P = &D.P;
+    const int total = *n_items, nk = k_end - k_begin;
+    for (int it = gt; it < total; it += nt) {
+        /* flagged entry of this item: first k with item_off[k] > it */
+        int lo_ = 0, hi_ = nk - 1;
+        while (lo_ < hi_) { int mid = (lo_ + hi_) >> 1; if (item_off[mid] > it) hi_ = mid; else lo_ = mid + 1; }
+        const int kl = lo_, k = k_begin + kl;
+        int m = it - (kl ? item_off[kl - 1] : 0);                              /* m-th triggering read of the column */
+        CgTrig *tr = &D.trig[k];
+        const int c = tr->col, pos = tr->pos, jI = tr->jI, jS = tr->jS;
+        const int strall = (D.ev[c] & CG_EV_STRALL) != 0;
+        const int t = c >> 5;
+        const int lo = D.tile_lo[t], hi = D.tile_start[t + 1];
+        for (int j = lo; j < hi; j++) {
+            const CgRead q = D.rd[j]; CgCell cell;
+            if (!cg_cell(&D, &q, c, &cell)) continue;
+            if (cell.is_refskip) continue;
+            const int is_indel = (cell.indel || cell.is_del);
+            if (!(is_indel || strall) || q.l_qseq <= 0) continue;
+            if (m-- > 0) continue;
+            const int phantom = (q.l_qseq & 1) ? (D.seq[(CG_OFF(&q) >> 1) + (q.l_qseq >> 1)] & 0xf)
+                                               : (cg_cap_qual(D.qual[CG_OFF(&q)], P, D.T) >> 4);
+            int lo_r = pos, hi_r = pos;                                        /* 1732-1739: the two calls are identical in effect */
+            cg_mask_lc(D.seq + (CG_OFF(&q) >> 1), q.l_qseq, phantom, D.cigar + q.cig_off, q.n_cigar, q.pos,
+                       cell.qpos + 1, is_indel ? P->iSTR_add : P->sSTR_add, S->win, &S->reps, &lo_r, &hi_r);
+            if (S->reps.overflow) *D.err = CG_ERR_OVERFLOW;
+            if (lo_r < pos) { atomicMin(&tr->A, lo_r); if (j <= jI) atomicMin(&tr->PI, lo_r); if (j <= jS) atomicMin(&tr->PS, lo_r); }
+            if (hi_r > pos) { atomicMax(&tr->B, hi_r); if (j <= jI) atomicMax(&tr->QI, hi_r); if (j <= jS) atomicMax(&tr->QS, hi_r); }
+            break;
+        }
     }
 }
 
@@ -1104,7 +1122,7 @@ struct cg_ctx {
     dbuf b_tid, b_pos, b_flag, b_mapq, b_lq, b_nc, b_off, b_coff, b_cigar, b_seq, b_qual, b_qout;
     dbuf b_jmap, b_rspan, b_rd, b_ks, b_ke, b_gap, b_gapraw, b_pmax, b_orig, b_rbf;
     dbuf b_tlo, b_tstart, b_isl, b_cb, b_ev, b_depth, b_dump, b_dsum, b_csum, b_fcol, b_trig, b_twin;
-    dbuf b_aggr, b_scal, b_scratch, b_epoch, b_events, b_chain;
+    dbuf b_aggr, b_scal, b_scratch, b_epoch, b_events, b_chain, b_items;
     /* host mirrors */
     int32_t *h_dims;              /* pinned: [0] n_pile [1] n_cols [2] n_islands [3] n_flagged [4] maxdepth [5] err [6] n_events [7] n_epochs */
     unsigned long long *h_counters;
@@ -1200,7 +1218,7 @@ extern "C" void cg_destroy(cg_ctx *ctx) {
     dbuf *all[] = { &ctx->b_tid, &ctx->b_pos, &ctx->b_flag, &ctx->b_mapq, &ctx->b_lq, &ctx->b_nc, &ctx->b_off, &ctx->b_coff, &ctx->b_cigar,
         &ctx->b_seq, &ctx->b_qual, &ctx->b_qout, &ctx->b_jmap, &ctx->b_rspan, &ctx->b_rd, &ctx->b_ks, &ctx->b_ke, &ctx->b_gap, &ctx->b_gapraw,
         &ctx->b_pmax, &ctx->b_orig, &ctx->b_rbf, &ctx->b_tlo, &ctx->b_tstart, &ctx->b_isl, &ctx->b_cb, &ctx->b_ev, &ctx->b_depth, &ctx->b_dump,
-        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain };
+        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain, &ctx->b_items };
     for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); i++) if (all[i]->p) cudaFree(all[i]->p);
     if (ctx->dT) cudaFree(ctx->dT);
     if (ctx->h_dims) cudaFreeHost(ctx->h_dims);
@@ -1467,9 +1485,15 @@ static int run_slice(cg_ctx *ctx, int t0, int t1, int64_t r0, int64_t r1, int ti
     D->n_flagged = ke;
     if (nfs > 0) {
         int threads = FL_WARPS * 32, blocks = nblk(nfs, FL_WARPS);
-        if (blocks > 148 * 4) blocks = 148 * 4;
-        if ((e = ensure(ctx, &ctx->b_scratch, (size_t)blocks * threads * sizeof(CgFlagScratch)))) return e;
-        k_flagged<<<blocks, threads, 0, st>>>(*D, (CgFlagScratch *)ctx->b_scratch.p, kb, ke); ctx->launches++;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        const int sblocks = 148 * 8, sthreads = 64;
+        if ((e = ensure(ctx, &ctx->b_scratch, (size_t)sblocks * sthreads * sizeof(CgFlagScratch))) ||
+            (e = ensure(ctx, &ctx->b_items, ((size_t)nfs + 1) * 8))) return e;
+        int32_t *items = (int32_t *)ctx->b_items.p, *item_off = items + nfs;
+        k_flagged<<<blocks, threads, 0, st>>>(*D, items, kb, ke); ctx->launches++;
+        LdI32 li = { items }; StI32Incl si = { item_off };
+        if ((e = run_scan<int32_t, OpSum>(ctx, li, si, nfs, 0, scal + 10))) return e;
+        k_str_items<<<sblocks, sthreads, 0, st>>>(*D, (CgFlagScratch *)ctx->b_scratch.p, item_off, scal + 10, kb, ke); ctx->launches++;
     }
     if (timed) { T1(CG_T_FLAGGED); T0(CG_T_DEPTH); }
     if (ctx->need_depth && ncs > 0) {
