@@ -822,24 +822,35 @@ __global__ void k_paint(const __grid_constant__ CgDev D, int k_begin, int k_end)
 /* Per-read quality rewrite.  A block owns RW_READS consecutive records; their quality strings, packed sequences
  * and the column bytes under them are three CONTIGUOUS ranges, fetched with three bulk async copies (TMA,
  * cp.async.bulk + mbarrier) into shared memory.  Then
- *   phase A (warp per read): replay of the rewrite loop in place in shared memory.  Single-M reads without
- *            back-fill run SIMD-within-register, 8 bases per lane: kept / match / binning are byte-parallel
- *            mask arithmetic on the 64-bit quality word, the 64-bit column word and the 8 expanded nt16 codes.
- *            Other reads (indels, clips, back-fill) are replayed op by op;
- *   phase B (thread per read): P-block, a sequential greedy scan, in place; runs of one value are not refilled;
+ *   phase A1 (thread per read):  whole-read facts from the staged column bytes (any keep_qual column, head column
+ *            processed) and the word map: which read each staged 8-byte quality word belongs to;
+ *   phase A2 (thread per WORD, all lanes busy whatever the read length): single-M reads without back-fill are
+ *            rewritten SIMD-within-register, 8 bases per word: kept / match / binning are byte-parallel mask
+ *            arithmetic on the 64-bit quality word, the 64-bit column word and the 8 expanded nt16 codes;
+ *   phase A3 (warp per read): reads with indels, clips or back-fill are replayed op by op;
+ *   phase B  (thread per read): P-block, a sequential greedy scan, in place, one 8-byte word per step where the word
+ *            holds a single value (nearly all words after the rewrite), byte by byte elsewhere;
  *   phase C: one bulk async store of the block's output range (8-byte edges by the owning threads).
  * Blocks whose ranges do not fit the staging buffers (long reads) run the one-thread-per-read body (cg_rewrite). */
 #define RW_THREADS 128
 #define RW_READS   128
 #define RW_QCAP    (RW_READS * 168)     /* staged quality bytes (152 per padded 150-base read) */
 #define RW_CCAP    3072                 /* staged column bytes */
+#define RW_L_M     0x000fffffu          /* RwMeta.lk: L | kind << 20 | keep << 22 | init80 << 23 | tail_unreached << 24 */
+#define RW_KIND_SH 20
+#define RW_KEEP    (1u << 22)
+#define RW_INIT    (1u << 23)
+#define RW_TAILU   (1u << 24)
 
-struct RwMeta { int32_t qoff, L, coff, kind; int32_t j; uint8_t init_or, tail_unreached, pad0, pad1; };   /* offsets inside the staging buffers */
+struct __align__(16) RwMeta { int32_t qoff, coff; uint32_t lk; int32_t j; };   /* offsets inside the staging buffers */
 struct __align__(128) RwSmem {
     uint8_t q[RW_QCAP + 32];
     uint8_t s[RW_QCAP / 2 + 32];
     uint8_t c[RW_CCAP + 32];
+    uint8_t wmap[RW_QCAP / 8 + 8];      /* read slot of every staged quality word, 0xff = none */
     RwMeta  m[RW_READS];
+    uint8_t glist[RW_READS];            /* slots taking the general path */
+    int     n_general;
     unsigned long long bar;
     long long red[4][4];
     long long rng[6];                   /* qa, qbytes, sa, sbytes, ca, cbytes (cbytes < 0: fallback) */
@@ -875,6 +886,47 @@ __device__ __noinline__ uint64_t rw_visit8_scalar(uint64_t q8, uint64_t cb8, uin
     return out;
 }
 
+/* P-block (pblock, snp_score.c:803-834) on an 8-byte aligned string in shared memory.  A word whose eight bytes are
+ * equal behaves like its first byte (the other seven cannot move min/max again), so it costs one step; the byte
+ * loop of cg_pblock_t handles the remaining words from the register copy.  Runs are filled with word stores. */
+__device__ __forceinline__ void rw_fill(uint8_t *q, int j, int i, int mid) {
+    int k = j;
+    while (k < i && (k & 7)) q[k++] = (uint8_t)mid;
+    const uint64_t mw = (uint64_t)(uint32_t)mid * 0x0101010101010101ULL;
+    for (; k + 8 <= i; k += 8) *reinterpret_cast<uint64_t *>(q + k) = mw;
+    while (k < i) q[k++] = (uint8_t)mid;
+}
+__device__ __forceinline__ void rw_run_end(uint8_t *q, int j, int i, int lmin, int lmax, int qcap) {
+    int mid = (lmin + lmax) / 2;
+    if (mid > qcap) mid = qcap;
+    if (lmin != lmax || mid != lmin) rw_fill(q, j, i, mid);
+}
+__device__ __forceinline__ void rw_pblock_words(uint8_t *q, int len, int level, int qcap) {
+    int qmin = INT_MAX, qmax = INT_MIN, lmin = 0, lmax = 0, j = 0;
+    level *= 2;
+    const int nw = (len + 7) >> 3;
+    for (int k = 0; k < nw; k++) {
+        const uint64_t w = *reinterpret_cast<const uint64_t *>(q + 8 * k);
+        const int nb = len - 8 * k;
+        const int v = (int)((uint32_t)w & 0xffu);
+        if (nb >= 8 && w == (uint64_t)(uint32_t)v * 0x0101010101010101ULL) {
+            int nmin = qmin < v ? qmin : v, nmax = qmax > v ? qmax : v;
+            if (nmax - nmin > level) { rw_run_end(q, j, 8 * k, lmin, lmax, qcap); nmin = nmax = v; j = 8 * k; }
+            qmin = lmin = nmin; qmax = lmax = nmax;
+        } else {
+            const int ne = nb < 8 ? nb : 8;
+            for (int b = 0; b < ne; b++) {
+                const int qv = (int)((w >> (8 * b)) & 0xff), i = 8 * k + b;
+                if (qmin > qv) qmin = qv;
+                if (qmax < qv) qmax = qv;
+                if (qmax - qmin > level) { rw_run_end(q, j, i, lmin, lmax, qcap); qmin = qmax = qv; j = i; }
+                lmin = qmin; lmax = qmax;
+            }
+        }
+    }
+    if (lmin != lmax) rw_fill(q, j, len, (lmin + lmax) / 2);      /* the last run is not capped (832-833) */
+}
+
 __device__ __forceinline__ void rw_mbar_init(unsigned long long *bar) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -904,8 +956,8 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
     const int nf = D.n_flagged;
 
     /* ---- phase 0: per-read facts, block ranges, bulk loads ---- */
-    if (threadIdx.x == 0) rw_mbar_init(&S.bar);
-    int64_t off = 0; int L = 0, kind = 0, col0 = 0, span = 0, j = -1; uint8_t init_mq = 0, tail_unreached = 0;
+    if (threadIdx.x == 0) { rw_mbar_init(&S.bar); S.n_general = 0; }
+    int64_t off = 0; int L = 0, kind = 0, col0 = 0, span = 0, j = -1; uint32_t init_mq = 0, tail_unreached = 0;
     {
         const int64_t r = base + threadIdx.x;
         if (r < rec_end) { L = D.l_qseq[r]; off = D.off[r]; }
@@ -917,7 +969,7 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
                 col0 = q.col0; span = q.span;
                 tail_unreached = (P->region_tid >= 0 && q.pos + q.span - 1 >= P->region_end);
                 init_mq = q.mapq <= P->min_mqual;
-                kind = ((q.rf & CG_RF_SIMPLE) && q.span == L && L <= 256 && !D.r_bf[j]) ? 2 : 3;
+                kind = ((q.rf & CG_RF_SIMPLE) && q.span == L && !D.r_bf[j]) ? 2 : 3;
             }
         }
         long long v0 = L > 0 ? off : LLONG_MAX, v1 = L > 0 ? off + L : LLONG_MIN;
@@ -961,123 +1013,134 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
         if (r < rec_end) cg_rewrite(&D, r, nf);
         return;
     }
-    {
-        RwMeta m; m.qoff = (int32_t)(off - qa); m.L = L; m.coff = (int32_t)(col0 - ca); m.kind = kind; m.j = j;
-        m.init_or = init_mq; m.tail_unreached = tail_unreached; m.pad0 = m.pad1 = 0;
-        S.m[threadIdx.x] = m;
-    }
+    const int nwords = (int)(qbytes >> 3);
+    for (int i = threadIdx.x; i < (nwords + 3) >> 2; i += RW_THREADS) reinterpret_cast<uint32_t *>(S.wmap)[i] = 0xffffffffu;
     __syncthreads();
     rw_mbar_wait(&S.bar, 0);
 
-    /* ---- phase A ---- */
+    /* ---- phase A1: whole-read facts, word map ---- */
+    {
+        const int qoff = (int)(off - qa), coff = (int)(col0 - ca);
+        uint32_t lk = (uint32_t)L | ((uint32_t)kind << RW_KIND_SH) | (tail_unreached ? RW_TAILU : 0u);
+        if (kind >= 2) {
+            /* OR of the column bytes under the read: aligned words, ragged ends masked */
+            const int a0 = coff & ~7, e = coff + span;
+            uint32_t acc = 0;
+            for (int a = a0; a < e; a += 8) {
+                uint2 v = *reinterpret_cast<const uint2 *>(S.c + a);
+                if (a < coff) { const int sh = (coff - a) * 8; if (sh >= 32) { v.x = 0; v.y &= 0xffffffffu << (sh - 32); } else v.x &= 0xffffffffu << sh; }
+                if (a + 8 > e) { const int nb = (e - a) * 8; if (nb <= 32) { v.y = 0; v.x &= nb == 32 ? 0xffffffffu : ((1u << nb) - 1u); } else v.y &= (1u << (nb - 32)) - 1u; }
+                acc |= v.x | v.y;
+            }
+            if ((acc & 0x80808080u) && !tail_unreached) lk |= RW_KEEP;          /* keep_qual on any covered column (1847, 1939-1940) */
+            if (init_mq && !(S.c[coff] & CG_CB_UNPROC)) lk |= RW_INIT;          /* head column processed and mapq <= -m (1852-1859) */
+        }
+        RwMeta m; m.qoff = qoff; m.coff = coff; m.lk = lk; m.j = j;
+        S.m[threadIdx.x] = m;
+        if (kind == 1 || kind == 2) {
+            const int w0 = qoff >> 3, nwr = (L + 7) >> 3;
+            for (int i = 0; i < nwr; i++) S.wmap[w0 + i] = (uint8_t)threadIdx.x;
+        } else if (kind == 3) S.glist[atomicAdd(&S.n_general, 1)] = (uint8_t)threadIdx.x;
+    }
+    __syncthreads();
+
+    /* ---- phase A2: one staged quality word per thread and step ---- */
     RwK K;
     K.QH = (uint32_t)(P->qhigh & 0xff) * 0x01010101u; K.QL = (uint32_t)(P->qlow & 0xff) * 0x01010101u;
     K.mode = !P->reduce_qual ? 0 : (P->binary_qual ? 2 : 1);
     { int cq = P->qcutoff < 0 ? 0 : (P->qcutoff > 128 ? 128 : P->qcutoff); K.cut = (uint32_t)((128 - cq) & 0xff) * 0x01010101u; }
     K.capadd = P->qcap >= 127 ? 0u : (uint32_t)(127 - (P->qcap < 0 ? 0 : P->qcap)) * 0x01010101u;
     const bool swar_ok = !P->any_preserve_qual;
-    for (int i = 0; i < RW_READS / (RW_THREADS / 32); i++) {
-        const int slot = w * (RW_READS / (RW_THREADS / 32)) + i;
+    const int sdelta = (int)((qa >> 1) - sa);                  /* staged sequence byte of staged quality byte b: sdelta + b/2 */
+    for (int wi = threadIdx.x; wi < nwords; wi += RW_THREADS) {
+        const uint32_t slot = S.wmap[wi];
+        if (slot == 0xffu) continue;
         const RwMeta m = S.m[slot];
-        if (m.kind == 0) continue;
+        const int x0 = wi * 8 - m.qoff, nv = (int)(m.lk & RW_L_M) - x0;         /* nv >= 1 */
+        const uint64_t vm = nv >= 8 ? ~0ULL : ((1ULL << (8 * nv)) - 1);
+        const uint64_t q8 = *reinterpret_cast<const uint64_t *>(S.q + wi * 8);
+        uint64_t res;
+        if (((m.lk >> RW_KIND_SH) & 3u) == 1u) res = q8 & 0x7f7f7f7f7f7f7f7fULL;  /* never in the pileup: strip bit 7 only (P-block follows) */
+        else {
+            const uint32_t s4 = *reinterpret_cast<const uint32_t *>(S.s + sdelta + wi * 4);
+            /* column bytes [coff + x0, +8): two aligned words, funnel-shifted */
+            const int cpos = m.coff + x0;
+            const uint2 *cw = reinterpret_cast<const uint2 *>(S.c + (cpos & ~7));
+            const uint2 w0 = cw[0], w1 = cw[1];
+            const int sh = cpos & 7;
+            const uint32_t Wa = (sh & 4) ? w0.y : w0.x, Wb = (sh & 4) ? w1.x : w0.y, Wc = (sh & 4) ? w1.y : w1.x;
+            const uint32_t clo = __funnelshift_r(Wa, Wb, (sh & 3) * 8), chi = __funnelshift_r(Wb, Wc, (sh & 3) * 8);
+            const int keep = (m.lk & RW_KEEP) != 0;
+            const uint32_t qlo = (uint32_t)q8, qhi = (uint32_t)(q8 >> 32);
+            const uint32_t bad = (((((qlo & 0x7f7f7f7fu) + K.capadd) | qlo) & (uint32_t)vm) | ((((qhi & 0x7f7f7f7fu) + K.capadd) | qhi) & (uint32_t)(vm >> 32))) & 0x80808080u;
+            if (swar_ok && !bad) {
+                if (keep) res = q8;                             /* memcpy of the (uncapped: <= -U) originals, snp_score.c:1939-1940 */
+                else {
+                    const uint32_t init80 = (m.lk & RW_INIT) ? 0x80808080u : 0u;
+                    const uint32_t t0 = __byte_perm(s4, 0, 0x1100), t1 = __byte_perm(s4, 0, 0x3322);
+                    const uint32_t n0 = ((t0 >> 4) & 0x000f000fu) | (t0 & 0x0f000f00u), n1 = ((t1 >> 4) & 0x000f000fu) | (t1 & 0x0f000f00u);
+                    res = (uint64_t)rw_swar4(qlo, clo, n0, init80, K) | ((uint64_t)rw_swar4(qhi, chi, n1, init80, K) << 32);
+                }
+            } else {
+                res = rw_visit8_scalar(q8, (uint64_t)clo | ((uint64_t)chi << 32), s4, (m.lk & RW_INIT) ? 0x80 : 0, keep, P, T);
+            }
+        }
+        *reinterpret_cast<uint64_t *>(S.q + wi * 8) = (res & vm) | (q8 & ~vm);
+    }
+
+    /* ---- phase A3: general path, warp per read: replay inside the slot; originals from global memory ---- */
+    for (int gi = w; gi < S.n_general; gi += RW_THREADS / 32) {
+        const RwMeta m = S.m[S.glist[gi]];
         uint8_t *sl = S.q + m.qoff;
-        const int Lr = m.L;
-        if (m.kind == 1) {
-            /* never in the pileup: strip bit 7 only (P-block follows) */
-            for (int x0 = lane * 8; x0 < Lr; x0 += 256) {
-                uint64_t q8 = *(const uint64_t *)(sl + x0);
-                const int nv = Lr - x0;
-                const uint64_t vm = nv >= 8 ? ~0ULL : ((1ULL << (8 * nv)) - 1);
-                *(uint64_t *)(sl + x0) = (q8 & 0x7f7f7f7f7f7f7f7fULL & vm) | (q8 & ~vm);
-            }
-            continue;
-        }
+        const int Lr = (int)(m.lk & RW_L_M);
         const uint8_t *cbp = S.c + m.coff;
-        const uint8_t init_or = (m.init_or && !(cbp[0] & CG_CB_UNPROC)) ? 0x80 : 0;      /* head column processed and mapq <= -m */
-        if (m.kind == 2) {
-            /* L <= 256: lane owns bases [8*lane, 8*lane+8) */
-            const uint8_t *sp = S.s + (((qa + m.qoff) >> 1) - sa);
-            const int x0 = lane * 8, nv = Lr - x0;                  /* nv <= 0: idle lane */
-            const uint64_t vm = nv >= 8 ? ~0ULL : (nv > 0 ? ((1ULL << (8 * nv)) - 1) : 0ULL);
-            uint64_t q8 = 0; uint32_t s4 = 0, clo = 0, chi = 0;
-            if (nv > 0) {
-                q8 = *(const uint64_t *)(sl + x0);
-                s4 = *(const uint32_t *)(sp + (x0 >> 1));
-                /* column bytes [coff + x0, +8): two aligned words, funnel-shifted */
-                const uintptr_t ca_ = (uintptr_t)(cbp + x0);
-                const uint2 *cw = (const uint2 *)(ca_ & ~(uintptr_t)7);
-                const uint2 w0 = cw[0], w1 = cw[1];
-                const int sh = (int)(ca_ & 7);
-                const uint32_t Wa = (sh & 4) ? w0.y : w0.x, Wb = (sh & 4) ? w1.x : w0.y, Wc = (sh & 4) ? w1.y : w1.x;
-                clo = __funnelshift_r(Wa, Wb, (sh & 3) * 8) & (uint32_t)vm; chi = __funnelshift_r(Wb, Wc, (sh & 3) * 8) & (uint32_t)(vm >> 32);
-            }
-            /* whole-read keep: any covered column with keep_qual */
-            const int keep = __any_sync(0xffffffffu, (clo | chi) & 0x80808080u) && !m.tail_unreached;
-            if (nv > 0) {
-                const uint32_t init80 = init_or ? 0x80808080u : 0u;
-                const uint32_t qlo = (uint32_t)q8, qhi = (uint32_t)(q8 >> 32);
-                uint64_t res;
-                const uint32_t bad = ((((qlo & 0x7f7f7f7fu) + K.capadd) | qlo) | (((qhi & 0x7f7f7f7fu) + K.capadd) | qhi)) & 0x80808080u;
-                if (swar_ok && !bad) {
-                    if (keep) res = q8;                             /* memcpy of the (uncapped: <= -U) originals, snp_score.c:1939-1940 */
-                    else {
-                        const uint32_t t0 = __byte_perm(s4, 0, 0x1100), t1 = __byte_perm(s4, 0, 0x3322);
-                        const uint32_t n0 = ((t0 >> 4) & 0x000f000fu) | (t0 & 0x0f000f00u), n1 = ((t1 >> 4) & 0x000f000fu) | (t1 & 0x0f000f00u);
-                        res = (uint64_t)rw_swar4(qlo, clo, n0, init80, K) | ((uint64_t)rw_swar4(qhi, chi, n1, init80, K) << 32);
-                    }
-                } else {
-                    res = rw_visit8_scalar(q8, (uint64_t)clo | ((uint64_t)chi << 32), s4, init_or, keep, P, T);
+        const uint8_t init_or = (m.lk & RW_INIT) ? 0x80 : 0;
+        const int keep = (m.lk & RW_KEEP) != 0;
+        const CgRead q = D.rd[m.j];
+        const uint8_t *qin = D.qual + (qa + m.qoff);
+        const uint32_t *cig = D.cigar + q.cig_off;
+        for (int x = lane; x < Lr; x += 32) sl[x] = qin[x] | init_or;
+        __syncwarp();
+        int c = 0, y = 0;
+        for (int k = 0; k < q.n_cigar; k++) {
+            const int op = cg_cig_op(cig[k]), l = cg_cig_len(cig[k]);
+            if (cg_is_mop(op)) {
+                for (int ii = lane; ii < l; ii += 32) {
+                    int x = y + ii;
+                    if (x < Lr) sl[x] = cg_visit(sl[x], cbp[c + ii], cg_cap_qual(qin[x], P, T), cg_seq_nib(&D, &q, x), P, T);
                 }
-                *(uint64_t *)(sl + x0) = (res & vm) | (q8 & ~vm);
-            }
-        } else {
-            /* general path: replay inside the slot; originals and column bytes from global memory */
-            const CgRead q = D.rd[m.j];
-            const uint8_t *qin = D.qual + (qa + m.qoff);
-            const uint32_t *cig = D.cigar + q.cig_off;
-            for (int x = lane; x < Lr; x += 32) sl[x] = qin[x] | init_or;
-            int keepbits = 0;
-            for (int c = q.col0 + lane; c < q.col0 + q.span; c += 32) keepbits |= D.cb[c];
-            int keep = __any_sync(0xffffffffu, keepbits & CG_CB_KEEP) && !m.tail_unreached;
+                c += l; y += l;
+            } else if (op == 2 || op == 3) {
+                if (lane == 0 && y < Lr) {
+                    uint8_t oc = cg_cap_qual(qin[y], P, T); int nib = cg_seq_nib(&D, &q, y); uint8_t v = sl[y];
+                    for (int ii = 0; ii < l; ii++) v = cg_visit(v, cbp[c + ii], oc, nib, P, T);
+                    sl[y] = v;
+                }
+                c += l;
+            } else if (op == 1 || op == 4) y += l;
             __syncwarp();
-            int c = q.col0, y = 0;
-            for (int k = 0; k < q.n_cigar; k++) {
-                const int op = cg_cig_op(cig[k]), l = cg_cig_len(cig[k]);
-                if (cg_is_mop(op)) {
-                    for (int ii = lane; ii < l; ii += 32) {
-                        int x = y + ii;
-                        if (x < Lr) sl[x] = cg_visit(sl[x], D.cb[c + ii], cg_cap_qual(qin[x], P, T), cg_seq_nib(&D, &q, x), P, T);
-                    }
-                    c += l; y += l;
-                } else if (op == 2 || op == 3) {
-                    if (lane == 0 && y < Lr) {
-                        uint8_t oc = cg_cap_qual(qin[y], P, T); int nib = cg_seq_nib(&D, &q, y); uint8_t v = sl[y];
-                        for (int ii = 0; ii < l; ii++) v = cg_visit(v, D.cb[c + ii], oc, nib, P, T);
-                        sl[y] = v;
-                    }
-                    c += l;
-                } else if (op == 1 || op == 4) y += l;
-                __syncwarp();
-            }
-            if (D.r_bf[m.j]) {
-                for (int k = cg_trig_lower_bound(&D, nf, q.col0); k < nf && D.fcol[k] < q.col0 + q.span; k++) {
-                    const CgTrig *t = &D.trig[k];
-                    if (!(t->hasI || t->hasS)) continue;
-                    CgCell cell;
-                    if (!cg_cell(&D, &q, t->col, &cell)) continue;
-                    int xs = cg_ref2query_pos(cig, q.n_cigar, q.pos, D.twin[k].min_pos2);
-                    for (int x = xs + lane; x <= cell.qpos && x < Lr; x += 32) sl[x] = (uint8_t)(cg_cap_qual(qin[x], P, T) | 0x80);
-                }
-                __syncwarp();
-            }
-            for (int x = lane; x < Lr; x += 32) sl[x] = (keep ? cg_cap_qual(qin[x], P, T) : sl[x]) & 0x7f;
         }
+        if (D.r_bf[m.j]) {
+            for (int k = cg_trig_lower_bound(&D, nf, q.col0); k < nf && D.fcol[k] < q.col0 + q.span; k++) {
+                const CgTrig *t = &D.trig[k];
+                if (!(t->hasI || t->hasS)) continue;
+                CgCell cell;
+                if (!cg_cell(&D, &q, t->col, &cell)) continue;
+                int xs = cg_ref2query_pos(cig, q.n_cigar, q.pos, D.twin[k].min_pos2);
+                for (int x = xs + lane; x <= cell.qpos && x < Lr; x += 32) sl[x] = (uint8_t)(cg_cap_qual(qin[x], P, T) | 0x80);
+            }
+            __syncwarp();
+        }
+        for (int x = lane; x < Lr; x += 32) sl[x] = (keep ? cg_cap_qual(qin[x], P, T) : sl[x]) & 0x7f;
     }
     __syncthreads();
     /* ---- phase B: P-block, thread per read ---- */
     if (P->pblock) {
         const RwMeta m = S.m[threadIdx.x];
-        if (m.kind) { if (P->any_preserve_qual) cg_pblock_t<1>(S.q + m.qoff, m.L, P->pblock, P->qcap, T); else cg_pblock_t<0>(S.q + m.qoff, m.L, P->pblock, P->qcap, T); }
+        if ((m.lk >> RW_KIND_SH) & 3u) {
+            if (P->any_preserve_qual) cg_pblock_t<1>(S.q + m.qoff, (int)(m.lk & RW_L_M), P->pblock, P->qcap, T);
+            else rw_pblock_words(S.q + m.qoff, (int)(m.lk & RW_L_M), P->pblock, P->qcap);
+        }
     }
     /* ---- phase C: the block's output range ---- */
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
