@@ -224,6 +224,9 @@ __global__ void k_tile_index(const __grid_constant__ CgDev D) {
 #ifndef COL_PEEK
 #define COL_PEEK     1
 #endif
+#ifndef COL_TPW
+#define COL_TPW      16         /* tiles per warp: amortises the block's table set-up and the counter flush */
+#endif
 #define COL_ROWS     80         /* rows per chunk: 80 x 64 B = 20 x 32 doubles, the un-permute scratch */
 #define CELL_VALID   0x8000u
 #define CELL_BASE_SH 12         /* bits 14..12: base 0..4 = ACGT*, 5 = N, 6 = ref-skip, 7 = no contribution */
@@ -413,6 +416,7 @@ __device__ __forceinline__ void col_stage(const CgDev &D, ColSmem *S, uint16_t (
 
 __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __grid_constant__ CgDev D, int t_begin, int t_end) {
     __shared__ ColSmem S;
+    __shared__ unsigned cntw[COL_WARPS][32];
     const CgTables *T = D.T;
     const CgDevParams *P = &D.P;
     for (int i = threadIdx.x; i < 104; i += blockDim.x) {
@@ -426,30 +430,34 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
         for (int i = 0; i < 4; i++) m[i] = ((2 * i >= a && 2 * i < b) ? 0xffffu : 0u) | ((2 * i + 1 >= a && 2 * i + 1 < b) ? 0xffff0000u : 0u);
         S.mask[a][b] = make_uint4(m[0], m[1], m[2], m[3]);
     }
+    cntw[threadIdx.x >> 5][threadIdx.x & 31] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int t = t_begin + blockIdx.x * COL_WARPS + w;   /* this warp's 32-column tile */
-    const int tile_c0 = t * 32;
-    const int c = tile_c0 + lane;
-    CgColOut o; o.cnt = 0; o.n_plp = 0;
-    int lo = 0, hi = 0;
-    if (t < t_end) { lo = D.tile_lo[t]; hi = D.tile_start[t + 1]; }
-    const bool live = t < t_end && c < D.n_cols;
     const int doB = P->min_qual_B != 0;
     const int min_mqual = P->min_mqual;
     uint16_t (*cells)[32] = S.w[w].cell;
+    const char *tab = reinterpret_cast<const char *>(S.tab);
+    double *rare = &S.rare[w][0][lane];
+    int depth_max = 0;
+    /* the block's tables are built once for COL_TPW tiles per warp; warps walk their tiles on their own */
+    for (int ti = 0; ti < COL_TPW; ti++) {
+    const int t = t_begin + (blockIdx.x * COL_TPW + ti) * COL_WARPS + w;
+    if (t >= t_end) break;
+    const int tile_c0 = t * 32;
+    const int c = tile_c0 + lane;
+    CgColOut o; o.cnt = 0; o.n_plp = 0;
+    const int lo = D.tile_lo[t], hi = D.tile_start[t + 1];
+    const bool live = c < D.n_cols;
 
     /* ranks 0 and 1 (and their pairs) in registers; H2 H3 H4 C2 C3 C4 P23 P24 P34 in shared memory */
     double H0 = 0, H1 = 0, C0 = 0, C1 = 0;
     double P01 = 0, P02 = 0, P03 = 0, P04 = 0, P12 = 0, P13 = 0, P14 = 0;
-    double *rare = &S.rare[w][0][lane];
 #pragma unroll
     for (int i = 0; i < 9; i++) rare[i * 32] = 0;
     uint32_t pi = 0xfffffu, nseen = 0;               /* base -> rank, 4 bits per base, 15 = not seen yet */
     uint32_t b0s = 0xffffffffu, b1s = 0xffffffffu;   /* first and second base of the column, in cell position */
     int n_plp = 0, n_skip = 0, n_none = 0, nN = 0, low_mq = 0, n_overlap = 0, indel_cnt = 0, clipped = 0;
     uint32_t ins_seen = 0;
-    const char *tab = reinterpret_cast<const char *>(S.tab);
 
     for (int j0 = lo; j0 < hi; j0 += COL_ROWS) {
         const int n = hi - j0 < COL_ROWS ? hi - j0 : COL_ROWS;
@@ -554,15 +562,20 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
         if (nN) col_gather_generic(&D, c, lo, hi, &A);      /* N bases add to 14 slots: exact slow path */
         o = cg_column_finish(&D, c, lo, hi, &st, &A);
     }
-    /* counters: one atomic per warp and counter */
+    /* counters: per warp in shared memory, flushed once when the warp runs out of tiles */
     unsigned un = __reduce_or_sync(0xffffffffu, o.cnt);
     while (un) {
         int b = __ffs(un) - 1; un &= un - 1;
         unsigned m = __ballot_sync(0xffffffffu, (o.cnt >> b) & 1);
-        if (lane == 0) atomicAdd(&D.counters[b], (unsigned long long)__popc(m));
+        if (lane == 0) cntw[w][b] += __popc(m);
     }
     int mx = __reduce_max_sync(0xffffffffu, o.n_plp);
-    if (lane == 0 && mx > 0) atomicMax(D.maxdepth, mx);
+    depth_max = mx > depth_max ? mx : depth_max;
+    __syncwarp();                                    /* the dump scratch is the next tile's cell matrix */
+    }
+    __syncwarp();
+    if (lane < CG_N_COUNTERS && cntw[w][lane]) atomicAdd(&D.counters[lane], (unsigned long long)cntw[w][lane]);
+    if (lane == 0 && depth_max > 0) atomicMax(D.maxdepth, depth_max);
 }
 
 /* Flagged columns (had an indel / may open a keep window): the decisions of cg_flagged (cg_pipeline.h;
@@ -886,45 +899,47 @@ __device__ __noinline__ uint64_t rw_visit8_scalar(uint64_t q8, uint64_t cb8, uin
     return out;
 }
 
-/* P-block (pblock, snp_score.c:803-834) on an 8-byte aligned string in shared memory.  A word whose eight bytes are
- * equal behaves like its first byte (the other seven cannot move min/max again), so it costs one step; the byte
- * loop of cg_pblock_t handles the remaining words from the register copy.  Runs are filled with word stores. */
+/* P-block (pblock, snp_score.c:803-834) on an 8-byte aligned string in shared memory, in run-length form: equal
+ * neighbouring bytes cannot move the running min/max, so only the positions where the value CHANGES are visited
+ * (chg = one bit per byte, built word-parallel by the whole block beforehand).  After the rewrite most of a read is
+ * one value, so a thread steps through a handful of positions instead of 150 bytes, and the divergent part of the
+ * warp's work shrinks with it.  Runs are filled with masked word stores, and only when the fill changes a byte. */
 __device__ __forceinline__ void rw_fill(uint8_t *q, int j, int i, int mid) {
-    int k = j;
-    while (k < i && (k & 7)) q[k++] = (uint8_t)mid;
     const uint64_t mw = (uint64_t)(uint32_t)mid * 0x0101010101010101ULL;
-    for (; k + 8 <= i; k += 8) *reinterpret_cast<uint64_t *>(q + k) = mw;
-    while (k < i) q[k++] = (uint8_t)mid;
+    for (int k0 = j & ~7; k0 < i; k0 += 8) {                       /* masked read-modify-write, whole words */
+        uint64_t mask = ~0ULL;
+        if (k0 < j) mask &= ~0ULL << (8 * (j - k0));
+        if (k0 + 8 > i) mask &= ~0ULL >> (8 * (k0 + 8 - i));
+        uint64_t *p = reinterpret_cast<uint64_t *>(q + k0);
+        *p = (*p & ~mask) | (mw & mask);
+    }
 }
-__device__ __forceinline__ void rw_run_end(uint8_t *q, int j, int i, int lmin, int lmax, int qcap) {
-    int mid = (lmin + lmax) / 2;
-    if (mid > qcap) mid = qcap;
-    if (lmin != lmax || mid != lmin) rw_fill(q, j, i, mid);
-}
-__device__ __forceinline__ void rw_pblock_words(uint8_t *q, int len, int level, int qcap) {
-    int qmin = INT_MAX, qmax = INT_MIN, lmin = 0, lmax = 0, j = 0;
+__device__ __forceinline__ void rw_pblock_rle(uint8_t *q, const uint8_t *chg, int len, int level, int qcap) {
     level *= 2;
+    int qmin = q[0], qmax = qmin, j = 0;
     const int nw = (len + 7) >> 3;
-    for (int k = 0; k < nw; k++) {
-        const uint64_t w = *reinterpret_cast<const uint64_t *>(q + 8 * k);
-        const int nb = len - 8 * k;
-        const int v = (int)((uint32_t)w & 0xffu);
-        if (nb >= 8 && w == (uint64_t)(uint32_t)v * 0x0101010101010101ULL) {
+    for (int g = 0; g < nw; g += 4) {
+        uint32_t m = chg[g];
+        if (g + 1 < nw) m |= (uint32_t)chg[g + 1] << 8;
+        if (g + 2 < nw) m |= (uint32_t)chg[g + 2] << 16;
+        if (g + 3 < nw) m |= (uint32_t)chg[g + 3] << 24;
+        if (g == 0) m &= ~1u;
+        const int rem = len - 8 * g;
+        if (rem < 32) m &= (1u << rem) - 1u;
+        while (m) {
+            const int i = 8 * g + __ffs(m) - 1; m &= m - 1;
+            const int v = q[i];
             int nmin = qmin < v ? qmin : v, nmax = qmax > v ? qmax : v;
-            if (nmax - nmin > level) { rw_run_end(q, j, 8 * k, lmin, lmax, qcap); nmin = nmax = v; j = 8 * k; }
-            qmin = lmin = nmin; qmax = lmax = nmax;
-        } else {
-            const int ne = nb < 8 ? nb : 8;
-            for (int b = 0; b < ne; b++) {
-                const int qv = (int)((w >> (8 * b)) & 0xff), i = 8 * k + b;
-                if (qmin > qv) qmin = qv;
-                if (qmax < qv) qmax = qv;
-                if (qmax - qmin > level) { rw_run_end(q, j, i, lmin, lmax, qcap); qmin = qmax = qv; j = i; }
-                lmin = qmin; lmax = qmax;
+            if (nmax - nmin > level) {
+                int mid = (qmin + qmax) / 2;
+                if (mid > qcap) mid = qcap;
+                if (qmin != qmax || mid != qmin) rw_fill(q, j, i, mid);
+                nmin = nmax = v; j = i;
             }
+            qmin = nmin; qmax = nmax;
         }
     }
-    if (lmin != lmax) rw_fill(q, j, len, (lmin + lmax) / 2);      /* the last run is not capped (832-833) */
+    if (qmin != qmax) rw_fill(q, j, len, (qmin + qmax) / 2);      /* the last run is not capped (832-833) */
 }
 
 __device__ __forceinline__ void rw_mbar_init(unsigned long long *bar) {
@@ -1134,12 +1149,23 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
         for (int x = lane; x < Lr; x += 32) sl[x] = (keep ? cg_cap_qual(qin[x], P, T) : sl[x]) & 0x7f;
     }
     __syncthreads();
-    /* ---- phase B: P-block, thread per read ---- */
+    /* ---- phase B: P-block: change bits of every staged word (word map storage reused), then thread per read ---- */
     if (P->pblock) {
+        if (!P->any_preserve_qual) {
+            for (int wi = threadIdx.x; wi < nwords; wi += RW_THREADS) {
+                const uint2 v = *reinterpret_cast<const uint2 *>(S.q + wi * 8);
+                const uint32_t prev = wi ? S.q[wi * 8 - 1] : 0u;
+                const uint32_t dx = v.x ^ ((v.x << 8) | prev), dy = v.y ^ __funnelshift_l(v.x, v.y, 8);
+                const uint32_t tx = ((((dx & 0x7f7f7f7fu) + 0x7f7f7f7fu) | dx) & 0x80808080u) >> 7;
+                const uint32_t ty = ((((dy & 0x7f7f7f7fu) + 0x7f7f7f7fu) | dy) & 0x80808080u) >> 7;
+                S.wmap[wi] = (uint8_t)(((tx * 0x01020408u) >> 24) | (((ty * 0x01020408u) >> 24) << 4));
+            }
+            __syncthreads();
+        }
         const RwMeta m = S.m[threadIdx.x];
         if ((m.lk >> RW_KIND_SH) & 3u) {
             if (P->any_preserve_qual) cg_pblock_t<1>(S.q + m.qoff, (int)(m.lk & RW_L_M), P->pblock, P->qcap, T);
-            else rw_pblock_words(S.q + m.qoff, (int)(m.lk & RW_L_M), P->pblock, P->qcap);
+            else rw_pblock_rle(S.q + m.qoff, S.wmap + (m.qoff >> 3), (int)(m.lk & RW_L_M), P->pblock, P->qcap);
         }
     }
     /* ---- phase C: the block's output range ---- */
@@ -1532,7 +1558,10 @@ static int run_slice(cg_ctx *ctx, int t0, int t1, int64_t r0, int64_t r1, int ti
     int nfs = 0;
     const int kb = ctx->nf_total;
     if (timed) T0(CG_T_COLUMNS);
-    if (t1 > t0) { k_column<<<nblk(t1 - t0, COL_WARPS), COL_WARPS * 32, 0, st>>>(*D, t0, t1); ctx->launches++; }
+    if (t1 > t0) {
+        const int blocks = nblk(t1 - t0, COL_WARPS * COL_TPW);
+        k_column<<<blocks, COL_WARPS * 32, 0, st>>>(*D, t0, t1); ctx->launches++;
+    }
     if (timed) { T1(CG_T_COLUMNS); T0(CG_T_FLAGGED); }
     if (ncs > 0) {
         LdEvFlagOff lf = { D->ev + c0, CG_EV_FLAGGED }; StCompactOff sc = { D->fcol + kb, D->ev + c0, CG_EV_FLAGGED, c0 };
