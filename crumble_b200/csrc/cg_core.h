@@ -67,6 +67,11 @@ typedef struct CgDevParams {
     int32_t any_preserve_qual;
 } CgDevParams;
 
+#include <stddef.h>
+#ifdef __cplusplus
+static_assert(offsetof(CgTables, e_tab2) == offsetof(CgTables, e_tab) + 1002 * sizeof(double), "cg_fast_exp indexes e_tab2 through e_tab");
+#endif
+
 /* ---- CIGAR ------------------------------------------------------------------------- */
 CG_HD int cg_cig_op(uint32_t c)  { return (int)(c & 0xf); }
 CG_HD int cg_cig_len(uint32_t c) { return (int)(c >> 4); }
@@ -150,10 +155,12 @@ CG_HD int cg_qpos2rpos(const uint32_t *cig, int n, int rpos0, int qpos) {
 
 /* ---- fast math (snp_score.c:491-527) ------------------------------------------------ */
 CG_HD double cg_fast_exp(const CgTables *T, double y) {
-    if (y >= -50 && y <= 50) return T->e_tab2[(int)(y * 10) + 500];
-    if (y < -500) y = -500;
-    if (y > 500) y = 500;
-    return T->e_tab[(int)y + 500];
+    /* one load from the pair of adjacent tables (e_tab2 follows e_tab): the index is selected, not the value */
+    const bool fine = y >= -50 && y <= 50;
+    double yc = y < -500 ? -500 : y;
+    if (yc > 500) yc = 500;
+    const int idx = fine ? 1002 + 500 + (int)(y * 10) : 500 + (int)yc;
+    return T->e_tab[idx];
 }
 
 CG_HD double cg_fast_log2(const CgTables *T, double val) {

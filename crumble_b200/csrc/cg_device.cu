@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
     const int doB = P->min_qual_B != 0;
     const int min_mqual = P->min_mqual;
     uint16_t (*cells)[32] = S.w[w].cell;
-    const char *tab = reinterpret_cast<const char *>(S.tab);
+    const uint32_t tab = (uint32_t)__cvta_generic_to_shared(S.tab);
     double *rare = &S.rare[w][0][lane];
     int depth_max = 0;
     /* the block's tables are built once for COL_TPW tiles per warp; warps walk their tiles on their own */
@@ -497,9 +497,10 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
                 if (cell & CELL_VALID) {
                     n_plp++;
                     pk += ((cell & 0x1fu) * 0x00108421u) & 0x01041041u;
-                    const char *row = tab + (cell & CELL_E_M);
-                    const double2 mh = *reinterpret_cast<const double2 *>(row);
-                    const double om = *reinterpret_cast<const double *>(row + 16);
+                    /* shared-window address arithmetic: a generic pointer costs five instructions per row to rebuild */
+                    double2 mh; double om;
+                    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(mh.x), "=d"(mh.y) : "r"(tab + (cell & CELL_E_M)));
+                    asm("ld.shared.f64 %0, [%1+16];" : "=d"(om) : "r"(tab + (cell & CELL_E_M)));
                     if ((cell & CELL_BASE_M) == b0s) {
                         H0 += mh.x; P01 += mh.y; P02 += mh.y; P03 += mh.y; P04 += mh.y; C0 += om;
                     } else if ((cell & CELL_BASE_M) == b1s) {
@@ -845,8 +846,10 @@ __global__ void k_paint(const __grid_constant__ CgDev D, int k_begin, int k_end)
  *            holds a single value (nearly all words after the rewrite), byte by byte elsewhere;
  *   phase C: one bulk async store of the block's output range (8-byte edges by the owning threads).
  * Blocks whose ranges do not fit the staging buffers (long reads) run the one-thread-per-read body (cg_rewrite). */
+#ifndef RW_THREADS
 #define RW_THREADS 128
-#define RW_READS   128
+#endif
+#define RW_READS   RW_THREADS
 #define RW_QCAP    (RW_READS * 168)     /* staged quality bytes (152 per padded 150-base read) */
 #define RW_CCAP    3072                 /* staged column bytes */
 #define RW_L_M     0x000fffffu          /* RwMeta.lk: L | kind << 20 | keep << 22 | init80 << 23 | tail_unreached << 24 */
