@@ -178,6 +178,12 @@ __global__ void k_finish_read(const __grid_constant__ CgDev D, const int32_t *n_
     }
     if (j == 0 && np == 0) dims[1] = 0;
 }
+/* device scalars -> MAPPED pinned host memory, written by the SMs: a cudaMemcpy would queue behind the bulk quality
+ * downloads on the D2H copy engine and stall the host's per-slice sync by a whole chunk */
+__global__ void k_publish(const int32_t *src, int32_t *dst_mapped, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst_mapped[i] = src[i];
+    __threadfence_system();
+}
 __global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -1216,7 +1222,8 @@ struct cg_ctx {
     dbuf b_tlo, b_tstart, b_isl, b_cb, b_ev, b_depth, b_dump, b_dsum, b_csum, b_fcol, b_trig, b_twin;
     dbuf b_aggr, b_scal, b_scratch, b_epoch, b_events, b_chain, b_items;
     /* host mirrors */
-    int32_t *h_dims;              /* pinned: [0] n_pile [1] n_cols [2] n_islands [3] n_flagged [4] maxdepth [5] err [6] n_events [7] n_epochs */
+    int32_t *d_hdims;             /* device alias of h_dims (mapped pinned memory) */
+    int32_t *h_dims;              /* pinned, mapped: [0] n_pile [1] n_cols [2] n_islands [3] n_flagged [4] maxdepth [5] err [6] n_events [7] n_epochs */
     unsigned long long *h_counters;
     CgDev D;
     int resident; int dump_columns;
@@ -1294,7 +1301,8 @@ extern "C" cg_ctx *cg_create(const cg_params *p, int device, int *err) {
     ctx->own_stream = 1;
     ctx->hT = (CgTables *)malloc(sizeof(CgTables));
     if (!e && cudaMalloc((void **)&ctx->dT, sizeof(CgTables)) != cudaSuccess) e = CG_ERR_CUDA;
-    if (!e && cudaHostAlloc((void **)&ctx->h_dims, 64, cudaHostAllocDefault) != cudaSuccess) e = CG_ERR_CUDA;
+    if (!e && cudaHostAlloc((void **)&ctx->h_dims, 64, cudaHostAllocMapped) != cudaSuccess) e = CG_ERR_CUDA;
+    if (!e && cudaHostGetDevicePointer((void **)&ctx->d_hdims, ctx->h_dims, 0) != cudaSuccess) e = CG_ERR_CUDA;
     if (!e && cudaHostAlloc((void **)&ctx->h_counters, sizeof(unsigned long long) * 32, cudaHostAllocDefault) != cudaSuccess) e = CG_ERR_CUDA;
     for (int i = 0; i < CG_N_TIMERS && !e; i++)
         for (int k = 0; k < 2; k++) if (cudaEventCreate(&ctx->ev[i][k]) != cudaSuccess) e = CG_ERR_CUDA;
@@ -1569,7 +1577,7 @@ static int run_slice(cg_ctx *ctx, int t0, int t1, int64_t r0, int64_t r1, int ti
     if (ncs > 0) {
         LdEvFlagOff lf = { D->ev + c0, CG_EV_FLAGGED }; StCompactOff sc = { D->fcol + kb, D->ev + c0, CG_EV_FLAGGED, c0 };
         if ((e = run_scan<int32_t, OpSum>(ctx, lf, sc, ncs, 0, scal + 3))) return e;
-        CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 32, cudaMemcpyDeviceToHost, st));
+        k_publish<<<1, 32, 0, st>>>(scal, ctx->d_hdims, 8); ctx->launches++;
         CG_CHECK(cudaStreamSynchronize(st));
         nfs = ctx->h_dims[3];
     }
@@ -1746,7 +1754,11 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
     for (int i = 0; i < nch; i++) {
         int64_t r = n;
         if (i + 1 < nch) {
-            const int64_t target = in->qual_bytes / nch * (i + 1);
+            /* equal chunks, except that the last two are 1/2 and 1/4 of a chunk: what remains to be done after the last
+             * byte has landed (last slice + its download) shrinks with the last chunk */
+            const double wtot = nch >= 4 ? (nch - 2) + 0.75 : (double)nch;
+            const double wacc = nch >= 4 ? (i + 1 <= nch - 2 ? (double)(i + 1) : (nch - 2) + 0.5) : (double)(i + 1);
+            const int64_t target = (int64_t)((double)in->qual_bytes * (wacc / wtot));
             int64_t lo = i ? B.rb[i - 1] : 0, hi = n;
             while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (in->off[mid] < target) lo = mid + 1; else hi = mid; }
             r = lo;
