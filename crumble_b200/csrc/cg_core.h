@@ -65,6 +65,7 @@ typedef struct CgDevParams {
     int32_t region_tid, region_beg, region_end;
     int32_t str_snp;          /* sSTR_add || sSTR_mul (snp_score.c:1345) */
     int32_t any_preserve_qual;
+    int32_t nbed;             /* -R regions (snp_score.c:1443-1463) */
 } CgDevParams;
 
 #include <stddef.h>
@@ -347,6 +348,8 @@ CG_HD void cg_cons_finalize(const CgTables *T, CgConsAcc *a, CgCons *o) {
 #define CG_EV_STRALL      0x0200    /* str_snp && preserve: every read triggers (snp_score.c:1718) */
 #define CG_EV_HADINDEL    0x0400
 #define CG_EV_PROCESSED   0x0800
+#define CG_EV_BED         0x1000    /* preserve > 1: column inside a -R region, reads seen here skip the P-block (snp_score.c:1461,1890-1892) */
+#define CG_EV_IMPERFECT   0x2000    /* !perfect: preserved quality values disagree with the call (snp_score.c:1606-1608,1633-1645) */
 
 /* call1 | call2 as the set of nt16 codes a base must equal to agree with the call (snp_score.c:1526-1542, 1906-1910):
  * calls 0..3 are A C G T; call 4 ('*' = 16) and 5 (N = 32) never equal an nt16 base code */
@@ -359,10 +362,11 @@ CG_HD int cg_call_code(const CgCons *c) {
 
 /* ---- per-byte visit of the rewrite loop (snp_score.c:1880-1919), see SURVEY.md §9.7 ---- */
 CG_HD uint8_t cg_visit(uint8_t val, uint8_t cbv, uint8_t orig_capped, int nib,
-                       const CgDevParams *P, const CgTables *T) {
+                       const CgDevParams *P, const CgTables *T, int imperfect = 0) {
     if (cbv & CG_CB_UNPROC) return val;
     if (cbv & CG_CB_ACTIVE) val = (uint8_t)(orig_capped | 0x80);
-    if (cbv & CG_CB_PRESERVE) val |= 0x80;
+    /* 1885: preserve || preserve_qual[*qual & 0x7f] >= 1 + perfect */
+    if ((cbv & CG_CB_PRESERVE) || (P->any_preserve_qual && T->preserve_qual[val & 0x7f] >= 2 - imperfect)) val |= 0x80;
     if (!(val & 0x80)) {
         /* base == call1 || base == call2: an nt16 code equals a one-hot call mask iff it is one-hot and inside the set */
         bool match = nib && !(nib & (nib - 1)) && (nib & cbv & CG_CB_CALL_MASK);

@@ -585,6 +585,27 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
     if (lane == 0 && depth_max > 0) atomicMax(D.maxdepth, depth_max);
 }
 
+/* Options outside the hand-tuned kernels (-S, -k/-K/-y, -N, -R; cg_params_generic): one column / one record per thread
+ * through the plain bodies of cg_pipeline.h.  Same results as the reference, lower throughput. */
+__global__ void __launch_bounds__(128) k_column_generic(const __grid_constant__ CgDev D, int t_begin, int t_end) {
+    const int c = t_begin * 32 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int c_end = t_end * 32 < D.n_cols ? t_end * 32 : D.n_cols;
+    CgColOut o; o.cnt = 0; o.n_plp = 0;
+    if (c < c_end) o = cg_column_body(&D, c);
+    unsigned un = __reduce_or_sync(0xffffffffu, o.cnt);
+    while (un) {
+        const int b = __ffs(un) - 1; un &= un - 1;
+        const unsigned m = __ballot_sync(0xffffffffu, (o.cnt >> b) & 1);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&D.counters[b], (unsigned long long)__popc(m));
+    }
+    const int mx = __reduce_max_sync(0xffffffffu, o.n_plp);
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(D.maxdepth, mx);
+}
+__global__ void __launch_bounds__(128) k_rewrite_generic(const __grid_constant__ CgDev D, int64_t rec_begin, int64_t rec_end) {
+    const int64_t r = rec_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rec_end) cg_rewrite(&D, r, D.n_flagged);
+}
+
 /* Flagged columns (had an indel / may open a keep window): the decisions of cg_flagged (cg_pipeline.h;
  * snp_score.c:1690-1762, 1775-1819) in two kernels.
  *  k_flagged    one WARP per column, lanes over the column's reads: indel count, insertion-size spectrum tests, and
@@ -1220,7 +1241,8 @@ struct cg_ctx {
     dbuf b_tid, b_pos, b_flag, b_mapq, b_lq, b_nc, b_off, b_coff, b_cigar, b_seq, b_qual, b_qout;
     dbuf b_jmap, b_rspan, b_rd, b_ks, b_ke, b_gap, b_gapraw, b_pmax, b_orig, b_rbf;
     dbuf b_tlo, b_tstart, b_isl, b_cb, b_ev, b_depth, b_dump, b_dsum, b_csum, b_fcol, b_trig, b_twin;
-    dbuf b_aggr, b_scal, b_scratch, b_epoch, b_events, b_chain, b_items;
+    dbuf b_aggr, b_scal, b_scratch, b_epoch, b_events, b_chain, b_items, b_bed, b_bedpm;
+    int generic;                  /* cg_params_generic(): column and rewrite stages through the plain bodies */
     /* host mirrors */
     int32_t *d_hdims;             /* device alias of h_dims (mapped pinned memory) */
     int32_t *h_dims;              /* pinned, mapped: [0] n_pile [1] n_cols [2] n_islands [3] n_flagged [4] maxdepth [5] err [6] n_events [7] n_epochs */
@@ -1282,8 +1304,20 @@ extern "C" int cg_set_params(cg_ctx *ctx, const cg_params *p) {
     int e = cg_params_check(p, &why);
     if (e) { snprintf(ctx->err, sizeof ctx->err, "not implemented on the device path: %s", why); return e; }
     ctx->params = *p;
+    ctx->generic = cg_params_generic(p);
     cg_tables_init(ctx->hT, p);
     CG_CHECK(cudaMemcpyAsync(ctx->dT, ctx->hT, sizeof(CgTables), cudaMemcpyHostToDevice, ctx->stream));
+    if (p->nbed > 0) {                                          /* -R regions and the prefix max cg_bed_hit searches */
+        int64_t *pm = (int64_t *)malloc(sizeof(int64_t) * (size_t)p->nbed);
+        if (!pm) return CG_ERR_NOMEM;
+        cg_bed_prefix_max(p->bed, p->nbed, pm);
+        if ((e = ensure(ctx, &ctx->b_bed, sizeof(cg_bed_reg) * (size_t)p->nbed)) || (e = ensure(ctx, &ctx->b_bedpm, sizeof(int64_t) * (size_t)p->nbed))) { free(pm); return e; }
+        cudaMemcpyAsync(ctx->b_bed.p, p->bed, sizeof(cg_bed_reg) * (size_t)p->nbed, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(ctx->b_bedpm.p, pm, sizeof(int64_t) * (size_t)p->nbed, cudaMemcpyHostToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        free(pm);
+        ctx->params.bed = NULL;                                 /* borrowed pointer: not kept */
+    }
     CG_CHECK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -1318,7 +1352,7 @@ extern "C" void cg_destroy(cg_ctx *ctx) {
     dbuf *all[] = { &ctx->b_tid, &ctx->b_pos, &ctx->b_flag, &ctx->b_mapq, &ctx->b_lq, &ctx->b_nc, &ctx->b_off, &ctx->b_coff, &ctx->b_cigar,
         &ctx->b_seq, &ctx->b_qual, &ctx->b_qout, &ctx->b_jmap, &ctx->b_rspan, &ctx->b_rd, &ctx->b_ks, &ctx->b_ke, &ctx->b_gap, &ctx->b_gapraw,
         &ctx->b_pmax, &ctx->b_orig, &ctx->b_rbf, &ctx->b_tlo, &ctx->b_tstart, &ctx->b_isl, &ctx->b_cb, &ctx->b_ev, &ctx->b_depth, &ctx->b_dump,
-        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain, &ctx->b_items };
+        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain, &ctx->b_items, &ctx->b_bed, &ctx->b_bedpm };
     for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); i++) if (all[i]->p) cudaFree(all[i]->p);
     if (ctx->dT) cudaFree(ctx->dT);
     if (ctx->h_dims) cudaFreeHost(ctx->h_dims);
@@ -1470,6 +1504,7 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
     ctx->launches = 0;
     for (int i = 0; i < CG_N_TIMERS; i++) if (i != CG_T_H2D && i != CG_T_D2H) ctx->ms[i] = 0;
     D->T = ctx->dT; cg_devparams_from(&D->P, &ctx->params);
+    D->bed = (const cg_bed_reg *)ctx->b_bed.p; D->bed_pm = (const int64_t *)ctx->b_bedpm.p;
     if ((e = ensure(ctx, &ctx->b_scal, 2048))) return e;
     int32_t *scal = (int32_t *)ctx->b_scal.p;
     D->counters = (unsigned long long *)((char *)ctx->b_scal.p + 128);
@@ -1571,7 +1606,9 @@ static int run_slice(cg_ctx *ctx, int t0, int t1, int64_t r0, int64_t r1, int ti
     if (timed) T0(CG_T_COLUMNS);
     if (t1 > t0) {
         const int blocks = nblk(t1 - t0, COL_WARPS * COL_TPW);
-        k_column<<<blocks, COL_WARPS * 32, 0, st>>>(*D, t0, t1); ctx->launches++;
+        if (ctx->generic) k_column_generic<<<nblk((int64_t)(t1 - t0) * 32, 128), 128, 0, st>>>(*D, t0, t1);
+        else k_column<<<blocks, COL_WARPS * 32, 0, st>>>(*D, t0, t1);
+        ctx->launches++;
     }
     if (timed) { T1(CG_T_COLUMNS); T0(CG_T_FLAGGED); }
     if (ncs > 0) {
@@ -1623,7 +1660,11 @@ static int run_slice(cg_ctx *ctx, int t0, int t1, int64_t r0, int64_t r1, int ti
         k_chain_carry<<<1, 32, 0, st>>>(*D, bmax - kb, umax - kb, ccarry, kb, ke); ctx->launches += 3;
     }
     if (timed) { T1(CG_T_CHAIN); T0(CG_T_REWRITE); }
-    if (r1 > r0) { k_rewrite<<<nblk(r1 - r0, RW_READS), RW_THREADS, 0, st>>>(*D, r0, r1); ctx->launches++; }
+    if (r1 > r0) {
+        if (ctx->generic) k_rewrite_generic<<<nblk(r1 - r0, 128), 128, 0, st>>>(*D, r0, r1);
+        else k_rewrite<<<nblk(r1 - r0, RW_READS), RW_THREADS, 0, st>>>(*D, r0, r1);
+        ctx->launches++;
+    }
     if (timed) T1(CG_T_REWRITE);
     ctx->nf_total = ke;
     CG_CHECK(cudaGetLastError());

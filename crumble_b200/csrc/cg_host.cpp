@@ -14,15 +14,26 @@
 /* Which option combinations the device path implements today. */
 int cg_params_check(const cg_params *p, const char **why) {
     static const char *w_mul = "negative -i/-s STR multipliers";
-    static const char *w_soft = "-S (soft-clip quantisation)";
-    static const char *w_keepq = "-k/-K/-N/-y pbccs (preserved quality values)";
-    static const char *w_bed = "-R keep.bed";
+    static const char *w_bed = "-R regions must be sorted by (tid, start) as bed_load leaves them";
     if (p->iSTR_mul < 0 || p->sSTR_mul < 0) { if (why) *why = w_mul; return CG_ERR_UNSUPPORTED; }
-    if (p->softclip) { if (why) *why = w_soft; return CG_ERR_UNSUPPORTED; }
-    if (p->perfect_col) { if (why) *why = w_keepq; return CG_ERR_UNSUPPORTED; }
-    for (int i = 0; i < 256; i++) if (p->preserve_qual[i]) { if (why) *why = w_keepq; return CG_ERR_UNSUPPORTED; }
-    if (p->nbed) { if (why) *why = w_bed; return CG_ERR_UNSUPPORTED; }
+    if (p->nbed < 0 || (p->nbed > 0 && !p->bed)) { if (why) *why = w_bed; return CG_ERR_BAD_ARG; }
+    for (int i = 1; i < p->nbed; i++)
+        if (p->bed[i].tid < p->bed[i - 1].tid || (p->bed[i].tid == p->bed[i - 1].tid && p->bed[i].start < p->bed[i - 1].start)) { if (why) *why = w_bed; return CG_ERR_BAD_ARG; }
     return 0;
+}
+
+/* Options the hand-tuned kernels do not cover (-S, -k/-K/-y, -N, -R): the chain then runs the one-item-per-thread
+ * bodies of cg_pipeline.h for the column and rewrite stages (same results, lower throughput). */
+int cg_params_generic(const cg_params *p) {
+    if (p->softclip || p->perfect_col || p->nbed) return 1;
+    for (int i = 0; i < 256; i++) if (p->preserve_qual[i]) return 1;
+    return 0;
+}
+
+/* inclusive prefix max of the (tid, end) keys: see cg_bed_hit */
+void cg_bed_prefix_max(const cg_bed_reg *bed, int n, int64_t *pm) {
+    int64_t m = INT64_MIN;
+    for (int i = 0; i < n; i++) { int64_t k = ((int64_t)bed[i].tid << 32) | (uint32_t)bed[i].end; if (k > m) m = k; pm[i] = m; }
 }
 
 void cg_devparams_from(CgDevParams *d, const cg_params *p) {
@@ -39,6 +50,7 @@ void cg_devparams_from(CgDevParams *d, const cg_params *p) {
     d->region_tid = p->region_tid; d->region_beg = p->region_beg; d->region_end = p->region_end;
     d->str_snp = (p->sSTR_add || p->sSTR_mul != 0.0);                   /* snp_score.c:1345 */
     for (int i = 0; i < 256; i++) if (p->preserve_qual[i]) d->any_preserve_qual = 1;
+    d->nbed = p->nbed;
 }
 
 /* ---- tables (host libm; never recomputed on the device) ----------------------------------- */

@@ -3,6 +3,8 @@
 #define CG_HOST_H
 #include "cg_pipeline.h"
 int  cg_params_check(const cg_params *p, const char **why);
+int  cg_params_generic(const cg_params *p);
+void cg_bed_prefix_max(const cg_bed_reg *bed, int n, int64_t *pm);
 void cg_devparams_from(CgDevParams *d, const cg_params *p);
 void cg_tables_init(CgTables *T, const cg_params *p);
 extern "C" int cg_enable_pinned(void);   /* installs the pinned-memory hooks when a device exists */

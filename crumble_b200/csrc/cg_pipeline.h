@@ -81,6 +81,8 @@ typedef struct CgDev {
     int32_t *maxdepth; int32_t *err;
     int32_t *beyond;          /* set when a counted column exists at/after the -r region end (the reference counts one, then breaks) */
     const CgTables *T;
+    const cg_bed_reg *bed;    /* -R regions as bed.c:20-40 leaves them (sorted, collapsed) */
+    const int64_t *bed_pm;    /* inclusive prefix max of (tid << 32 | end) over bed[] */
     CgDevParams P;
     int32_t want_dump;
     int32_t cons_only;        /* debug */
@@ -178,6 +180,18 @@ CG_HD int cg_seq_nib(const CgDev *D, const CgRead *q, int x) {
     return (D->seq[(CG_OFF(q) >> 1) + (x >> 1)] >> ((~x & 1) << 2)) & 0xf;
 }
 
+/* -R keep.bed (snp_score.c:1443-1463): bed_idx only moves forward, past regions with tid < tid or (same tid, end < pos);
+ * both conditions are monotone along the sorted column order, so the index reached at a column is the FIRST region with
+ * (tid, end) >= (tid, pos) -- found by binary search on the prefix max of the (tid, end) keys -- whatever came before. */
+CG_HD int cg_bed_hit(const CgDev *D, int tid, int pos) {
+    const int64_t K = ((int64_t)tid << 32) | (uint32_t)pos;
+    int lo = 0, hi = D->P.nbed;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (D->bed_pm[mid] < K) lo = mid + 1; else hi = mid; }
+    if (lo >= D->P.nbed) return 0;
+    const cg_bed_reg b = D->bed[lo];
+    return b.tid == tid && b.start <= pos && b.end > pos;
+}
+
 /* ---- stage: column (one per dense column) --------------------------------------------
  * transcode's column loop up to the point where cross-column state is needed
  * (snp_score.c:1466-1472, 1490-1500, 1520-1649, 1658-1669, 1694-1713, 1764-1773).
@@ -202,7 +216,7 @@ CG_HD void cg_column_cons(const CgDev *D, int c, int lo, int hi, CgCons *out) {
     cg_cons_finalize(T, &a, out);
 }
 
-typedef struct CgColStats { int n_plp, n_skip, low_mq, had_indel, indel_cnt, clipped, n_overlap, ins_seen; } CgColStats;
+typedef struct CgColStats { int n_plp, n_skip, low_mq, had_indel, indel_cnt, clipped, n_overlap, ins_seen; int cp; /* call_preserve (611-623) */ } CgColStats;
 
 /* everything after the per-read loop: consensus finalisation and the column decisions */
 CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgColStats *st, CgConsAcc *acc) {
@@ -222,7 +236,7 @@ CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgC
         return o;
     }
     int tid = 0, pos = 0;
-    const int need_pos = (P->region_tid >= 0) || D->want_dump;
+    const int need_pos = (P->region_tid >= 0) || D->want_dump || P->nbed;
     if (need_pos) {
         int is = cg_island_of(D, c);
         tid = D->isl[is].tid; pos = D->isl[is].pos_start + (c - D->isl[is].col_start);
@@ -254,20 +268,31 @@ CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgC
             hB = cB.het_phred > 0 ? cB.het_call : cB.call * 5 + cB.call;
             sB = cB.het_phred > 0 ? cB.het_phred : cB.phred;
         }
-        int preserve = 0;
-        if (P->min_qual_A && doB && hA != hB) { o.cnt |= 1u << CG_CNT_DIFF; preserve = 1; }    /* 1593,1624 */
+        int preserve = 0, perfect = 1;
+        if (P->nbed && cg_bed_hit(D, tid, pos)) preserve = 2;               /* 1443-1463: *really* preserve; disallow P-block */
+        if (P->min_qual_A && doB && hA != hB) { o.cnt |= 1u << CG_CNT_DIFF; preserve |= 1; }    /* 1593,1624 */
         if (P->min_qual_A) {                                               /* 1594-1609 */
             if (cA.het_phred > 0) { o.cnt |= 1u << CG_CNT_HET_A; if (sA < P->min_qual_A) o.cnt |= 1u << CG_CNT_HET_QUAL_A; }
             else { o.cnt |= 1u << CG_CNT_HOM_A; if (sA < P->min_qual_A) o.cnt |= 1u << CG_CNT_HOM_QUAL_A; }
-            if (cA.discrep >= P->min_discrep_A) { o.cnt |= 1u << CG_CNT_DISCREP_A; preserve = 1; }
-            if (sA < P->min_qual_A) preserve = 1;
+            if (cA.discrep >= P->min_discrep_A) { o.cnt |= 1u << CG_CNT_DISCREP_A; preserve |= 1; }
+            if (sA < P->min_qual_A) preserve |= 1;
+            if (st->cp != (1 << cA.call)) perfect = 0;                      /* 1606-1608: evaluated whatever preserve is */
         }
         if (doB) {                                                         /* 1610-1622 */
             if (cB.het_phred > 0) { o.cnt |= 1u << CG_CNT_HET_B; if (sB < P->min_qual_B) o.cnt |= 1u << CG_CNT_HET_QUAL_B; }
             else { o.cnt |= 1u << CG_CNT_HOM_B; if (sB < P->min_qual_B) o.cnt |= 1u << CG_CNT_HOM_QUAL_B; }
-            if (cB.discrep >= P->min_discrep_B) { o.cnt |= 1u << CG_CNT_DISCREP_B; preserve = 1; }
-            if (sB < P->min_qual_B) preserve = 1;
+            if (cB.discrep >= P->min_discrep_B) { o.cnt |= 1u << CG_CNT_DISCREP_B; preserve |= 1; }
+            if (sB < P->min_qual_B) preserve |= 1;
         }
+        if (P->any_preserve_qual || P->perfect_col) {                      /* 1630-1649 */
+            const int m5 = st->cp & 31;
+            const int b2c = (m5 && !(m5 & (m5 - 1))) ? (m5 == 1 ? 0 : m5 == 2 ? 1 : m5 == 4 ? 2 : m5 == 8 ? 3 : 4) : 99;   /* bit2call, 1384-1417 */
+            if (P->min_qual_A && !preserve && ((cA.het_phred <= 0 && b2c != cA.call) || (st->cp >> 8))) perfect = 0;
+            if (doB && !preserve && ((cB.het_phred <= 0 && b2c != cB.call) || (st->cp >> 8))) perfect = 0;
+            if (P->perfect_col && !perfect) preserve = 1;                   /* assignment: a -R hit loses its "2" here, as in the reference */
+        }
+        if (preserve > 1) ev |= CG_EV_BED;
+        if (!perfect) ev |= CG_EV_IMPERFECT;
         int keep = low_mq > P->low_mqual_perc * (n_plp + .01);             /* 1668 */
         if (keep) o.cnt |= 1u << CG_CNT_LOW_MQUAL_PERC;
         if ((clipped - 1.0) >= P->clip_perc * n_overlap) {                 /* 1764-1773 */
@@ -308,7 +333,7 @@ CG_HD CgColOut cg_column_body(const CgDev *D, int c) {
     const int t = c >> 5;
     const int lo = D->tile_lo[t], hi = D->tile_start[t + 1];
     int n_plp = 0, n_skip = 0, low_mq = 0, had_indel = 0, indel_cnt = 0, clipped = 0, n_overlap = 0;
-    int ins_seen = 0;
+    int ins_seen = 0, cp = 0;
     CgConsAcc a; cg_cons_init(&a);
     const int doB = P->min_qual_B != 0;
     for (int j = lo; j < hi; j++) {
@@ -321,13 +346,21 @@ CG_HD CgColOut cg_column_body(const CgDev *D, int c) {
         if (cell.is_refskip) { n_skip++; continue; }
         if ((cell.is_head && cell.qpos > 0) || (cell.is_tail && cell.qpos + 1 < q.l_qseq)) clipped++;   /* 1701-1703 */
         if (!cell.is_tail && !cell.is_head) { n_overlap++; if (cell.indel > 0) ins_seen = 1; }       /* 1705-1708 */
-        if (!q.l_qseq || !doB) continue;
+        if (!q.l_qseq) continue;
         int nib = cg_seq_nib(D, &q, cell.qpos);
         int base = cell.is_del ? 4 : cg_nt16_to_base(nib);
         uint8_t qv = cg_cap_qual(D->qual[CG_OFF(&q) + cell.qpos], P, T);
+        if (P->any_preserve_qual) {                                        /* 611-623, on the pileup's (capped) copy */
+            const int pq = T->preserve_qual[qv];
+            if (pq) cp |= 1 << base;
+            if (pq > 1) cp |= (1 << base) << 8;
+            for (int ins = 1; ins <= cell.indel; ins++)
+                if (cell.qpos + ins < q.l_qseq && T->preserve_qual[cg_cap_qual(D->qual[CG_OFF(&q) + cell.qpos + ins], P, T)]) cp |= 1 << 4;
+        }
+        if (!doB) continue;
         cg_cons_add(T, &a, base, T->effB[((int)q.mapq << 8) | qv]);
     }
-    CgColStats st; st.n_plp = n_plp; st.n_skip = n_skip; st.low_mq = low_mq; st.had_indel = had_indel; st.indel_cnt = indel_cnt;
+    CgColStats st; st.cp = cp; st.n_plp = n_plp; st.n_skip = n_skip; st.low_mq = low_mq; st.had_indel = had_indel; st.indel_cnt = indel_cnt;
     st.clipped = clipped; st.n_overlap = n_overlap; st.ins_seen = ins_seen;
     (void)o;
     return cg_column_finish(D, c, lo, hi, &st, &a);
@@ -480,6 +513,8 @@ CG_HDN void cg_rewrite(const CgDev *D, int64_t r, int n_flagged) {
     for (int c = q.col0; c < q.col0 + q.span; c++) keep |= D->cb[c];
     keep = (keep & CG_CB_KEEP) != 0;
     if (P->region_tid >= 0 && q.pos + q.span - 1 >= P->region_end) keep = 0;      /* tail column never reached */
+    if (P->nbed) for (int c = q.col0; c < q.col0 + q.span; c++) if (D->ev[c] & CG_EV_BED) nopblock = 1;     /* 1890-1892 */
+    const int apq = P->any_preserve_qual;
     const int head_proc = !(D->cb[q.col0] & CG_CB_UNPROC);
     const uint8_t init_or = (head_proc && q.mapq <= P->min_mqual) ? 0x80 : 0;     /* 1852-1859 */
     for (int x = 0; x < L; x++) out[x] = qin[x] | init_or;
@@ -491,23 +526,35 @@ CG_HDN void cg_rewrite(const CgDev *D, int64_t r, int n_flagged) {
             if (cg_is_mop(op)) {
                 for (int i = 0; i < l; i++) {
                     int x = y + i;
-                    out[x] = cg_visit(out[x], D->cb[c + i], cg_cap_qual(qin[x], P, T), cg_seq_nib(D, &q, x), P, T);
+                    out[x] = cg_visit(out[x], D->cb[c + i], cg_cap_qual(qin[x], P, T), cg_seq_nib(D, &q, x), P, T,
+                                      apq && (D->ev[c + i] & CG_EV_IMPERFECT));
                 }
                 c += l; y += l;
             } else if (op == 2 || op == 3) {
                 if (y < L) {
                     uint8_t oc = cg_cap_qual(qin[y], P, T); int nib = cg_seq_nib(D, &q, y); uint8_t v = out[y];
-                    for (int i = 0; i < l; i++) v = cg_visit(v, D->cb[c + i], oc, nib, P, T);
+                    for (int i = 0; i < l; i++) v = cg_visit(v, D->cb[c + i], oc, nib, P, T, apq && (D->ev[c + i] & CG_EV_IMPERFECT));
                     out[y] = v;
                 }
                 c += l;
             } else if (op == 1 || op == 4) y += l;
         }
     }
+    /* -S (1894-1904): at the read's head column the bases before qpos, at its tail column the bases after qpos, are
+     * binned in place unless that column set keep_qual.  Only back-fills reach those bases: the head column's own
+     * back-fill comes before the binning, those of later trigger columns after it. */
+    int head_bin = 0, tail_bin = 0, qh = 0, qt = L - 1;
+    if (P->softclip) {
+        CgCell ch, ct;
+        const uint8_t cbh = D->cb[q.col0], cbt = D->cb[q.col0 + q.span - 1];
+        if (cg_cell(D, &q, q.col0, &ch)) { qh = ch.qpos; head_bin = !(cbh & (CG_CB_UNPROC | CG_CB_KEEP)) && qh > 0; }
+        if (q.span > 1 && cg_cell(D, &q, q.col0 + q.span - 1, &ct)) { qt = ct.qpos; tail_bin = !(cbt & (CG_CB_UNPROC | CG_CB_KEEP)); }
+    }
     /* back-fills from trigger columns under this read (1870-1879) */
     if (D->r_bf[j]) {
         for (int k = cg_trig_lower_bound(D, n_flagged, q.col0); k < n_flagged && D->fcol[k] < q.col0 + q.span; k++) {
             const CgTrig *t = &D->trig[k];
+            if (head_bin && t->col > q.col0) { for (int x = 0; x < qh && x < L; x++) out[x] = T->bin2[out[x]]; head_bin = 0; }
             if (!(t->hasI || t->hasS)) continue;
             CgCell cell;
             if (!cg_cell(D, &q, t->col, &cell)) continue;
@@ -515,10 +562,11 @@ CG_HDN void cg_rewrite(const CgDev *D, int64_t r, int n_flagged) {
             for (int x = x0; x <= cell.qpos && x < L; x++) out[x] = (uint8_t)(cg_cap_qual(qin[x], P, T) | 0x80);
         }
     }
+    if (head_bin) for (int x = 0; x < qh && x < L; x++) out[x] = T->bin2[out[x]];
+    if (tail_bin) for (int x = qt + 1; x < L; x++) out[x] = T->bin2[out[x]];
     if (keep) for (int x = 0; x < L; x++) out[x] = cg_cap_qual(qin[x], P, T);      /* 1939-1940 */
     for (int x = 0; x < L; x++) out[x] &= 0x7f;                                     /* 1093-1096 */
-    (void)nopblock;
-    if (P->pblock) cg_pblock(out, L, P->pblock, P->qcap, T);                        /* 1098-1099 */
+    if (P->pblock && !nopblock) cg_pblock(out, L, P->pblock, P->qcap, T);           /* 1098-1099 */
 }
 
 /* ---- stage: deep (one per dense column) after the depth scan: over-depth test

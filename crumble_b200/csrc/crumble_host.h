@@ -35,6 +35,7 @@ void crumble_usage(FILE *fp);
 void crumble_print_params(const crumble_opts *o);          /* -v block, snp_score.c:2506-2540 */
 void crumble_print_counters(const crumble_opts *o);        /* -v block, snp_score.c:2650-2666 */
 void crumble_purge_tags(const crumble_opts *o, bam1_t *b); /* snp_score.c:989-1054 */
+cg_bed_reg *crumble_bed_load(const char *fn, bam_hdr_t *header, int *nreg);   /* bed.c:42-103 */
 int  transcode_gpu(crumble_opts *o, samFile *in, samFile *out, bam_hdr_t *header, hts_itr_t *h_iter);
 int  crumble_main(int argc, char **argv);
 

@@ -43,7 +43,12 @@ int crumble_main(int argc, char **argv) {
     sam_open_mode(mode + 1, fnout, NULL);
     if (!(out = sam_open_format(fnout, mode, &out_fmt))) { perror("(stdout)"); return 1; }
     if (!(header = sam_hdr_read(in))) { fprintf(stderr, "Failed to read file header\n"); return 1; }
-    if (o.bed_fn) { fprintf(stderr, "crumble: -R keep.bed is not supported by the device path yet\n"); return 1; }
+    cg_bed_reg *keep_bed = NULL;
+    if (o.bed_fn) {                                                      /* snp_score.c:2580-2586 */
+        int nb = 0;
+        if (!(keep_bed = crumble_bed_load(o.bed_fn, header, &nb))) return 1;
+        o.p.bed = keep_bed; o.p.nbed = nb;
+    }
     if (!o.p.noPG) {                                                     /* snp_score.c:2588-2609 */
         SAM_hdr *sh = sam_hdr_parse_(header->text, (int)header->l_text);
         if (!sh) return 1;
@@ -68,7 +73,7 @@ int crumble_main(int argc, char **argv) {
     if (out && sam_close(out) != 0) { fprintf(stderr, "Error while closing output fd\n"); return 1; }
     if (o.p.verbose) crumble_print_counters(&o);
     if (o.bed_fp) fclose(o.bed_fp);
-    free(o.aux_whitelist); free(o.aux_blacklist);
+    free(o.aux_whitelist); free(o.aux_blacklist); free(keep_bed);
     return 0;
 }
 

@@ -14,7 +14,7 @@
 #include <vector>
 #include "../../crumble_b200/csrc/cg_host.h"
 
-struct cg_ctx { cg_params p; CgTables T; char err[256]; int64_t n_cols; };
+struct cg_ctx { cg_params p; CgTables T; char err[256]; int64_t n_cols; std::vector<cg_bed_reg> bed; std::vector<int64_t> bed_pm; };
 
 extern "C" int cg_device_count(void) { return 0; }
 extern "C" int cg_enable_pinned(void) { return 0; }
@@ -25,6 +25,7 @@ extern "C" cg_ctx *cg_create(const cg_params *p, int device, int *err) {
     if (e) { if (err) *err = e; fprintf(stderr, "unsupported: %s\n", why); return NULL; }
     cg_ctx *c = new cg_ctx();
     c->p = *p; cg_tables_init(&c->T, p); c->err[0] = 0; c->n_cols = 0;
+    if (p->nbed) { c->bed.assign(p->bed, p->bed + p->nbed); c->bed_pm.resize(p->nbed); cg_bed_prefix_max(c->bed.data(), p->nbed, c->bed_pm.data()); c->p.bed = c->bed.data(); }
     if (err) *err = 0;
     return c;
 }
@@ -42,6 +43,7 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
     D.n_cigar = in->n_cigar; D.off = in->off; D.cigar_off = in->cigar_off; D.cigar = in->cigar; D.seq = in->seq; D.qual = in->qual;
     D.qual_out = out->qual_out;
     D.T = &ctx->T; cg_devparams_from(&D.P, &ctx->p);
+    D.bed = ctx->bed.data(); D.bed_pm = ctx->bed_pm.data();
     int32_t err = 0, maxdepth = 0, beyond = 0; D.err = &err; D.maxdepth = &maxdepth; D.beyond = &beyond;
     unsigned long long counters[CG_N_COUNTERS] = {0}; D.counters = counters;
     std::vector<int32_t> jmap(n + 1), rspan(n + 1);

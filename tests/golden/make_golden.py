@@ -27,6 +27,13 @@ from util import run_oracle, valid_mask  # noqa: E402
 SETS = {"tiny": ("tiny", 1.0, 3), "c1s": ("C1", 0.1, 11), "c2s": ("C2", 1 / 512, 5), "c4s": ("C4", 0.02, 4)}
 ARGS = [["-9"], ["-8"], ["-7"], ["-5"], ["-3"], ["-1"], ["-1", "-B"], ["-9", "-Y0.1"], ["-5", "-q30"], ["-9", "-U30"],
         ["-1", "-m10", "-C0.05", "-Z0.01"], ["-9", "-p0", "-L0"], ["-9", "-X0.5", "-D200"], ["-3", "-i0.5,3", "-s2.0,1"]]
+# options served by the plain per-item kernels (-S, -k/-K/-y, -N, -R); BED = tests/golden/keep.<set>.bed
+OPT_SETS = ("tiny", "c1s")
+OPT_ARGS = [["-9", "-S"], ["-1", "-S", "-B"], ["-9", "-k", "37"], ["-9", "-K", "11", "-k", "25"], ["-9", "-N", "-k", "25"], ["-9", "-N"],
+            ["-9", "-y", "pbccs"], ["-9", "-R", "BED"], ["-1", "-R", "BED", "-p", "8"], ["-5", "-S", "-K", "37", "-N", "-R", "BED"],
+            ["-1", "-q", "30", "-k", "37", "-S"]]
+KEEP_BED = {"tiny": "chr1\t1000\t3000\nchr1\t2500\t2600\nchr1\t2800\t5000\n# nested + overlapping on purpose (bed.c:20-40)\nchr2\t100\t200\nchr2\t20000\t26000\nchr1\t40000\t41000\n",
+            "c1s": "track name=keep\nchr20\t1000\t3000\nchr20\t2500\t2600\nchr20\t2800\t5000\nchr20\t20000\t20100\nchr20\t40000\t49000\nchr20\t90000\t90001\n"}
 EDGE = {"l9": ["-9"], "l1B": ["-1", "-B"], "l5q30": ["-5", "-q30"], "l3U35": ["-3", "-U35", "-Y0.2"],
         "l9r": ["-9", "-r", "chrA:900-1600"], "l1r": ["-1", "-r", "chrA:1200-2100"]}
 
@@ -45,6 +52,14 @@ def main():
             r = run_oracle(data, a, kind="reference")
             gold[name]["runs"][" ".join(a)] = {"qual_sha256": hashlib.sha256(r["qual"][m].tobytes()).hexdigest(),
                                                "bed": r["bed"], "counters": r["counters"]}
+        if name in OPT_SETS:
+            bedf = HERE / f"keep.{name}.bed"
+            bedf.write_text(KEEP_BED[name])
+            gold[name]["opt_runs"] = {}
+            for a in OPT_ARGS:
+                r = run_oracle(data, [str(bedf) if x == "BED" else x for x in a], kind="reference")
+                gold[name]["opt_runs"][" ".join(a)] = {"qual_sha256": hashlib.sha256(r["qual"][m].tobytes()).hexdigest(),
+                                                       "bed": r["bed"], "counters": r["counters"]}
         bb.close()
     json.dump(gold, open(HERE / "golden.json", "w"), indent=1, sort_keys=True)
     sam = HERE / "edge_cases.sam"

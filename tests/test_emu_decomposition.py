@@ -30,3 +30,21 @@ def test_emulated_pipeline_edge_cases(tag):
     exp = [tuple(l.rstrip("\n").split("\t")) for l in open(GDIR / f"edge_cases.{tag}.qual.txt")]
     assert quals == exp
     assert bed == open(GDIR / f"edge_cases.{tag}.bed").read()
+
+
+OPT = [(n, a) for n in sorted(GOLD) for a in sorted(GOLD[n].get("opt_runs", {}))]
+
+
+@pytest.mark.parametrize("name,args", OPT, ids=lambda v: v.replace(" ", "") if isinstance(v, str) else None)
+def test_emulated_pipeline_options(name, args):
+    """-S, -k/-K/-y pbccs, -N and -R keep.bed (the options the device serves through the plain per-item bodies)
+    against golden vectors made with the verbatim reference."""
+    data = sim(name)
+    bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data); bb.finish()
+    m = valid_mask(bb)
+    exp = GOLD[name]["opt_runs"][args]
+    argv = [str(GDIR / f"keep.{name}.bed") if x == "BED" else x for x in args.split()]
+    r = run_oracle(data, argv, binary=EMU_BIN, kind="emu")
+    assert hashlib.sha256(r["qual"][m].tobytes()).hexdigest() == exp["qual_sha256"]
+    assert r["bed"] == exp["bed"]
+    assert r["counters"] == exp["counters"]

@@ -162,6 +162,23 @@ def test_gpu_matches_golden(name):
 EDGE = {"l9": ["-9"], "l1B": ["-1", "-B"], "l5q30": ["-5", "-q30"], "l3U35": ["-3", "-U35", "-Y0.2"],
         "l9r": ["-9", "-r", "chrA:900-1600"], "l1r": ["-1", "-r", "chrA:1200-2100"]}
 
+OPT = [(n, a) for n in sorted(GOLD) for a in sorted(GOLD[n].get("opt_runs", {}))]
+
+
+@pytest.mark.parametrize("name,args", OPT, ids=lambda v: v.replace(" ", "") if isinstance(v, str) else None)
+def test_gpu_cli_options(name, args):
+    """-S, -k/-K/-y pbccs, -N, -R keep.bed through the crumble_gpu command line (option parsing, bed loading, host driver,
+    device path with the plain per-item kernels) against golden vectors made with the verbatim reference."""
+    g0 = GOLD[name]
+    data, nr, nb = cb.simulate(g0["preset"], g0["scale"], g0["seed"], threads=2)
+    bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data); bb.finish(); m = valid_mask(bb)
+    exp = g0["opt_runs"][args]
+    argv = [str(GDIR / f"keep.{name}.bed") if x == "BED" else x for x in args.split()]
+    r = run_oracle(data, argv, binary=ROOT / "crumble_b200" / "lib" / "crumble_gpu", kind="gpu-cli")
+    assert hashlib.sha256(r["qual"][m].tobytes()).hexdigest() == exp["qual_sha256"]
+    assert r["bed"] == exp["bed"]
+    assert r["counters"] == exp["counters"]
+
 
 @pytest.mark.parametrize("tag", sorted(EDGE))
 def test_gpu_cli_edge_cases(tag):
