@@ -66,6 +66,8 @@ typedef struct CgDevParams {
     int32_t str_snp;          /* sSTR_add || sSTR_mul (snp_score.c:1345) */
     int32_t any_preserve_qual;
     int32_t nbed;             /* -R regions (snp_score.c:1443-1463) */
+    /* column window of a chained call (cg_process_window, include/crumble_gpu.h): which columns this call owns */
+    int32_t win_on, win_lo_tid, win_lo_pos, win_cnt_pos, win_hi_tid, win_hi_pos;
 } CgDevParams;
 
 #include <stddef.h>
@@ -350,6 +352,7 @@ CG_HD void cg_cons_finalize(const CgTables *T, CgConsAcc *a, CgCons *o) {
 #define CG_EV_PROCESSED   0x0800
 #define CG_EV_BED         0x1000    /* preserve > 1: column inside a -R region, reads seen here skip the P-block (snp_score.c:1461,1890-1892) */
 #define CG_EV_IMPERFECT   0x2000    /* !perfect: preserved quality values disagree with the call (snp_score.c:1606-1608,1633-1645) */
+#define CG_EV_REPLAY      0x4000    /* chained call: column already counted by the previous call; processed again for the cross-column state only */
 
 /* call1 | call2 as the set of nt16 codes a base must equal to agree with the call (snp_score.c:1526-1542, 1906-1910):
  * calls 0..3 are A C G T; call 4 ('*' = 16) and 5 (N = 32) never equal an nt16 base code */

@@ -164,6 +164,29 @@ CG_HD int cg_island_of(const CgDev *D, int c) {
     return lo;
 }
 
+/* first dense column whose (tid, pos) is at or after the given one; n_cols when there is none */
+CG_HD int cg_find_col(const CgDev *D, int tid, int pos) {
+    const int64_t K = cg_key(tid, pos);
+    int lo = 0, hi = D->n_islands;                         /* first island starting after K */
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (cg_key(D->isl[mid].tid, D->isl[mid].pos_start) <= K) lo = mid + 1; else hi = mid; }
+    if (lo == 0) return 0;
+    const CgIsland I = D->isl[lo - 1];
+    const int next = lo < D->n_islands ? D->isl[lo].col_start : D->n_cols;
+    if (I.tid != tid) return next;
+    const int64_t c = (int64_t)I.col_start + ((int64_t)pos - I.pos_start);
+    return c < next ? (int)c : next;
+}
+
+/* Chained calls (cg_process_window): 0 = column owned by this call; 1 = replayed (already counted by the previous call,
+ * processed again because the cross-column state and the reads still open need it); 2 = not this call's business
+ * (before the window: done earlier; at/after its end: reads that cover it have not all arrived yet). */
+CG_HD int cg_window_class(const CgDevParams *P, int tid, int pos) {
+    if (!P->win_on) return 0;
+    if (tid == P->win_lo_tid) { if (pos < P->win_lo_pos) return 2; if (pos < P->win_cnt_pos) return 1; }
+    if (P->win_hi_tid >= 0 && (tid > P->win_hi_tid || (tid == P->win_hi_tid && pos >= P->win_hi_pos))) return 2;
+    return 0;
+}
+
 /* resolve a pileup cell for compact read j at dense column c; false if not covering */
 CG_HD bool cg_cell(const CgDev *D, const CgRead *q, int c, CgCell *cell) {
     unsigned d = (unsigned)(c - q->col0);
@@ -236,10 +259,16 @@ CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgC
         return o;
     }
     int tid = 0, pos = 0;
-    const int need_pos = (P->region_tid >= 0) || D->want_dump || P->nbed;
+    const int need_pos = (P->region_tid >= 0) || D->want_dump || P->nbed || P->win_on;
     if (need_pos) {
         int is = cg_island_of(D, c);
         tid = D->isl[is].tid; pos = D->isl[is].pos_start + (c - D->isl[is].col_start);
+    }
+    const int wclass = cg_window_class(P, tid, pos);
+    if (wclass == 2) {                                                    /* outside this call's column window */
+        D->cb[c] = (uint8_t)(cb | (D->cb[c] & CG_CB_ACTIVE)); D->ev[c] = 0;
+        if (D->want_dump) { cg_column z = {0}; z.tid = -1; D->coldump[c] = z; }
+        return o;
     }
     /* region end acts as a hard stop (the reference breaks out of the loop, 1516-1517) */
     if (P->region_tid >= 0 && pos >= P->region_end) { *D->beyond = 1; D->cb[c] = (uint8_t)(cb | (D->cb[c] & CG_CB_ACTIVE)); D->ev[c] = 0; if (D->want_dump) { cg_column z = {0}; z.tid = -1; D->coldump[c] = z; } return o; }
@@ -314,8 +343,10 @@ CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgC
         if (preserve) dflags |= 1;
         if (keep) dflags |= 2;
     }
+    if (wclass == 1) { ev |= CG_EV_REPLAY; o.cnt = 0; }                   /* counted (and dumped) by the previous call */
     D->cb[c] = (uint8_t)(cb | (D->cb[c] & CG_CB_ACTIVE)); D->ev[c] = ev;
-    if (D->want_dump) {
+    if (D->want_dump && wclass == 1) { cg_column z = {0}; z.tid = -1; D->coldump[c] = z; }
+    else if (D->want_dump) {
         cg_column z;
         const CgCons *cc = doB ? &cB : &cA;
         z.tid = tid; z.pos = pos; z.n_plp = n_plp;
@@ -442,7 +473,7 @@ CG_HDN uint32_t cg_flagged(const CgDev *D, int k, CgFlagScratch *S) {
     }
     if (ev_add) D->ev[c] = (uint16_t)(ev | ev_add);
     if (keep) D->cb[c] |= CG_CB_KEEP;
-    return cnt;
+    return (ev & CG_EV_REPLAY) ? 0 : cnt;
 }
 
 /* ---- stage: chain (sequential, one thread): window state after every flagged column ---- */
@@ -481,6 +512,23 @@ CG_HD void cg_paint(const CgDev *D, int k, int n_flagged) {
         c = D->isl[is].col_start; pos = D->isl[is].pos_start;
     }
 }
+
+/* chained calls: the window the previous call left open stays active over [pos_from, pos_to] of contig tid */
+CG_HD void cg_paint_range(const CgDev *D, int tid, int pos_from, int pos_to) {
+    int c = cg_find_col(D, tid, pos_from);
+    while (c < D->n_cols) {
+        const int is = cg_island_of(D, c);
+        if (D->isl[is].tid != tid) break;
+        const int isl_end_col = (is + 1 < D->n_islands) ? D->isl[is + 1].col_start : D->n_cols;
+        int pos = D->isl[is].pos_start + (c - D->isl[is].col_start);
+        if (pos > pos_to) break;
+        while (c < isl_end_col && pos <= pos_to) { D->cb[c] |= CG_CB_ACTIVE; c++; pos++; }
+        if (pos > pos_to) break;                           /* else: on to the next island */
+    }
+}
+
+/* number of BED events a column emits (none when it was counted by the previous call of a chain) */
+CG_HD int cg_event_bits(uint16_t ev) { return (ev & CG_EV_REPLAY) ? 0 : (ev & CG_EV_BEDMASK); }
 
 /* ---- stage: rewrite (one per record): replay of the per-base rewrite loop for ONE read
  * (snp_score.c:1822-1920 seen from the read), tail keep (1939-1940),
@@ -579,7 +627,7 @@ CG_HD uint32_t cg_deep_test(const CgDev *D, int c, int64_t tdepth, int64_t tcol)
     if ((double)(n * (tcol + 1)) > D->P.over_depth * (double)(tdepth + 1)) {
         D->ev[c] = (uint16_t)(ev | CG_EV_DEEP);
         D->cb[c] |= CG_CB_KEEP;
-        return 1u << CG_CNT_OVER_DEPTH;
+        return (ev & CG_EV_REPLAY) ? 0 : 1u << CG_CNT_OVER_DEPTH;
     }
     return 0;
 }

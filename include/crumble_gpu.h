@@ -154,6 +154,26 @@ int cg_sync(cg_ctx *ctx);
  * slice i of the kernel chain starts when chunk i has landed.  Results do not depend on it. */
 int cg_set_chunk_bytes(cg_ctx *ctx, int64_t bytes);
 
+/* ---- chained calls: a coordinate-sorted stream of any length in bounded memory ------------
+ * (region shards with a read halo, SURVEY.md §8(e): the reference keeps its state in a streaming loop, snp_score.c:1437-1975)
+ * The caller cuts the stream wherever it likes.  Let X be the position of the first record AFTER call k (same contig),
+ * S <= X the smallest start of a record of call k that reaches column X or beyond (S = X if none).  Then
+ *   call k   owns the columns below X:    hi_tid/hi_pos = X, next_lo_pos = S; records ending at or below X are final,
+ *   call k+1 = every pileup record seen so far that reaches beyond column S (the read halo, original order and
+ *              original qualities) followed by the new records, with lo_pos = S and cnt_pos = X: columns [S,X) are
+ *              processed again for the reads still open but neither counted nor reported twice.
+ * The two pieces of cross-column state (keep-window chain, depth average) are kept inside the context between calls,
+ * as they stand before column S.  Results are bit-identical to one call on the whole stream.                           */
+typedef struct cg_window {
+    int32_t first;                 /* 1: no earlier call to continue (also after a contig change): state is reset */
+    int32_t lo_tid, lo_pos;        /* columns of lo_tid below lo_pos belong to earlier calls (ignored when first) */
+    int32_t cnt_pos;               /* columns of lo_tid in [lo_pos, cnt_pos) were counted by the previous call */
+    int32_t hi_tid, hi_pos;        /* columns at/after (hi_tid, hi_pos) are left to the next call; hi_tid < 0: none */
+    int32_t next_lo_pos;           /* the next call's lo_pos (contig hi_tid); ignored when hi_tid < 0 */
+} cg_window;
+/* cg_process restricted to the window's columns; the records the caller treats as final are its own business */
+int cg_process_window(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out);
+
 /* measurement helpers */
 enum { CG_T_TOTAL = 0, CG_T_TILES, CG_T_COLUMNS, CG_T_FLAGGED, CG_T_DEPTH, CG_T_CHAIN, CG_T_REWRITE, CG_T_PBLOCK, CG_T_EVENTS, CG_T_H2D, CG_T_D2H, CG_N_TIMERS };
 float   cg_last_ms(const cg_ctx *ctx, int which);        /* CUDA-event time of the last cg_run / copies */

@@ -12,9 +12,11 @@
 #include <string.h>
 #include <stdio.h>
 #include <vector>
+#include <limits.h>
 #include "../../crumble_b200/csrc/cg_host.h"
 
-struct cg_ctx { cg_params p; CgTables T; char err[256]; int64_t n_cols; std::vector<cg_bed_reg> bed; std::vector<int64_t> bed_pm; };
+struct EmuCarry { CgWin w; int chain_tid; int64_t td, tc; int depth_tid; };
+struct cg_ctx { cg_params p; CgTables T; char err[256]; int64_t n_cols; std::vector<cg_bed_reg> bed; std::vector<int64_t> bed_pm; EmuCarry carry; std::vector<cg_bed_event> events; };
 
 extern "C" int cg_device_count(void) { return 0; }
 extern "C" int cg_enable_pinned(void) { return 0; }
@@ -35,7 +37,17 @@ extern "C" float cg_last_ms(const cg_ctx *, int) { return 0; }
 extern "C" int64_t cg_last_launches(const cg_ctx *) { return 0; }
 extern "C" int64_t cg_n_columns(const cg_ctx *c) { return c->n_cols; }
 
-extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
+static int emu_process(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out);
+/* events of the last call again (the caller's buffer was too small); qualities are already in the caller's buffer */
+extern "C" int cg_download(cg_ctx *ctx, cg_result *out) {
+    out->n_events = (int64_t)ctx->events.size();
+    for (int64_t i = 0; i < out->n_events && i < out->events_cap; i++) out->events[i] = ctx->events[i];
+    return 0;
+}
+extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) { return emu_process(ctx, in, NULL, out); }
+extern "C" int cg_process_window(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out) { return emu_process(ctx, in, win, out); }
+
+static int emu_process(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out) {
     CgDev D; memset(&D, 0, sizeof(D));
     const int64_t n = in->n_reads;
     D.n_reads = n;
@@ -43,6 +55,14 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
     D.n_cigar = in->n_cigar; D.off = in->off; D.cigar_off = in->cigar_off; D.cigar = in->cigar; D.seq = in->seq; D.qual = in->qual;
     D.qual_out = out->qual_out;
     D.T = &ctx->T; cg_devparams_from(&D.P, &ctx->p);
+    EmuCarry cy; cg_win_reset(&cy.w); cy.chain_tid = -2; cy.td = cy.tc = 0; cy.depth_tid = -2;
+    if (win) {
+        D.P.win_on = 1;
+        D.P.win_lo_tid = win->first ? -1 : win->lo_tid; D.P.win_lo_pos = win->lo_pos; D.P.win_cnt_pos = win->cnt_pos;
+        D.P.win_hi_tid = win->hi_tid; D.P.win_hi_pos = win->hi_pos;
+        if (!win->first) cy = ctx->carry;
+    }
+    EmuCarry snap = cy; bool snapped_depth = false, snapped_chain = false;
     D.bed = ctx->bed.data(); D.bed_pm = ctx->bed_pm.data();
     int32_t err = 0, maxdepth = 0, beyond = 0; D.err = &err; D.maxdepth = &maxdepth; D.beyond = &beyond;
     unsigned long long counters[CG_N_COUNTERS] = {0}; D.counters = counters;
@@ -77,6 +97,7 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
     for (int j = 0; j < np; j++) cg_tile_index(&D, j);
     std::vector<uint8_t> cb(D.n_cols + 1); std::vector<uint16_t> ev(D.n_cols + 1); std::vector<uint32_t> depth(D.n_cols + 1);
     D.cb = cb.data(); D.ev = ev.data(); D.depth = depth.data();
+    const int cS = (win && win->hi_tid >= 0) ? cg_find_col(&D, win->hi_tid, win->next_lo_pos) : D.n_cols;
     std::vector<cg_column> dump;
     D.want_dump = out->columns != NULL;
     if (D.want_dump) { dump.resize(D.n_cols + 1); D.coldump = dump.data(); }
@@ -100,8 +121,9 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
     if (err) { snprintf(ctx->err, sizeof ctx->err, "overflow"); return err; }
     /* depth average (sequential restatement of snp_score.c:1478-1491,1673-1687) */
     {
-        int64_t td = 0, tc = 0; int is = 0, last_tid = -2;
+        int64_t td = cy.td, tc = cy.tc; int is = 0, last_tid = cy.depth_tid;
         for (int c = 0; c < D.n_cols; c++) {
+            if (c == cS && !snapped_depth) { snap.td = td; snap.tc = tc; snap.depth_tid = last_tid; snapped_depth = true; }
             while (is + 1 < D.n_islands && isl[is + 1].col_start <= c) is++;
             if (!(ev[c] & CG_EV_COUNTED)) continue;
             if (isl[is].tid != last_tid) { td = 0; tc = 0; last_tid = isl[is].tid; }
@@ -112,22 +134,39 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
                 if (tc > 1024 * 1024) { tc >>= 1; td >>= 1; }
             }
         }
+        if (!snapped_depth) { snap.td = td; snap.tc = tc; snap.depth_tid = last_tid; }
     }
-    cg_chain(&D, nf);
+    /* keep-window chain, sequential as cg_chain, continuing the state the previous call of a chain left */
+    {
+        CgWin w = cy.w; int last_tid = cy.chain_tid;
+        for (int k = 0; k < nf; k++) {
+            if (fcol[k] >= cS && !snapped_chain) { snap.w = w; snap.chain_tid = last_tid; snapped_chain = true; }
+            const CgTrig t = trig[k];
+            if (t.hasI || t.hasS) {
+                if (t.tid != last_tid) { cg_win_reset(&w); last_tid = t.tid; }
+                cg_win_step(&w, &t, &D.P);
+            }
+            twin[k] = w;
+        }
+        if (!snapped_chain) { snap.w = w; snap.chain_tid = last_tid; }
+    }
+    if (win && !win->first && cy.chain_tid == win->lo_tid && cy.w.min_pos != INT_MAX && cy.w.max_pos2 >= win->lo_pos)
+        cg_paint_range(&D, win->lo_tid, win->lo_pos, cy.w.max_pos2);
+    ctx->carry = snap;
     for (int k = 0; k < nf; k++) cg_paint(&D, k, nf);
     for (int64_t r = 0; r < n; r++) cg_rewrite(&D, r, nf);
     /* events */
     out->n_events = 0;
+    ctx->events.clear();
     {
         int is = 0;
         for (int c = 0; c < D.n_cols; c++) {
             while (is + 1 < D.n_islands && isl[is + 1].col_start <= c) is++;
-            int bits = ev[c] & CG_EV_BEDMASK;
+            int bits = cg_event_bits(ev[c]);
             for (int t = 0; t < 5; t++) if (bits >> t & 1) {
-                if (out->events && out->n_events < out->events_cap) {
-                    cg_bed_event e; e.tid = isl[is].tid; e.pos = isl[is].pos_start + (c - isl[is].col_start); e.tag = t;
-                    out->events[out->n_events] = e;
-                }
+                cg_bed_event e; e.tid = isl[is].tid; e.pos = isl[is].pos_start + (c - isl[is].col_start); e.tag = t;
+                ctx->events.push_back(e);
+                if (out->events && out->n_events < out->events_cap) out->events[out->n_events] = e;
                 out->n_events++;
             }
         }
