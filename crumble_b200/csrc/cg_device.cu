@@ -143,11 +143,11 @@ struct StCompact { int32_t *out; const uint16_t *ev; uint16_t mask; __device__ v
 struct LdDepthCounted { const uint32_t *depth; const uint16_t *ev; __device__ int64_t operator()(int64_t c) const { return (ev[c] & CG_EV_COUNTED) ? (int64_t)depth[c] : 0; } };
 struct LdCounted { const uint16_t *ev; __device__ int32_t operator()(int64_t c) const { return (ev[c] & CG_EV_COUNTED) != 0; } };
 struct StI32Incl { int32_t *p; __device__ void operator()(int64_t i, int32_t inc, int32_t) const { p[i] = inc; } };
-struct LdEvCount { const uint16_t *ev; __device__ int32_t operator()(int64_t c) const { return __popc(ev[c] & CG_EV_BEDMASK); } };
+struct LdEvCount { const uint16_t *ev; __device__ int32_t operator()(int64_t c) const { return __popc(cg_event_bits(ev[c])); } };
 struct StEvents {
     cg_bed_event *out; const uint16_t *ev; CgDev D; int64_t cap;
     __device__ void operator()(int64_t c, int32_t, int32_t ex) const {
-        int bits = ev[c] & CG_EV_BEDMASK;
+        int bits = cg_event_bits(ev[c]);
         if (!bits) return;
         int is = cg_island_of(&D, (int)c);
         int tid = D.isl[is].tid, pos = D.isl[is].pos_start + ((int)c - D.isl[is].col_start);
@@ -693,6 +693,7 @@ __global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant
             if (tr.hasI || tr.hasS) ev_add |= CG_EV_TRIGGER;
             if (ev_add) D.ev[c] = (uint16_t)(ev | ev_add);
             if (keep) D.cb[c] |= CG_CB_KEEP;
+            if (ev & CG_EV_REPLAY) cnt = 0;                                      /* counted by the previous call of the chain */
             while (cnt) { int b = __ffs(cnt) - 1; cnt &= cnt - 1; atomicAdd(&D.counters[b], 1ULL); }
         }
         __syncwarp();
@@ -753,8 +754,13 @@ __global__ void k_epochs(const __grid_constant__ CgDev D, CgEpoch *ep, CgEpochCa
         const int c1_true = (is2 + 1 < D.n_islands) ? D.isl[is2 + 1].col_start : D.n_cols;
         const int c1 = c1_true < ce ? c1_true : ce;
         int64_t d_off, c_off, td, tc; int s = c0;
-        if (carry->valid && carry->tid == tid) { td = carry->td; tc = carry->tc; d_off = carry->d_off; c_off = carry->c_off; }
-        else {
+        if (carry->valid && carry->tid == tid) {
+            td = carry->td; tc = carry->tc; d_off = carry->d_off; c_off = carry->c_off;
+            if (ne == 0) {                                  /* resumed from an earlier call (cg_process_window): its epoch list is gone */
+                if (ne < cap) { CgEpoch e; e.col_begin = s; e.pad = 0; e.td_base = td; e.tc_base = tc; e.d_off = d_off; e.c_off = c_off; ep[ne] = e; }
+                ne++;
+            }
+        } else {
             d_off = c0 ? D.dsum[c0 - 1] : 0; c_off = c0 ? D.csum[c0 - 1] : 0; td = tc = 0;
             if (ne < cap) { CgEpoch e; e.col_begin = s; e.pad = 0; e.td_base = td; e.tc_base = tc; e.d_off = d_off; e.c_off = c_off; ep[ne] = e; }
             ne++;
@@ -803,7 +809,7 @@ __global__ void k_deep(const __grid_constant__ CgDev D, const CgEpoch *ep, const
  *   max_pos2 after trigger i  <=  U_i = max_{i' <= i} ceil( pos_i' + (Bmax_i' - pos_i') * mul + add ),  Bmax = prefix max of B
  * (both prefix maxima restricted to the contig by packing tid into the high word).  pos_k > U_{k-1} proves a reset at k;
  * each proven head then replays its segment sequentially (unproven resets inside are found by the replay itself). */
-struct CgChainCarry { int64_t bkey, ukey; CgWin w; int32_t has, pad; };    /* state after the last trigger of the previous slice */
+struct CgChainCarry { int64_t bkey, ukey; CgWin w; int32_t has, wtid; };    /* state after the last trigger of the previous slice (wtid = its contig) */
 struct LdTrigB {
     const CgTrig *t; const CgChainCarry *cy;
     __device__ int64_t operator()(int64_t k) const {
@@ -853,13 +859,33 @@ __global__ void k_chain_carry(const __grid_constant__ CgDev D, const int64_t *bm
     cy->bkey = bmax[k_end - 1]; cy->ukey = umax[k_end - 1];
     for (int k = k_end - 1; k >= k_begin; k--) {
         const CgTrig *t = &D.trig[k];
-        if (t->hasI || t->hasS) { cy->w = D.twin[k]; cy->has = 1; break; }
+        if (t->hasI || t->hasS) { cy->w = D.twin[k]; cy->has = 1; cy->wtid = t->tid; break; }
     }
 }
 __global__ void k_paint(const __grid_constant__ CgDev D, int k_begin, int k_end) {
     int k = k_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (k < k_end) cg_paint(&D, k, k_end);
 }
+/* ---- chained calls (cg_process_window) ----
+ * What one call hands to the next: both carries as they stand before the next call's first column, with the depth
+ * carry's prefix-sum offsets rebased so that the next call's prefix sums may start from zero. */
+struct CgSavedCarry { CgChainCarry cc; CgEpochCarry ec; };
+__global__ void k_carry_save(const CgChainCarry *cc, const CgEpochCarry *ec, CgSavedCarry *out) {
+    if (threadIdx.x || blockIdx.x) return;
+    CgSavedCarry s; s.cc = *cc; s.ec = *ec;
+    s.ec.d_off -= s.ec.dsum_last; s.ec.c_off -= s.ec.csum_last; s.ec.dsum_last = 0; s.ec.csum_last = 0; s.ec.n_ep = 0;
+    *out = s;
+}
+__global__ void k_find_col(const __grid_constant__ CgDev D, int tid, int pos, int32_t *out) {
+    if (threadIdx.x || blockIdx.x) return;
+    *out = cg_find_col(&D, tid, pos);
+}
+/* the keep window the previous call left open stays active from this call's first column up to its max_pos2 */
+__global__ void k_paint_carry(const __grid_constant__ CgDev D, const CgChainCarry *cy, int lo_tid, int lo_pos) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (cy->has && cy->wtid == lo_tid && cy->w.min_pos != INT_MAX && cy->w.max_pos2 >= lo_pos) cg_paint_range(&D, lo_tid, lo_pos, cy->w.max_pos2);
+}
+
 /* Per-read quality rewrite.  A block owns RW_READS consecutive records; their quality strings, packed sequences
  * and the column bytes under them are three CONTIGUOUS ranges, fetched with three bulk async copies (TMA,
  * cp.async.bulk + mbarrier) into shared memory.  Then
@@ -1252,6 +1278,7 @@ struct cg_ctx {
     int64_t qual_bytes, events_cap_dev;
     int need_depth, epoch_cap, nf_total;
     int64_t chunk_bytes;
+    int win_on, have_saved; cg_window win; dbuf b_saved;       /* chained calls: this call's window, the carries of the previous one */
     cudaStream_t s_h2d, s_d2h; cudaEvent_t ev_up[32], ev_done[32], ev_misc;
     char h_carry_init[64];
     cudaEvent_t ev[CG_N_TIMERS][2];
@@ -1352,7 +1379,7 @@ extern "C" void cg_destroy(cg_ctx *ctx) {
     dbuf *all[] = { &ctx->b_tid, &ctx->b_pos, &ctx->b_flag, &ctx->b_mapq, &ctx->b_lq, &ctx->b_nc, &ctx->b_off, &ctx->b_coff, &ctx->b_cigar,
         &ctx->b_seq, &ctx->b_qual, &ctx->b_qout, &ctx->b_jmap, &ctx->b_rspan, &ctx->b_rd, &ctx->b_ks, &ctx->b_ke, &ctx->b_gap, &ctx->b_gapraw,
         &ctx->b_pmax, &ctx->b_orig, &ctx->b_rbf, &ctx->b_tlo, &ctx->b_tstart, &ctx->b_isl, &ctx->b_cb, &ctx->b_ev, &ctx->b_depth, &ctx->b_dump,
-        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain, &ctx->b_items, &ctx->b_bed, &ctx->b_bedpm };
+        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain, &ctx->b_items, &ctx->b_bed, &ctx->b_bedpm, &ctx->b_saved };
     for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); i++) if (all[i]->p) cudaFree(all[i]->p);
     if (ctx->dT) cudaFree(ctx->dT);
     if (ctx->h_dims) cudaFreeHost(ctx->h_dims);
@@ -1431,7 +1458,7 @@ static int upload_bases(cg_ctx *ctx, const cg_batch *in, int64_t b0, int64_t b1,
 extern "C" int cg_upload(cg_ctx *ctx, const cg_batch *in) {
     CG_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    ctx->resident = 0;
+    ctx->resident = 0; ctx->win_on = 0;
     int e;
     if ((e = alloc_inputs(ctx, in))) return e;
     T0(CG_T_H2D);
@@ -1504,6 +1531,11 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
     ctx->launches = 0;
     for (int i = 0; i < CG_N_TIMERS; i++) if (i != CG_T_H2D && i != CG_T_D2H) ctx->ms[i] = 0;
     D->T = ctx->dT; cg_devparams_from(&D->P, &ctx->params);
+    if (ctx->win_on) {
+        const cg_window *w = &ctx->win;
+        D->P.win_on = 1; D->P.win_lo_tid = w->first ? -1 : w->lo_tid; D->P.win_lo_pos = w->lo_pos; D->P.win_cnt_pos = w->cnt_pos;
+        D->P.win_hi_tid = w->hi_tid; D->P.win_hi_pos = w->hi_pos;
+    }
     D->bed = (const cg_bed_reg *)ctx->b_bed.p; D->bed_pm = (const int64_t *)ctx->b_bedpm.p;
     if ((e = ensure(ctx, &ctx->b_scal, 2048))) return e;
     int32_t *scal = (int32_t *)ctx->b_scal.p;
@@ -1525,6 +1557,11 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
         CgChainCarry cc; memset(&cc, 0, sizeof cc); cc.bkey = INT64_MIN; cc.ukey = INT64_MIN; cg_win_reset(&cc.w);
         memcpy(ctx->h_carry_init, &cc, sizeof cc);
         CG_CHECK(cudaMemcpyAsync((char *)ctx->b_scal.p + 512, ctx->h_carry_init, sizeof cc, cudaMemcpyHostToDevice, st));
+        if (ctx->win_on && !ctx->win.first && ctx->have_saved) {       /* continue where the previous call of the chain stopped */
+            const CgSavedCarry *sv = (const CgSavedCarry *)ctx->b_saved.p;
+            CG_CHECK(cudaMemcpyAsync((char *)ctx->b_scal.p + 512, &sv->cc, sizeof(CgChainCarry), cudaMemcpyDeviceToDevice, st));
+            CG_CHECK(cudaMemcpyAsync((char *)ctx->b_scal.p + 640, &sv->ec, sizeof(CgEpochCarry), cudaMemcpyDeviceToDevice, st));
+        }
     }
     if (n > 0) {
         k_prep_read<<<nblk(n, 256), 256, 0, st>>>(*D); ctx->launches++;
@@ -1579,6 +1616,7 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
         CG_CHECK(cudaStreamSynchronize(st));
         /* over-depth (snp_score.c:1673) needs n_plp > -P * mean depth >= -P: impossible when no tile has more than -P candidates */
         ctx->need_depth = ctx->params.over_depth < 1.0 || (double)ctx->h_dims[9] > ctx->params.over_depth;
+        if (ctx->win_on) ctx->need_depth = 1;                       /* a later call of the chain may need the running average */
         if (ctx->need_depth) {
             if ((e = ensure(ctx, &ctx->b_dsum, nc1 * 8)) || (e = ensure(ctx, &ctx->b_csum, nc1 * 4))) return e;
             D->dsum = (int64_t *)ctx->b_dsum.p; D->csum = (int32_t *)ctx->b_csum.p;
@@ -1592,15 +1630,14 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
 }
 
 /* one slice: tiles [t0,t1) -> their columns -> sparse passes -> records [r0,r1) */
-static int run_slice(cg_ctx *ctx, int t0, int t1, int64_t r0, int64_t r1, int timed) {
+static int run_slice(cg_ctx *ctx, int t0, int t1, int c0, int c1, int64_t r0, int64_t r1, int timed) {
     cudaStream_t st = ctx->stream;
     CgDev *D = &ctx->D;
     int32_t *scal = (int32_t *)ctx->b_scal.p;
     CgChainCarry *ccarry = (CgChainCarry *)((char *)ctx->b_scal.p + 512);
     CgEpochCarry *ecarry = (CgEpochCarry *)((char *)ctx->b_scal.p + 640);
     int e;
-    const int c0 = t0 * 32, c1 = t1 * 32 < D->n_cols ? t1 * 32 : D->n_cols;
-    const int ncs = c1 - c0;
+    const int ncs = c1 > c0 ? c1 - c0 : 0;                      /* columns of the sparse passes: the tiles' own, except in chained calls */
     int nfs = 0;
     const int kb = ctx->nf_total;
     if (timed) T0(CG_T_COLUMNS);
@@ -1720,7 +1757,7 @@ extern "C" int cg_run(cg_ctx *ctx) {
     int e;
     T0(CG_T_TOTAL);
     if ((e = run_prep(ctx, &B, hb))) return e;
-    if ((e = run_slice(ctx, 0, ctx->D.n_tiles, 0, ctx->D.n_reads, 1))) return e;
+    if ((e = run_slice(ctx, 0, ctx->D.n_tiles, 0, ctx->D.n_cols, 0, ctx->D.n_reads, 1))) return e;
     return run_finish(ctx, 1);
 }
 
@@ -1773,7 +1810,7 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
     CG_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int e;
-    ctx->resident = 0;
+    ctx->resident = 0; ctx->win_on = 0;
     ctx->dump_columns = out->columns != NULL;
     if ((e = alloc_inputs(ctx, in))) return e;
     if (!ctx->s_h2d) {
@@ -1834,7 +1871,7 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
         if (t1 < tprev) t1 = tprev;
         if (r1 < rprev) r1 = rprev;
         CG_CHECK(cudaStreamWaitEvent(st, ctx->ev_up[i], 0));
-        if ((e = run_slice(ctx, tprev, t1, rprev, r1, 0))) return e;
+        if ((e = run_slice(ctx, tprev, t1, tprev * 32, t1 * 32 < ctx->D.n_cols ? t1 * 32 : ctx->D.n_cols, rprev, r1, 0))) return e;
         if (r1 > rprev && out->qual_out) {
             const int64_t b0 = in->off[rprev], b1 = r1 < n ? in->off[r1] : in->qual_bytes;
             CG_CHECK(cudaEventRecord(ctx->ev_done[i], st));
@@ -1851,6 +1888,53 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
     CG_CHECK(cudaStreamSynchronize(ctx->s_d2h));
     CG_TRACE_AT("d2h drained", 0);
     CG_CHECK(cudaStreamSynchronize(ctx->s_h2d));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_D2H][0], ctx->ev[CG_T_D2H][1]) == cudaSuccess) ctx->ms[CG_T_D2H] = ms; else cudaGetLastError();
+    if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_H2D][0], ctx->ev[CG_T_H2D][1]) == cudaSuccess) ctx->ms[CG_T_H2D] = ms; else cudaGetLastError();
+    return 0;
+}
+
+/* One call of a chain (include/crumble_gpu.h): the batch is uploaded whole, the column stage runs over all of its tiles
+ * (columns outside the window come out inert, cg_window_class), the sparse passes run over the columns before the next
+ * call's first column, the two carries are saved there, and the sparse passes finish the rest. */
+extern "C" int cg_process_window(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out) {
+    if (!win) return CG_ERR_BAD_ARG;
+    if (ctx->params.region_tid >= 0) { snprintf(ctx->err, sizeof ctx->err, "chained calls and a -r region do not combine"); return CG_ERR_BAD_ARG; }
+    CG_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int e;
+    ctx->resident = 0;
+    ctx->dump_columns = out->columns != NULL;
+    if ((e = alloc_inputs(ctx, in))) return e;
+    if ((e = ensure(ctx, &ctx->b_saved, sizeof(CgSavedCarry)))) return e;
+    ctx->win = *win; ctx->win_on = 1;
+    T0(CG_T_TOTAL);
+    T0(CG_T_H2D);
+    if ((e = upload_meta(ctx, in, st)) || (e = upload_bases(ctx, in, 0, in->qual_bytes, st))) { ctx->win_on = 0; return e; }
+    T1(CG_T_H2D);
+    CgBounds B; memset(&B, 0, sizeof B); B.n = 1; B.rb[0] = in->n_reads;
+    int64_t hb[2 * CG_MAX_CHUNKS];
+    e = run_prep(ctx, &B, hb);
+    CgDev *D = &ctx->D;
+    const int nc = D->n_cols;
+    int cS = nc;
+    if (!e && nc > 0) {
+        CgChainCarry *ccarry = (CgChainCarry *)((char *)ctx->b_scal.p + 512);
+        CgEpochCarry *ecarry = (CgEpochCarry *)((char *)ctx->b_scal.p + 640);
+        if (!win->first && ctx->have_saved) { k_paint_carry<<<1, 32, 0, st>>>(*D, ccarry, win->lo_tid, win->lo_pos); ctx->launches++; }
+        if (win->hi_tid >= 0) {
+            k_find_col<<<1, 32, 0, st>>>(*D, win->hi_tid, win->next_lo_pos, ctx->d_hdims + 11); ctx->launches++;
+            if (cudaStreamSynchronize(st) != cudaSuccess) e = CG_ERR_CUDA; else cS = ctx->h_dims[11];
+        }
+        if (!e) e = run_slice(ctx, 0, D->n_tiles, 0, cS, 0, 0, 0);
+        if (!e && win->hi_tid >= 0) { k_carry_save<<<1, 32, 0, st>>>(ccarry, ecarry, (CgSavedCarry *)ctx->b_saved.p); ctx->launches++; }
+        if (!e) e = run_slice(ctx, 0, 0, cS, nc, 0, in->n_reads, 0);
+    } else if (!e && in->n_reads > 0) e = run_slice(ctx, 0, 0, 0, 0, 0, in->n_reads, 0);      /* nothing in the pileup: strip + P-block only */
+    ctx->have_saved = !e && win->hi_tid >= 0 && nc > 0;
+    if (!e) e = run_finish(ctx, 0);
+    ctx->win_on = 0;
+    if (e) return e;
+    if ((e = download_results(ctx, out, 1))) return e;
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_D2H][0], ctx->ev[CG_T_D2H][1]) == cudaSuccess) ctx->ms[CG_T_D2H] = ms; else cudaGetLastError();
     if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_H2D][0], ctx->ev[CG_T_H2D][1]) == cudaSuccess) ctx->ms[CG_T_H2D] = ms; else cudaGetLastError();

@@ -48,3 +48,46 @@ def test_emulated_pipeline_options(name, args):
     assert hashlib.sha256(r["qual"][m].tobytes()).hexdigest() == exp["qual_sha256"]
     assert r["bed"] == exp["bed"]
     assert r["counters"] == exp["counters"]
+
+
+# ---- chained calls: the host driver cuts the stream into region shards with a read halo (transcode_gpu.c, cg_process_window) ----
+CHAIN = [("tiny", 1), ("tiny", 97), ("c1s", 1500), ("c2s", 4000), ("c4s", 333)]
+CHAIN_ARGS = ["-9", "-1", "-3", "-5 -q30", "-1 -m10 -C0.05 -Z0.01", "-3 -i0.5,3 -s2.0,1"]
+
+
+@pytest.mark.parametrize("name,batch", CHAIN, ids=lambda v: str(v))
+def test_chained_calls_match_golden(name, batch):
+    """The same golden vectors with the input cut every `batch` records: every cut leaves reads open, so the halo, the
+    replayed columns and both carried states (keep-window chain, depth average at -1/-3/-5) are all exercised."""
+    data = sim(name)
+    bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data); bb.finish()
+    m = valid_mask(bb)
+    for args in CHAIN_ARGS if batch > 1 else CHAIN_ARGS[:2]:
+        exp = GOLD[name]["runs"][args]
+        r = run_oracle(data, args.split(), binary=EMU_BIN, kind="emu", env_extra={"CRUMBLE_BATCH_READS": str(batch)})
+        assert hashlib.sha256(r["qual"][m].tobytes()).hexdigest() == exp["qual_sha256"], args
+        assert r["bed"] == exp["bed"], args
+        assert r["counters"] == exp["counters"], args
+
+
+@pytest.mark.parametrize("batch", [1, 5, 40])
+def test_chained_calls_edge_cases(batch):
+    """odd CIGARs (N skips, long reads, clips), FUNMAP-placed and unplaced reads, two contigs, across cuts"""
+    for tag in ("l9", "l1B", "l5q30", "l3U35"):
+        quals, bed = run_cli_sam(EMU_BIN, EDGE[tag], GDIR / "edge_cases.sam", env_extra={"CRUMBLE_BATCH_READS": str(batch)})
+        exp = [tuple(l.rstrip("\n").split("\t")) for l in open(GDIR / f"edge_cases.{tag}.qual.txt")]
+        assert quals == exp, tag
+        assert bed == open(GDIR / f"edge_cases.{tag}.bed").read(), tag
+
+
+def test_chained_calls_options():
+    """-S, -k/-K, -N, -R across cuts (the plain per-item bodies)"""
+    data = sim("tiny")
+    bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data); bb.finish()
+    m = valid_mask(bb)
+    for args, exp in GOLD["tiny"]["opt_runs"].items():
+        argv = [str(GDIR / "keep.tiny.bed") if x == "BED" else x for x in args.split()]
+        r = run_oracle(data, argv, binary=EMU_BIN, kind="emu", env_extra={"CRUMBLE_BATCH_READS": "211"})
+        assert hashlib.sha256(r["qual"][m].tobytes()).hexdigest() == exp["qual_sha256"], args
+        assert r["bed"] == exp["bed"], args
+        assert r["counters"] == exp["counters"], args

@@ -265,3 +265,50 @@ def test_gpu_empty_and_degenerate_batches():
     assert out["counters"]["columns"] == 0
     assert list(out["qual"][:8]) == [31, 31, 31, 10, 10, 40, 40, 2] and list(out["qual"][8:16]) == [31, 31, 31, 10, 10, 40, 40, 2]
     g.close()
+
+
+CHAIN = [("tiny", 97), ("c1s", 1500), ("c1s", 20000), ("c2s", 4000), ("c4s", 333)]
+
+
+@pytest.mark.parametrize("name,batch", CHAIN, ids=lambda v: str(v))
+def test_gpu_chained_calls(name, batch):
+    """cg_process_window through the crumble_gpu command line: the stream cut every `batch` records (region shards with a
+    read halo, replayed columns, keep-window and depth-average state carried on the device) must reproduce the golden
+    vectors of the uncut run bit for bit: qualities, BED lines, counters."""
+    g0 = GOLD[name]
+    data, nr, nb = cb.simulate(g0["preset"], g0["scale"], g0["seed"], threads=2)
+    bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data); bb.finish(); m = valid_mask(bb)
+    for args in ["-9", "-1", "-3", "-5 -q30", "-1 -m10 -C0.05 -Z0.01", "-3 -i0.5,3 -s2.0,1"]:
+        exp = g0["runs"][args]
+        r = run_oracle(data, args.split(), binary=ROOT / "crumble_b200" / "lib" / "crumble_gpu", kind="gpu-cli",
+                       env_extra={"CRUMBLE_BATCH_READS": str(batch)})
+        assert hashlib.sha256(r["qual"][m].tobytes()).hexdigest() == exp["qual_sha256"], args
+        assert r["bed"] == exp["bed"], args
+        assert r["counters"] == exp["counters"], args
+
+
+@pytest.mark.parametrize("batch", [1, 5, 40])
+def test_gpu_chained_calls_edge_cases(batch):
+    cli = ROOT / "crumble_b200" / "lib" / "crumble_gpu"
+    env = dict(os.environ, CRUMBLE_BATCH_READS=str(batch))
+    for tag in ("l9", "l1B", "l5q30", "l3U35"):
+        with tempfile.TemporaryDirectory() as td:
+            out, bed = os.path.join(td, "o.sam"), os.path.join(td, "o.bed")
+            r = subprocess.run([str(cli), "-z"] + EDGE[tag] + ["-b", bed, str(GDIR / "edge_cases.sam"), out], stderr=subprocess.PIPE, text=True, env=env)
+            assert r.returncode == 0, r.stderr
+            quals = [(l.rstrip("\n").split("\t")[0], l.rstrip("\n").split("\t")[10]) for l in open(out) if not l.startswith("@")]
+            exp = [tuple(l.rstrip("\n").split("\t")) for l in open(GDIR / f"edge_cases.{tag}.qual.txt")]
+            assert quals == exp, tag
+            assert open(bed).read() == open(GDIR / f"edge_cases.{tag}.bed").read(), tag
+
+
+def test_gpu_chained_calls_options():
+    g0 = GOLD["tiny"]
+    data, nr, nb = cb.simulate(g0["preset"], g0["scale"], g0["seed"], threads=2)
+    bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data); bb.finish(); m = valid_mask(bb)
+    for args, exp in g0["opt_runs"].items():
+        argv = [str(GDIR / "keep.tiny.bed") if x == "BED" else x for x in args.split()]
+        r = run_oracle(data, argv, binary=ROOT / "crumble_b200" / "lib" / "crumble_gpu", kind="gpu-cli", env_extra={"CRUMBLE_BATCH_READS": "211"})
+        assert hashlib.sha256(r["qual"][m].tobytes()).hexdigest() == exp["qual_sha256"], args
+        assert r["bed"] == exp["bed"], args
+        assert r["counters"] == exp["counters"], args

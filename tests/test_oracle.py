@@ -51,10 +51,11 @@ def test_port_matches_reference_binary_fresh_seed():
         assert np.array_equal(a["qual"][m], b["qual"][m]) and a["bed"] == b["bed"] and a["counters"] == b["counters"]
 
 
-def run_cli_sam(binary, args, sam_in):
+def run_cli_sam(binary, args, sam_in, env_extra=None):
     with tempfile.TemporaryDirectory() as td:
         out, bed = os.path.join(td, "o.sam"), os.path.join(td, "o.bed")
-        subprocess.run([str(binary), "-z"] + args + ["-b", bed, str(sam_in), out], check=True, stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
+        subprocess.run([str(binary), "-z"] + args + ["-b", bed, str(sam_in), out], check=True, stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL,
+                       env=dict(os.environ, **(env_extra or {})))
         quals = [(l.rstrip("\n").split("\t")[0], l.rstrip("\n").split("\t")[10]) for l in open(out) if not l.startswith("@")]
         return quals, open(bed).read()
 

@@ -60,7 +60,7 @@ def header_names(data: np.ndarray):
     return names
 
 
-def run_oracle(data: np.ndarray, args, kind=None, binary=None, timing=False):
+def run_oracle(data: np.ndarray, args, kind=None, binary=None, timing=False, env_extra=None):
     """Run the oracle CLI on an uncompressed BAM stream; returns quals in batch layout, BED text, counters."""
     import crumble_b200 as cb
     if binary is None:
@@ -71,6 +71,7 @@ def run_oracle(data: np.ndarray, args, kind=None, binary=None, timing=False):
         data.tofile(fin)
         env = dict(os.environ)
         env["CRUMBLE_REF_TIMING"] = "1"
+        env.update(env_extra or {})
         cmd = [str(binary), "-z", "-v"] + list(args) + ["-b", fbed, "-O", "bam,raw", fin, fout]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
         if r.returncode != 0:
