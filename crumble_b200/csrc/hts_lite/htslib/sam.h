@@ -169,6 +169,8 @@ void   hts_lite_mem_drop(const char *name);
  * most recent sam_write1/sam_read1 call (brackets transcode()). */
 double hts_lite_io_span_seconds(void);
 void   hts_lite_io_span_reset(void);
+/* BGZF worker threads per open file (default: online cores, at most 16; readers use at most 4); also -I/-O nthreads=N */
+void   hts_lite_set_threads(int n);
 /* parse one SAM text line (NUL terminated, no newline) into b; <0 on error */
 int    sam_parse_line(char *line, size_t len, bam_hdr_t *h, bam1_t *b);
 /* format b as a SAM text line into *buf (realloc'ed), returns length */

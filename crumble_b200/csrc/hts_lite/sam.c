@@ -15,6 +15,8 @@
 #include <ctype.h>
 #include <time.h>
 #include <zlib.h>
+#include <pthread.h>
+#include <unistd.h>
 #include "htslib/sam.h"
 
 const char seq_nt16_str[] = "=ACMGRSVTWYHKDBN";
@@ -117,6 +119,75 @@ const void *hts_lite_mem_get(const char *name, size_t *len) {
 }
 
 /* ------------------------------------------------------------------------- */
+/* fork-join worker pool: BGZF blocks are independent, so a reader inflates and a writer
+ * deflates a run of blocks in parallel (one pool per open file; the caller takes part). */
+typedef struct ppool {
+    pthread_t *th; int nth;
+    pthread_mutex_t mu; pthread_cond_t cv_go, cv_done;
+    void (*fn)(void *, int); void *arg; int n, next, pending, gen, stop;
+} ppool;
+
+static void *ppool_main(void *v) {
+    ppool *p = (ppool *)v;
+    int seen = 0;
+    pthread_mutex_lock(&p->mu);
+    for (;;) {
+        while (!p->stop && p->gen == seen) pthread_cond_wait(&p->cv_go, &p->mu);
+        if (p->stop) break;
+        seen = p->gen;
+        while (p->next < p->n) {
+            int i = p->next++;
+            pthread_mutex_unlock(&p->mu);
+            p->fn(p->arg, i);
+            pthread_mutex_lock(&p->mu);
+            if (--p->pending == 0) pthread_cond_signal(&p->cv_done);
+        }
+    }
+    pthread_mutex_unlock(&p->mu);
+    return NULL;
+}
+static ppool *ppool_create(int nth) {
+    ppool *p = (ppool *)calloc(1, sizeof(*p));
+    if (!p) return NULL;
+    pthread_mutex_init(&p->mu, NULL); pthread_cond_init(&p->cv_go, NULL); pthread_cond_init(&p->cv_done, NULL);
+    p->th = (pthread_t *)calloc((size_t)(nth > 0 ? nth : 1), sizeof(pthread_t));
+    for (int i = 0; i < nth; i++) { if (pthread_create(&p->th[p->nth], NULL, ppool_main, p) == 0) p->nth++; }
+    return p;
+}
+static void ppool_destroy(ppool *p) {
+    if (!p) return;
+    pthread_mutex_lock(&p->mu); p->stop = 1; pthread_cond_broadcast(&p->cv_go); pthread_mutex_unlock(&p->mu);
+    for (int i = 0; i < p->nth; i++) pthread_join(p->th[i], NULL);
+    pthread_mutex_destroy(&p->mu); pthread_cond_destroy(&p->cv_go); pthread_cond_destroy(&p->cv_done);
+    free(p->th); free(p);
+}
+/* fn(arg, i) for i in [0, n); returns when all are done */
+static void ppool_run(ppool *p, int n, void (*fn)(void *, int), void *arg) {
+    if (!p || p->nth == 0 || n < 2) { for (int i = 0; i < n; i++) fn(arg, i); return; }
+    pthread_mutex_lock(&p->mu);
+    p->fn = fn; p->arg = arg; p->n = n; p->next = 0; p->pending = n; p->gen++;
+    pthread_cond_broadcast(&p->cv_go);
+    while (p->next < p->n) {
+        int i = p->next++;
+        pthread_mutex_unlock(&p->mu);
+        fn(arg, i);
+        pthread_mutex_lock(&p->mu);
+        --p->pending;
+    }
+    while (p->pending > 0) pthread_cond_wait(&p->cv_done, &p->mu);
+    pthread_mutex_unlock(&p->mu);
+}
+static int g_threads = -1;
+void hts_lite_set_threads(int n) { g_threads = n; }
+static int default_threads(void) {
+    if (g_threads >= 0) return g_threads;
+    const char *e = getenv("HTS_LITE_THREADS");
+    if (e) return atoi(e) > 0 ? atoi(e) : 0;
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return (int)(n < 1 ? 1 : (n > 16 ? 16 : n));
+}
+
+/* ------------------------------------------------------------------------- */
 /* timing span                                                                */
 static double g_t_first = 0, g_t_last = 0;
 static double now_s(void) {
@@ -139,8 +210,10 @@ struct hts_lite_file {
     enum htsExactFormat format;   /* sam or bam */
     int raw;                      /* bam without BGZF framing */
     int level;                    /* deflate level for BGZF */
-    /* reading */
-    uint8_t *rbuf; size_t rlen, rpos; int rbuf_owned;
+    /* reading: rbuf[rpos, rlen) is decoded input not yet consumed; a file-backed reader refills it chunk by chunk */
+    uint8_t *rbuf; size_t rlen, rpos, rcap; int rbuf_owned;
+    FILE *in; int in_eof, in_bgzf; bbuf cbuf;  /* cbuf: compressed bytes read ahead (may end inside a block) */
+    int nthreads; ppool *pool;
     /* writing */
     FILE *out; char *mem_name; bbuf wbuf;     /* formatted bytes not yet compressed/flushed */
     bbuf zbuf;                                /* BGZF output staging */
@@ -188,55 +261,127 @@ int sam_open_mode(char *mode, const char *fn, const char *format) {
 }
 
 /* ---- BGZF ------------------------------------------------------------------ */
-static int bgzf_inflate_all(const uint8_t *in, size_t inlen, uint8_t **out, size_t *outlen) {
-    bbuf o = {0};
-    size_t p = 0;
-    while (p + 18 <= inlen) {
-        if (in[p] != 0x1f || in[p + 1] != 0x8b) break;
+typedef struct { const uint8_t *c; uint32_t clen, isize; size_t ooff; } zblk;
+typedef struct { zblk *b; uint8_t *out; int err; } inf_job;
+static void inf_one(void *v, int i) {
+    inf_job *j = (inf_job *)v;
+    const zblk *k = &j->b[i];
+    if (!k->isize) return;
+    z_stream zs; memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) { j->err = 1; return; }
+    zs.next_in = (Bytef *)k->c; zs.avail_in = k->clen;
+    zs.next_out = j->out + k->ooff; zs.avail_out = k->isize;
+    int r = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    if (r != Z_STREAM_END) j->err = 1;
+}
+/* complete BGZF blocks at the front of in[0,inlen), at most maxb of them: block table, bytes consumed, bytes they
+ * inflate to.  Returns -1 on a malformed block. */
+static int bgzf_scan(const uint8_t *in, size_t inlen, int maxb, zblk **bv, int *bcap, int *nb, size_t *used, size_t *osize) {
+    size_t p = 0, o = 0; int n = 0;
+    while (p + 18 <= inlen && n < maxb) {
+        if (in[p] != 0x1f || in[p + 1] != 0x8b) return -1;
         unsigned xlen = in[p + 10] | (in[p + 11] << 8);
-        /* find BC subfield */
         size_t x = p + 12, xend = x + xlen;
+        if (xend > inlen) break;
         int bsize = -1;
-        while (x + 4 <= xend && xend <= inlen) {
+        while (x + 4 <= xend) {
             unsigned slen = in[x + 2] | (in[x + 3] << 8);
-            if (in[x] == 'B' && in[x + 1] == 'C' && slen == 2) bsize = in[x + 4] | (in[x + 5] << 8);
+            if (in[x] == 'B' && in[x + 1] == 'C' && slen == 2 && x + 6 <= xend) bsize = in[x + 4] | (in[x + 5] << 8);
             x += 4 + slen;
         }
-        if (bsize < 0) { free(o.p); return -1; }
+        if (bsize < 0) return -1;
         size_t blk = (size_t)bsize + 1;
-        if (p + blk > inlen) { free(o.p); return -1; }
-        const uint8_t *cdata = in + p + 12 + xlen;
-        size_t clen = blk - 12 - xlen - 8;
-        uint32_t isize = in[p + blk - 4] | (in[p + blk - 3] << 8) | (in[p + blk - 2] << 16) | ((uint32_t)in[p + blk - 1] << 24);
-        if (isize) {
-            if (bb_reserve(&o, isize) < 0) { free(o.p); return -1; }
-            z_stream zs; memset(&zs, 0, sizeof(zs));
-            if (inflateInit2(&zs, -15) != Z_OK) { free(o.p); return -1; }
-            zs.next_in = (Bytef *)cdata; zs.avail_in = (uInt)clen;
-            zs.next_out = o.p + o.n; zs.avail_out = isize;
-            int r = inflate(&zs, Z_FINISH);
-            inflateEnd(&zs);
-            if (r != Z_STREAM_END) { free(o.p); return -1; }
-            o.n += isize;
+        if (blk < 12 + (size_t)xlen + 8) return -1;
+        if (p + blk > inlen) break;
+        if (n == *bcap) {
+            int nc = *bcap ? *bcap * 2 : 256;
+            zblk *nv = (zblk *)realloc(*bv, (size_t)nc * sizeof(zblk));
+            if (!nv) return -1;
+            *bv = nv; *bcap = nc;
         }
+        zblk *k = &(*bv)[n++];
+        k->c = in + p + 12 + xlen; k->clen = (uint32_t)(blk - 12 - xlen - 8);
+        k->isize = in[p + blk - 4] | (in[p + blk - 3] << 8) | (in[p + blk - 2] << 16) | ((uint32_t)in[p + blk - 1] << 24);
+        k->ooff = o; o += k->isize;
         p += blk;
     }
-    *out = o.p; *outlen = o.n;
+    *nb = n; *used = p; *osize = o;
     return 0;
 }
 
-static int bgzf_write_block(struct hts_lite_file *fp, const uint8_t *src, size_t len) {
-    /* one BGZF block: gzip member with BC extra field */
-    uLong bound = compressBound((uLong)len) + 32;
-    if (bb_reserve(&fp->zbuf, bound + 26) < 0) return -1;
-    uint8_t *o = fp->zbuf.p + fp->zbuf.n;
+/* a whole BGZF stream held in memory (mem: files) */
+static int bgzf_inflate_all(ppool *pool, const uint8_t *in, size_t inlen, uint8_t **out, size_t *outlen) {
+    zblk *bv = NULL; int bcap = 0, nb = 0; size_t used = 0, osize = 0;
+    if (bgzf_scan(in, inlen, INT32_MAX, &bv, &bcap, &nb, &used, &osize) < 0) { free(bv); return -1; }
+    uint8_t *o = (uint8_t *)malloc(osize ? osize : 1);
+    if (!o) { free(bv); return -1; }
+    inf_job j = { bv, o, 0 };
+    ppool_run(pool, nb, inf_one, &j);
+    free(bv);
+    if (j.err) { free(o); return -1; }
+    *out = o; *outlen = osize;
+    return 0;
+}
+
+/* ---- streaming reader: keep [rpos, rlen) and append the next chunk of decoded input ---------- */
+#define RCHUNK (8u << 20)
+static int rfill(struct hts_lite_file *fp) {
+    if (!fp->in || !fp->rbuf_owned) return 0;                /* memory-backed: everything is there already */
+    if (fp->in_eof && !(fp->in_bgzf && fp->cbuf.n > 0)) return 0;
+    if (fp->rpos > 0) {                                       /* compact */
+        memmove(fp->rbuf, fp->rbuf + fp->rpos, fp->rlen - fp->rpos);
+        fp->rlen -= fp->rpos; fp->rpos = 0;
+    }
+    bbuf rb = { fp->rbuf, fp->rlen, fp->rcap };
+    int got = 0;
+    if (!fp->in_bgzf) {
+        if (bb_reserve(&rb, RCHUNK) < 0) return -1;
+        size_t r = fread(rb.p + rb.n, 1, RCHUNK, fp->in);
+        if (r < RCHUNK) fp->in_eof = 1;
+        rb.n += r; got = r > 0;
+    } else {
+        while (!got) {
+            if (!fp->in_eof && fp->cbuf.n < RCHUNK) {
+                if (bb_reserve(&fp->cbuf, RCHUNK) < 0) return -1;
+                size_t r = fread(fp->cbuf.p + fp->cbuf.n, 1, RCHUNK, fp->in);
+                if (r < RCHUNK) fp->in_eof = 1;
+                fp->cbuf.n += r;
+            }
+            zblk *bv = NULL; int bcap = 0, nb = 0; size_t used = 0, osize = 0;
+            if (bgzf_scan(fp->cbuf.p, fp->cbuf.n, 512, &bv, &bcap, &nb, &used, &osize) < 0) { free(bv); return -1; }
+            if (nb == 0) { free(bv); if (fp->in_eof) { fp->cbuf.n = 0; break; } continue; }
+            if (bb_reserve(&rb, osize + 1) < 0) { free(bv); return -1; }
+            inf_job j = { bv, rb.p + rb.n, 0 };
+            if (!fp->pool && fp->nthreads > 1) fp->pool = ppool_create(fp->nthreads - 1);
+            ppool_run(fp->pool, nb, inf_one, &j);
+            free(bv);
+            if (j.err) return -1;
+            rb.n += osize; got = osize > 0;
+            memmove(fp->cbuf.p, fp->cbuf.p + used, fp->cbuf.n - used);
+            fp->cbuf.n -= used;
+            if (!got && fp->in_eof && fp->cbuf.n == 0) break;   /* only empty blocks (EOF marker) were left */
+        }
+    }
+    fp->rbuf = rb.p; fp->rlen = rb.n; fp->rcap = rb.cap;
+    return got;
+}
+/* bytes available at rpos after trying to have at least n there */
+static size_t rneed(struct hts_lite_file *fp, size_t n) {
+    while (fp->rlen - fp->rpos < n) { if (rfill(fp) <= 0) break; }
+    return fp->rlen - fp->rpos;
+}
+
+/* one BGZF block (gzip member with the BC extra field) from src[0,len) into o (>= ZSLOT bytes); returns its size or -1 */
+#define ZSLOT 66560
+static long bgzf_pack(uint8_t *o, const uint8_t *src, size_t len, int level) {
     static const uint8_t hdr[12] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0 };
     memcpy(o, hdr, 12);
     o[12] = 'B'; o[13] = 'C'; o[14] = 2; o[15] = 0;
     z_stream zs; memset(&zs, 0, sizeof(zs));
-    if (deflateInit2(&zs, fp->level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return -1;
+    if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return -1;
     zs.next_in = (Bytef *)src; zs.avail_in = (uInt)len;
-    zs.next_out = o + 18; zs.avail_out = (uInt)bound;
+    zs.next_out = o + 18; zs.avail_out = ZSLOT - 26;
     int r = deflate(&zs, Z_FINISH);
     size_t clen = zs.total_out;
     deflateEnd(&zs);
@@ -248,11 +393,16 @@ static int bgzf_write_block(struct hts_lite_file *fp, const uint8_t *src, size_t
     uint8_t *t = o + 18 + clen;
     t[0] = crc & 0xff; t[1] = (crc >> 8) & 0xff; t[2] = (crc >> 16) & 0xff; t[3] = (crc >> 24) & 0xff;
     t[4] = len & 0xff; t[5] = (len >> 8) & 0xff; t[6] = (len >> 16) & 0xff; t[7] = (len >> 24) & 0xff;
-    fp->zbuf.n += blk;
-    return 0;
+    return (long)blk;
 }
-
+typedef struct { const uint8_t *src; size_t total; uint8_t *slots; long *size; int level; } def_job;
 #define BGZF_PAYLOAD 0xff00
+#define WBLOCKS 256           /* blocks compressed per parallel round by a multi-threaded writer */
+static void def_one(void *v, int i) {
+    def_job *j = (def_job *)v;
+    size_t off = (size_t)i * BGZF_PAYLOAD, l = j->total - off; if (l > BGZF_PAYLOAD) l = BGZF_PAYLOAD;
+    j->size[i] = bgzf_pack(j->slots + (size_t)i * ZSLOT, j->src + off, l, j->level);
+}
 
 static int sink_bytes(struct hts_lite_file *fp, const uint8_t *p, size_t n) {
     if (fp->mem_name) return 0;                 /* kept in zbuf/wbuf until close */
@@ -260,18 +410,31 @@ static int sink_bytes(struct hts_lite_file *fp, const uint8_t *p, size_t n) {
     return 0;
 }
 
-/* push completed wbuf content downstream; final!=0 at close */
+/* push completed wbuf content downstream; final: 1 at close (drain + EOF block), 2 = drain only */
 static int wflush(struct hts_lite_file *fp, int final) {
     if (fp->format == bam && !fp->raw) {
+        /* a multi-threaded writer waits for WBLOCKS payloads and deflates them side by side */
+        const size_t round = (fp->nthreads > 1 ? WBLOCKS : 1) * (size_t)BGZF_PAYLOAD;
         size_t off = 0;
-        while (fp->wbuf.n - off >= BGZF_PAYLOAD || (final && fp->wbuf.n > off)) {
-            size_t l = fp->wbuf.n - off; if (l > BGZF_PAYLOAD) l = BGZF_PAYLOAD;
-            if (bgzf_write_block(fp, fp->wbuf.p + off, l) < 0) return -1;
-            off += l;
+        while (fp->wbuf.n - off >= round || (final && fp->wbuf.n > off)) {
+            size_t tot = fp->wbuf.n - off; if (tot > round) tot = round;
+            int nb = (int)((tot + BGZF_PAYLOAD - 1) / BGZF_PAYLOAD);
+            uint8_t *slots = (uint8_t *)malloc((size_t)nb * ZSLOT);
+            long *size = (long *)malloc((size_t)nb * sizeof(long));
+            if (!slots || !size) { free(slots); free(size); return -1; }
+            def_job j = { fp->wbuf.p + off, tot, slots, size, fp->level };
+            if (!fp->pool && fp->nthreads > 1) fp->pool = ppool_create(fp->nthreads - 1);
+            ppool_run(fp->pool, nb, def_one, &j);
+            int bad = 0;
+            for (int i = 0; i < nb && !bad; i++) { if (size[i] < 0 || bb_put(&fp->zbuf, slots + (size_t)i * ZSLOT, (size_t)size[i]) < 0) bad = 1; }
+            free(slots); free(size);
+            if (bad) return -1;
+            off += tot;
+            if (!fp->mem_name && fp->zbuf.n > (4u << 20)) { if (sink_bytes(fp, fp->zbuf.p, fp->zbuf.n) < 0) return -1; fp->zbuf.n = 0; }
         }
         memmove(fp->wbuf.p, fp->wbuf.p + off, fp->wbuf.n - off);
         fp->wbuf.n -= off;
-        if (final) {
+        if (final == 1) {
             static const uint8_t eof[28] = { 0x1f,0x8b,8,4,0,0,0,0,0,0xff,6,0,'B','C',2,0,0x1b,0,3,0,0,0,0,0,0,0,0,0 };
             if (bb_put(&fp->zbuf, eof, 28) < 0) return -1;
         }
@@ -285,19 +448,6 @@ static int wflush(struct hts_lite_file *fp, int final) {
             fp->wbuf.n = 0;
         }
     }
-    return 0;
-}
-
-static int slurp(FILE *f, uint8_t **buf, size_t *len) {
-    bbuf b = {0};
-    for (;;) {
-        if (bb_reserve(&b, 1 << 20) < 0) { free(b.p); return -1; }
-        size_t r = fread(b.p + b.n, 1, 1 << 20, f);
-        b.n += r;
-        if (r < (1 << 20)) break;
-    }
-    if (ferror(f)) { free(b.p); return -1; }
-    *buf = b.p; *len = b.n;
     return 0;
 }
 
@@ -318,41 +468,47 @@ samFile *sam_open_format(const char *fn, const char *mode, const htsFormat *fmt)
             if (fmt->raw) fp->raw = 1;
             if (fmt->level >= 0) fp->level = fmt->level;
         }
+        fp->nthreads = (fmt && fmt->nthreads > 0) ? fmt->nthreads : default_threads();
         if (!strncmp(fn, "mem:", 4)) fp->mem_name = strdup(fn + 4);
         else if (!strcmp(fn, "-")) fp->out = stdout;
         else if (!(fp->out = fopen(fn, "wb"))) { free(fp); return NULL; }
         return fp;
     }
     /* read */
-    uint8_t *buf = NULL; size_t len = 0;
+    {
+        int t = (fmt && fmt->nthreads > 0) ? fmt->nthreads : default_threads();
+        fp->nthreads = t > 4 ? 4 : t;                        /* inflate is cheap: a few threads keep up with any writer */
+    }
     if (!strncmp(fn, "mem:", 4)) {
-        const void *p = hts_lite_mem_get(fn + 4, &len);
-        if (!p) { free(fp); errno = ENOENT; return NULL; }
-        buf = (uint8_t *)p; fp->rbuf_owned = 0;
-    } else {
-        FILE *f = !strcmp(fn, "-") ? stdin : fopen(fn, "rb");
-        if (!f) { free(fp); return NULL; }
-        int r = slurp(f, &buf, &len);
-        if (f != stdin) fclose(f);
-        if (r < 0) { free(fp); return NULL; }
-        fp->rbuf_owned = 1;
-    }
-    if (len >= 2 && buf[0] == 0x1f && buf[1] == 0x8b) {
-        uint8_t *o; size_t ol;
-        if (bgzf_inflate_all(buf, len, &o, &ol) < 0) {
-            fprintf(stderr, "hts_lite: not a valid BGZF stream: %s\n", fn);
-            if (fp->rbuf_owned) free(buf);
-            free(fp); return NULL;
+        size_t len = 0;
+        const uint8_t *buf = (const uint8_t *)hts_lite_mem_get(fn + 4, &len);
+        if (!buf) { free(fp); errno = ENOENT; return NULL; }
+        fp->rbuf = (uint8_t *)buf; fp->rlen = len; fp->rbuf_owned = 0;
+        if (len >= 2 && buf[0] == 0x1f && buf[1] == 0x8b) {
+            uint8_t *o; size_t ol;
+            ppool *pool = fp->nthreads > 1 ? ppool_create(fp->nthreads - 1) : NULL;
+            int r = bgzf_inflate_all(pool, buf, len, &o, &ol);
+            ppool_destroy(pool);
+            if (r < 0) { fprintf(stderr, "hts_lite: not a valid BGZF stream: %s\n", fn); free(fp); return NULL; }
+            fp->rbuf = o; fp->rlen = fp->rcap = ol; fp->rbuf_owned = 1;
         }
-        if (fp->rbuf_owned) free(buf);
-        buf = o; len = ol; fp->rbuf_owned = 1;
+    } else {
+        fp->in = !strcmp(fn, "-") ? stdin : fopen(fn, "rb");
+        if (!fp->in) { free(fp); return NULL; }
+        fp->rbuf_owned = 1;
+        /* the first bytes decide between BGZF and plain (SAM text, raw BAM) */
+        if (bb_reserve(&fp->cbuf, 65536) < 0) { sam_close(fp); return NULL; }
+        fp->cbuf.n = fread(fp->cbuf.p, 1, 65536, fp->in);
+        if (fp->cbuf.n < 65536) fp->in_eof = 1;
+        if (fp->cbuf.n >= 2 && fp->cbuf.p[0] == 0x1f && fp->cbuf.p[1] == 0x8b) fp->in_bgzf = 1;
+        else { fp->rbuf = fp->cbuf.p; fp->rlen = fp->cbuf.n; fp->rcap = fp->cbuf.cap; memset(&fp->cbuf, 0, sizeof fp->cbuf); }
+        if (fp->in_bgzf && rfill(fp) < 0) { fprintf(stderr, "hts_lite: not a valid BGZF stream: %s\n", fn); sam_close(fp); return NULL; }
     }
-    fp->rbuf = buf; fp->rlen = len; fp->rpos = 0;
-    fp->format = (len >= 4 && !memcmp(buf, "BAM\1", 4)) ? bam : sam;
-    if (len >= 4 && !memcmp(buf, "CRAM", 4)) {
+    rneed(fp, 4);
+    fp->format = (fp->rlen >= 4 && !memcmp(fp->rbuf, "BAM\1", 4)) ? bam : sam;
+    if (fp->rlen >= 4 && !memcmp(fp->rbuf, "CRAM", 4)) {
         fprintf(stderr, "hts_lite: CRAM input needs the real htslib\n");
-        if (fp->rbuf_owned) free(buf);
-        free(fp); errno = ENOTSUP; return NULL;
+        sam_close(fp); errno = ENOTSUP; return NULL;
     }
     return fp;
 }
@@ -375,7 +531,10 @@ int sam_close(samFile *fp) {
         free(fp->wbuf.p); free(fp->zbuf.p); free(fp->mem_name);
     } else {
         if (fp->rbuf_owned) free(fp->rbuf);
+        if (fp->in && fp->in != stdin) fclose(fp->in);
+        free(fp->cbuf.p);
     }
+    ppool_destroy(fp->pool);
     free(fp->line);
     free(fp);
     return ret;
@@ -445,7 +604,18 @@ bam_hdr_t *sam_hdr_read(samFile *fp) {
     bam_hdr_t *h = bam_hdr_init();
     if (!h) return NULL;
     if (fp->format == bam) {
-        if (fp->rlen < 12) goto fail;
+        /* have the whole header in the window before parsing it (a streaming reader holds one chunk) */
+        if (rneed(fp, 12) < 12) goto fail;
+        {
+            size_t want = 8 + (size_t)rd_u32(fp->rbuf + fp->rpos + 4) + 4;
+            if (rneed(fp, want) < want) goto fail;
+            uint32_t nr = rd_u32(fp->rbuf + fp->rpos + want - 4);
+            for (uint32_t i = 0; i < nr; i++) {
+                if (rneed(fp, want + 4) < want + 4) goto fail;
+                want += 4 + (size_t)rd_u32(fp->rbuf + fp->rpos + want) + 4;
+                if (rneed(fp, want) < want) goto fail;
+            }
+        }
         const uint8_t *p = fp->rbuf + 4;
         uint32_t lt = rd_u32(p); p += 4;
         if ((size_t)(p - fp->rbuf) + lt + 4 > fp->rlen) goto fail;
@@ -464,8 +634,11 @@ bam_hdr_t *sam_hdr_read(samFile *fp) {
         fp->rpos = (size_t)(p - fp->rbuf);
     } else {
         size_t p = 0;
-        while (p < fp->rlen && fp->rbuf[p] == '@') {
-            uint8_t *eol = (uint8_t *)memchr(fp->rbuf + p, '\n', fp->rlen - p);
+        for (;;) {
+            if (p >= fp->rlen && rneed(fp, fp->rlen - fp->rpos + 1) <= p) break;
+            if (fp->rbuf[p] != '@') break;
+            uint8_t *eol;
+            while (!(eol = (uint8_t *)memchr(fp->rbuf + p, '\n', fp->rlen - p))) { size_t have = fp->rlen; if (rneed(fp, have + 1) <= have) break; }
             p = eol ? (size_t)(eol - fp->rbuf) + 1 : fp->rlen;
         }
         h->text = (char *)malloc(p + 1);
@@ -495,7 +668,7 @@ int sam_hdr_write(samFile *fp, const bam_hdr_t *h) {
             wr_u32(t, h->target_len[i]); bb_put(&fp->wbuf, t, 4);
         }
         /* htslib flushes the header into its own BGZF block(s) */
-        if (!fp->raw) { if (wflush(fp, 0) < 0) return -1; if (fp->wbuf.n) { if (bgzf_write_block(fp, fp->wbuf.p, fp->wbuf.n) < 0) return -1; fp->wbuf.n = 0; } }
+        if (!fp->raw && wflush(fp, 2) < 0) return -1;
     } else {
         if (bb_put(&fp->wbuf, h->text, h->l_text) < 0) return -1;
         if (h->l_text && h->text[h->l_text - 1] != '\n') bb_putc(&fp->wbuf, '\n');
@@ -553,10 +726,11 @@ static int reg2bin(int64_t beg, int64_t end) {
 }
 
 static int bam_read_rec(samFile *fp, bam1_t *b) {
-    if (fp->rpos + 4 > fp->rlen) return -1;
+    if (fp->rpos + 4 > fp->rlen && rneed(fp, 4) < 4) return -1;
+    uint32_t bs = rd_u32(fp->rbuf + fp->rpos);
+    if (bs < 32) return -2;
+    if (fp->rpos + 4 + bs > fp->rlen && rneed(fp, 4 + (size_t)bs) < 4 + (size_t)bs) return -2;
     const uint8_t *p = fp->rbuf + fp->rpos;
-    uint32_t bs = rd_u32(p);
-    if (bs < 32 || fp->rpos + 4 + bs > fp->rlen) return -2;
     p += 4;
     bam1_core_t *c = &b->core;
     c->tid = (int32_t)rd_u32(p);
@@ -814,9 +988,13 @@ int sam_read1(samFile *fp, bam_hdr_t *h, bam1_t *b) {
     span_touch();
     if (fp->format == bam) return bam_read_rec(fp, b);
     for (;;) {
-        if (fp->rpos >= fp->rlen) return -1;
+        if (fp->rpos >= fp->rlen && rneed(fp, 1) < 1) return -1;
+        uint8_t *eol;
+        while (!(eol = (uint8_t *)memchr(fp->rbuf + fp->rpos, '\n', fp->rlen - fp->rpos))) {
+            size_t have = fp->rlen - fp->rpos;
+            if (rneed(fp, have + 1) <= have) break;              /* last line without a newline */
+        }
         uint8_t *s = fp->rbuf + fp->rpos;
-        uint8_t *eol = (uint8_t *)memchr(s, '\n', fp->rlen - fp->rpos);
         size_t l = eol ? (size_t)(eol - s) : fp->rlen - fp->rpos;
         fp->rpos += l + (eol ? 1 : 0);
         if (l && s[l - 1] == '\r') l--;

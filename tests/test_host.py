@@ -125,3 +125,26 @@ def test_batcher_rejects_unsorted():
     bb.add(0, 50, 0, 60, c, s, q)
     with pytest.raises(cb.CrumbleError, match="sorted"):
         bb.finish()
+
+
+def test_hts_lite_streaming_bgzf_multithreaded():
+    """A BAM larger than the reader's chunk and the writer's parallel round: raw BAM -> BGZF BAM (4 deflate threads) must
+    gunzip to the single-threaded raw stream, and reading it back in chunks (inflate threads) must give the same records."""
+    import gzip
+    import numpy as np
+    import crumble_b200 as cb
+    data, nr, nb = cb.simulate("C1", 1.0, seed=21, threads=2)
+    assert data.nbytes > 40 << 20
+    ident = ["-z", "-p0", "-Q0", "-L0"]
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=tmpdir) as td:
+        raw, bam_mt, bam_st, back = (os.path.join(td, x) for x in ("in.ubam", "mt.bam", "st.bam", "back.ubam"))
+        data.tofile(raw)
+        subprocess.run([str(PORT_BIN)] + ident + ["-O", "bam,nthreads=4", raw, bam_mt], check=True)
+        subprocess.run([str(PORT_BIN)] + ident + ["-O", "bam,nthreads=1", raw, bam_st], check=True, env=dict(os.environ, HTS_LITE_THREADS="1"))
+        assert os.path.getsize(bam_mt) > 9 << 20                      # more than one 8 MiB read chunk
+        a, b = gzip.open(bam_mt).read(), gzip.open(bam_st).read()
+        assert a == b and a == data.tobytes()
+        assert open(bam_mt, "rb").read() == open(bam_st, "rb").read()  # block boundaries do not depend on the thread count
+        subprocess.run([str(PORT_BIN)] + ident + ["-I", "bam,nthreads=3", "-O", "bam,raw", bam_mt, back], check=True)
+        assert np.array_equal(np.fromfile(back, dtype=np.uint8), data)
