@@ -208,6 +208,16 @@ extern "C" int cgb_add(cg_batch_builder *b, int32_t tid, int32_t pos, uint16_t f
     return 0;
 }
 
+/* size the (pinned) arrays once: growing a pinned allocation means a new cudaHostAlloc and a copy */
+extern "C" int cgb_reserve(cg_batch_builder *b, int64_t n_reads, int64_t qual_bytes, int64_t n_cigar) {
+    if (n_reads < 0 || qual_bytes < 0 || n_cigar < 0) return CG_ERR_BAD_ARG;
+    size_t i = (size_t)n_reads, q = (size_t)qual_bytes + 8 * (size_t)n_reads + 16;
+    if (b->tid.reserve(i) || b->pos.reserve(i) || b->l_qseq.reserve(i) || b->cigar_off.reserve(i) || b->flag.reserve(i) ||
+        b->n_cigar.reserve(i) || b->mapq.reserve(i) || b->off.reserve(i) || b->qual.reserve(q) || b->seq.reserve(q / 2 + 16) ||
+        b->cigar.reserve((size_t)n_cigar + 2)) return CG_ERR_NOMEM;
+    return 0;
+}
+
 extern "C" int cgb_add_bam_stream(cg_batch_builder *b, const uint8_t *buf, size_t len) {
     if (len < 12 || memcmp(buf, "BAM\1", 4)) return CG_ERR_BAD_ARG;
     size_t p = 4; uint32_t lt, nref;

@@ -188,6 +188,8 @@ typedef struct cg_batch_builder cg_batch_builder;
 cg_batch_builder *cgb_create(int pinned);
 void  cgb_destroy(cg_batch_builder *b);
 void  cgb_reset(cg_batch_builder *b);
+/* optional: capacity for this many records / quality bytes / CIGAR operations up front (pinned memory is costly to grow) */
+int   cgb_reserve(cg_batch_builder *b, int64_t n_reads, int64_t qual_bytes, int64_t n_cigar);
 /* one record; the pointers are BAM-layout fields (bam1_t core + data) */
 int   cgb_add(cg_batch_builder *b, int32_t tid, int32_t pos, uint16_t flag, uint8_t mapq,
               int32_t l_qseq, uint32_t n_cigar, const uint32_t *cigar, const uint8_t *seq4, const uint8_t *qual);
