@@ -30,8 +30,8 @@ PY
 }
 run "warm-up (raw->raw, one call)" "CRUMBLE_BATCH_READS=100000000" -O bam,raw $D/in.ubam $D/o1.ubam
 run "raw->raw, one call" "CRUMBLE_BATCH_READS=100000000" -O bam,raw $D/in.ubam $D/o1.ubam
-run "raw->raw, chained 2Mi" "" -O bam,raw $D/in.ubam $D/o2.ubam
-run "raw->raw, chained 256Ki" "CRUMBLE_BATCH_READS=262144" -O bam,raw $D/in.ubam $D/o3.ubam
+run "raw->raw, chained (default 512Ki)" "" -O bam,raw $D/in.ubam $D/o2.ubam
+run "raw->raw, chained 128Ki" "CRUMBLE_BATCH_READS=131072" -O bam,raw $D/in.ubam $D/o3.ubam
 cmp $D/o1.ubam $D/o2.ubam && cmp $D/o1.ubam $D/o3.ubam && echo "chained output identical to the single call"
 run "raw->bgzf (16 threads)" "" -O bam $D/in.ubam $D/o4.bam
 run "bgzf->bgzf (16 threads)" "" -O bam $D/o4.bam $D/o5.bam
