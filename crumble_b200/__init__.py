@@ -5,6 +5,6 @@ kernels, see ``csrc/``); this package is the thin Python mirror used by the test
 ``bench.py``.  See DESIGN.md.
 """
 from .api import (  # noqa: F401
-    BatchBuilder, Crumble, CrumbleError, Params, default_params, simulate, algorithmic_bytes,
+    BatchBuilder, Crumble, CrumbleError, Params, Window, default_params, simulate, algorithmic_bytes,
     aligned_bases, bed_text, crumble_cli, load_lib, lib_path, COUNTER_NAMES, BED_TAGS, EXPORTS,
 )

@@ -92,14 +92,20 @@ class Result(C.Structure):
     ]
 
 
+class Window(C.Structure):
+    """cg_window: the reference columns one call of a chain owns (include/crumble_gpu.h)."""
+    _fields_ = [("first", C.c_int32), ("lo_tid", C.c_int32), ("lo_pos", C.c_int32), ("cnt_pos", C.c_int32),
+                ("hi_tid", C.c_int32), ("hi_pos", C.c_int32), ("next_lo_pos", C.c_int32)]
+
+
 _lib = None
 _sim = None
 
 EXPORTS = [
     "cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_set_params", "cg_strerror", "cg_last_error",
-    "cg_set_stream", "cg_process", "cg_upload", "cg_run", "cg_download", "cg_sync", "cg_last_ms", "cg_last_launches",
+    "cg_set_stream", "cg_process", "cg_process_window", "cg_upload", "cg_run", "cg_download", "cg_sync", "cg_last_ms", "cg_last_launches",
     "cg_algorithmic_bytes", "cg_aligned_bases", "cg_n_columns", "cg_params_default", "cg_params_level",
-    "cgb_create", "cgb_destroy", "cgb_reset", "cgb_add", "cgb_add_bam_stream", "cgb_finish", "cgb_bytes",
+    "cgb_create", "cgb_destroy", "cgb_reset", "cgb_add", "cgb_add_bam_stream", "cgb_finish", "cgb_bytes", "cgb_reserve",
 ]
 
 
@@ -130,6 +136,8 @@ def load_lib():
     lib.cg_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     for f in ("cg_process",):
         getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Result)]
+    lib.cg_process_window.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Window), C.POINTER(Result)]
+    lib.cgb_reserve.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64]
     lib.cg_upload.argtypes = [C.c_void_p, C.POINTER(Batch)]
     lib.cg_run.argtypes = [C.c_void_p]
     lib.cg_sync.argtypes = [C.c_void_p]
@@ -210,6 +218,10 @@ class BatchBuilder:
         n = self.batch.n_reads
         return np.ctypeslib.as_array(self.batch.off, shape=(n,)).copy() if n else np.zeros(0, np.int64)
 
+    def positions(self) -> np.ndarray:
+        n = self.batch.n_reads
+        return np.ctypeslib.as_array(self.batch.pos, shape=(n,)).copy() if n else np.zeros(0, np.int32)
+
     def lengths(self) -> np.ndarray:
         n = self.batch.n_reads
         return np.ctypeslib.as_array(self.batch.l_qseq, shape=(n,)).copy() if n else np.zeros(0, np.int32)
@@ -287,6 +299,17 @@ class Crumble:
         if want_columns:
             out["columns"] = cols[: int(res.n_columns)]
         return out
+
+    def process_window(self, batch: Batch, window: Window, events_cap: int = 1 << 16):
+        """One call of a chain (cg_process_window): ``batch`` = read halo + new records, ``window`` = the columns it owns.
+        The keep-window and depth-average state stay inside the context between calls."""
+        res, qout, ev, _ = self._result(batch, False, events_cap)
+        _check(self.lib, self.lib.cg_process_window(self.h, C.byref(batch), C.byref(window), C.byref(res)), self.h)
+        if res.n_events > events_cap:                      # the chain's state has moved on: fetch again, do not redo
+            res, qout, ev, _ = self._result(batch, False, int(res.n_events))
+            _check(self.lib, self.lib.cg_download(self.h, C.byref(res)), self.h)
+        return {"qual": qout[: int(batch.qual_bytes)], "events": ev[: int(res.n_events)],
+                "counters": {k: int(res.counters[i]) for i, k in enumerate(COUNTER_NAMES)}}
 
     # split phase (resident timing)
     def set_chunk_bytes(self, nbytes: int):

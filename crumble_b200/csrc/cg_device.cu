@@ -701,9 +701,21 @@ __global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant
 }
 
 /* item_off = inclusive scan of items[] over the slice's flagged entries; *n_items = total */
-__global__ void __launch_bounds__(64) k_str_items(const __grid_constant__ CgDev D, CgFlagScratch *scratch, const int32_t *item_off, const int32_t *n_items, int k_begin, int k_end) {
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-    CgFlagScratch *S = scratch + gt;
+#define STR_THREADS 128
+#ifndef STR_LANES
+#define STR_LANES 8                 /* working lanes per warp */
+#endif
+#define STR_WIN_STRIDE 516          /* 2 * CG_MASK_WIN + 1 window bytes, padded so that threads at the same offset use different banks */
+__global__ void __launch_bounds__(STR_THREADS) k_str_items(const __grid_constant__ CgDev D, const int32_t *item_off, const int32_t *n_items, int k_begin, int k_end) {
+    /* The search is a chain of short data-dependent branches (which period repeats here, how far does it extend), so the lanes of
+     * a warp spend most of their time waiting for each other: only STR_LANES lanes per warp take items, and the grid supplies the
+     * parallelism in warps instead.  The 2-bit window of each working lane lives in shared memory, its repeat list in local memory. */
+    __shared__ __align__(4) uint8_t win_all[(STR_THREADS / 32) * STR_LANES * STR_WIN_STRIDE];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (lane >= STR_LANES) return;
+    CgRepList reps;
+    uint8_t *win = win_all + (wib * STR_LANES + lane) * STR_WIN_STRIDE;
+    const int gt = (blockIdx.x * (STR_THREADS / 32) + wib) * STR_LANES + lane, nt = gridDim.x * (STR_THREADS / 32) * STR_LANES;
     const CgDevParams *P = &D.P;
     const int total = *n_items, nk = k_end - k_begin;
     for (int it = gt; it < total; it += nt) {
@@ -728,8 +740,8 @@ __global__ void __launch_bounds__(64) k_str_items(const __grid_constant__ CgDev 
                                                : (cg_cap_qual(D.qual[CG_OFF(&q)], P, D.T) >> 4);
             int lo_r = pos, hi_r = pos;                                        /* 1732-1739: the two calls are identical in effect */
             cg_mask_lc(D.seq + (CG_OFF(&q) >> 1), q.l_qseq, phantom, D.cigar + q.cig_off, q.n_cigar, q.pos,
-                       cell.qpos + 1, is_indel ? P->iSTR_add : P->sSTR_add, S->win, &S->reps, &lo_r, &hi_r);
-            if (S->reps.overflow) *D.err = CG_ERR_OVERFLOW;
+                       cell.qpos + 1, is_indel ? P->iSTR_add : P->sSTR_add, win, &reps, &lo_r, &hi_r);
+            if (reps.overflow) *D.err = CG_ERR_OVERFLOW;
             if (lo_r < pos) { atomicMin(&tr->A, lo_r); if (j <= jI) atomicMin(&tr->PI, lo_r); if (j <= jS) atomicMin(&tr->PS, lo_r); }
             if (hi_r > pos) { atomicMax(&tr->B, hi_r); if (j <= jI) atomicMax(&tr->QI, hi_r); if (j <= jS) atomicMax(&tr->QS, hi_r); }
             break;
@@ -1663,14 +1675,13 @@ static int run_slice(cg_ctx *ctx, int t0, int t1, int c0, int c1, int64_t r0, in
     if (nfs > 0) {
         int threads = FL_WARPS * 32, blocks = nblk(nfs, FL_WARPS);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        const int sblocks = 148 * 8, sthreads = 64;
-        if ((e = ensure(ctx, &ctx->b_scratch, (size_t)sblocks * sthreads * sizeof(CgFlagScratch))) ||
-            (e = ensure(ctx, &ctx->b_items, ((size_t)nfs + 1) * 8))) return e;
+        const int sblocks = 148 * 8, sthreads = STR_THREADS;
+        if ((e = ensure(ctx, &ctx->b_items, ((size_t)nfs + 1) * 8))) return e;
         int32_t *items = (int32_t *)ctx->b_items.p, *item_off = items + nfs;
         k_flagged<<<blocks, threads, 0, st>>>(*D, items, kb, ke); ctx->launches++;
         LdI32 li = { items }; StI32Incl si = { item_off };
         if ((e = run_scan<int32_t, OpSum>(ctx, li, si, nfs, 0, scal + 10))) return e;
-        k_str_items<<<sblocks, sthreads, 0, st>>>(*D, (CgFlagScratch *)ctx->b_scratch.p, item_off, scal + 10, kb, ke); ctx->launches++;
+        k_str_items<<<sblocks, sthreads, 0, st>>>(*D, item_off, scal + 10, kb, ke); ctx->launches++;
     }
     if (timed) { T1(CG_T_FLAGGED); T0(CG_T_DEPTH); }
     if (ctx->need_depth && ncs > 0) {

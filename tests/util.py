@@ -82,7 +82,7 @@ def run_oracle(data: np.ndarray, args, kind=None, binary=None, timing=False, env
     bb.add_bam_stream(out)
     bb.finish()
     m = re.search(r"transcode_seconds=([0-9.]+)", r.stderr)
-    res = {"qual": bb.qual().copy(), "bed": bed, "counters": parse_counters(r.stderr), "names": header_names(data),
+    res = {"qual": bb.qual().copy(), "pos": bb.positions(), "len": bb.lengths(), "off": bb.offsets(), "bed": bed, "counters": parse_counters(r.stderr), "names": header_names(data),
            "kind": kind, "seconds": float(m[1]) if m else None, "stderr": r.stderr}
     bb.close()
     return res
