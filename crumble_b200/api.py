@@ -106,7 +106,9 @@ EXPORTS = [
     "cg_set_stream", "cg_process", "cg_process_window", "cg_upload", "cg_run", "cg_download", "cg_sync", "cg_last_ms", "cg_last_launches",
     "cg_algorithmic_bytes", "cg_aligned_bases", "cg_n_columns", "cg_params_default", "cg_params_level",
     "cgb_create", "cgb_destroy", "cgb_reset", "cgb_add", "cgb_add_bam_stream", "cgb_finish", "cgb_bytes", "cgb_reserve",
+    "cg_carry_export", "cg_carry_import", "cg_carry_is_neutral", "cg_batch_ends",
 ]
+CARRY_BYTES = 128
 
 
 def lib_path() -> Path:
@@ -138,6 +140,10 @@ def load_lib():
         getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Result)]
     lib.cg_process_window.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Window), C.POINTER(Result)]
     lib.cgb_reserve.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64]
+    lib.cg_carry_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.cg_carry_import.argtypes = [C.c_void_p, C.c_void_p]
+    lib.cg_carry_is_neutral.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    lib.cg_batch_ends.argtypes = [C.POINTER(Batch), C.c_void_p]
     lib.cg_upload.argtypes = [C.c_void_p, C.POINTER(Batch)]
     lib.cg_run.argtypes = [C.c_void_p]
     lib.cg_sync.argtypes = [C.c_void_p]
@@ -311,6 +317,19 @@ class Crumble:
         return {"qual": qout[: int(batch.qual_bytes)], "events": ev[: int(res.n_events)],
                 "counters": {k: int(res.counters[i]) for i, k in enumerate(COUNTER_NAMES)}}
 
+    def carry_export(self) -> bytes:
+        """the cross-column state the last ``process_window`` saved at its ``next_lo_pos`` (opaque, CARRY_BYTES long)"""
+        buf = C.create_string_buffer(CARRY_BYTES)
+        _check(self.lib, self.lib.cg_carry_export(self.h, buf), self.h)
+        return buf.raw
+
+    def carry_import(self, blob: bytes):
+        _check(self.lib, self.lib.cg_carry_import(self.h, C.create_string_buffer(blob, CARRY_BYTES)), self.h)
+
+    def carry_is_neutral(self, blob: bytes, tid: int, lo_pos: int) -> int:
+        """1 neutral, 0 open keep window (re-run this shard from blob), -1 depth average in play (re-run the chain in order)"""
+        return int(self.lib.cg_carry_is_neutral(self.h, C.create_string_buffer(blob, CARRY_BYTES), tid, lo_pos))
+
     # split phase (resident timing)
     def set_chunk_bytes(self, nbytes: int):
         """Upload-chunk size of the streamed ``process`` (results do not depend on it)."""
@@ -350,6 +369,143 @@ class Crumble:
             self.close()
         except Exception:
             pass
+
+
+def batch_ends(batch: Batch) -> np.ndarray:
+    """pos + reference span of every record (pos itself outside the pileup): cg_batch_ends"""
+    out = np.empty(int(batch.n_reads), dtype=np.int32)
+    load_lib().cg_batch_ends(C.byref(batch), out.ctypes.data)
+    return out
+
+
+def sub_batch(batch: Batch, i0: int, i1: int):
+    """Records [i0, i1) of a batch as a batch of their own: the big arrays are shared, the two offset arrays rebased.
+    Returns (Batch, keepalive)."""
+    n_all = int(batch.n_reads)
+    off = np.ctypeslib.as_array(batch.off, shape=(n_all,))
+    coff = np.ctypeslib.as_array(batch.cigar_off, shape=(n_all,))
+    q0 = int(off[i0]); q1 = int(off[i1]) if i1 < n_all else int(batch.qual_bytes)
+    c0 = int(coff[i0]); c1 = int(coff[i1]) if i1 < n_all else int(batch.n_cigar_total)
+    off2 = (off[i0:i1] - q0).astype(np.int64); coff2 = (coff[i0:i1] - c0).astype(np.int32)
+
+    def at(ptr, ctype, idx):
+        return C.cast(C.addressof(ptr.contents) + C.sizeof(ctype) * idx, C.POINTER(ctype))
+    b = Batch()
+    b.n_reads = i1 - i0
+    b.tid = at(batch.tid, C.c_int32, i0); b.pos = at(batch.pos, C.c_int32, i0); b.flag = at(batch.flag, C.c_uint16, i0)
+    b.mapq = at(batch.mapq, C.c_uint8, i0); b.l_qseq = at(batch.l_qseq, C.c_int32, i0); b.n_cigar = at(batch.n_cigar, C.c_uint16, i0)
+    b.off = off2.ctypes.data_as(C.POINTER(C.c_int64)); b.cigar_off = coff2.ctypes.data_as(C.POINTER(C.c_int32))
+    b.cigar = at(batch.cigar, C.c_uint32, c0); b.n_cigar_total = c1 - c0
+    b.seq = at(batch.seq, C.c_uint8, q0 // 2); b.seq_bytes = (q1 - q0) // 2
+    b.qual = at(batch.qual, C.c_uint8, q0); b.qual_bytes = q1 - q0
+    return b, (off2, coff2)
+
+
+def plan_region_shards(batch: Batch, n_shards: int):
+    """Cut a batch into n_shards region shards of about equal record counts, each with its read halo.
+    Returns a list of dicts: records [h0, r1) form the shard's batch (halo [h0, r0) + own records [r0, r1)), with the
+    cg_window fields of the call.  A record is final in the first shard that holds it and whose right cut X it does not
+    reach (end <= X), or that has no right cut on its contig."""
+    n = int(batch.n_reads)
+    pos = np.ctypeslib.as_array(batch.pos, shape=(n,))
+    tid = np.ctypeslib.as_array(batch.tid, shape=(n,))
+    end = batch_ends(batch)
+    cuts = [0] + [int(round(n * k / n_shards)) for k in range(1, n_shards)] + [n]
+    shards = []
+    lo = None                                         # (tid, S, X) of the previous cut
+    for k in range(n_shards):
+        r0, r1 = cuts[k], cuts[k + 1]
+        sh = {"r0": r0, "r1": r1, "first": 1 if lo is None else 2, "lo_tid": -1, "lo_pos": 0, "cnt_pos": 0, "h0": r0,
+              "hi_tid": -1, "hi_pos": 0, "next_lo_pos": 0}
+        if lo is not None:
+            t, S, X = lo
+            sh["lo_tid"], sh["lo_pos"], sh["cnt_pos"] = t, S, X
+            same = tid[:r0] == t                                              # the halo: records of that contig reaching beyond S
+            reach = np.nonzero(same & (end[:r0] > S))[0]
+            sh["h0"] = int(reach[0]) if reach.size else r0
+        lo = None
+        if r1 < n and r1 > 0 and tid[r1] >= 0 and tid[r1] == tid[r1 - 1]:
+            t, X = int(tid[r1]), int(pos[r1])
+            h = sh["h0"]
+            open_ = np.nonzero((tid[h:r1] == t) & (end[h:r1] > X))[0]
+            S = int(pos[h + open_[0]]) if open_.size else X
+            sh["hi_tid"], sh["hi_pos"], sh["next_lo_pos"] = t, X, S
+            lo = (t, S, X)
+        shards.append(sh)
+    return shards, end
+
+
+def shard_window(sh) -> Window:
+    return Window(first=sh["first"], lo_tid=sh["lo_tid"], lo_pos=sh["lo_pos"], cnt_pos=sh["cnt_pos"],
+                  hi_tid=sh["hi_tid"], hi_pos=sh["hi_pos"], next_lo_pos=sh["next_lo_pos"])
+
+
+def shard_final_mask(batch: Batch, sh, end: np.ndarray, done: np.ndarray) -> np.ndarray:
+    """which records of [h0, r1) turn final in this shard (not done before, not reaching its right cut)"""
+    n = int(batch.n_reads)
+    tid = np.ctypeslib.as_array(batch.tid, shape=(n,))
+    pos = np.ctypeslib.as_array(batch.pos, shape=(n,))
+    idx = np.arange(sh["h0"], sh["r1"])
+    fin = ~done[idx]
+    if sh["hi_tid"] >= 0:
+        in_pileup = end[idx] > pos[idx]
+        fin &= ~(in_pileup & (tid[idx] == sh["hi_tid"]) & (end[idx] > sh["hi_pos"]))
+    return fin
+
+
+def run_region_shards(contexts, batch: Batch, n_shards: int):
+    """Region shards of one batch on independent contexts (one per GPU, or several on one GPU): every shard starts on its own
+    from the reset state, then the saved states are checked in position order and a shard whose incoming state was not
+    neutral runs again from the true one.  Returns the merged result and the number of re-runs."""
+    shards, end = plan_region_shards(batch, n_shards)
+    n = int(batch.n_reads)
+    off = np.ctypeslib.as_array(batch.off, shape=(n,))
+    subs = [sub_batch(batch, sh["h0"], sh["r1"]) for sh in shards]
+    outs = [contexts[k % len(contexts)].process_window(subs[k][0], shard_window(sh)) for k, sh in enumerate(shards)] \
+        if len(contexts) >= n_shards else None
+    reruns = 0
+    if outs is None:                                   # fewer contexts than shards: the sequential chain on one context
+        outs = []
+        g = contexts[0]
+        for k, sh in enumerate(shards):
+            w = shard_window(sh)
+            if w.first == 2: w.first = 0
+            outs.append(g.process_window(subs[k][0], w))
+    else:
+        spec = [k for k in range(1, n_shards) if shards[k]["first"] == 2]
+        in_order = any(contexts[k].carry_is_neutral(contexts[k - 1].carry_export(), shards[k]["lo_tid"], shards[k]["lo_pos"]) < 0 for k in spec)
+        for k in spec:
+            sh = shards[k]
+            carry = contexts[k - 1].carry_export()
+            if in_order or contexts[k].carry_is_neutral(carry, sh["lo_tid"], sh["lo_pos"]) != 1:
+                contexts[k].carry_import(carry)
+                w = shard_window(sh); w.first = 0
+                outs[k] = contexts[k].process_window(subs[k][0], w)
+                reruns += 1
+    qual = np.zeros(int(batch.qual_bytes), dtype=np.uint8)
+    done = np.zeros(n, dtype=bool)
+    counters = {k: 0 for k in COUNTER_NAMES}
+    events = []
+    for k, sh in enumerate(shards):
+        fin = shard_final_mask(batch, sh, end, done)
+        idx = np.arange(sh["h0"], sh["r1"])[fin]
+        base = int(off[sh["h0"]])
+        oq = outs[k]["qual"]
+        if idx.size:
+            # one block copy for the long contiguous run, record by record for the ragged edges
+            brk = np.nonzero(np.diff(idx) != 1)[0]
+            starts = np.concatenate(([0], brk + 1)); stops = np.concatenate((brk + 1, [idx.size]))
+            for a, b in zip(starts, stops):
+                i0, i1 = int(idx[a]), int(idx[b - 1]) + 1
+                q0 = int(off[i0]); q1 = int(off[i1]) if i1 < n else int(batch.qual_bytes)
+                qual[q0:q1] = oq[q0 - base: q1 - base]
+            done[idx] = True
+        for c in COUNTER_NAMES:
+            counters[c] += outs[k]["counters"][c]
+        events.append(outs[k]["events"])
+    assert done.all()
+    return {"qual": qual, "events": np.concatenate(events) if events else np.zeros(0, EVENT_DTYPE), "counters": counters,
+            "reruns": reruns, "shards": shards}
 
 
 def algorithmic_bytes(batch: Batch) -> int:

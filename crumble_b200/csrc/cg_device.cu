@@ -1290,7 +1290,7 @@ struct cg_ctx {
     int64_t qual_bytes, events_cap_dev;
     int need_depth, epoch_cap, nf_total;
     int64_t chunk_bytes;
-    int win_on, have_saved; cg_window win; dbuf b_saved;       /* chained calls: this call's window, the carries of the previous one */
+    int win_on, have_saved, depth_matters; cg_window win; dbuf b_saved;       /* chained calls: this call's window, the carries of the previous one */
     cudaStream_t s_h2d, s_d2h; cudaEvent_t ev_up[32], ev_done[32], ev_misc;
     char h_carry_init[64];
     cudaEvent_t ev[CG_N_TIMERS][2];
@@ -1545,7 +1545,7 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
     D->T = ctx->dT; cg_devparams_from(&D->P, &ctx->params);
     if (ctx->win_on) {
         const cg_window *w = &ctx->win;
-        D->P.win_on = 1; D->P.win_lo_tid = w->first ? -1 : w->lo_tid; D->P.win_lo_pos = w->lo_pos; D->P.win_cnt_pos = w->cnt_pos;
+        D->P.win_on = 1; D->P.win_lo_tid = w->first == 1 ? -1 : w->lo_tid; D->P.win_lo_pos = w->lo_pos; D->P.win_cnt_pos = w->cnt_pos;
         D->P.win_hi_tid = w->hi_tid; D->P.win_hi_pos = w->hi_pos;
     }
     D->bed = (const cg_bed_reg *)ctx->b_bed.p; D->bed_pm = (const int64_t *)ctx->b_bedpm.p;
@@ -1628,6 +1628,7 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
         CG_CHECK(cudaStreamSynchronize(st));
         /* over-depth (snp_score.c:1673) needs n_plp > -P * mean depth >= -P: impossible when no tile has more than -P candidates */
         ctx->need_depth = ctx->params.over_depth < 1.0 || (double)ctx->h_dims[9] > ctx->params.over_depth;
+        ctx->depth_matters = ctx->need_depth;
         if (ctx->win_on) ctx->need_depth = 1;                       /* a later call of the chain may need the running average */
         if (ctx->need_depth) {
             if ((e = ensure(ctx, &ctx->b_dsum, nc1 * 8)) || (e = ensure(ctx, &ctx->b_csum, nc1 * 4))) return e;
@@ -1918,7 +1919,7 @@ extern "C" int cg_process_window(cg_ctx *ctx, const cg_batch *in, const cg_windo
     ctx->dump_columns = out->columns != NULL;
     if ((e = alloc_inputs(ctx, in))) return e;
     if ((e = ensure(ctx, &ctx->b_saved, sizeof(CgSavedCarry)))) return e;
-    ctx->win = *win; ctx->win_on = 1;
+    ctx->win = *win; ctx->win_on = 1; ctx->depth_matters = 0;
     T0(CG_T_TOTAL);
     T0(CG_T_H2D);
     if ((e = upload_meta(ctx, in, st)) || (e = upload_bases(ctx, in, 0, in->qual_bytes, st))) { ctx->win_on = 0; return e; }
@@ -1950,4 +1951,32 @@ extern "C" int cg_process_window(cg_ctx *ctx, const cg_batch *in, const cg_windo
     if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_D2H][0], ctx->ev[CG_T_D2H][1]) == cudaSuccess) ctx->ms[CG_T_D2H] = ms; else cudaGetLastError();
     if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_H2D][0], ctx->ev[CG_T_H2D][1]) == cudaSuccess) ctx->ms[CG_T_H2D] = ms; else cudaGetLastError();
     return 0;
+}
+
+extern "C" int cg_carry_export(cg_ctx *ctx, void *buf) {
+    static_assert(sizeof(CgSavedCarry) <= CG_CARRY_BYTES, "carry blob");
+    if (!ctx->have_saved) return CG_ERR_STATE;
+    CG_CHECK(cudaSetDevice(ctx->device));
+    memset(buf, 0, CG_CARRY_BYTES);
+    CG_CHECK(cudaMemcpyAsync(buf, ctx->b_saved.p, sizeof(CgSavedCarry), cudaMemcpyDeviceToHost, ctx->stream));
+    CG_CHECK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int cg_carry_import(cg_ctx *ctx, const void *buf) {
+    CG_CHECK(cudaSetDevice(ctx->device));
+    int e = ensure(ctx, &ctx->b_saved, sizeof(CgSavedCarry));
+    if (e) return e;
+    CG_CHECK(cudaMemcpyAsync(ctx->b_saved.p, buf, sizeof(CgSavedCarry), cudaMemcpyHostToDevice, ctx->stream));
+    CG_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_saved = 1;
+    return 0;
+}
+extern "C" int cg_carry_is_neutral(const cg_ctx *ctx, const void *buf, int32_t tid, int32_t lo_pos) {
+    CgSavedCarry s; memcpy(&s, buf, sizeof s);
+    /* keep-window chain: an open window matters only if it still covers the shard's first column; a trigger beyond
+     * max_pos2 resets the state anyway (snp_score.c:1508-1511) and the two prefix-max keys only serve to find segment heads */
+    const int open_window = s.cc.has && s.cc.wtid == tid && s.cc.w.min_pos != INT_MAX && s.cc.w.max_pos2 >= lo_pos;
+    /* depth average: matters only when the over-depth test could fire at all in that call (run_prep) */
+    if (ctx->depth_matters && s.ec.valid && s.ec.tid == tid) return -1;
+    return open_window ? 0 : 1;
 }

@@ -284,6 +284,16 @@ static int batch_in_pileup(const cg_batch *in, int64_t i) {
     for (int k = 0; k < in->n_cigar[i]; k++) if (cg_cig_type(cg_cig_op(c[k])) & 2) return 1;
     return 0;
 }
+extern "C" void cg_batch_ends(const cg_batch *in, int32_t *end_out) {
+    for (int64_t i = 0; i < in->n_reads; i++) {
+        int span = 0, hasref = 0;
+        const uint32_t *c = in->cigar + in->cigar_off[i];
+        for (int k = 0; k < in->n_cigar[i]; k++) if (cg_cig_type(cg_cig_op(c[k])) & 2) { span += cg_cig_len(c[k]); hasref = 1; }
+        const int inp = in->tid[i] >= 0 && !(in->flag[i] & 4) && hasref;
+        if (inp && span == 0) span = 1;
+        end_out[i] = in->pos[i] + (inp ? span : 0);
+    }
+}
 extern "C" int64_t cg_algorithmic_bytes(const cg_batch *in) {           /* SURVEY.md §8(d) */
     int64_t s = 0;
     for (int64_t i = 0; i < in->n_reads; i++)

@@ -190,6 +190,7 @@ int transcode_gpu(crumble_opts *o, samFile *in, samFile *out, bam_hdr_t *header,
     ctx = cg_create(&p, o->device, &err);
     if (!ctx) { fprintf(stderr, "crumble: cannot create GPU context: %s\n", cg_strerror(err)); goto done; }
     res.events_cap = 1 << 16;
+    if (getenv("CRUMBLE_EVENTS_CAP") && atoll(getenv("CRUMBLE_EVENTS_CAP")) > 0) res.events_cap = atoll(getenv("CRUMBLE_EVENTS_CAP"));   /* tests: force the regrow path */
     res.events = (cg_bed_event *)malloc(sizeof(cg_bed_event) * (size_t)res.events_cap);
     if (!res.events) goto done;
 

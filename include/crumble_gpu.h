@@ -165,7 +165,8 @@ int cg_set_chunk_bytes(cg_ctx *ctx, int64_t bytes);
  * The two pieces of cross-column state (keep-window chain, depth average) are kept inside the context between calls,
  * as they stand before column S.  Results are bit-identical to one call on the whole stream.                           */
 typedef struct cg_window {
-    int32_t first;                 /* 1: no earlier call to continue (also after a contig change): state is reset */
+    int32_t first;                 /* 1: no earlier call to continue (also after a contig change): state is reset and lo/cnt are
+                                      ignored; 2: state is reset but lo/cnt apply (a region shard started on its own, see below) */
     int32_t lo_tid, lo_pos;        /* columns of lo_tid below lo_pos belong to earlier calls (ignored when first) */
     int32_t cnt_pos;               /* columns of lo_tid in [lo_pos, cnt_pos) were counted by the previous call */
     int32_t hi_tid, hi_pos;        /* columns at/after (hi_tid, hi_pos) are left to the next call; hi_tid < 0: none */
@@ -173,6 +174,22 @@ typedef struct cg_window {
 } cg_window;
 /* cg_process restricted to the window's columns; the records the caller treats as final are its own business */
 int cg_process_window(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out);
+
+/* Region shards of ONE contig on several contexts / GPUs at once.  The column stage (2/3 of the time) never depends on the
+ * carried state and the sparse passes only do where a keep window is still open at the shard's first column or the -P
+ * over-depth test can fire, so shards may start on their own (first = 2: reset state, halo and lo/cnt as usual) and be
+ * checked afterwards, in position order: shard r exports the state it saved at shard r+1's lo_pos; if that state is neutral for
+ * shard r+1 (no open window reaching lo_pos; depth average out of play) shard r+1's results stand, otherwise shard r+1 imports
+ * it and runs again with first = 0 (and its own exported state is then the one to hand on).  Bit-identical to one call. */
+#define CG_CARRY_BYTES 128
+int cg_carry_export(cg_ctx *ctx, void *buf);                       /* CG_ERR_STATE unless the last window call had hi_tid >= 0 */
+int cg_carry_import(cg_ctx *ctx, const void *buf);                 /* what the next cg_process_window(first = 0) resumes from */
+/* Would the last window call of ctx (run with first = 2 at (tid, lo_pos)) have given the same results resuming from buf?
+ * 1 yes; 0 no: a keep window is still open there (run it again from buf); -1 no: the depth average is in play (-P can fire) —
+ * then only a chain run in position order from the contig's first shard hands on exact depth sums */
+int cg_carry_is_neutral(const cg_ctx *ctx, const void *buf, int32_t tid, int32_t lo_pos);
+/* pos + reference span of every record (pos itself for records outside the pileup): what a host needs to plan shards and halos */
+void cg_batch_ends(const cg_batch *in, int32_t *end_out);
 
 /* measurement helpers */
 enum { CG_T_TOTAL = 0, CG_T_TILES, CG_T_COLUMNS, CG_T_FLAGGED, CG_T_DEPTH, CG_T_CHAIN, CG_T_REWRITE, CG_T_PBLOCK, CG_T_EVENTS, CG_T_H2D, CG_T_D2H, CG_N_TIMERS };

@@ -58,7 +58,7 @@ static int emu_process(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg
     EmuCarry cy; cg_win_reset(&cy.w); cy.chain_tid = -2; cy.td = cy.tc = 0; cy.depth_tid = -2;
     if (win) {
         D.P.win_on = 1;
-        D.P.win_lo_tid = win->first ? -1 : win->lo_tid; D.P.win_lo_pos = win->lo_pos; D.P.win_cnt_pos = win->cnt_pos;
+        D.P.win_lo_tid = win->first == 1 ? -1 : win->lo_tid; D.P.win_lo_pos = win->lo_pos; D.P.win_cnt_pos = win->cnt_pos;
         D.P.win_hi_tid = win->hi_tid; D.P.win_hi_pos = win->hi_pos;
         if (!win->first) cy = ctx->carry;
     }

@@ -80,6 +80,19 @@ def test_chained_calls_edge_cases(batch):
         assert bed == open(GDIR / f"edge_cases.{tag}.bed").read(), tag
 
 
+def test_chained_calls_event_buffer_regrow():
+    """more BED events in one call than the caller's buffer holds: the driver fetches them again (cg_download) instead of
+    redoing the call, because the chain's state has already moved on"""
+    data = sim("c1s")
+    bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data); bb.finish()
+    m = valid_mask(bb)
+    exp = GOLD["c1s"]["runs"]["-1"]
+    assert exp["bed"].count("\n") > 8
+    r = run_oracle(data, ["-1"], binary=EMU_BIN, kind="emu", env_extra={"CRUMBLE_BATCH_READS": "6000", "CRUMBLE_EVENTS_CAP": "1"})
+    assert hashlib.sha256(r["qual"][m].tobytes()).hexdigest() == exp["qual_sha256"]
+    assert r["bed"] == exp["bed"] and r["counters"] == exp["counters"]
+
+
 def test_chained_calls_options():
     """-S, -k/-K, -N, -R across cuts (the plain per-item bodies)"""
     data = sim("tiny")

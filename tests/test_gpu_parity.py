@@ -302,6 +302,17 @@ def test_gpu_chained_calls_edge_cases(batch):
             assert open(bed).read() == open(GDIR / f"edge_cases.{tag}.bed").read(), tag
 
 
+def test_gpu_chained_calls_event_buffer_regrow():
+    g0 = GOLD["c1s"]
+    data, nr, nb = cb.simulate(g0["preset"], g0["scale"], g0["seed"], threads=2)
+    bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data); bb.finish(); m = valid_mask(bb)
+    exp = g0["runs"]["-1"]
+    r = run_oracle(data, ["-1"], binary=ROOT / "crumble_b200" / "lib" / "crumble_gpu", kind="gpu-cli",
+                   env_extra={"CRUMBLE_BATCH_READS": "6000", "CRUMBLE_EVENTS_CAP": "1"})
+    assert hashlib.sha256(r["qual"][m].tobytes()).hexdigest() == exp["qual_sha256"]
+    assert r["bed"] == exp["bed"] and r["counters"] == exp["counters"]
+
+
 def test_gpu_chained_calls_options():
     g0 = GOLD["tiny"]
     data, nr, nb = cb.simulate(g0["preset"], g0["scale"], g0["seed"], threads=2)
@@ -312,3 +323,25 @@ def test_gpu_chained_calls_options():
         assert hashlib.sha256(r["qual"][m].tobytes()).hexdigest() == exp["qual_sha256"], args
         assert r["bed"] == exp["bed"], args
         assert r["counters"] == exp["counters"], args
+
+
+@pytest.mark.parametrize("name,n_shards", [("c1s", 4), ("tiny", 5), ("c2s", 8), ("c4s", 3)])
+@pytest.mark.parametrize("args", [["-9"], ["-1"], ["-3", "-P1.5"]], ids=lambda a: "".join(a))
+def test_gpu_region_shards_on_independent_contexts(name, n_shards, args):
+    """Region shards of one batch on independent contexts, every shard started from the reset state (as it would on its own
+    GPU), states checked afterwards in position order (cg_carry_export / cg_carry_is_neutral / cg_carry_import): identical
+    to one call on the whole batch.  At -1/-3 the depth average is in play, so the check must fall back to the ordered chain."""
+    data, bb, batch, mask = dataset(name)
+    p = params_from_args(args)
+    whole = cb.Crumble(p, device=0)
+    ref = whole.process(batch)
+    ctxs = [cb.Crumble(p, device=0) for _ in range(n_shards)]
+    out = cb.run_region_shards(ctxs, batch, n_shards)
+    assert np.array_equal(out["qual"][mask], ref["qual"][mask])
+    assert np.array_equal(out["events"], ref["events"])
+    assert out["counters"] == ref["counters"]
+    # and the same shards as an ordered chain on ONE context
+    seq = cb.run_region_shards([whole], batch, n_shards)
+    assert np.array_equal(seq["qual"][mask], ref["qual"][mask]) and seq["counters"] == ref["counters"]
+    for g in ctxs + [whole]:
+        g.close()

@@ -148,3 +148,33 @@ def test_hts_lite_streaming_bgzf_multithreaded():
         assert open(bam_mt, "rb").read() == open(bam_st, "rb").read()  # block boundaries do not depend on the thread count
         subprocess.run([str(PORT_BIN)] + ident + ["-I", "bam,nthreads=3", "-O", "bam,raw", bam_mt, back], check=True)
         assert np.array_equal(np.fromfile(back, dtype=np.uint8), data)
+
+
+def test_region_shard_plan_invariants():
+    """the host-side shard planner: windows are monotone, halos hold every earlier record that reaches beyond the shard's
+    first column, every record turns final in exactly one shard"""
+    import numpy as np
+    import crumble_b200 as cb
+    for preset, scale, seed, k in (("tiny", 1.0, 3, 7), ("C1", 0.1, 11, 4), ("C4", 0.02, 4, 3)):
+        data, nr, nb = cb.simulate(preset, scale, seed=seed)
+        bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data); batch = bb.finish()
+        shards, end = cb.plan_region_shards(batch, k)
+        n = int(batch.n_reads)
+        pos, tid = bb.positions(), np.ctypeslib.as_array(batch.tid, shape=(n,))
+        done = np.zeros(n, dtype=bool)
+        prev = None
+        for sh in shards:
+            assert sh["h0"] <= sh["r0"] < sh["r1"]
+            if sh["first"] == 2:
+                assert prev is not None and (sh["lo_tid"], sh["lo_pos"], sh["cnt_pos"]) == (prev["hi_tid"], prev["next_lo_pos"], prev["hi_pos"])
+                assert sh["lo_pos"] <= sh["cnt_pos"]
+                reach = np.nonzero((tid[:sh["r0"]] == sh["lo_tid"]) & (end[:sh["r0"]] > sh["lo_pos"]))[0]
+                assert reach.size == 0 or reach[0] >= sh["h0"]
+                assert not np.any(~done[: sh["h0"]])                       # nothing before the halo is still open
+            fin = cb.shard_final_mask(batch, sh, end, done)
+            idx = np.arange(sh["h0"], sh["r1"])[fin]
+            assert not done[idx].any()
+            done[idx] = True
+            prev = sh
+        assert done.all()
+        bb.close()
