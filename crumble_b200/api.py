@@ -306,13 +306,13 @@ class Crumble:
             out["columns"] = cols[: int(res.n_columns)]
         return out
 
-    def process_window(self, batch: Batch, window: Window, events_cap: int = 1 << 16):
+    def process_window(self, batch: Batch, window: Window, events_cap: int = 1 << 16, pinned_out=None):
         """One call of a chain (cg_process_window): ``batch`` = read halo + new records, ``window`` = the columns it owns.
         The keep-window and depth-average state stay inside the context between calls."""
-        res, qout, ev, _ = self._result(batch, False, events_cap)
+        res, qout, ev, _ = self._result(batch, False, events_cap, pinned_out)
         _check(self.lib, self.lib.cg_process_window(self.h, C.byref(batch), C.byref(window), C.byref(res)), self.h)
         if res.n_events > events_cap:                      # the chain's state has moved on: fetch again, do not redo
-            res, qout, ev, _ = self._result(batch, False, int(res.n_events))
+            res, qout, ev, _ = self._result(batch, False, int(res.n_events), pinned_out)
             _check(self.lib, self.lib.cg_download(self.h, C.byref(res)), self.h)
         return {"qual": qout[: int(batch.qual_bytes)], "events": ev[: int(res.n_events)],
                 "counters": {k: int(res.counters[i]) for i, k in enumerate(COUNTER_NAMES)}}
