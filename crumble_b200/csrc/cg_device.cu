@@ -1818,13 +1818,17 @@ extern "C" int cg_download(cg_ctx *ctx, cg_result *out) {
 
 /* End to end, streamed: the base data goes up in chunks on a copy stream; slice i of the chain starts when chunk i has
  * landed; the qualities of the records it finalises go down on a second copy stream while later chunks still arrive. */
-extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
+static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, const cg_window *win) {
     CG_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int e;
     ctx->resident = 0; ctx->win_on = 0;
     ctx->dump_columns = out->columns != NULL;
     if ((e = alloc_inputs(ctx, in))) return e;
+    if (win) {                                                 /* one call of a chain (cg_process_window) */
+        if ((e = ensure(ctx, &ctx->b_saved, sizeof(CgSavedCarry)))) return e;
+        ctx->win = *win; ctx->win_on = 1; ctx->depth_matters = 0;
+    }
     if (!ctx->s_h2d) {
         CG_CHECK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
         CG_CHECK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
@@ -1873,8 +1877,20 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
     struct timespec ts0, ts1; clock_gettime(CLOCK_MONOTONIC, &ts0);
 #define CG_TRACE_AT(what, i) do { if (trace) { clock_gettime(CLOCK_MONOTONIC, &ts1); \
         fprintf(stderr, "[cg_process] %8.3f ms  %s %d\n", (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6, what, i); } } while (0)
-    if ((e = run_prep(ctx, &B, hb))) return e;
+    if ((e = run_prep(ctx, &B, hb))) { ctx->win_on = 0; return e; }
     CG_TRACE_AT("prep done, chunks", nch);
+    /* chained call: re-open the window the previous call left active, find the column where the state is saved for the next one */
+    CgChainCarry *ccarry = (CgChainCarry *)((char *)ctx->b_scal.p + 512);
+    CgEpochCarry *ecarry = (CgEpochCarry *)((char *)ctx->b_scal.p + 640);
+    int cS = -1;                                               /* -1: nothing to save */
+    if (win && ctx->D.n_cols > 0) {
+        if (!win->first && ctx->have_saved) { k_paint_carry<<<1, 32, 0, st>>>(ctx->D, ccarry, win->lo_tid, win->lo_pos); ctx->launches++; }
+        if (win->hi_tid >= 0) {
+            k_find_col<<<1, 32, 0, st>>>(ctx->D, win->hi_tid, win->next_lo_pos, ctx->d_hdims + 11); ctx->launches++;
+            CG_CHECK(cudaStreamSynchronize(st));
+            cS = ctx->h_dims[11];
+        }
+    }
     int tprev = 0; int64_t rprev = 0;
     cudaEventRecord(ctx->ev[CG_T_D2H][0], ctx->s_d2h);
     for (int i = 0; i < nch; i++) {
@@ -1883,7 +1899,15 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
         if (t1 < tprev) t1 = tprev;
         if (r1 < rprev) r1 = rprev;
         CG_CHECK(cudaStreamWaitEvent(st, ctx->ev_up[i], 0));
-        if ((e = run_slice(ctx, tprev, t1, tprev * 32, t1 * 32 < ctx->D.n_cols ? t1 * 32 : ctx->D.n_cols, rprev, r1, 0))) return e;
+        const int c0 = tprev * 32 < ctx->D.n_cols ? tprev * 32 : ctx->D.n_cols, c1 = t1 * 32 < ctx->D.n_cols ? t1 * 32 : ctx->D.n_cols;
+        if (cS >= 0 && cS < c1) {
+            /* the next call's first column lies in this slice: sparse passes up to it, save both carries, then the rest */
+            if ((e = run_slice(ctx, tprev, t1, c0, cS, 0, 0, 0))) { ctx->win_on = 0; return e; }
+            k_carry_save<<<1, 32, 0, st>>>(ccarry, ecarry, (CgSavedCarry *)ctx->b_saved.p); ctx->launches++;
+            e = run_slice(ctx, t1, t1, cS, c1, rprev, r1, 0);
+            cS = -2;                                           /* saved */
+        } else e = run_slice(ctx, tprev, t1, c0, c1, rprev, r1, 0);
+        if (e) { ctx->win_on = 0; return e; }
         if (r1 > rprev && out->qual_out) {
             const int64_t b0 = in->off[rprev], b1 = r1 < n ? in->off[r1] : in->qual_bytes;
             CG_CHECK(cudaEventRecord(ctx->ev_done[i], st));
@@ -1894,7 +1918,11 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
         CG_TRACE_AT("slice enqueued (host passed its column sync)", i);
     }
     cudaEventRecord(ctx->ev[CG_T_D2H][1], ctx->s_d2h);
-    if ((e = run_finish(ctx, 0))) return e;
+    if (cS >= 0) { k_carry_save<<<1, 32, 0, st>>>(ccarry, ecarry, (CgSavedCarry *)ctx->b_saved.p); ctx->launches++; }   /* next call starts beyond this batch's columns */
+    if (win) ctx->have_saved = win->hi_tid >= 0 && ctx->D.n_cols > 0;
+    e = run_finish(ctx, 0);
+    ctx->win_on = 0;
+    if (e) return e;
     CG_TRACE_AT("finish done", 0);
     if ((e = download_results(ctx, out, 0))) return e;
     CG_CHECK(cudaStreamSynchronize(ctx->s_d2h));
@@ -1906,51 +1934,15 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
     return 0;
 }
 
-/* One call of a chain (include/crumble_gpu.h): the batch is uploaded whole, the column stage runs over all of its tiles
- * (columns outside the window come out inert, cg_window_class), the sparse passes run over the columns before the next
- * call's first column, the two carries are saved there, and the sparse passes finish the rest. */
+extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) { return process_streamed(ctx, in, out, NULL); }
+
+/* One call of a chain (include/crumble_gpu.h): the streamed driver above with a column window.  The column stage runs over all
+ * tiles of the batch (columns outside the window come out inert, cg_window_class); the sparse passes of the slice holding the next
+ * call's first column stop there, both carries are saved, and the passes finish the rest. */
 extern "C" int cg_process_window(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out) {
     if (!win) return CG_ERR_BAD_ARG;
     if (ctx->params.region_tid >= 0) { snprintf(ctx->err, sizeof ctx->err, "chained calls and a -r region do not combine"); return CG_ERR_BAD_ARG; }
-    CG_CHECK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    int e;
-    ctx->resident = 0;
-    ctx->dump_columns = out->columns != NULL;
-    if ((e = alloc_inputs(ctx, in))) return e;
-    if ((e = ensure(ctx, &ctx->b_saved, sizeof(CgSavedCarry)))) return e;
-    ctx->win = *win; ctx->win_on = 1; ctx->depth_matters = 0;
-    T0(CG_T_TOTAL);
-    T0(CG_T_H2D);
-    if ((e = upload_meta(ctx, in, st)) || (e = upload_bases(ctx, in, 0, in->qual_bytes, st))) { ctx->win_on = 0; return e; }
-    T1(CG_T_H2D);
-    CgBounds B; memset(&B, 0, sizeof B); B.n = 1; B.rb[0] = in->n_reads;
-    int64_t hb[2 * CG_MAX_CHUNKS];
-    e = run_prep(ctx, &B, hb);
-    CgDev *D = &ctx->D;
-    const int nc = D->n_cols;
-    int cS = nc;
-    if (!e && nc > 0) {
-        CgChainCarry *ccarry = (CgChainCarry *)((char *)ctx->b_scal.p + 512);
-        CgEpochCarry *ecarry = (CgEpochCarry *)((char *)ctx->b_scal.p + 640);
-        if (!win->first && ctx->have_saved) { k_paint_carry<<<1, 32, 0, st>>>(*D, ccarry, win->lo_tid, win->lo_pos); ctx->launches++; }
-        if (win->hi_tid >= 0) {
-            k_find_col<<<1, 32, 0, st>>>(*D, win->hi_tid, win->next_lo_pos, ctx->d_hdims + 11); ctx->launches++;
-            if (cudaStreamSynchronize(st) != cudaSuccess) e = CG_ERR_CUDA; else cS = ctx->h_dims[11];
-        }
-        if (!e) e = run_slice(ctx, 0, D->n_tiles, 0, cS, 0, 0, 0);
-        if (!e && win->hi_tid >= 0) { k_carry_save<<<1, 32, 0, st>>>(ccarry, ecarry, (CgSavedCarry *)ctx->b_saved.p); ctx->launches++; }
-        if (!e) e = run_slice(ctx, 0, 0, cS, nc, 0, in->n_reads, 0);
-    } else if (!e && in->n_reads > 0) e = run_slice(ctx, 0, 0, 0, 0, 0, in->n_reads, 0);      /* nothing in the pileup: strip + P-block only */
-    ctx->have_saved = !e && win->hi_tid >= 0 && nc > 0;
-    if (!e) e = run_finish(ctx, 0);
-    ctx->win_on = 0;
-    if (e) return e;
-    if ((e = download_results(ctx, out, 1))) return e;
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_D2H][0], ctx->ev[CG_T_D2H][1]) == cudaSuccess) ctx->ms[CG_T_D2H] = ms; else cudaGetLastError();
-    if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_H2D][0], ctx->ev[CG_T_H2D][1]) == cudaSuccess) ctx->ms[CG_T_H2D] = ms; else cudaGetLastError();
-    return 0;
+    return process_streamed(ctx, in, out, win);
 }
 
 extern "C" int cg_carry_export(cg_ctx *ctx, void *buf) {
