@@ -178,3 +178,30 @@ def test_region_shard_plan_invariants():
             prev = sh
         assert done.all()
         bb.close()
+
+
+def test_streaming_driver_error_paths():
+    """transcode_gpu's reader / writer threads must surface failures as the reference does (exit 1, "Error while reducing file"):
+    a truncated BAM stream, input that stops being coordinate sorted across a cut, an output that cannot be written."""
+    import numpy as np
+    import crumble_b200 as cb
+    from util import EMU_BIN
+    data, nr, nb = cb.simulate("tiny", 0.3, seed=5)
+    with tempfile.TemporaryDirectory() as td:
+        good, cut, out = (os.path.join(td, x) for x in ("in.ubam", "cut.ubam", "out.ubam"))
+        data.tofile(good); data[: data.size // 2 + 7].tofile(cut)
+        env = dict(os.environ, CRUMBLE_BATCH_READS="500")
+        r = subprocess.run([str(EMU_BIN), "-z", "-9", "-O", "bam,raw", good, out], env=env, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+        r = subprocess.run([str(EMU_BIN), "-z", "-9", "-O", "bam,raw", cut, out], env=env, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 1 and "Error while reducing file" in r.stderr
+        # unsorted across a cut: the second half of the records first
+        sam = [l for l in open(GDIR / "edge_cases.sam")]
+        hdr = [l for l in sam if l.startswith("@")]; body = [l for l in sam if not l.startswith("@")]
+        mapped = [l for l in body if l.split("\t")[2] == "chrA"]
+        bad = os.path.join(td, "bad.sam")
+        open(bad, "w").write("".join(hdr + mapped[len(mapped) // 2:] + mapped[: len(mapped) // 2]))
+        r = subprocess.run([str(EMU_BIN), "-z", "-9", bad, out], env=dict(os.environ, CRUMBLE_BATCH_READS="3"), stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 1 and "Error while reducing file" in r.stderr
+        r = subprocess.run([str(EMU_BIN), "-z", "-9", good, "/nonexistent_dir/out.bam"], env=env, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 1
