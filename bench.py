@@ -101,6 +101,33 @@ class ClockSampler:
         return out
 
 
+def bind_near_gpu(local):
+    """Run this rank (and allocate its pinned buffers) on the CPUs of the NUMA node its GPU hangs off: with one rank per GPU the
+    host side of every copy then stays on the local socket.  Best effort: any missing piece of sysfs leaves the affinity alone."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        if bus is None:
+            return None
+        path = Path(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0")
+        node = int((path / "numa_node").read_text().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -213,6 +240,7 @@ def bench_region_shards(a, rank, world, local):
     import crumble_b200 as cb
     torch.cuda.set_device(local)
     if world > 1:
+        bind_near_gpu(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     preset, args, desc = WORKLOADS[a.workload]
     data, n_reads, n_bases = cb.simulate(preset, a.scale, seed=100)          # the same contig on every rank
@@ -347,6 +375,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU path")
     torch.cuda.set_device(local)
+    numa = bind_near_gpu(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -413,7 +442,7 @@ def main():
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = all_bases * a.e2e_steps / float(te.item())
-    h2d = int(cb.load_lib().cgb_bytes(bb.h)); d2h = int(batch.qual_bytes) + 12 * len(out["events"]) + 8 * 19
+    h2d = g.h2d_bytes(); d2h = int(batch.qual_bytes) + 12 * len(out["events"]) + 8 * 19
     e2e_timers = g.timers()
 
     if rank == 0:
@@ -433,7 +462,7 @@ def main():
                          "whole_chain_frac": algo_bytes / (dev_ms_max / a.steps * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "aligned bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * float(te.item()) / a.e2e_steps, "h2d_ms": e2e_timers["h2d"], "d2h_ms": e2e_timers["d2h"],
-                    "steps": a.e2e_steps, "how": "cg_process: per-record arrays, then base data in ~96 MB chunks on a copy stream; slice i of the chain starts "
+                    "steps": a.e2e_steps, "host_binding": numa, "how": "cg_process: per-record arrays, then base data in ~96 MB chunks on a copy stream; slice i of the chain starts "
                     "when chunk i has landed; qualities return on a second copy stream (h2d_ms / d2h_ms are the spans of the two copy streams and overlap)"},
             "gpu_launches": int(launches), "clocks": clocks,
         }

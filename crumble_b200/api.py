@@ -65,6 +65,7 @@ class Batch(C.Structure):
         ("cigar", C.POINTER(C.c_uint32)), ("n_cigar_total", C.c_int64),
         ("seq", C.POINTER(C.c_uint8)), ("seq_bytes", C.c_int64),
         ("qual", C.POINTER(C.c_uint8)), ("qual_bytes", C.c_int64),
+        ("packed", C.c_int32),
     ]
 
 
@@ -103,7 +104,7 @@ _sim = None
 
 EXPORTS = [
     "cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_set_params", "cg_strerror", "cg_last_error",
-    "cg_set_stream", "cg_process", "cg_process_window", "cg_upload", "cg_run", "cg_download", "cg_sync", "cg_last_ms", "cg_last_launches",
+    "cg_set_stream", "cg_process", "cg_process_window", "cg_upload", "cg_run", "cg_download", "cg_sync", "cg_last_ms", "cg_last_launches", "cg_last_h2d_bytes",
     "cg_algorithmic_bytes", "cg_aligned_bases", "cg_n_columns", "cg_params_default", "cg_params_level",
     "cgb_create", "cgb_destroy", "cgb_reset", "cgb_add", "cgb_add_bam_stream", "cgb_finish", "cgb_bytes", "cgb_reserve",
     "cg_carry_export", "cg_carry_import", "cg_carry_is_neutral", "cg_batch_ends",
@@ -153,6 +154,8 @@ def load_lib():
     lib.cg_last_ms.argtypes = [C.c_void_p, C.c_int]
     lib.cg_last_launches.restype = C.c_int64
     lib.cg_last_launches.argtypes = [C.c_void_p]
+    lib.cg_last_h2d_bytes.restype = C.c_int64
+    lib.cg_last_h2d_bytes.argtypes = [C.c_void_p]
     lib.cg_n_columns.restype = C.c_int64
     lib.cg_n_columns.argtypes = [C.c_void_p]
     lib.cg_algorithmic_bytes.restype = C.c_int64
@@ -353,6 +356,9 @@ class Crumble:
     def timers(self) -> dict:
         return {k: self.ms(k) for k in TIMERS}
 
+    def h2d_bytes(self) -> int:
+        return int(self.lib.cg_last_h2d_bytes(self.h))
+
     def launches(self) -> int:
         return int(self.lib.cg_last_launches(self.h))
 
@@ -398,6 +404,7 @@ def sub_batch(batch: Batch, i0: int, i1: int):
     b.cigar = at(batch.cigar, C.c_uint32, c0); b.n_cigar_total = c1 - c0
     b.seq = at(batch.seq, C.c_uint8, q0 // 2); b.seq_bytes = (q1 - q0) // 2
     b.qual = at(batch.qual, C.c_uint8, q0); b.qual_bytes = q1 - q0
+    b.packed = batch.packed                            # running sums stay running sums after rebasing
     return b, (off2, coff2)
 
 

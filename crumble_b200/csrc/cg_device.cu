@@ -138,6 +138,10 @@ struct StIsland {
         }
     }
 };
+struct LdPad8 { const int32_t *lq; __device__ int64_t operator()(int64_t i) const { return ((int64_t)lq[i] + 7) & ~(int64_t)7; } };
+struct LdNCig { const uint16_t *nc; __device__ int32_t operator()(int64_t i) const { return (int32_t)nc[i]; } };
+struct StExcl64 { int64_t *p; __device__ void operator()(int64_t i, int64_t, int64_t ex) const { p[i] = ex; } };
+struct StExcl32 { int32_t *p; __device__ void operator()(int64_t i, int32_t, int32_t ex) const { p[i] = ex; } };
 struct LdEvFlag { const uint16_t *ev; uint16_t mask; __device__ int32_t operator()(int64_t c) const { return (ev[c] & mask) != 0; } };
 struct StCompact { int32_t *out; const uint16_t *ev; uint16_t mask; __device__ void operator()(int64_t c, int32_t, int32_t ex) const { if (ev[c] & mask) out[ex] = (int32_t)c; } };
 struct LdDepthCounted { const uint32_t *depth; const uint16_t *ev; __device__ int64_t operator()(int64_t c) const { return (ev[c] & CG_EV_COUNTED) ? (int64_t)depth[c] : 0; } };
@@ -1290,7 +1294,8 @@ struct cg_ctx {
     int64_t qual_bytes, events_cap_dev;
     int need_depth, epoch_cap, nf_total;
     int64_t chunk_bytes;
-    int win_on, have_saved, depth_matters; cg_window win; dbuf b_saved;       /* chained calls: this call's window, the carries of the previous one */
+    int win_on, have_saved, depth_matters; cg_window win; dbuf b_saved;
+    int packed, offsets_ready; int64_t h2d_bytes;                           /* offsets rebuilt on the device; bytes copied up by the last call */       /* chained calls: this call's window, the carries of the previous one */
     cudaStream_t s_h2d, s_d2h; cudaEvent_t ev_up[32], ev_done[32], ev_misc;
     char h_carry_init[64];
     cudaEvent_t ev[CG_N_TIMERS][2];
@@ -1413,6 +1418,7 @@ extern "C" int cg_set_chunk_bytes(cg_ctx *ctx, int64_t bytes) { ctx->chunk_bytes
 extern "C" int cg_sync(cg_ctx *ctx) { CG_CHECK(cudaStreamSynchronize(ctx->stream)); return 0; }
 extern "C" float cg_last_ms(const cg_ctx *ctx, int which) { return (which >= 0 && which < CG_N_TIMERS) ? ctx->ms[which] : -1.f; }
 extern "C" int64_t cg_last_launches(const cg_ctx *ctx) { return ctx->launches; }
+extern "C" int64_t cg_last_h2d_bytes(const cg_ctx *ctx) { return ctx->h2d_bytes; }
 extern "C" int64_t cg_n_columns(const cg_ctx *ctx) { return ctx->D.n_cols; }
 
 #define T0(i) cudaEventRecord(ctx->ev[i][0], st)
@@ -1438,6 +1444,8 @@ static int alloc_inputs(cg_ctx *ctx, const cg_batch *in) {
     D->off = (const int64_t *)ctx->b_off.p; D->cigar_off = (const int32_t *)ctx->b_coff.p; D->cigar = (const uint32_t *)ctx->b_cigar.p;
     D->seq = (const uint8_t *)ctx->b_seq.p + CG_FRONT_PAD; D->qual = (const uint8_t *)ctx->b_qual.p + CG_FRONT_PAD; D->qual_out = (uint8_t *)ctx->b_qout.p;
     ctx->qual_bytes = in->qual_bytes;
+    ctx->packed = in->packed == 1; ctx->offsets_ready = 0;
+    ctx->h2d_bytes = 0;
     return 0;
 }
 
@@ -1451,8 +1459,12 @@ static int upload_meta(cg_ctx *ctx, const cg_batch *in, cudaStream_t st) {
     CG_CHECK(cudaMemcpyAsync(ctx->b_mapq.p, in->mapq, (size_t)n, cudaMemcpyHostToDevice, st));
     CG_CHECK(cudaMemcpyAsync(ctx->b_lq.p, in->l_qseq, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CG_CHECK(cudaMemcpyAsync(ctx->b_nc.p, in->n_cigar, (size_t)n * 2, cudaMemcpyHostToDevice, st));
-    CG_CHECK(cudaMemcpyAsync(ctx->b_off.p, in->off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    CG_CHECK(cudaMemcpyAsync(ctx->b_coff.p, in->cigar_off, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    ctx->h2d_bytes += n * (4 + 4 + 2 + 1 + 4 + 2) + in->n_cigar_total * 4;
+    if (!ctx->packed) {                                        /* a packed batch gets its two offset arrays from scans (run_prep) */
+        CG_CHECK(cudaMemcpyAsync(ctx->b_off.p, in->off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_coff.p, in->cigar_off, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        ctx->h2d_bytes += n * 12;
+    }
     if (in->n_cigar_total) CG_CHECK(cudaMemcpyAsync(ctx->b_cigar.p, in->cigar, (size_t)in->n_cigar_total * 4, cudaMemcpyHostToDevice, st));
     return 0;
 }
@@ -1464,6 +1476,7 @@ static int upload_bases(cg_ctx *ctx, const cg_batch *in, int64_t b0, int64_t b1,
     int64_t s0 = b0 >> 1, s1 = (b1 + 1) >> 1;
     if (s1 > in->seq_bytes) s1 = in->seq_bytes;
     if (s1 > s0) CG_CHECK(cudaMemcpyAsync((char *)ctx->b_seq.p + CG_FRONT_PAD + s0, in->seq + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, st));
+    ctx->h2d_bytes += (b1 - b0) + (s1 > s0 ? s1 - s0 : 0);
     return 0;
 }
 
@@ -1574,6 +1587,13 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
             CG_CHECK(cudaMemcpyAsync((char *)ctx->b_scal.p + 512, &sv->cc, sizeof(CgChainCarry), cudaMemcpyDeviceToDevice, st));
             CG_CHECK(cudaMemcpyAsync((char *)ctx->b_scal.p + 640, &sv->ec, sizeof(CgEpochCarry), cudaMemcpyDeviceToDevice, st));
         }
+    }
+    if (n > 0 && ctx->packed && !ctx->offsets_ready) {         /* once per uploaded batch: off = running sum of the padded lengths, cigar_off = running sum of n_cigar */
+        LdPad8 lp = { D->l_qseq }; StExcl64 so = { (int64_t *)ctx->b_off.p };
+        if ((e = run_scan<int64_t, OpSum>(ctx, lp, so, n, (int64_t)0, (int64_t *)NULL))) return e;
+        LdNCig ln = { D->n_cigar }; StExcl32 sc = { (int32_t *)ctx->b_coff.p };
+        if ((e = run_scan<int32_t, OpSum>(ctx, ln, sc, n, 0, (int32_t *)NULL))) return e;
+        ctx->offsets_ready = 1;
     }
     if (n > 0) {
         k_prep_read<<<nblk(n, 256), 256, 0, st>>>(*D); ctx->launches++;

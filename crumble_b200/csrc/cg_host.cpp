@@ -271,6 +271,7 @@ extern "C" int cgb_finish(cg_batch_builder *b, cg_batch *o) {
     o->cigar = b->cigar.p; o->n_cigar_total = (int64_t)b->cigar.n;
     o->seq = b->seq.p; o->seq_bytes = (int64_t)b->seq.n;
     o->qual = b->qual.p; o->qual_bytes = (int64_t)b->qual.n;
+    o->packed = 1;                                   /* cgb_add lays records out back to back */
     return 0;
 }
 

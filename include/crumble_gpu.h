@@ -94,6 +94,8 @@ typedef struct cg_batch {
     const uint32_t *cigar;  int64_t n_cigar_total;
     const uint8_t  *seq;    int64_t seq_bytes;
     const uint8_t  *qual;   int64_t qual_bytes;
+    int32_t  packed;            /* 1: off[] and cigar_off[] are the running sums of ((l_qseq + 7) & ~7) and n_cigar starting at 0 (what the
+                                   cgb_* batcher builds): the device rebuilds them with two scans instead of receiving 12 bytes per record */
 } cg_batch;
 
 /* BED_DIST-expanded suspicious-region events (snp_score.c:1496-1498,1676-1678,
@@ -195,6 +197,7 @@ void cg_batch_ends(const cg_batch *in, int32_t *end_out);
 enum { CG_T_TOTAL = 0, CG_T_TILES, CG_T_COLUMNS, CG_T_FLAGGED, CG_T_DEPTH, CG_T_CHAIN, CG_T_REWRITE, CG_T_PBLOCK, CG_T_EVENTS, CG_T_H2D, CG_T_D2H, CG_N_TIMERS };
 float   cg_last_ms(const cg_ctx *ctx, int which);        /* CUDA-event time of the last cg_run / copies */
 int64_t cg_last_launches(const cg_ctx *ctx);             /* kernels launched by the last cg_run */
+int64_t cg_last_h2d_bytes(const cg_ctx *ctx);            /* bytes the last cg_upload / cg_process / cg_process_window copied to the device */
 int64_t cg_algorithmic_bytes(const cg_batch *in);        /* sum ceil(l/2)+2l+4*n_cigar+16 over pileup reads */
 int64_t cg_aligned_bases(const cg_batch *in);            /* sum l_qseq over records entering the pileup */
 int64_t cg_n_columns(const cg_ctx *ctx);                 /* covered reference columns in the resident batch */

@@ -35,6 +35,7 @@ extern "C" void cg_destroy(cg_ctx *c) { delete c; }
 extern "C" const char *cg_last_error(const cg_ctx *c) { return c->err; }
 extern "C" float cg_last_ms(const cg_ctx *, int) { return 0; }
 extern "C" int64_t cg_last_launches(const cg_ctx *) { return 0; }
+extern "C" int64_t cg_last_h2d_bytes(const cg_ctx *) { return 0; }
 extern "C" int64_t cg_n_columns(const cg_ctx *c) { return c->n_cols; }
 
 static int emu_process(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out);
