@@ -350,12 +350,11 @@ def test_gpu_region_shards_on_independent_contexts(name, n_shards, args):
 def test_gpu_packed_and_unpacked_batches_agree():
     """cg_batch.packed = 1 (the batcher's layout): the two offset arrays are rebuilt on the device by scans instead of being
     uploaded; a caller's own layout (packed = 0) takes them from the host.  Same results, 12 bytes per record less to copy."""
-    import copy
     data, bb, batch, mask = dataset("c1s")
     assert batch.packed == 1
     g = cb.Crumble(params_from_args(["-9"]), device=0)
     a = g.process(batch); up_packed = g.h2d_bytes()
-    loose = copy.copy(batch); loose.packed = 0
+    loose = cb.api.Batch.from_buffer_copy(batch); loose.packed = 0
     b = g.process(loose); up_loose = g.h2d_bytes()
     assert np.array_equal(a["qual"][mask], b["qual"][mask]) and a["counters"] == b["counters"] and np.array_equal(a["events"], b["events"])
     assert up_loose - up_packed == 12 * int(batch.n_reads)
