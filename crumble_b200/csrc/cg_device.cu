@@ -978,10 +978,17 @@ __device__ __noinline__ uint64_t rw_visit8_scalar(uint64_t q8, uint64_t cb8, uin
  * warp's work shrinks with it.  Runs are filled with masked word stores, and only when the fill changes a byte. */
 __device__ __forceinline__ void rw_fill(uint8_t *q, int j, int i, int mid) {
     const uint64_t mw = (uint64_t)(uint32_t)mid * 0x0101010101010101ULL;
-    for (int k0 = j & ~7; k0 < i; k0 += 8) {                       /* masked read-modify-write, whole words */
-        uint64_t mask = ~0ULL;
-        if (k0 < j) mask &= ~0ULL << (8 * (j - k0));
+    int k0 = j & ~7;
+    if (k0 < j) {                                                  /* ragged first word: masked read-modify-write */
+        uint64_t mask = ~0ULL << (8 * (j - k0));
         if (k0 + 8 > i) mask &= ~0ULL >> (8 * (k0 + 8 - i));
+        uint64_t *p = reinterpret_cast<uint64_t *>(q + k0);
+        *p = (*p & ~mask) | (mw & mask);
+        k0 += 8;
+    }
+    for (; k0 + 8 <= i; k0 += 8) *reinterpret_cast<uint64_t *>(q + k0) = mw;   /* whole words: plain stores */
+    if (k0 < i) {                                                  /* ragged last word */
+        const uint64_t mask = ~0ULL >> (8 * (k0 + 8 - i));
         uint64_t *p = reinterpret_cast<uint64_t *>(q + k0);
         *p = (*p & ~mask) | (mw & mask);
     }
@@ -1113,11 +1120,18 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
             /* OR of the column bytes under the read: aligned words, ragged ends masked */
             const int a0 = coff & ~7, e = coff + span;
             uint32_t acc = 0;
-            for (int a = a0; a < e; a += 8) {
-                uint2 v = *reinterpret_cast<const uint2 *>(S.c + a);
-                if (a < coff) { const int sh = (coff - a) * 8; if (sh >= 32) { v.x = 0; v.y &= 0xffffffffu << (sh - 32); } else v.x &= 0xffffffffu << sh; }
-                if (a + 8 > e) { const int nb = (e - a) * 8; if (nb <= 32) { v.y = 0; v.x &= nb == 32 ? 0xffffffffu : ((1u << nb) - 1u); } else v.y &= (1u << (nb - 32)) - 1u; }
-                acc |= v.x | v.y;
+            {   /* first word: bytes before the read's first column masked off (and those past its last one, for short reads) */
+                uint64_t v = *reinterpret_cast<const uint64_t *>(S.c + a0);
+                v &= ~0ULL << (8 * (coff - a0));
+                if (a0 + 8 > e) v &= ~0ULL >> (8 * (a0 + 8 - e));
+                acc = (uint32_t)v | (uint32_t)(v >> 32);
+            }
+            int a = a0 + 8;
+            for (; a + 8 <= e; a += 8) { const uint2 v = *reinterpret_cast<const uint2 *>(S.c + a); acc |= v.x | v.y; }
+            if (a < e) {                                         /* last word: bytes past the read's last column masked off */
+                uint64_t v = *reinterpret_cast<const uint64_t *>(S.c + a);
+                v &= ~0ULL >> (8 * (a + 8 - e));
+                acc |= (uint32_t)v | (uint32_t)(v >> 32);
             }
             if ((acc & 0x80808080u) && !tail_unreached) lk |= RW_KEEP;          /* keep_qual on any covered column (1847, 1939-1940) */
             if (init_mq && !(S.c[coff] & CG_CB_UNPROC)) lk |= RW_INIT;          /* head column processed and mapq <= -m (1852-1859) */
