@@ -921,6 +921,7 @@ __global__ void k_paint_carry(const __grid_constant__ CgDev D, const CgChainCarr
 #define RW_READS   RW_THREADS
 #define RW_QCAP    (RW_READS * 168)     /* staged quality bytes (152 per padded 150-base read) */
 #define RW_CCAP    3072                 /* staged column bytes */
+#define RW_GORIG   176                  /* general path: reads up to this length keep their originals in shared memory */
 #define RW_L_M     0x000fffffu          /* RwMeta.lk: L | kind << 20 | keep << 22 | init80 << 23 | tail_unreached << 24 */
 #define RW_KIND_SH 20
 #define RW_KEEP    (1u << 22)
@@ -935,6 +936,7 @@ struct __align__(128) RwSmem {
     uint8_t wmap[RW_QCAP / 8 + 8];      /* read slot of every staged quality word, 0xff = none */
     RwMeta  m[RW_READS];
     uint8_t glist[RW_READS];            /* slots taking the general path */
+    uint8_t gorig[RW_THREADS / 32][RW_GORIG];   /* general path: the read's original qualities, one buffer per warp */
     int     n_general;
     unsigned long long bar;
     long long red[4][4];
@@ -1189,7 +1191,9 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
         *reinterpret_cast<uint64_t *>(S.q + wi * 8) = (res & vm) | (q8 & ~vm);
     }
 
-    /* ---- phase A3: general path, warp per read: replay inside the slot; originals from global memory ---- */
+    /* ---- phase A3: general path, warp per read: replay inside the slot.  The slot still holds the staged originals (phase A2
+     * skips these reads); they move to the warp's side buffer first, and bases come from the staged sequence, so the replay's
+     * inner loops touch shared memory only (reads longer than the side buffer take originals from global memory). ---- */
     for (int gi = w; gi < S.n_general; gi += RW_THREADS / 32) {
         const RwMeta m = S.m[S.glist[gi]];
         uint8_t *sl = S.q + m.qoff;
@@ -1198,22 +1202,30 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
         const uint8_t init_or = (m.lk & RW_INIT) ? 0x80 : 0;
         const int keep = (m.lk & RW_KEEP) != 0;
         const CgRead q = D.rd[m.j];
-        const uint8_t *qin = D.qual + (qa + m.qoff);
         const uint32_t *cig = D.cigar + q.cig_off;
+        const uint8_t *qin = D.qual + (qa + m.qoff);
+        const uint8_t *ss = S.s + sdelta + (m.qoff >> 1);            /* staged sequence of this read (qoff is a multiple of 8) */
+        if (Lr <= RW_GORIG) {
+            __syncwarp();
+            for (int x = lane; x < Lr; x += 32) S.gorig[w][x] = sl[x];
+            qin = S.gorig[w];
+        }
+        __syncwarp();
         for (int x = lane; x < Lr; x += 32) sl[x] = qin[x] | init_or;
         __syncwarp();
+#define RW_NIB(x_) ((ss[(x_) >> 1] >> ((~(x_) & 1) << 2)) & 0xf)
         int c = 0, y = 0;
         for (int k = 0; k < q.n_cigar; k++) {
             const int op = cg_cig_op(cig[k]), l = cg_cig_len(cig[k]);
             if (cg_is_mop(op)) {
                 for (int ii = lane; ii < l; ii += 32) {
                     int x = y + ii;
-                    if (x < Lr) sl[x] = cg_visit(sl[x], cbp[c + ii], cg_cap_qual(qin[x], P, T), cg_seq_nib(&D, &q, x), P, T);
+                    if (x < Lr) sl[x] = cg_visit(sl[x], cbp[c + ii], cg_cap_qual(qin[x], P, T), RW_NIB(x), P, T);
                 }
                 c += l; y += l;
             } else if (op == 2 || op == 3) {
                 if (lane == 0 && y < Lr) {
-                    uint8_t oc = cg_cap_qual(qin[y], P, T); int nib = cg_seq_nib(&D, &q, y); uint8_t v = sl[y];
+                    uint8_t oc = cg_cap_qual(qin[y], P, T); int nib = RW_NIB(y); uint8_t v = sl[y];
                     for (int ii = 0; ii < l; ii++) v = cg_visit(v, cbp[c + ii], oc, nib, P, T);
                     sl[y] = v;
                 }
@@ -1221,6 +1233,7 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
             } else if (op == 1 || op == 4) y += l;
             __syncwarp();
         }
+#undef RW_NIB
         if (D.r_bf[m.j]) {
             for (int k = cg_trig_lower_bound(&D, nf, q.col0); k < nf && D.fcol[k] < q.col0 + q.span; k++) {
                 const CgTrig *t = &D.trig[k];
