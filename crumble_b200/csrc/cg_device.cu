@@ -705,7 +705,12 @@ __global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant
 }
 
 /* item_off = inclusive scan of items[] over the slice's flagged entries; *n_items = total */
+#ifndef STR_THREADS
 #define STR_THREADS 128
+#endif
+#ifndef STR_BPS
+#define STR_BPS 8                   /* blocks per SM in the grid */
+#endif
 #ifndef STR_LANES
 #define STR_LANES 8                 /* working lanes per warp */
 #endif
@@ -1723,7 +1728,7 @@ static int run_slice(cg_ctx *ctx, int t0, int t1, int c0, int c1, int64_t r0, in
     if (nfs > 0) {
         int threads = FL_WARPS * 32, blocks = nblk(nfs, FL_WARPS);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        const int sblocks = 148 * 8, sthreads = STR_THREADS;
+        const int sblocks = 148 * STR_BPS, sthreads = STR_THREADS;
         if ((e = ensure(ctx, &ctx->b_items, ((size_t)nfs + 1) * 8))) return e;
         int32_t *items = (int32_t *)ctx->b_items.p, *item_off = items + nfs;
         k_flagged<<<blocks, threads, 0, st>>>(*D, items, kb, ke); ctx->launches++;
