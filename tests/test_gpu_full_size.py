@@ -67,3 +67,26 @@ def test_full_size_c2_properties():
         checked += int(inside.sum())
     assert checked > 60_000
     g.close(); bb.close()
+
+
+@pytest.mark.parametrize("preset,seed,args", [("C1", 1, ["-9"]), ("C4", 4, ["-9"]), ("C4", 4, ["-1"]), ("C1", 1, ["-1", "-B"])],
+                         ids=lambda v: "".join(v) if isinstance(v, list) else str(v))
+def test_full_size_c1_c4_exact(preset, seed, args):
+    """BASELINE.json configs[0] (1 Mb at 30x) and configs[3] (1000x amplicon panel: hot columns, STR-rich, every read of an amplicon
+    starting at the same column) at their full sizes, where the CPU oracle still finishes in seconds: bit-exact qualities, BED
+    lines and counters, resident and streamed."""
+    from test_gpu_parity import params_from_args
+    data, n_reads, n_bases = cb.simulate(preset, 1.0, seed=seed)
+    bb = cb.BatchBuilder(); bb.add_bam_stream(data); batch = bb.finish()
+    mask = valid_mask(bb)
+    ref = run_oracle(data, args)
+    g = cb.Crumble(params_from_args(args), device=0)
+    g.set_chunk_bytes(8 << 20)
+    out = g.process(batch)
+    nbad = int((out["qual"][mask] != ref["qual"][mask]).sum())
+    assert nbad == 0, f"{nbad} quality bytes differ from the oracle ({ref['kind']})"
+    assert cb.bed_text(out["events"], ref["names"]) == ref["bed"]
+    assert out["counters"] == ref["counters"]
+    g.upload(batch); g.run(); res = g.download(batch)
+    assert np.array_equal(res["qual"][mask], out["qual"][mask]) and res["counters"] == out["counters"]
+    g.close(); bb.close()
