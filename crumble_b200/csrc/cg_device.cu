@@ -1971,7 +1971,8 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
     }
     cudaEventRecord(ctx->ev[CG_T_D2H][1], ctx->s_d2h);
     if (cS >= 0) { k_carry_save<<<1, 32, 0, st>>>(ccarry, ecarry, (CgSavedCarry *)ctx->b_saved.p); ctx->launches++; }   /* next call starts beyond this batch's columns */
-    if (win) ctx->have_saved = win->hi_tid >= 0 && ctx->D.n_cols > 0;
+    /* a call without any pileup column (placed-unmapped reads in a coverage gap) leaves the state it resumed from untouched */
+    if (win) ctx->have_saved = win->hi_tid >= 0 && (ctx->D.n_cols > 0 || (!win->first && ctx->have_saved));
     e = run_finish(ctx, 0);
     ctx->win_on = 0;
     if (e) return e;
