@@ -104,3 +104,20 @@ def test_chained_calls_options():
         assert hashlib.sha256(r["qual"][m].tobytes()).hexdigest() == exp["qual_sha256"], args
         assert r["bed"] == exp["bed"], args
         assert r["counters"] == exp["counters"], args
+
+
+SPARSE_ARGS = [["-9"], ["-1"], ["-3", "-P1.5"]]
+
+
+@pytest.mark.parametrize("depth", [1.2, 3.0])
+def test_chained_calls_sparse_coverage(depth):
+    """1-3x coverage with placed-unmapped reads, cut after every record: coverage gaps, calls whose only new record never enters
+    the pileup (no column at all), and at -1 / -P1.5 a depth average that must survive all of them"""
+    data, nr, nb = cb.simulate("tiny", 3.0, seed=17, depth=depth, features_per_mb=200.0)
+    bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data); bb.finish()
+    m = valid_mask(bb)
+    for args in SPARSE_ARGS:
+        ref = run_oracle(data, args)
+        for batch in ("1", "7"):
+            r = run_oracle(data, args, binary=EMU_BIN, kind="emu", env_extra={"CRUMBLE_BATCH_READS": batch})
+            assert (r["qual"][m] == ref["qual"][m]).all() and r["bed"] == ref["bed"] and r["counters"] == ref["counters"], (args, batch)

@@ -361,3 +361,16 @@ def test_gpu_packed_and_unpacked_batches_agree():
     g.upload(loose); g.run(); c = g.download(loose)
     assert np.array_equal(a["qual"][mask], c["qual"][mask])
     g.close()
+
+
+@pytest.mark.parametrize("depth", [1.2, 3.0])
+def test_gpu_chained_calls_sparse_coverage(depth):
+    """1-3x coverage with placed-unmapped reads, cut after every record (and every 7): coverage gaps, window calls without a single
+    pileup column, and at -1 / -P1.5 a depth average that must survive all of them on the device"""
+    data, nr, nb = cb.simulate("tiny", 3.0, seed=17, depth=depth, features_per_mb=200.0)
+    bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data); bb.finish(); m = valid_mask(bb)
+    for args in (["-9"], ["-1"], ["-3", "-P1.5"]):
+        ref = run_oracle(data, args)
+        for batch in ("1", "7"):
+            r = run_oracle(data, args, binary=ROOT / "crumble_b200" / "lib" / "crumble_gpu", kind="gpu-cli", env_extra={"CRUMBLE_BATCH_READS": batch})
+            assert (r["qual"][m] == ref["qual"][m]).all() and r["bed"] == ref["bed"] and r["counters"] == ref["counters"], (args, batch)
