@@ -186,7 +186,10 @@ int transcode_gpu(crumble_opts *o, samFile *in, samFile *out, bam_hdr_t *header,
     if (h_iter) batch_reads = INT64_MAX;                    /* a -r region is one call: the region logic owns the column limits */
 
     if (!(bb = cgb_create(1))) goto done;
-    if (!h_iter && cgb_reserve(bb, batch_reads + 4096, (batch_reads + 4096) * 160, (batch_reads + 4096) * 2) != 0) goto done;
+    {   /* pre-size the pinned arrays for one shard (capped: a huge CRUMBLE_BATCH_READS just grows them on demand) */
+        const int64_t rsv = (batch_reads < (4 << 20) ? batch_reads : (4 << 20)) + 4096;
+        if (!h_iter && cgb_reserve(bb, rsv, rsv * 160, rsv * 2) != 0) goto done;
+    }
     ctx = cg_create(&p, o->device, &err);
     if (!ctx) { fprintf(stderr, "crumble: cannot create GPU context: %s\n", cg_strerror(err)); goto done; }
     res.events_cap = 1 << 16;
