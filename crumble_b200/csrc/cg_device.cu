@@ -1323,7 +1323,7 @@ struct cg_ctx {
     unsigned long long *h_counters;
     CgDev D;
     int resident; int dump_columns;
-    int64_t qual_bytes, events_cap_dev;
+    int64_t qual_bytes, cigar_total, events_cap_dev;
     int need_depth, epoch_cap, nf_total;
     int64_t chunk_bytes;
     int win_on, have_saved, depth_matters; cg_window win; dbuf b_saved;
@@ -1461,6 +1461,19 @@ static int alloc_inputs(cg_ctx *ctx, const cg_batch *in) {
     const int64_t n = in->n_reads;
     if (n < 0 || in->qual_bytes < 0) return CG_ERR_BAD_ARG;
     if (n > 0x7fffff00LL || in->n_cigar_total > 0x7fffff00LL || in->qual_bytes >= (1LL << 35)) { snprintf(ctx->err, sizeof ctx->err, "batch too large: split it"); return CG_ERR_BAD_ARG; }
+    if (n > 0 && in->packed != 1) {
+        /* a caller's own layout: every kernel takes record i's bytes at [off[i], off[i] + l_qseq[i]) and k_rewrite / the streamed driver move whole
+         * byte RANGES of consecutive records, so the layout must be 8-aligned, ascending and non-overlapping (gaps are fine) */
+        for (int64_t i = 0; i < n; i++) {
+            const int64_t o = in->off[i], nx = i + 1 < n ? in->off[i + 1] : in->qual_bytes;
+            const int64_t c = in->cigar_off[i], cn = i + 1 < n ? in->cigar_off[i + 1] : in->n_cigar_total;
+            if (o < 0 || (o & 7) || in->l_qseq[i] < 0 || o + in->l_qseq[i] > nx || nx > in->qual_bytes || c < 0 || c + in->n_cigar[i] > cn || cn > in->n_cigar_total) {
+                snprintf(ctx->err, sizeof ctx->err, "record %lld: off[] / cigar_off[] must be 8-aligned (off), ascending and non-overlapping, inside qual_bytes / n_cigar_total", (long long)i);
+                return CG_ERR_BAD_ARG;
+            }
+        }
+        if (in->seq_bytes < (in->qual_bytes + 1) / 2) { snprintf(ctx->err, sizeof ctx->err, "seq_bytes must cover qual_bytes / 2"); return CG_ERR_BAD_ARG; }
+    }
     size_t n1 = (size_t)n + 1;
     int e;
     if ((e = ensure(ctx, &ctx->b_tid, n1 * 4)) || (e = ensure(ctx, &ctx->b_pos, n1 * 4)) || (e = ensure(ctx, &ctx->b_flag, n1 * 2)) ||
@@ -1470,12 +1483,12 @@ static int alloc_inputs(cg_ctx *ctx, const cg_batch *in) {
         (e = ensure(ctx, &ctx->b_qual, (size_t)in->qual_bytes + 128 + CG_FRONT_PAD)) || (e = ensure(ctx, &ctx->b_qout, (size_t)in->qual_bytes + 16))) return e;
     CgDev *D = &ctx->D;
     memset(D, 0, sizeof(*D));
-    D->n_reads = n;
+    D->n_reads = n; D->n_cigar_total = in->n_cigar_total;
     D->tid = (const int32_t *)ctx->b_tid.p; D->pos = (const int32_t *)ctx->b_pos.p; D->flag = (const uint16_t *)ctx->b_flag.p;
     D->mapq = (const uint8_t *)ctx->b_mapq.p; D->l_qseq = (const int32_t *)ctx->b_lq.p; D->n_cigar = (const uint16_t *)ctx->b_nc.p;
     D->off = (const int64_t *)ctx->b_off.p; D->cigar_off = (const int32_t *)ctx->b_coff.p; D->cigar = (const uint32_t *)ctx->b_cigar.p;
     D->seq = (const uint8_t *)ctx->b_seq.p + CG_FRONT_PAD; D->qual = (const uint8_t *)ctx->b_qual.p + CG_FRONT_PAD; D->qual_out = (uint8_t *)ctx->b_qout.p;
-    ctx->qual_bytes = in->qual_bytes;
+    ctx->qual_bytes = in->qual_bytes; ctx->cigar_total = in->n_cigar_total;
     ctx->packed = in->packed == 1; ctx->offsets_ready = 0;
     ctx->h2d_bytes = 0;
     return 0;
@@ -1584,7 +1597,7 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
     CgDev *D = &ctx->D;
     const int64_t n = D->n_reads;
     const size_t n1 = (size_t)n + 1;
-    int e;
+    int e, check_packed = 0;
     ctx->launches = 0;
     for (int i = 0; i < CG_N_TIMERS; i++) if (i != CG_T_H2D && i != CG_T_D2H) ctx->ms[i] = 0;
     D->T = ctx->dT; cg_devparams_from(&D->P, &ctx->params);
@@ -1622,10 +1635,10 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
     }
     if (n > 0 && ctx->packed && !ctx->offsets_ready) {         /* once per uploaded batch: off = running sum of the padded lengths, cigar_off = running sum of n_cigar */
         LdPad8 lp = { D->l_qseq }; StExcl64 so = { (int64_t *)ctx->b_off.p };
-        if ((e = run_scan<int64_t, OpSum>(ctx, lp, so, n, (int64_t)0, (int64_t *)NULL))) return e;
+        if ((e = run_scan<int64_t, OpSum>(ctx, lp, so, n, (int64_t)0, (int64_t *)(scal + 12)))) return e;
         LdNCig ln = { D->n_cigar }; StExcl32 sc = { (int32_t *)ctx->b_coff.p };
-        if ((e = run_scan<int32_t, OpSum>(ctx, ln, sc, n, 0, (int32_t *)NULL))) return e;
-        ctx->offsets_ready = 1;
+        if ((e = run_scan<int32_t, OpSum>(ctx, ln, sc, n, 0, scal + 14))) return e;
+        ctx->offsets_ready = 1; check_packed = 1;
     }
     if (n > 0) {
         k_prep_read<<<nblk(n, 256), 256, 0, st>>>(*D); ctx->launches++;
@@ -1633,8 +1646,16 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
         if ((e = run_scan<int32_t, OpSum>(ctx, lpf, sj, n, 0, scal + 0))) return e;
         k_prep_keys<<<nblk(n, 256), 256, 0, st>>>(*D); ctx->launches++;
         /* ke := inclusive prefix max (only the first n_pile entries are meaningful; the tail is never read) */
-        CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 4, cudaMemcpyDeviceToHost, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 64, cudaMemcpyDeviceToHost, st));
         CG_CHECK(cudaStreamSynchronize(st));
+        if (check_packed) {                                        /* packed = 1 is a promise about the layout: the running sums must end where the buffers do */
+            int64_t qtot; memcpy(&qtot, ctx->h_dims + 12, 8);
+            if (qtot > ctx->qual_bytes || (int64_t)ctx->h_dims[14] > ctx->cigar_total) {
+                snprintf(ctx->err, sizeof ctx->err, "packed batch: the padded lengths sum to %lld quality bytes (buffer holds %lld), the CIGARs to %d operations (buffer holds %lld)",
+                         (long long)qtot, (long long)ctx->qual_bytes, ctx->h_dims[14], (long long)ctx->cigar_total);
+                return CG_ERR_BAD_ARG;
+            }
+        }
         D->n_pile = ctx->h_dims[0];
     } else D->n_pile = 0;
     const int np = D->n_pile;

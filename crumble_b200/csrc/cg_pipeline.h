@@ -48,6 +48,7 @@ typedef struct CgDev {
     int32_t n_islands;
     int32_t n_flagged;
     int32_t n_trig_cap;
+    int64_t n_cigar_total;    /* entries in cigar[] */
     /* batch (SoA) */
     const int32_t *tid, *pos; const uint16_t *flag; const uint8_t *mapq; const int32_t *l_qseq;
     const uint16_t *n_cigar; const int64_t *off; const int32_t *cigar_off;
@@ -95,6 +96,7 @@ CG_HD int64_t cg_key(int32_t tid, int32_t pos) { return ((int64_t)tid << 32) | (
 CG_HD void cg_prep_read(const CgDev *D, int64_t r) {
     int32_t tid = D->tid[r];
     int n = D->n_cigar[r];
+    if (D->cigar_off[r] < 0 || (int64_t)D->cigar_off[r] + n > D->n_cigar_total) { *D->err = CG_ERR_BAD_ARG; D->rspan[r] = 0; return; }   /* a layout that lies about its CIGARs */
     const uint32_t *cig = D->cigar + D->cigar_off[r];
     int span = 0, hasref = 0;
     for (int k = 0; k < n; k++) {

@@ -745,7 +745,11 @@ static int bam_read_rec(samFile *fp, bam1_t *b) {
     c->mpos = (int32_t)rd_u32(p + 24);
     c->isize = (int32_t)rd_u32(p + 28);
     c->unused1 = 0;
+    /* a corrupt or truncated record must end in an error, not in an out-of-bounds copy: the fixed part, the name, the CIGAR,
+     * the packed sequence and the qualities all have to fit inside block_size */
+    if (c->l_qseq < 0 || (uint64_t)32 + lq + 4ull * c->n_cigar + ((uint64_t)c->l_qseq + 1) / 2 + (uint64_t)c->l_qseq > bs) return -2;
     unsigned pad = (4 - (lq & 3)) & 3;
+    if (lq + pad > 255) pad = 0;                               /* htslib's rule: no extra NULs when they would not fit l_qname */
     c->l_extranul = (uint8_t)pad;
     c->l_qname = (uint8_t)(lq + pad);
     size_t rest = bs - 32 - lq;
@@ -815,6 +819,7 @@ int sam_parse_line(char *line, size_t len, bam_hdr_t *h, bam1_t *b) {
     size_t lq = strlen(qname) + 1;
     if (lq > 255) return -2;
     unsigned pad = (4 - (lq & 3)) & 3;
+    if (lq + pad > 255) pad = 0;                               /* htslib's rule: l_qname is 8 bit, so no extra NULs when they would not fit */
     c->l_qname = (uint8_t)(lq + pad); c->l_extranul = (uint8_t)pad;
     c->flag = (uint16_t)strtol(flag, NULL, 0);
     c->tid = strcmp(rname, "*") ? bam_name2id(h, rname) : -1;

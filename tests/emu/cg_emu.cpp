@@ -51,7 +51,7 @@ extern "C" int cg_process_window(cg_ctx *ctx, const cg_batch *in, const cg_windo
 static int emu_process(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out) {
     CgDev D; memset(&D, 0, sizeof(D));
     const int64_t n = in->n_reads;
-    D.n_reads = n;
+    D.n_reads = n; D.n_cigar_total = in->n_cigar_total;
     D.tid = in->tid; D.pos = in->pos; D.flag = in->flag; D.mapq = in->mapq; D.l_qseq = in->l_qseq;
     D.n_cigar = in->n_cigar; D.off = in->off; D.cigar_off = in->cigar_off; D.cigar = in->cigar; D.seq = in->seq; D.qual = in->qual;
     D.qual_out = out->qual_out;

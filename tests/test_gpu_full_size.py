@@ -1,10 +1,6 @@
-"""BASELINE.json's full-size configuration (synthetic chr20, 64 Mb at 30x: 1.29e7 reads, 1.92e9 aligned bases) on the GPU.
-The CPU oracle needs minutes for the whole of it, so parity at this size is checked through properties:
-  * slicing invariance: resident (upload + run + download, one slice) and streamed (cg_process, two chunk sizes, up to 32
-    slices with the cross-slice state carried on the device) give the same qualities, BED events and counters;
-  * windowed oracle parity: for three 150 kb windows the verbatim reference is run on the window alone (-r) and every read
-    lying at least 5 kb inside it must carry exactly the qualities the full-size GPU run gave it;
-  * counter sanity: the number of columns the path counts equals the number of covered reference positions."""
+"""BASELINE.json's full-size configurations on the GPU against the reference's own code (oracle/_ref) at the SAME size:
+synthetic chr20 (64 Mb at 30x: 1.29e7 reads, 1.92e9 aligned bases) at -9 (configs[1]) and -1 -B (configs[2]) over the whole file,
+the 1 Mb region (configs[0]) and the 1000x amplicon panel (configs[3]); plus slicing invariance at full size."""
 import numpy as np
 import pytest
 
@@ -21,52 +17,75 @@ def _bytes_of(off, ln):
     return starts + np.arange(tot, dtype=np.int64)
 
 
-def test_full_size_c2_properties():
+def _start_reference(fin, td, tag, args):
+    """the verbatim reference (oracle/_ref) on the whole file, in the background: one core, about 75 s for chr20 at 30x"""
+    import os, subprocess
+    from util import oracle_bin
+    binary, kind = oracle_bin()
+    assert kind == "reference"
+    fout, fbed = os.path.join(td, f"out.{tag}.ubam"), os.path.join(td, f"out.{tag}.bed")
+    pr = subprocess.Popen([str(binary), "-z", "-v"] + args + ["-b", fbed, "-O", "bam,raw", fin, fout], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    return pr, fout, fbed
+
+
+def _collect_reference(pr, fout, fbed):
+    from util import parse_counters
+    err = pr.communicate()[1]
+    assert pr.returncode == 0, err[-2000:]
+    out = np.fromfile(fout, dtype=np.uint8)
+    rb = cb.BatchBuilder(pinned=False); rb.add_bam_stream(out); rb.finish()
+    del out
+    res = {"qual": rb.qual().copy(), "off": rb.offsets(), "len": rb.lengths(), "bed": open(fbed).read(), "counters": parse_counters(err)}
+    rb.close()
+    return res
+
+
+def test_full_size_c2_c3_whole_file_vs_reference():
+    """BASELINE.json configs[1] (crumble -9) and configs[2] (crumble -1 -B) on the WHOLE synthetic chr20 (64 Mb, 30x: 1.29e7 reads,
+    1.92e9 aligned bases): every quality byte, the BED text and the 19 counters of the GPU path against the reference's own code
+    (oracle/_ref) run over the whole file, one process per option set, while the GPU does its part; plus slicing invariance
+    (resident == streamed at two chunk sizes) at this size."""
+    import os, tempfile
     data, n_reads, n_bases = cb.simulate("C2", 1.0, seed=2)
     assert n_reads > 12_000_000 and n_bases > 1_900_000_000
-    bb = cb.BatchBuilder()
-    bb.add_bam_stream(data)
-    batch = bb.finish()
-    mask = valid_mask(bb)
-    g = cb.Crumble(cb.default_params(9), device=0)
-
-    # --- slicing invariance ---
-    g.upload(batch); g.run()
-    res = g.download(batch)
-    ncols = g.n_columns()
-    outs = []
-    for chunk in (96 << 20, 40 << 20):
-        g.set_chunk_bytes(chunk)
-        o = g.process(batch)
-        assert np.array_equal(o["qual"][mask], res["qual"][mask]), f"streamed ({chunk >> 20} MiB chunks) differs from resident"
-        assert o["counters"] == res["counters"]
-        outs.append(o)
-    assert np.array_equal(outs[0]["events"], outs[1]["events"]) and len(outs[0]["events"]) == res["n_events"]
-    assert res["counters"]["columns"] == ncols                      # every covered position is a counted column at -9
-    full = outs[0]["qual"].copy()
-    del outs, res
-    pos, ln, off = bb.positions(), bb.lengths().astype(np.int64), bb.offsets()
-
-    # --- windowed oracle parity ---
-    name = header_names(data)[0]
-    margin, width = 5000, 150_000
-    checked = 0
-    for beg in (1_000_000, 9_000_000, 20_000_000):
-        end = beg + width
-        ref = run_oracle(data, ["-9", "-r", f"{name}:{beg + 1}-{end}"])
-        # records starting inside the window appear in both, in the same order
-        i0, i1 = int(np.searchsorted(pos, beg, side="left")), int(np.searchsorted(pos, end, side="left"))
-        j0, j1 = int(np.searchsorted(ref["pos"], beg, side="left")), int(np.searchsorted(ref["pos"], end, side="left"))
-        assert i1 - i0 == j1 - j0 and i1 - i0 > 20_000
-        assert np.array_equal(pos[i0:i1], ref["pos"][j0:j1]) and np.array_equal(ln[i0:i1], ref["len"][j0:j1])
-        inside = (pos[i0:i1] >= beg + margin) & (pos[i0:i1] + 1000 <= end - margin)
-        a = full[_bytes_of(off[i0:i1][inside], ln[i0:i1][inside])]
-        b = ref["qual"][_bytes_of(ref["off"][j0:j1][inside], ref["len"][j0:j1][inside].astype(np.int64))]
-        nbad = int((a != b).sum())
-        assert nbad == 0, f"window {beg}-{end}: {nbad} quality bytes differ from the reference ({ref['kind']}) run on the window"
-        checked += int(inside.sum())
-    assert checked > 60_000
-    g.close(); bb.close()
+    names = header_names(data)
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=tmpdir) as td:
+        fin = os.path.join(td, "in.ubam"); data.tofile(fin)
+        runs = {"C2": (["-9"], cb.default_params(9)), "C3": (["-1", "-B"], cb.default_params(1, binary_qual=1))}
+        procs = {k: _start_reference(fin, td, k, a) for k, (a, _) in runs.items()}
+        bb = cb.BatchBuilder()
+        bb.add_bam_stream(data)
+        del data
+        batch = bb.finish()
+        mask = valid_mask(bb)
+        got = {}
+        for k, (a, p) in runs.items():
+            g = cb.Crumble(p, device=0)
+            g.upload(batch); g.run()
+            res = g.download(batch)
+            ncols = g.n_columns()
+            for chunk in ((96 << 20, 40 << 20) if k == "C2" else (64 << 20,)):
+                g.set_chunk_bytes(chunk)
+                o = g.process(batch)
+                assert np.array_equal(o["qual"][mask], res["qual"][mask]), f"{k}: streamed ({chunk >> 20} MiB chunks) differs from resident"
+                assert o["counters"] == res["counters"] and len(o["events"]) == res["n_events"]
+            if k == "C2":
+                assert res["counters"]["columns"] == ncols              # every covered position is a counted column at -9
+            got[k] = {"qual": o["qual"][mask].copy(), "bed": cb.bed_text(o["events"], names), "counters": o["counters"]}
+            del o, res
+            g.close()
+        off, ln = bb.offsets(), bb.lengths()
+        for k in runs:
+            ref = _collect_reference(*procs[k])
+            assert np.array_equal(ref["off"], off) and np.array_equal(ref["len"], ln), f"{k}: the reference wrote different records"
+            nbad = int((got[k]["qual"] != ref["qual"][mask]).sum())
+            assert nbad == 0, f"{k}: {nbad} of {int(mask.sum())} quality bytes differ from the reference run over the whole file"
+            assert got[k]["bed"] == ref["bed"], f"{k}: BED text differs"
+            assert got[k]["counters"] == ref["counters"], f"{k}: counters differ"
+            if k == "C3":
+                assert ref["counters"]["over_depth"] > 0 and ref["bed"].count("DEEP") > 0          # the sequential depth average is live at -1
+        bb.close()
 
 
 @pytest.mark.parametrize("preset,seed,args", [("C1", 1, ["-9"]), ("C4", 4, ["-9"]), ("C4", 4, ["-1"]), ("C1", 1, ["-1", "-B"])],

@@ -114,16 +114,6 @@ GOLD = json.load(open(ROOT / "tests" / "golden" / "golden.json"))
 GDIR = ROOT / "tests" / "golden"
 
 
-def params_from_args2(args):
-    out = []
-    for a in args:
-        if a.startswith("-i") or a.startswith("-s") or a.startswith("-X") or a.startswith("-D"):
-            out.append(a)
-        else:
-            out.append(a)
-    return out
-
-
 @pytest.mark.parametrize("name", sorted(GOLD))
 def test_gpu_matches_golden(name):
     g0 = GOLD[name]
@@ -220,6 +210,32 @@ def test_gpu_columns_bit_exact():
             assert np.array_equal(cols["flags"] & bit, exp["flags"] & bit), nm
         assert np.array_equal((cols["flags"] >> 8) & 31, (exp["flags"] >> 8) & 31), "BED tags"
         g.close()
+
+
+@pytest.mark.parametrize("name,args", [("tiny", ["-9"]), ("c1s", ["-9"]), ("c1s", ["-1"])], ids=lambda v: "".join(v) if isinstance(v, list) else v)
+def test_gpu_columns_match_reference_debug_dump(name, args):
+    """the same per-column dump against the REFERENCE's own -DDEBUG printout (snp_score.c:1545-1573; oracle/_ref/crumble_ref_debug,
+    compiled from the reference's sources): position, depth, call or het call, score, and the preserve mark, for every processed column"""
+    from util import REF_BIN
+    dbg_bin = REF_BIN.parent / "crumble_ref_debug"
+    assert dbg_bin.exists(), f"{dbg_bin} is missing (make -C oracle ref where /root/reference exists)"
+    data, bb, batch, mask = dataset(name)
+    g = cb.Crumble(params_from_args(args), device=0)
+    cols = g.process(batch, want_columns=True)["columns"]
+    g.close()
+    with tempfile.TemporaryDirectory() as td:
+        fin = os.path.join(td, "i.ubam"); data.tofile(fin)
+        txt = subprocess.run([str(dbg_bin), "-z"] + args + [fin, "mem:x"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, check=True).stdout
+    exp = [l.split("\t") for l in txt.splitlines() if l.startswith("Depth ")]
+    proc = cols[(cols["flags"] & 8) != 0]
+    assert len(proc) == len(exp) and len(exp) > 1000
+    het = proc["het_phred"] > 0
+    for i, e in enumerate(exp):
+        c = proc[i]
+        assert int(e[0].split(" ")[1]) == c["tid"] and int(e[1]) == c["pos"] + 1 and int(e[2]) == c["n_plp"], (e, c)
+        s = ("%c/%c %4d" % ("ACGT*"[c["het_call"] // 5], "ACGT*"[c["het_call"] % 5], c["het_phred"])) if het[i] else ("%c   %4d" % ("ACGT*N"[c["call"]], c["phred"]))
+        assert e[3] == s, (e, c)
+        assert (len(e) > 4 and e[4] == "*") == bool(c["flags"] & 1), (e, c)
 
 
 def test_gpu_contig_sharding_invariance():

@@ -2,8 +2,9 @@
 same structure-of-arrays layout the GPU path uses.
 
 Oracle choice: oracle/_ref/crumble_ref (the reference's own sources compiled verbatim,
-built where /root/reference exists and shipped as a binary) when present, otherwise
-oracle/bin/crumble_oracle (this repository's plain-C restatement)."""
+built where /root/reference exists and shipped as a binary).  A missing binary is an error,
+not a downgrade; oracle/bin/crumble_oracle (this repository's plain-C restatement) is used
+only where a test asks for it by name."""
 import os
 import re
 import subprocess
@@ -19,9 +20,16 @@ EMU_BIN = ROOT / "tests" / "emu" / "emu_crumble"
 
 
 def oracle_bin(kind=None):
-    if kind in (None, "reference") and REF_BIN.exists():
-        return REF_BIN, "reference"
-    if kind in (None, "port") and PORT_BIN.exists():
+    """kind None = the checker of record: the verbatim reference (oracle/_ref).  There is no silent downgrade to the port: a parity
+    claim made against the restatement must say so (kind="port", or CRUMBLE_ORACLE=port in the environment)."""
+    if kind is None:
+        kind = os.environ.get("CRUMBLE_ORACLE", "reference")
+    if kind == "reference":
+        if REF_BIN.exists():
+            return REF_BIN, "reference"
+        raise FileNotFoundError(f"{REF_BIN} is missing: the parity tests compare with the reference's own code. Build it where /root/reference exists "
+                                "(make -C oracle ref; it travels to the GPU box with the snapshot) or set CRUMBLE_ORACLE=port to knowingly test against the restatement")
+    if kind == "port" and PORT_BIN.exists():
         return PORT_BIN, "port"
     raise FileNotFoundError("no oracle binary: run __graft_entry__.build()")
 
