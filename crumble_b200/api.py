@@ -24,7 +24,7 @@ COUNTER_NAMES = [
     "clip_perc", "ins_len_perc", "indel_ov_perc", "over_depth",
 ]
 BED_TAGS = ["VDEEP", "DEEP", "CLIP", "INDEL_LEN", "INDEL_COVERAGE"]
-TIMERS = ["total", "tiles", "columns", "flagged", "depth", "chain", "rewrite", "pblock", "events", "h2d", "d2h"]
+TIMERS = ["total", "tiles", "columns", "flagged", "depth", "chain", "rewrite", "cells", "events", "h2d", "d2h"]
 
 
 class CrumbleError(RuntimeError):

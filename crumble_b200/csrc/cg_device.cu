@@ -18,6 +18,7 @@
 #include <string.h>
 #include <time.h>
 #include "cg_host.h"
+#include "cg_column_lean.h"
 
 #define CG_CHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     snprintf(ctx->err, sizeof ctx->err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
@@ -197,236 +198,114 @@ __global__ void k_tile_index(const __grid_constant__ CgDev D) {
     if (j < D.n_pile) cg_tile_index(&D, j);
 }
 
-/* The hot kernel: one thread per dense reference column, one warp per 32-column tile; warps are independent
- * (no block barrier inside the loop).  Per chunk of COL_ROWS candidate reads a warp runs two phases:
+/* the plain finalisation, out of line: columns holding an N base (recomputed exactly) and mode A (-q) */
+__device__ __noinline__ CgColOut col_finish_plain(const CgDev *D, int c, int lo, int hi, const CgColStats *st, CgConsAcc *A, int nN) {
+    if (nN) cg_col_gather_generic(D, c, lo, hi, A);
+    return cg_column_finish(D, c, lo, hi, st, A);
+}
+
+/* ============================== column stage ============================================
+ * Two kernels (cell format and per-lane bodies: cg_cells.h, cg_column_lean.h):
  *
- *  stage   every read of the chunk is decoded ONCE into a row of 32 16-bit pileup cells in the warp's shared
- *          memory (4 lanes per read, 8 adjacent columns per lane: two aligned 64-bit quality loads and two 32-bit
- *          sequence loads are funnel-shifted into place, the eight nt16 codes are mapped to bases in one
- *          SIMD-within-register pass, quality x mapq goes through the effective-quality table; the ragged ends of
- *          a read are cut with mask rows from a small shared table; reads with a non-trivial CIGAR walk it once
- *          per lane, out of line).  A cell carries everything the column loop needs: valid | base | effective
- *          quality | ins | clip | indel | mid | low-mapq.  Uncovered cells are zero.
- *  column  each lane walks its column down the rows: one 16-bit LDS per cell, flag counters kept as four packed
- *          8-bit fields, the per-quality constants (MM, _M, 1-q2p) from a 32-byte shared-memory row addressed by
- *          the cell's own bits, and the in-order FP64 accumulation.
- *
- * Accumulators live in RANK space: the bases of a column are numbered in order of first appearance and the 15
- * genotype sums + 5 discrepancy sums are kept as H[rank], C[rank], P[rank pair].  A read of rank k adds to H[k], C[k]
- * and the four pairs holding k, exactly the six adds of the reference's switch (snp_score.c:656-683), in the same
- * order per slot, so every slot sees the same IEEE add sequence.  Because nearly all cells of a column carry its
- * first base, the fast path (cell's base == first base) is taken by whole warps whatever the reference base under
- * each lane is; a switch on the base itself diverged ~4 ways per row.  The permutation is undone once per column.
- * sumsE of the reference is dead (never read after the loop) and is not computed. */
+ *  k_cells    read-major pre-pass: every pileup read is decoded ONCE into a row of 16-bit cells, one per reference column it covers,
+ *             in groups of 8 cells = 16 bytes aligned to the dense column axis.  Four lanes per read, one group per lane and step:
+ *             two aligned 64-bit quality loads and two 32-bit sequence loads funnel-shifted into place, the eight nt16 codes mapped
+ *             to bases in one SIMD-within-register pass, quality x mapq through the effective-quality table.  Reads with a
+ *             non-trivial CIGAR (a few percent) are left to k_cells_general: one warp per read, lane = column.
+ *  k_column   one lane per dense column, one warp per 32-column tile, warps independent (no block barrier in the loop) and
+ *             scheduled dynamically (a global tile counter), so a 1000x amplicon tile occupies one warp while the others move on.
+ *             Per chunk of COL_R candidate reads: the tile's four groups of every row arrive by 16-byte cp.async (zero-filled where
+ *             the read does not reach), double-buffered: the next chunk is in flight while this one is walked.  Each lane then walks
+ *             its column down the rows (cg_rank_rows): one 16-bit LDS per cell, the per-quality constants from a 32-byte
+ *             shared-memory row addressed by the cell's own bits, six in-order FP64 adds in rank space.  The tile ends with the
+ *             lean finalisation (cg_cons_finalize_lean) and the column decisions (cg_column_finish). */
 #define COL_WARPS    4
 #ifndef COL_MINB
-#define COL_MINB     5          /* resident blocks per SM the register allocation is sized for (96 registers: 6 blocks at 80 registers spill and run 4 % slower) */
+#define COL_MINB     5          /* resident blocks per SM the register allocation is sized for */
 #endif
-#ifndef COL_PIPE
-#define COL_PIPE     1
+#ifndef COL_R
+#define COL_R        60         /* rows per staged chunk: (COL_R + 1) x 64 B must hold the 15 x 32 doubles of the un-permute scratch */
 #endif
-#ifndef COL_RECUP
-#define COL_RECUP    0
-#endif
-#ifndef COL_LOOK
-#define COL_LOOK     1
-#endif
-#ifndef COL_PEEK
-#define COL_PEEK     1
-#endif
-#ifndef COL_TPW
-#define COL_TPW      16         /* tiles per warp: amortises the block's table set-up and the counter flush */
-#endif
-#define COL_ROWS     80         /* rows per chunk: 80 x 64 B = 20 x 32 doubles, the un-permute scratch */
-#define CELL_VALID   0x8000u
-#define CELL_BASE_SH 12         /* bits 14..12: base 0..4 = ACGT*, 5 = N, 6 = ref-skip, 7 = no contribution */
-#define CELL_BASE_M  0x7000u
-#define CELL_E_SH    5          /* bits 11..5: effective quality (1..100) == byte offset / 32 of its table row */
-#define CELL_E_M     0x0fe0u
-#define CELL_INS     0x0010u
-#define CELL_CLIP    0x0008u
-#define CELL_INDEL   0x0004u
-#define CELL_MID     0x0002u
-#define CELL_LOWMQ   0x0001u
 
-struct __align__(16) ColTabRow { double MM, hM, om, pad; };
 struct __align__(16) ColSmem {
-    union { uint16_t cell[COL_ROWS + 4][32]; double dump[20][32]; } w[COL_WARPS];   /* + padding rows for the look-ahead load */
+    uint16_t cell[COL_WARPS][2][COL_R + 1][32];     /* + 1: the column loop looks one row ahead */
     double rare[COL_WARPS][9][32];
     ColTabRow tab[104];
-    uint4 mask[9][9];            /* [a][b]: 0xffff in the 16-bit lanes k with a <= k < b */
+    unsigned cntw[COL_WARPS][32];
+};
+static_assert((COL_R + 1) * 64 >= 15 * 32 * 8, "un-permute scratch must fit one cell buffer");
+
+__device__ __forceinline__ void cp_async16(void *dst_shared, const void *src, unsigned src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" :: "r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+/* cell-matrix row records: ngrp per read -> exclusive scan -> first group of every row */
+struct LdNgrp { const CgRead *rd; __device__ int64_t operator()(int64_t j) const { return (int64_t)cg_cell_ngroups(rd[j].col0, rd[j].span); } };
+struct StCellRec {
+    CgCellRec *crec; const CgRead *rd;
+    __device__ void operator()(int64_t j, int64_t, int64_t ex) const {
+        CgCellRec r; r.cpos8 = (uint32_t)ex; r.col0 = rd[j].col0; r.span = rd[j].span; r.ngrp = cg_cell_ngroups(r.col0, r.span);
+        crec[j] = r;
+    }
 };
 
-/* exact recomputation of a column's accumulators with the generic code: used for the rare columns holding an N base */
-__device__ __noinline__ void col_gather_generic(const CgDev *D, int c, int lo, int hi, CgConsAcc *A) {
-    const CgTables *T = D->T;
-    cg_cons_init(A);
-    for (int j = lo; j < hi; j++) {
-        const CgRead q = D->rd[j];
-        CgCell cell;
-        if (!cg_cell(D, &q, c, &cell)) continue;
-        if (cell.is_refskip || !q.l_qseq) continue;
-        int nib = cg_seq_nib(D, &q, cell.qpos);
-        int base = cell.is_del ? 4 : cg_nt16_to_base(nib);
-        uint8_t qv = cg_cap_qual(D->qual[CG_OFF(&q) + cell.qpos], &D->P, T);
-        cg_cons_add(T, A, base, T->effB[((int)q.mapq << 8) | qv]);
+/* pileup reads [j_begin, j_end): 4 lanes per read */
+__global__ void __launch_bounds__(256) k_cells(const __grid_constant__ CgDev D, int j_begin, int j_end) {
+    const int j = j_begin + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 2);
+    if (j >= j_end) return;
+    const uint4 h = __ldg(reinterpret_cast<const uint4 *>(D.rd + j));             /* off8, col0, span, pk */
+    if (!(h.w & ((uint32_t)CG_RF_SIMPLE << 24))) return;                          /* k_cells_general */
+    const CgCellRec cr = D.crec[j];
+    CgRead q; q.off8 = h.x; q.col0 = (int32_t)h.y; q.span = (int32_t)h.z; q.mapq = (uint8_t)(h.w >> 16); q.rf = (uint8_t)(h.w >> 24);
+    const int doB = D.P.min_qual_B != 0;
+    uint4 *row = reinterpret_cast<uint4 *>(D.cells) + cr.cpos8;
+    for (uint32_t k = threadIdx.x & 3; k < cr.ngrp; k += 4) {
+        uint32_t o[4];
+        cg_cells8_simple(&D, &q, 8 * (int)k - (q.col0 & 7), doB, o);
+        row[k] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+/* reads with a non-trivial CIGAR: a warp scans 32 reads and resolves the general ones among them one at a time, lane = column */
+__global__ void __launch_bounds__(256) k_cells_general(const __grid_constant__ CgDev D, int j_begin, int j_end) {
+    const int lane = threadIdx.x & 31;
+    const int jw = j_begin + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5) * 32;
+    if (jw >= j_end) return;
+    const int j = jw + lane;
+    unsigned gm = __ballot_sync(0xffffffffu, j < j_end && !(D.rd[j].rf & CG_RF_SIMPLE));
+    const int doB = D.P.min_qual_B != 0;
+    while (gm) {
+        const int g = jw + __ffs(gm) - 1; gm &= gm - 1;
+        const CgRead q = D.rd[g];
+        const CgCellRec cr = D.crec[g];
+        uint16_t *row = D.cells + (size_t)cr.cpos8 * 8;
+        const int n = (int)cr.ngrp * 8, lead = q.col0 & 7;
+        for (int x = lane; x < n; x += 32) row[x] = (uint16_t)cg_cell_general(&D, &q, x - lead, doB);
     }
 }
 
-/* one cell of a read with a non-trivial CIGAR (a few percent of reads): the whole warp resolves one such read at a
- * time, lane = column, each lane walking the CIGAR to its own column (cg_plp_resolve) */
-__device__ __noinline__ uint32_t col_cell_general(const CgDev *D, int j, int d, uint32_t rowf, int doB) {
-    const CgRead q = D->rd[j];
-    if ((unsigned)d >= (unsigned)q.span) return 0;
-    CgCell cell;
-    if (!cg_plp_resolve(D->cigar + q.cig_off, q.n_cigar, d, q.span, &cell)) return 0;
-    uint32_t f = rowf, base = 7, e = 1;
-    if (cell.indel | cell.is_del) f |= CELL_INDEL;
-    if (cell.is_refskip) base = 6;
-    else {
-        if ((cell.is_head && cell.qpos > 0) || (cell.is_tail && cell.qpos + 1 < q.l_qseq)) f |= CELL_CLIP;
-        if (!cell.is_tail && !cell.is_head) { f |= CELL_MID; if (cell.indel > 0) f |= CELL_INS; }
-        if (q.l_qseq && doB) {
-            const int64_t off = CG_OFF(&q);
-            e = D->T->effB[((int)q.mapq << 8) | D->qual[off + cell.qpos]];
-            base = cell.is_del ? 4 : cg_nt16_to_base((D->seq[(off >> 1) + (cell.qpos >> 1)] >> ((~cell.qpos & 1) << 2)) & 0xf);
-        }
-    }
-    return f | (e << CELL_E_SH) | (base << CELL_BASE_SH);
-}
-
-/* eight nt16 codes (one per nibble) -> eight base codes (A0 C1 G2 T3, anything else 5) */
-__device__ __forceinline__ uint32_t col_bases8(uint32_t X) {
-    const uint32_t M = 0x11111111u;
-    const uint32_t p0 = X & M, p1 = (X >> 1) & M, p2 = (X >> 2) & M, p3 = (X >> 3) & M;
-    const uint32_t t = (p0 + p1 + p2 + p3) ^ M;                       /* nibble == 0 iff exactly one bit set */
-    const uint32_t one = ((t | (t >> 1) | (t >> 2)) & M) ^ M;
-    const uint32_t m = one * 15u;
-    return ((p1 + p2 * 2u + p3 * 3u) & m) | (0x55555555u & ~m);
-}
-
-/* decode rows [j0, j0+n) of the warp's read window into its cell matrix: 4 lanes per row, 8 columns per lane.
- * Global-memory latency is taken off the critical path twice: the 16-byte hot records of the whole chunk are
- * loaded up front (one per lane, three rounds) and handed out by shuffles, and the quality / sequence words of
- * pass i+1 are requested before pass i is decoded. */
-struct ColRaw { uint2 w0, w1; uint32_t v0, v1; };
-
-__device__ __forceinline__ uint4 col_rec_of(const uint4 (&rc)[3], int rb, int n, int lane) {
-    const int r = rb + (lane >> 2);
-    const int slot = rb >> 5;                                /* warp-uniform: rb is a multiple of 8 */
-    uint4 p = slot == 0 ? rc[0] : (slot == 1 ? rc[1] : rc[2]);
-    uint4 a;
-    a.x = __shfl_sync(0xffffffffu, p.x, r & 31); a.y = __shfl_sync(0xffffffffu, p.y, r & 31);
-    a.z = __shfl_sync(0xffffffffu, p.z, r & 31); a.w = __shfl_sync(0xffffffffu, p.w, r & 31);
-    if (r >= n) a.z = 0;                                     /* span 0: no cell */
-    return a;
-}
-__device__ __forceinline__ bool col_lane_simple(const uint4 &a, int d_first) {
-    return -d_first < 8 && (int)a.z - d_first > 0 && (a.w & ((uint32_t)CG_RF_SIMPLE << 24));
-}
-__device__ __forceinline__ ColRaw col_raw_load(const CgDev &D, const uint4 &a, int d_first) {
-    ColRaw R; R.w0 = make_uint2(0, 0); R.w1 = make_uint2(0, 0); R.v0 = R.v1 = 0;
-    if (col_lane_simple(a, d_first)) {
-        const int64_t A = ((int64_t)a.x << 3) + d_first;                    /* byte address of the first quality */
-        const uint2 *qa = reinterpret_cast<const uint2 *>(D.qual + (A & ~(int64_t)7));
-        R.w0 = __ldg(qa); R.w1 = __ldg(qa + 1);
-        const uint32_t *sa = reinterpret_cast<const uint32_t *>(D.seq + ((A >> 1) & ~(int64_t)3));
-        R.v0 = __ldg(sa); R.v1 = __ldg(sa + 1);
-    }
-    return R;
-}
-
-__device__ __forceinline__ void col_stage(const CgDev &D, ColSmem *S, uint16_t (*cells)[32], int j0, int n, int tile_c0, int doB, int min_mqual) {
-    const int lane = threadIdx.x & 31, x0 = (lane & 3) * 8;
-    const uint8_t *effB = D.T->effB;
-#if COL_RECUP
-    uint4 rc[3];
+/* Stage rows [j0, j0 + n) of the read window for tile t into buf: lane l owns rows l and 32 + l (their records were loaded ahead) */
+__device__ __forceinline__ void col_issue(const CgDev &D, uint16_t (*buf)[32], int tile_c0, int n, const CgCellRec &ra, const CgCellRec &rb, int lane) {
+    const uint4 *cells = reinterpret_cast<const uint4 *>(D.cells);
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-        rc[i] = make_uint4(0, 0, 0, 0);
-        if (i * 32 + lane < n) rc[i] = __ldg(reinterpret_cast<const uint4 *>(D.rd + j0 + i * 32 + lane));     /* off8, col0, span, pk */
-    }
-#define COL_REC(rb_) col_rec_of(rc, (rb_), n, lane)
-#else
-    const CgRead *rdp = D.rd + j0 + (lane >> 2);
-#define COL_REC(rb_) (((rb_) + (lane >> 2) < n) ? __ldg(reinterpret_cast<const uint4 *>(rdp + (rb_))) : make_uint4(0, 0, 0, 0))
-#endif
-    uint4 a = COL_REC(0);
-    ColRaw raw = col_raw_load(D, a, x0 + tile_c0 - (int)a.y);
-    for (int rb = 0; rb < n; rb += 8) {
-        const int r = rb + (lane >> 2);
-        /* request the next pass's words before decoding this one */
-        uint4 a_nx = make_uint4(0, 0, 0, 0); ColRaw raw_nx = raw;
-#if COL_PIPE
-        if (rb + 8 < n) { a_nx = COL_REC(rb + 8); raw_nx = col_raw_load(D, a_nx, x0 + tile_c0 - (int)a_nx.y); }
-#else
-        if (rb) { a = COL_REC(rb); raw = col_raw_load(D, a, x0 + tile_c0 - (int)a.y); }
-#endif
-        const int d_first = x0 + tile_c0 - (int)a.y;       /* column offset inside the read of this lane's first cell */
-        const int span = (int)a.z;                         /* 0 beyond the chunk: no cell */
-        int ka = -d_first, kb = span - d_first;            /* cells k in [ka, kb) lie on the read */
-        uint4 out = make_uint4(0, 0, 0, 0);
-        int general = 0;
-        if (ka < 8 && kb > 0) {
-            const uint32_t pk = a.w;
-            const int mapq = (pk >> 16) & 0xff;
-            const uint32_t rowf = CELL_VALID | (mapq <= min_mqual ? CELL_LOWMQ : 0u);
-            if (pk & ((uint32_t)CG_RF_SIMPLE << 24)) {
-                /* single-M read: query offset == column offset */
-                const int64_t A = ((int64_t)a.x << 3) + d_first;
-                const int64_t Bb = (A >> 1) & ~(int64_t)3;
-                const uint2 w0 = raw.w0, w1 = raw.w1;
-                uint32_t v0 = raw.v0, v1 = raw.v1;
-                const int s = (int)(A & 7);
-                const uint32_t Wa = (s & 4) ? w0.y : w0.x, Wb = (s & 4) ? w1.x : w0.y, Wc = (s & 4) ? w1.y : w1.x;
-                const uint32_t qlo = __funnelshift_r(Wa, Wb, (s & 3) * 8), qhi = __funnelshift_r(Wb, Wc, (s & 3) * 8);
-                const int m0 = (int)(A - (Bb << 1));                                /* first nibble inside the 64-bit word, 0..7 */
-                v0 = ((v0 & 0x0f0f0f0fu) << 4) | ((v0 >> 4) & 0x0f0f0f0fu);         /* high nibble first -> little-endian nibbles */
-                v1 = ((v1 & 0x0f0f0f0fu) << 4) | ((v1 >> 4) & 0x0f0f0f0fu);
-                const uint32_t Bs = doB ? col_bases8(__funnelshift_r(v0, v1, 4 * m0)) : 0x77777777u;
-                const uint8_t *er = effB + (mapq << 8);
-                uint32_t c[8];
+    for (int s = 0; s < 2; s++) {
+        const CgCellRec &r = s ? rb : ra;
+        const int row = s * 32 + lane;
+        if (row < n) {
+            const int g0 = (tile_c0 - (r.col0 & ~7)) >> 3;                  /* the tile's first group inside this row (may be negative) */
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const uint32_t qv = ((k < 4 ? qlo >> (8 * k) : qhi >> (8 * (k - 4)))) & 0xff;
-                    const uint32_t e = __ldg(er + qv);
-                    const uint32_t b = (4 * k <= CELL_BASE_SH) ? (Bs << (CELL_BASE_SH - 4 * k)) : (Bs >> (4 * k - CELL_BASE_SH));
-                    c[k] = (b & CELL_BASE_M) | (e << CELL_E_SH) | rowf;
-                }
-                /* ragged ends: valid cells [ka,kb), of which the read's first and last column are not "mid" */
-                const int va = ka < 0 ? 0 : ka, vb = kb > 8 ? 8 : kb;
-                const int ma = ka + 1 < 0 ? 0 : ka + 1, mb = kb - 1 > 8 ? 8 : (kb - 1 < 0 ? 0 : kb - 1);
-                const uint4 vm = S->mask[va][vb], mm = S->mask[ma > 8 ? 8 : ma][mb];
-                const uint32_t MIDW = CELL_MID | (CELL_MID << 16);
-                out.x = ((c[0] | c[1] << 16) & vm.x) | (mm.x & MIDW);
-                out.y = ((c[2] | c[3] << 16) & vm.y) | (mm.y & MIDW);
-                out.z = ((c[4] | c[5] << 16) & vm.z) | (mm.z & MIDW);
-                out.w = ((c[6] | c[7] << 16) & vm.w) | (mm.w & MIDW);
-            } else general = 1;
-        }
-        if (r < n) *reinterpret_cast<uint4 *>(&cells[r][x0]) = out;
-        /* rows with a non-trivial CIGAR: one at a time, lane = column */
-        unsigned gm = __ballot_sync(0xffffffffu, general);
-        gm = (gm | (gm >> 1) | (gm >> 2) | (gm >> 3)) & 0x11111111u;            /* one bit per lane group = row */
-        if (gm) {
-            __syncwarp();
-            while (gm) {
-                const int gl = __ffs(gm) - 1; gm &= gm - 1;
-                const int gr = rb + (gl >> 2);                             /* row of that lane group in this pass */
-                const uint4 ga = __ldg(reinterpret_cast<const uint4 *>(D.rd + j0 + gr));
-                const uint32_t grow = CELL_VALID | ((int)((ga.w >> 16) & 0xff) <= min_mqual ? CELL_LOWMQ : 0u);
-                cells[gr][lane] = (uint16_t)col_cell_general(&D, j0 + gr, tile_c0 + lane - (int)ga.y, grow, doB);
+            for (int p = 0; p < 4; p++) {
+                const bool ok = (unsigned)(g0 + p) < r.ngrp;
+                cp_async16(&buf[row][8 * p], cells + (ok ? (size_t)r.cpos8 + (size_t)(g0 + p) : (size_t)0), ok ? 16u : 0u);
             }
         }
-#if COL_PIPE
-        a = a_nx; raw = raw_nx;
-#endif
     }
+    cp_async_commit();
 }
 
-__global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __grid_constant__ CgDev D, int t_begin, int t_end) {
+__global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __grid_constant__ CgDev D, int t_begin, int t_end, int *tile_counter) {
     __shared__ ColSmem S;
-    __shared__ unsigned cntw[COL_WARPS][32];
     const CgTables *T = D.T;
     const CgDevParams *P = &D.P;
     for (int i = threadIdx.x; i < 104; i += blockDim.x) {
@@ -434,158 +313,92 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
         ColTabRow r; r.MM = T->MM[q]; r.hM = T->_M[q]; r.om = T->omq2p[q]; r.pad = 0;
         S.tab[i] = r;
     }
-    if (threadIdx.x < 81) {
-        const int a = threadIdx.x / 9, b = threadIdx.x % 9;
-        uint32_t m[4];
-        for (int i = 0; i < 4; i++) m[i] = ((2 * i >= a && 2 * i < b) ? 0xffffu : 0u) | ((2 * i + 1 >= a && 2 * i + 1 < b) ? 0xffff0000u : 0u);
-        S.mask[a][b] = make_uint4(m[0], m[1], m[2], m[3]);
-    }
-    cntw[threadIdx.x >> 5][threadIdx.x & 31] = 0;
+    S.cntw[threadIdx.x >> 5][threadIdx.x & 31] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int doB = P->min_qual_B != 0;
-    const int min_mqual = P->min_mqual;
-    uint16_t (*cells)[32] = S.w[w].cell;
+    const int lean = P->min_qual_B != 0 && P->min_qual_A == 0;
     const uint32_t tab = (uint32_t)__cvta_generic_to_shared(S.tab);
     double *rare = &S.rare[w][0][lane];
     int depth_max = 0;
-    /* the block's tables are built once for COL_TPW tiles per warp; warps walk their tiles on their own */
-    for (int ti = 0; ti < COL_TPW; ti++) {
-    const int t = t_begin + (blockIdx.x * COL_TPW + ti) * COL_WARPS + w;
-    if (t >= t_end) break;
-    const int tile_c0 = t * 32;
-    const int c = tile_c0 + lane;
-    CgColOut o; o.cnt = 0; o.n_plp = 0;
-    const int lo = D.tile_lo[t], hi = D.tile_start[t + 1];
-    const bool live = c < D.n_cols;
+    const CgCellRec zrec = { 0u, 0, 0, 0u };
 
-    /* ranks 0 and 1 (and their pairs) in registers; H2 H3 H4 C2 C3 C4 P23 P24 P34 in shared memory */
-    double H0 = 0, H1 = 0, C0 = 0, C1 = 0;
-    double P01 = 0, P02 = 0, P03 = 0, P04 = 0, P12 = 0, P13 = 0, P14 = 0;
-#pragma unroll
-    for (int i = 0; i < 9; i++) rare[i * 32] = 0;
-    uint32_t pi = 0xfffffu, nseen = 0;               /* base -> rank, 4 bits per base, 15 = not seen yet */
-    uint32_t b0s = 0xffffffffu, b1s = 0xffffffffu;   /* first and second base of the column, in cell position */
-    int n_plp = 0, n_skip = 0, n_none = 0, nN = 0, low_mq = 0, n_overlap = 0, indel_cnt = 0, clipped = 0;
-    uint32_t ins_seen = 0;
-
-    for (int j0 = lo; j0 < hi; j0 += COL_ROWS) {
-        const int n = hi - j0 < COL_ROWS ? hi - j0 : COL_ROWS;
+    /* work items: (tile, chunk of its read window).  `nt` is the tile after the current one, claimed one tile ahead. */
+    auto claim = [&]() -> int {
+        int v = 0;
+        if (lane == 0) v = t_begin + atomicAdd(tile_counter, 1);
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
+    int t = claim();
+    if (t >= t_end) return;
+    int nt = claim();
+    int lo = D.tile_lo[t], hi = D.tile_start[t + 1];
+    int nlo = 0, nhi = 0;
+    if (nt < t_end) { nlo = D.tile_lo[nt]; nhi = D.tile_start[nt + 1]; }
+    int j0 = lo, cur = 0;
+    {   /* prologue: first chunk of the first tile */
+        const int n = hi - j0 < COL_R ? hi - j0 : COL_R;
+        const CgCellRec ra = lane < n ? D.crec[j0 + lane] : zrec, rb = 32 + lane < n ? D.crec[j0 + 32 + lane] : zrec;
+        col_issue(D, S.cell[w][0], t * 32, n, ra, rb, lane);
+    }
+    CgRankAcc A;
+    cg_rank_init<32>(&A, rare);
+    for (;;) {
+        const int n = hi - j0 < COL_R ? hi - j0 : COL_R;          /* rows of the current item (<= 0 for an empty window) */
+        const bool last = j0 + COL_R >= hi;
+        /* the item after this one: next chunk of the same tile, or the first chunk of the next tile */
+        int xt = t, xj0 = j0 + COL_R, xhi = hi;
+        if (last) { xt = nt; xj0 = nlo; xhi = nhi; }
+        const bool more = xt < t_end;
+        int xn = 0;
+        CgCellRec ra = zrec, rb = zrec;
+        if (more) {
+            xn = xhi - xj0 < COL_R ? xhi - xj0 : COL_R;
+            if (lane < xn) ra = D.crec[xj0 + lane];
+            if (32 + lane < xn) rb = D.crec[xj0 + 32 + lane];
+        }
+        cp_async_wait_all();
         __syncwarp();
-        col_stage(D, &S, cells, j0, n, tile_c0, doB, min_mqual);
-        __syncwarp();
-        const uint16_t *col = &cells[0][lane];
-        if (COL_PEEK && nseen == 0) {
-            /* the column's first base is (nearly always) the base of its first covering read: look it up before the
-             * loop so that the first cell of every column does not take the rank-assignment path */
-            int r = 0; uint32_t cell = 0;
-            while (r < n && !((cell = col[r * 32]) & CELL_VALID)) r++;
-            if (r < n && ((cell >> CELL_BASE_SH) & 7u) < 5u) {
-                const uint32_t base = (cell >> CELL_BASE_SH) & 7u;
-                b0s = cell & CELL_BASE_M; nseen = 1; pi = (pi & ~(0xfu << (base << 2)));
-            }
+        const uint16_t *col = &S.cell[w][cur][0][lane];
+        if (n > 0) {
+            cg_rank_peek<32>(&A, col, n);
+            cg_rank_rows<32, 32>(&A, rare, col, n, tab);
         }
-        /* flag counters: five 6-bit fields in one word (ins | clip | indel | mid | lowmq), flushed every 32 rows */
-        for (int rb = 0; rb < n; rb += 32) {
-            const int re = n - rb < 32 ? n - rb : 32;
-            uint32_t pk = 0;
-            const uint16_t *cp = col + rb * 32;
-#if COL_LOOK == 2
-            uint32_t nxt = cp[0], nxt2 = cp[32];
-#else
-            uint32_t nxt = cp[0];
-#endif
-#pragma unroll 1
-            for (int r = 0; r < re; r++) {
-                const uint32_t cell = nxt;
-#if COL_LOOK == 2
-                nxt = nxt2;
-                nxt2 = cp[(r + 2) * 32];                     /* two rows ahead: the load's latency overlaps two rows of arithmetic (padding rows exist) */
-#else
-                nxt = cp[(r + 1) * 32];                      /* next row's cell: its latency overlaps this row's arithmetic (padding rows exist) */
-#endif
-                if (cell & CELL_VALID) {
-                    n_plp++;
-                    pk += ((cell & 0x1fu) * 0x00108421u) & 0x01041041u;
-                    /* shared-window address arithmetic: a generic pointer costs five instructions per row to rebuild */
-                    double2 mh; double om;
-                    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(mh.x), "=d"(mh.y) : "r"(tab + (cell & CELL_E_M)));
-                    asm("ld.shared.f64 %0, [%1+16];" : "=d"(om) : "r"(tab + (cell & CELL_E_M)));
-                    if ((cell & CELL_BASE_M) == b0s) {
-                        H0 += mh.x; P01 += mh.y; P02 += mh.y; P03 += mh.y; P04 += mh.y; C0 += om;
-                    } else if ((cell & CELL_BASE_M) == b1s) {
-                        P01 += mh.y; H1 += mh.x; P12 += mh.y; P13 += mh.y; P14 += mh.y; C1 += om;
-                    } else {
-                        const uint32_t base = (cell >> CELL_BASE_SH) & 7u;
-                        if (base < 5u) {
-                            uint32_t rank = (pi >> (base << 2)) & 0xfu;
-                            if (rank == 15u) {
-                                rank = nseen++; pi = (pi & ~(0xfu << (base << 2))) | (rank << (base << 2));
-                                if (rank == 0) b0s = cell & CELL_BASE_M;
-                                if (rank == 1) b1s = cell & CELL_BASE_M;
-                            }
-                            if (rank == 0)      { H0 += mh.x; P01 += mh.y; P02 += mh.y; P03 += mh.y; P04 += mh.y; C0 += om; }
-                            else if (rank == 1) { P01 += mh.y; H1 += mh.x; P12 += mh.y; P13 += mh.y; P14 += mh.y; C1 += om; }
-                            else {
-                                /* third and later bases of a column: their own sums live in shared memory */
-                                rare[(rank - 2) * 32] += mh.x; rare[(rank + 1) * 32] += om;
-                                rare[(rank == 4 ? 7 : 6) * 32] += mh.y; rare[(rank == 2 ? 7 : 8) * 32] += mh.y;
-                                if (rank == 2)      { P02 += mh.y; P12 += mh.y; }
-                                else if (rank == 3) { P03 += mh.y; P13 += mh.y; }
-                                else                { P04 += mh.y; P14 += mh.y; }
-                            }
-                        } else if (base == 5u) nN++;
-                        else if (base == 6u) n_skip++;
-                        else n_none++;
-                    }
-                }
+        if (more) col_issue(D, S.cell[w][cur ^ 1], xt * 32, xn, ra, rb, lane);
+        if (last) {
+            const int c = t * 32 + lane;
+            CgColOut o; o.cnt = 0; o.n_plp = 0;
+            if (c < D.n_cols) {
+                double *dump = reinterpret_cast<double *>(&S.cell[w][cur][0][0]) + lane;      /* the walked buffer is dead: lane-private scratch */
+                int rk[5];
+                CgConsAcc C;
+                cg_rank_of_bases(A.pi, A.nseen, rk);
+                cg_rank_dump_S<32, 32>(&A, rare, dump); cg_rank_unpermute_S<32>(dump, rk, C.S);
+                cg_rank_dump_C<32, 32>(&A, rare, dump); cg_rank_unpermute_C<32>(dump, rk, C.sumsC);
+                CgColStats st; st.cp = 0; st.n_plp = A.n_plp; st.n_skip = A.n_skip; st.low_mq = A.low_mq; st.had_indel = A.indel_cnt > 0; st.indel_cnt = A.indel_cnt;
+                st.clipped = A.clipped; st.n_overlap = A.n_overlap; st.ins_seen = A.ins_seen != 0;
+                C.depth = A.n_plp - A.n_skip - A.n_none - A.nN; C.nN = 0; C.sumsE = 0;
+                if (A.nN || !lean) o = col_finish_plain(&D, c, lo, hi, &st, &C, A.nN);        /* N bases add to 14 slots; mode A: the plain body */
+                else { CgCons cB; cg_cons_finalize_lean(T, &C, C.depth, &cB); o = cg_column_finish(&D, c, lo, hi, &st, (CgConsAcc *)0, &cB); }
             }
-            low_mq += pk & 0x3f; n_overlap += (pk >> 6) & 0x3f; indel_cnt += (pk >> 12) & 0x3f; clipped += (pk >> 18) & 0x3f; ins_seen |= pk >> 24;
-        }
-    }
-    __syncwarp();                                    /* the cell matrix is dead: reuse it to undo the rank permutation */
-    if (live) {
-        double *dump = &S.w[w].dump[0][lane];
-        dump[0 * 32] = H0; dump[1 * 32] = H1; dump[2 * 32] = rare[0 * 32]; dump[3 * 32] = rare[1 * 32]; dump[4 * 32] = rare[2 * 32];
-        dump[5 * 32] = C0; dump[6 * 32] = C1; dump[7 * 32] = rare[3 * 32]; dump[8 * 32] = rare[4 * 32]; dump[9 * 32] = rare[5 * 32];
-        dump[10 * 32] = P01; dump[11 * 32] = P02; dump[12 * 32] = P03; dump[13 * 32] = P04; dump[14 * 32] = P12;
-        dump[15 * 32] = P13; dump[16 * 32] = P14; dump[17 * 32] = rare[6 * 32]; dump[18 * 32] = rare[7 * 32]; dump[19 * 32] = rare[8 * 32];
-        int rk[5];
-#pragma unroll
-        for (int b = 0; b < 5; b++) { uint32_t r = (pi >> (4 * b)) & 0xfu; if (r == 15u) r = nseen++; rk[b] = (int)r; }   /* unseen bases take the unused ranks: their sums are 0 / pure */
-        CgConsAcc A;
-        int s = 0;
-#pragma unroll
-        for (int a = 0; a < 5; a++) {
-            A.sumsC[a] = dump[(5 + rk[a]) * 32];
-#pragma unroll
-            for (int b = a; b < 5; b++, s++) {
-                if (a == b) A.S[s] = dump[rk[a] * 32];
-                else {
-                    const int u = rk[a] < rk[b] ? rk[a] : rk[b], v = rk[a] < rk[b] ? rk[b] : rk[a];
-                    A.S[s] = dump[(10 + ((u * (9 - u)) >> 1) + (v - u - 1)) * 32];
-                }
+            /* counters: per warp in shared memory, flushed once when the warp runs out of tiles */
+            unsigned un = __reduce_or_sync(0xffffffffu, o.cnt);
+            while (un) {
+                int b = __ffs(un) - 1; un &= un - 1;
+                unsigned m = __ballot_sync(0xffffffffu, (o.cnt >> b) & 1);
+                if (lane == 0) S.cntw[w][b] += __popc(m);
             }
-        }
-        CgColStats st; st.n_plp = n_plp; st.n_skip = n_skip; st.low_mq = low_mq; st.had_indel = indel_cnt > 0; st.indel_cnt = indel_cnt;
-        st.clipped = clipped; st.n_overlap = n_overlap; st.ins_seen = ins_seen != 0;
-        A.depth = n_plp - n_skip - n_none - nN; A.nN = 0; A.sumsE = 0;
-        if (nN) col_gather_generic(&D, c, lo, hi, &A);      /* N bases add to 14 slots: exact slow path */
-        o = cg_column_finish(&D, c, lo, hi, &st, &A);
-    }
-    /* counters: per warp in shared memory, flushed once when the warp runs out of tiles */
-    unsigned un = __reduce_or_sync(0xffffffffu, o.cnt);
-    while (un) {
-        int b = __ffs(un) - 1; un &= un - 1;
-        unsigned m = __ballot_sync(0xffffffffu, (o.cnt >> b) & 1);
-        if (lane == 0) cntw[w][b] += __popc(m);
-    }
-    int mx = __reduce_max_sync(0xffffffffu, o.n_plp);
-    depth_max = mx > depth_max ? mx : depth_max;
-    __syncwarp();                                    /* the dump scratch is the next tile's cell matrix */
+            int mx = __reduce_max_sync(0xffffffffu, o.n_plp);
+            depth_max = mx > depth_max ? mx : depth_max;
+            if (!more) break;
+            cg_rank_init<32>(&A, rare);
+            t = nt; lo = nlo; hi = nhi; j0 = lo;
+            nt = claim();
+            if (nt < t_end) { nlo = D.tile_lo[nt]; nhi = D.tile_start[nt + 1]; }
+        } else j0 += COL_R;
+        cur ^= 1;
     }
     __syncwarp();
-    if (lane < CG_N_COUNTERS && cntw[w][lane]) atomicAdd(&D.counters[lane], (unsigned long long)cntw[w][lane]);
+    if (lane < CG_N_COUNTERS && S.cntw[w][lane]) atomicAdd(&D.counters[lane], (unsigned long long)S.cntw[w][lane]);
     if (lane == 0 && depth_max > 0) atomicMax(D.maxdepth, depth_max);
 }
 
@@ -1315,7 +1128,7 @@ struct cg_ctx {
     dbuf b_tid, b_pos, b_flag, b_mapq, b_lq, b_nc, b_off, b_coff, b_cigar, b_seq, b_qual, b_qout;
     dbuf b_jmap, b_rspan, b_rd, b_ks, b_ke, b_gap, b_gapraw, b_pmax, b_orig, b_rbf;
     dbuf b_tlo, b_tstart, b_isl, b_cb, b_ev, b_depth, b_dump, b_dsum, b_csum, b_fcol, b_trig, b_twin;
-    dbuf b_aggr, b_scal, b_scratch, b_epoch, b_events, b_chain, b_items, b_bed, b_bedpm;
+    dbuf b_aggr, b_scal, b_scratch, b_epoch, b_events, b_chain, b_items, b_bed, b_bedpm, b_crec, b_cells;
     int generic;                  /* cg_params_generic(): column and rewrite stages through the plain bodies */
     /* host mirrors */
     int32_t *d_hdims;             /* device alias of h_dims (mapped pinned memory) */
@@ -1411,7 +1224,7 @@ extern "C" cg_ctx *cg_create(const cg_params *p, int device, int *err) {
     ctx->own_stream = 1;
     ctx->hT = (CgTables *)malloc(sizeof(CgTables));
     if (!e && cudaMalloc((void **)&ctx->dT, sizeof(CgTables)) != cudaSuccess) e = CG_ERR_CUDA;
-    if (!e && cudaHostAlloc((void **)&ctx->h_dims, 64, cudaHostAllocMapped) != cudaSuccess) e = CG_ERR_CUDA;
+    if (!e && cudaHostAlloc((void **)&ctx->h_dims, 128, cudaHostAllocMapped) != cudaSuccess) e = CG_ERR_CUDA;
     if (!e && cudaHostGetDevicePointer((void **)&ctx->d_hdims, ctx->h_dims, 0) != cudaSuccess) e = CG_ERR_CUDA;
     if (!e && cudaHostAlloc((void **)&ctx->h_counters, sizeof(unsigned long long) * 32, cudaHostAllocDefault) != cudaSuccess) e = CG_ERR_CUDA;
     for (int i = 0; i < CG_N_TIMERS && !e; i++)
@@ -1428,7 +1241,7 @@ extern "C" void cg_destroy(cg_ctx *ctx) {
     dbuf *all[] = { &ctx->b_tid, &ctx->b_pos, &ctx->b_flag, &ctx->b_mapq, &ctx->b_lq, &ctx->b_nc, &ctx->b_off, &ctx->b_coff, &ctx->b_cigar,
         &ctx->b_seq, &ctx->b_qual, &ctx->b_qout, &ctx->b_jmap, &ctx->b_rspan, &ctx->b_rd, &ctx->b_ks, &ctx->b_ke, &ctx->b_gap, &ctx->b_gapraw,
         &ctx->b_pmax, &ctx->b_orig, &ctx->b_rbf, &ctx->b_tlo, &ctx->b_tstart, &ctx->b_isl, &ctx->b_cb, &ctx->b_ev, &ctx->b_depth, &ctx->b_dump,
-        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain, &ctx->b_items, &ctx->b_bed, &ctx->b_bedpm, &ctx->b_saved };
+        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain, &ctx->b_items, &ctx->b_bed, &ctx->b_bedpm, &ctx->b_saved, &ctx->b_crec, &ctx->b_cells };
     for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); i++) if (all[i]->p) cudaFree(all[i]->p);
     if (ctx->dT) cudaFree(ctx->dT);
     if (ctx->h_dims) cudaFreeHost(ctx->h_dims);
@@ -1564,7 +1377,8 @@ static inline int nblk(int64_t n, int t) { int64_t b = (n + t - 1) / t; return (
  * travel back while later chunks are still arriving (H2D, kernels and D2H overlap, PCIe is full duplex). */
 #define CG_MAX_CHUNKS 32
 struct CgBounds { int64_t rb[CG_MAX_CHUNKS]; int32_t n; };
-/* upload chunk i ends before record rb[i]; out[2i] = tiles complete once it has landed, out[2i+1] = records final then */
+/* upload chunk i ends before record rb[i]; out[3i] = tiles complete once it has landed, out[3i+1] = records final then,
+ * out[3i+2] = pileup reads whose bases are on the device then (their cell rows can be built) */
 __global__ void k_bounds(const __grid_constant__ CgDev D, const __grid_constant__ CgBounds B, int64_t *out) {
     const int i = threadIdx.x;
     if (i >= B.n) return;
@@ -1577,7 +1391,7 @@ __global__ void k_bounds(const __grid_constant__ CgDev D, const __grid_constant_
         rec = R < D.n_pile ? (int64_t)D.orig[R] : D.n_reads;
         if (rec > r) rec = r;
     }
-    out[2 * i] = T; out[2 * i + 1] = rec;
+    out[3 * i] = T; out[3 * i + 1] = rec; out[3 * i + 2] = j;
 }
 __global__ void k_window_max(const __grid_constant__ CgDev D, int32_t *out) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1591,7 +1405,8 @@ struct StI64Carry { int64_t *p; const CgEpochCarry *cy; __device__ void operator
 struct StI32Carry { int32_t *p; const CgEpochCarry *cy; __device__ void operator()(int64_t i, int32_t inc, int32_t) const { p[i] = inc + cy->csum_last; } };
 
 /* scalars on the device (b_scal): int32 [0] n_pile [1] n_cols [2] n_islands [3] n_flagged of the slice [4] maxdepth [5] err
- * [6] n_events [7] - [8] beyond [9] window max; counters at +128 B; chain carry at +512 B; epoch carry at +640 B; bounds at +768 B */
+ * [6] n_events [7] - [8] beyond [9] window max [10] STR items [12..13] packed quality bytes [14] packed CIGAR ops
+ * [16..17] cell groups [18] tile counter of k_column; counters at +128 B; chain carry at +512 B; epoch carry at +640 B; bounds at +768 B */
 static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
     cudaStream_t st = ctx->stream;
     CgDev *D = &ctx->D;
@@ -1668,13 +1483,25 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
         LdIslandFlag lif = { gapraw }; StIsland sis = { D->isl, D->ks, D->gap, gapraw };
         if ((e = run_scan<int32_t, OpSum>(ctx, lif, sis, np, 0, scal + 2))) return e;
         k_finish_read<<<nblk(np, 256), 256, 0, st>>>(*D, scal + 0, scal); ctx->launches++;
+        if (!ctx->generic) {                                       /* cell matrix: first group of every row, total in scal[16..17] */
+            if ((e = ensure(ctx, &ctx->b_crec, ((size_t)np + 1) * sizeof(CgCellRec)))) return e;
+            D->crec = (CgCellRec *)ctx->b_crec.p;
+            LdNgrp lg2 = { D->rd }; StCellRec sc2 = { D->crec, D->rd };
+            if ((e = run_scan<int64_t, OpSum>(ctx, lg2, sc2, np, (int64_t)0, (int64_t *)(scal + 16)))) return e;
+        }
     }
-    CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 32, cudaMemcpyDeviceToHost, st));
+    CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 96, cudaMemcpyDeviceToHost, st));
     CG_CHECK(cudaStreamSynchronize(st));
     if (ctx->h_dims[5]) { snprintf(ctx->err, sizeof ctx->err, "device reported error %d while building read records", ctx->h_dims[5]); return ctx->h_dims[5]; }
     D->n_cols = np > 0 ? ctx->h_dims[1] : 0; D->n_islands = np > 0 ? ctx->h_dims[2] : 0;
     D->n_tiles = (D->n_cols + 31) / 32;
     D->n_flagged = 0;
+    if (np > 0 && !ctx->generic) {
+        int64_t ng; memcpy(&ng, ctx->h_dims + 16, 8);
+        if (ng >= (1LL << 32)) { snprintf(ctx->err, sizeof ctx->err, "batch too large: split it"); return CG_ERR_BAD_ARG; }
+        if ((e = ensure(ctx, &ctx->b_cells, (size_t)ng * 16 + 64))) return e;
+        D->cells = (uint16_t *)ctx->b_cells.p;
+    }
     const int nc = D->n_cols;
     const size_t nc1 = (size_t)nc + 64;
     D->want_dump = 0;
@@ -1688,7 +1515,7 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
         D->coldump = (cg_column *)ctx->b_dump.p; D->want_dump = 1;
     }
     ctx->need_depth = 0;
-    for (int i = 0; i < 2 * CG_MAX_CHUNKS; i++) h_bounds[i] = 0;
+    for (int i = 0; i < 3 * CG_MAX_CHUNKS; i++) h_bounds[i] = 0;
     if (np > 0 && nc > 0) {
         CG_CHECK(cudaMemsetAsync(D->cb, 0, nc1, st));              /* k_paint may mark columns of a later slice before k_column fills them */
         k_fill_i32<<<nblk(D->n_tiles + 2, 256), 256, 0, st>>>(D->tile_lo, D->n_tiles + 2, np);
@@ -1697,7 +1524,7 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
         k_window_max<<<nblk(D->n_tiles, 256), 256, 0, st>>>(*D, scal + 9);
         k_bounds<<<1, CG_MAX_CHUNKS, 0, st>>>(*D, *bounds, (int64_t *)((char *)ctx->b_scal.p + 768)); ctx->launches += 5;
         CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 48, cudaMemcpyDeviceToHost, st));
-        CG_CHECK(cudaMemcpyAsync(h_bounds, (char *)ctx->b_scal.p + 768, sizeof(int64_t) * 2 * CG_MAX_CHUNKS, cudaMemcpyDeviceToHost, st));
+        CG_CHECK(cudaMemcpyAsync(h_bounds, (char *)ctx->b_scal.p + 768, sizeof(int64_t) * 3 * CG_MAX_CHUNKS, cudaMemcpyDeviceToHost, st));
         CG_CHECK(cudaStreamSynchronize(st));
         /* over-depth (snp_score.c:1673) needs n_plp > -P * mean depth >= -P: impossible when no tile has more than -P candidates */
         ctx->need_depth = ctx->params.over_depth < 1.0 || (double)ctx->h_dims[9] > ctx->params.over_depth;
@@ -1716,7 +1543,7 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
 }
 
 /* one slice: tiles [t0,t1) -> their columns -> sparse passes -> records [r0,r1) */
-static int run_slice(cg_ctx *ctx, int t0, int t1, int c0, int c1, int64_t r0, int64_t r1, int timed) {
+static int run_slice(cg_ctx *ctx, int t0, int t1, int c0, int c1, int64_t r0, int64_t r1, int jb, int je, int timed) {
     cudaStream_t st = ctx->stream;
     CgDev *D = &ctx->D;
     int32_t *scal = (int32_t *)ctx->b_scal.p;
@@ -1726,11 +1553,22 @@ static int run_slice(cg_ctx *ctx, int t0, int t1, int c0, int c1, int64_t r0, in
     const int ncs = c1 > c0 ? c1 - c0 : 0;                      /* columns of the sparse passes: the tiles' own, except in chained calls */
     int nfs = 0;
     const int kb = ctx->nf_total;
-    if (timed) T0(CG_T_COLUMNS);
+    if (timed) T0(CG_T_CELLS);
+    if (je > jb && !ctx->generic) {                             /* cell rows of the pileup reads whose bases have landed */
+        k_cells<<<nblk((int64_t)(je - jb) * 4, 256), 256, 0, st>>>(*D, jb, je);
+        k_cells_general<<<nblk((int64_t)(je - jb), 256), 256, 0, st>>>(*D, jb, je);
+        ctx->launches += 2;
+    }
+    if (timed) { T1(CG_T_CELLS); T0(CG_T_COLUMNS); }
     if (t1 > t0) {
-        const int blocks = nblk(t1 - t0, COL_WARPS * COL_TPW);
         if (ctx->generic) k_column_generic<<<nblk((int64_t)(t1 - t0) * 32, 128), 128, 0, st>>>(*D, t0, t1);
-        else k_column<<<blocks, COL_WARPS * 32, 0, st>>>(*D, t0, t1);
+        else {
+            /* persistent warps claim tiles from a counter: one warp slot per resident warp, never more warps than tiles */
+            int blocks = nblk(t1 - t0, COL_WARPS);
+            if (blocks > 148 * COL_MINB) blocks = 148 * COL_MINB;
+            CG_CHECK(cudaMemsetAsync(scal + 18, 0, 4, st));
+            k_column<<<blocks, COL_WARPS * 32, 0, st>>>(*D, t0, t1, scal + 18);
+        }
         ctx->launches++;
     }
     if (timed) { T1(CG_T_COLUMNS); T0(CG_T_FLAGGED); }
@@ -1838,11 +1676,11 @@ extern "C" int cg_run(cg_ctx *ctx) {
     CG_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     CgBounds B; memset(&B, 0, sizeof B); B.n = 1; B.rb[0] = ctx->D.n_reads;
-    int64_t hb[2 * CG_MAX_CHUNKS];
+    int64_t hb[3 * CG_MAX_CHUNKS];
     int e;
     T0(CG_T_TOTAL);
     if ((e = run_prep(ctx, &B, hb))) return e;
-    if ((e = run_slice(ctx, 0, ctx->D.n_tiles, 0, ctx->D.n_cols, 0, ctx->D.n_reads, 1))) return e;
+    if ((e = run_slice(ctx, 0, ctx->D.n_tiles, 0, ctx->D.n_cols, 0, ctx->D.n_reads, 0, ctx->D.n_pile, 1))) return e;
     return run_finish(ctx, 1);
 }
 
@@ -1945,7 +1783,7 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
         CG_CHECK(cudaEventRecord(ctx->ev_up[i], ctx->s_h2d));
     }
     cudaEventRecord(ctx->ev[CG_T_H2D][1], ctx->s_h2d);
-    int64_t hb[2 * CG_MAX_CHUNKS];
+    int64_t hb[3 * CG_MAX_CHUNKS];
     const int trace = getenv("CG_TRACE") != NULL;
     struct timespec ts0, ts1; clock_gettime(CLOCK_MONOTONIC, &ts0);
 #define CG_TRACE_AT(what, i) do { if (trace) { clock_gettime(CLOCK_MONOTONIC, &ts1); \
@@ -1964,22 +1802,24 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
             cS = ctx->h_dims[11];
         }
     }
-    int tprev = 0; int64_t rprev = 0;
+    int tprev = 0, jprev = 0; int64_t rprev = 0;
     cudaEventRecord(ctx->ev[CG_T_D2H][0], ctx->s_d2h);
     for (int i = 0; i < nch; i++) {
-        int t1 = (i + 1 == nch) ? ctx->D.n_tiles : (int)hb[2 * i];
-        int64_t r1 = (i + 1 == nch) ? n : hb[2 * i + 1];
+        int t1 = (i + 1 == nch) ? ctx->D.n_tiles : (int)hb[3 * i];
+        int64_t r1 = (i + 1 == nch) ? n : hb[3 * i + 1];
+        int j1 = (i + 1 == nch) ? ctx->D.n_pile : (int)hb[3 * i + 2];
         if (t1 < tprev) t1 = tprev;
         if (r1 < rprev) r1 = rprev;
+        if (j1 < jprev) j1 = jprev;
         CG_CHECK(cudaStreamWaitEvent(st, ctx->ev_up[i], 0));
         const int c0 = tprev * 32 < ctx->D.n_cols ? tprev * 32 : ctx->D.n_cols, c1 = t1 * 32 < ctx->D.n_cols ? t1 * 32 : ctx->D.n_cols;
         if (cS >= 0 && cS < c1) {
             /* the next call's first column lies in this slice: sparse passes up to it, save both carries, then the rest */
-            if ((e = run_slice(ctx, tprev, t1, c0, cS, 0, 0, 0))) { ctx->win_on = 0; return e; }
+            if ((e = run_slice(ctx, tprev, t1, c0, cS, 0, 0, jprev, j1, 0))) { ctx->win_on = 0; return e; }
             k_carry_save<<<1, 32, 0, st>>>(ccarry, ecarry, (CgSavedCarry *)ctx->b_saved.p); ctx->launches++;
-            e = run_slice(ctx, t1, t1, cS, c1, rprev, r1, 0);
+            e = run_slice(ctx, t1, t1, cS, c1, rprev, r1, j1, j1, 0);
             cS = -2;                                           /* saved */
-        } else e = run_slice(ctx, tprev, t1, c0, c1, rprev, r1, 0);
+        } else e = run_slice(ctx, tprev, t1, c0, c1, rprev, r1, jprev, j1, 0);
         if (e) { ctx->win_on = 0; return e; }
         if (r1 > rprev && out->qual_out) {
             const int64_t b0 = in->off[rprev], b1 = r1 < n ? in->off[r1] : in->qual_bytes;
@@ -1987,7 +1827,7 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
             CG_CHECK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[i], 0));
             if (b1 > b0) CG_CHECK(cudaMemcpyAsync(out->qual_out + b0, (char *)ctx->b_qout.p + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, ctx->s_d2h));
         }
-        tprev = t1; rprev = r1;
+        tprev = t1; rprev = r1; jprev = j1;
         CG_TRACE_AT("slice enqueued (host passed its column sync)", i);
     }
     cudaEventRecord(ctx->ev[CG_T_D2H][1], ctx->s_d2h);

@@ -38,6 +38,7 @@ typedef struct CgRead {       /* 32 bytes, one per pileup read (compacted, input
 #define CG_OFF(q) ((int64_t)(q)->off8 << 3)
 
 typedef struct CgIsland { int32_t col_start, tid, pos_start, pad; } CgIsland;
+struct CgCellRec;             /* cg_cells.h */
 
 typedef struct CgDev {
     /* sizes */
@@ -64,6 +65,8 @@ typedef struct CgDev {
     int32_t *pmaxcol;         /* dense inclusive prefix max of end columns */
     int32_t *orig;            /* compact index -> record index */
     uint8_t *r_bf;            /* read overlaps a trigger column: back-fill path in the rewrite */
+    struct CgCellRec *crec;   /* cell matrix: row record per pileup read (cg_cells.h) */
+    uint16_t *cells;          /* cell matrix: 16-bit pileup cells in groups of 8 */
     int64_t  K0;              /* key of the first pileup read */
     /* tiles of 32 dense columns */
     int32_t *tile_lo;         /* first pileup read whose prefix-max end column exceeds the tile start */
@@ -244,14 +247,14 @@ CG_HD void cg_column_cons(const CgDev *D, int c, int lo, int hi, CgCons *out) {
 typedef struct CgColStats { int n_plp, n_skip, low_mq, had_indel, indel_cnt, clipped, n_overlap, ins_seen; int cp; /* call_preserve (611-623) */ } CgColStats;
 
 /* everything after the per-read loop: consensus finalisation and the column decisions */
-CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgColStats *st, CgConsAcc *acc) {
+/* cB_ready: the mode-B consensus when the caller has already finalised it (the tuned kernel, cg_column_lean.h); else acc holds the sums */
+CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgColStats *st, CgConsAcc *acc, const CgCons *cB_ready = NULL) {
     const CgDevParams *P = &D->P;
     const CgTables *T = D->T;
     CgColOut o; o.cnt = 0; o.n_plp = 0;
     const int n_plp = st->n_plp, n_skip = st->n_skip, low_mq = st->low_mq, had_indel = st->had_indel;
     const int clipped = st->clipped, n_overlap = st->n_overlap, ins_seen = st->ins_seen;
     const int doB = P->min_qual_B != 0;
-    CgConsAcc &a = *acc;
     o.n_plp = n_plp;
     uint16_t ev = 0; uint8_t cb = CG_CB_UNPROC;
     D->depth[c] = (uint32_t)n_plp;
@@ -286,7 +289,7 @@ CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgC
     } else {
         ev |= CG_EV_PROCESSED;
         dflags |= 8;
-        if (doB) cg_cons_finalize(T, &a, &cB);
+        if (doB) { if (cB_ready) cB = *cB_ready; else cg_cons_finalize(T, acc, &cB); }
         if (P->min_qual_A != 0) cg_column_cons<0>(D, c, lo, hi, &cA);
         int hA = 0, sA = 0, hB = 0, sB = 0;
         const CgCons *cc = doB ? &cB : &cA;                                /* B's calls overwrite A's (1534-1543) */

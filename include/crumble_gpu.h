@@ -194,7 +194,7 @@ int cg_carry_is_neutral(const cg_ctx *ctx, const void *buf, int32_t tid, int32_t
 void cg_batch_ends(const cg_batch *in, int32_t *end_out);
 
 /* measurement helpers */
-enum { CG_T_TOTAL = 0, CG_T_TILES, CG_T_COLUMNS, CG_T_FLAGGED, CG_T_DEPTH, CG_T_CHAIN, CG_T_REWRITE, CG_T_PBLOCK, CG_T_EVENTS, CG_T_H2D, CG_T_D2H, CG_N_TIMERS };
+enum { CG_T_TOTAL = 0, CG_T_TILES, CG_T_COLUMNS, CG_T_FLAGGED, CG_T_DEPTH, CG_T_CHAIN, CG_T_REWRITE, CG_T_CELLS, CG_T_EVENTS, CG_T_H2D, CG_T_D2H, CG_N_TIMERS };
 float   cg_last_ms(const cg_ctx *ctx, int which);        /* CUDA-event time of the last cg_run / copies */
 int64_t cg_last_launches(const cg_ctx *ctx);             /* kernels launched by the last cg_run */
 int64_t cg_last_h2d_bytes(const cg_ctx *ctx);            /* bytes the last cg_upload / cg_process / cg_process_window copied to the device */

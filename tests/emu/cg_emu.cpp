@@ -14,6 +14,7 @@
 #include <vector>
 #include <limits.h>
 #include "../../crumble_b200/csrc/cg_host.h"
+#include "../../crumble_b200/csrc/cg_column_lean.h"
 
 struct EmuCarry { CgWin w; int chain_tid; int64_t td, tc; int depth_tid; };
 struct cg_ctx { cg_params p; CgTables T; char err[256]; int64_t n_cols; std::vector<cg_bed_reg> bed; std::vector<int64_t> bed_pm; EmuCarry carry; std::vector<cg_bed_event> events; };
@@ -100,12 +101,80 @@ static int emu_process(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg
     D.cb = cb.data(); D.ev = ev.data(); D.depth = depth.data();
     const int cS = (win && win->hi_tid >= 0) ? cg_find_col(&D, win->hi_tid, win->next_lo_pos) : D.n_cols;
     std::vector<cg_column> dump;
-    D.want_dump = out->columns != NULL;
-    if (D.want_dump) { dump.resize(D.n_cols + 1); D.coldump = dump.data(); }
+    D.want_dump = 1;                                     /* always: the tuned-path check below compares the consensus values themselves, not only the decisions */
+    dump.resize(D.n_cols + 1); D.coldump = dump.data();
     for (int c = 0; c < D.n_cols; c++) {
         CgColOut o = cg_column_body(&D, c);
         for (int i = 0; i < CG_N_COUNTERS; i++) if (o.cnt >> i & 1) counters[i]++;
         if (o.n_plp > maxdepth) maxdepth = o.n_plp;
+    }
+    /* The tuned column path (k_cells + k_column of cg_device.cu), lane by lane, with the same bodies the kernels run (cg_cells.h,
+     * cg_column_lean.h): cell matrix in groups of 8, staged rows of a tile in chunks, rank-space accumulation, lean finalisation.
+     * Every per-column output must equal what the plain body just produced. */
+    if (!cg_params_generic(&ctx->p) && np > 0) {
+        const int doB = D.P.min_qual_B != 0;
+        std::vector<CgCellRec> crec(np + 1);
+        uint64_t ng = 0;
+        for (int j = 0; j < np; j++) { CgCellRec r; r.cpos8 = (uint32_t)ng; r.col0 = rd[j].col0; r.span = rd[j].span; r.ngrp = cg_cell_ngroups(r.col0, r.span); crec[j] = r; ng += r.ngrp; }
+        std::vector<uint16_t> cells(ng * 8 + 8, 0xdead);
+        /* the kernels read whole aligned words around a read (CG_FRONT_PAD / tail padding on the device): give the host copies the same slack */
+        std::vector<uint8_t> qpad(in->qual_bytes + 512, 0), spad(in->seq_bytes + 512, 0);
+        memcpy(qpad.data() + 256, in->qual, in->qual_bytes); memcpy(spad.data() + 256, in->seq, in->seq_bytes);
+        CgDev D2 = D; D2.qual = qpad.data() + 256; D2.seq = spad.data() + 256;
+        for (int j = 0; j < np; j++)
+            for (uint32_t k = 0; k < crec[j].ngrp; k++) { uint32_t o4[4]; cg_cells8(&D2, &rd[j], (int)k, doB, o4); memcpy(&cells[((size_t)crec[j].cpos8 + k) * 8], o4, 16); }
+        ColTabRow tab[104];
+        for (int i = 0; i < 104; i++) { int q = i > 100 ? 100 : i; tab[i].MM = ctx->T.MM[q]; tab[i].hM = ctx->T._M[q]; tab[i].om = ctx->T.omq2p[q]; tab[i].pad = 0; }
+        std::vector<uint8_t> cb2(D.n_cols + 1, 0); std::vector<uint16_t> ev2(D.n_cols + 1, 0); std::vector<uint32_t> depth2(D.n_cols + 1, 0);
+        std::vector<cg_column> dump2(D.n_cols + 1);
+        unsigned long long counters2[CG_N_COUNTERS] = {0}; int32_t err2 = 0, maxdepth2 = 0, beyond2 = 0;
+        D2 = D; D2.cb = cb2.data(); D2.ev = ev2.data(); D2.depth = depth2.data(); D2.coldump = dump2.data(); D2.counters = counters2; D2.err = &err2; D2.maxdepth = &maxdepth2; D2.beyond = &beyond2;
+        const int R = getenv("CG_EMU_ROWS") ? atoi(getenv("CG_EMU_ROWS")) : 60;
+        std::vector<uint16_t> buf((size_t)(R + 1) * 32);
+        const int lean = doB && !D.P.min_qual_A;
+        for (int t = 0; t < D.n_tiles; t++) {
+            const int lo = tile_lo[t], hi = tile_start[t + 1], tile_c0 = t * 32;
+            CgRankAcc acc[32]; double rare[32][9];
+            for (int l = 0; l < 32; l++) cg_rank_init<1>(&acc[l], rare[l]);
+            for (int j0 = lo; j0 < hi; j0 += R) {
+                const int n = hi - j0 < R ? hi - j0 : R;
+                for (int r = 0; r < n; r++) {
+                    const CgCellRec cr = crec[j0 + r];
+                    for (int p4 = 0; p4 < 4; p4++) {
+                        const int gi = (tile_c0 + 8 * p4 - (cr.col0 & ~7)) >> 3;
+                        if ((unsigned)gi < cr.ngrp) memcpy(&buf[(size_t)r * 32 + 8 * p4], &cells[((size_t)cr.cpos8 + gi) * 8], 16);
+                        else memset(&buf[(size_t)r * 32 + 8 * p4], 0, 16);
+                    }
+                }
+                for (int l = 0; l < 32; l++) { cg_rank_peek<32>(&acc[l], &buf[l], n); cg_rank_rows<32, 1>(&acc[l], rare[l], &buf[l], n, (const ColTabRow *)tab); }
+            }
+            for (int l = 0; l < 32; l++) {
+                const int c = tile_c0 + l;
+                if (c >= D.n_cols) continue;
+                CgRankAcc &a = acc[l];
+                double dmp[15]; int rk[5]; CgConsAcc A;
+                cg_rank_dump_S<1, 1>(&a, rare[l], dmp); cg_rank_of_bases(a.pi, a.nseen, rk); cg_rank_unpermute_S<1>(dmp, rk, A.S);
+                cg_rank_dump_C<1, 1>(&a, rare[l], dmp); cg_rank_unpermute_C<1>(dmp, rk, A.sumsC);
+                CgColStats st; st.cp = 0; st.n_plp = a.n_plp; st.n_skip = a.n_skip; st.low_mq = a.low_mq; st.had_indel = a.indel_cnt > 0; st.indel_cnt = a.indel_cnt;
+                st.clipped = a.clipped; st.n_overlap = a.n_overlap; st.ins_seen = a.ins_seen != 0;
+                A.depth = a.n_plp - a.n_skip - a.n_none - a.nN; A.nN = 0; A.sumsE = 0;
+                CgColOut o;
+                if (a.nN) { cg_col_gather_generic(&D2, c, lo, hi, &A); o = cg_column_finish(&D2, c, lo, hi, &st, &A); }
+                else if (lean) { CgCons cB; cg_cons_finalize_lean(&ctx->T, &A, A.depth, &cB); o = cg_column_finish(&D2, c, lo, hi, &st, NULL, &cB); }
+                else o = cg_column_finish(&D2, c, lo, hi, &st, &A);
+                for (int i = 0; i < CG_N_COUNTERS; i++) if (o.cnt >> i & 1) counters2[i]++;
+                if (o.n_plp > maxdepth2) maxdepth2 = o.n_plp;
+            }
+        }
+        int bad = 0;
+        for (int c = 0; c < D.n_cols && bad < 10; c++) {
+            if (cb2[c] != cb[c] || ev2[c] != ev[c] || depth2[c] != depth[c]) { fprintf(stderr, "emu: tuned column path differs at column %d: cb %02x/%02x ev %04x/%04x depth %u/%u\n", c, cb2[c], cb[c], ev2[c], ev[c], depth2[c], depth[c]); bad++; }
+            if (D.want_dump && memcmp(&dump2[c], &dump[c], sizeof(cg_column))) { fprintf(stderr, "emu: tuned column path: column dump differs at column %d (phred %d/%d het %d/%d)\n", c, dump2[c].phred, dump[c].phred, dump2[c].het_phred, dump[c].het_phred); bad++; }
+        }
+        for (int i = 0; i < CG_N_COUNTERS; i++) if (counters2[i] != counters[i]) { fprintf(stderr, "emu: tuned column path: counter %d differs %llu/%llu\n", i, counters2[i], counters[i]); bad++; }
+        if (maxdepth2 != maxdepth || beyond2 != beyond) { fprintf(stderr, "emu: tuned column path: maxdepth/beyond differ\n"); bad++; }
+        if (bad) { snprintf(ctx->err, sizeof ctx->err, "tuned column path differs from the plain body"); return CG_ERR_CUDA; }
+        if (getenv("CG_EMU_VERBOSE")) fprintf(stderr, "emu: tuned column path verified on %d columns, %d tiles, %llu cell groups (rows per chunk %d, lean finalise %d)\n", D.n_cols, D.n_tiles, (unsigned long long)ng, R, lean);
     }
     /* flagged columns */
     std::vector<int32_t> fcol;
