@@ -376,6 +376,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pack", action="store_true", help="upload the plain 4-bit / 8-bit arrays instead of the batcher's compact planes")
     ap.add_argument("--region-shards", action="store_true", help="strong scaling of one contig over the ranks (not the default line)")
     a = ap.parse_args()
     if a.warmup < 3 and a.impl != "reference":
@@ -406,7 +407,7 @@ def main():
     bb = cb.BatchBuilder(pinned=True)
     bb.add_bam_stream(data)
     del data
-    batch = bb.finish()
+    batch = bb.finish(pack=not a.no_pack)                       # compact planes: 2-bit bases + exceptions, dictionary-coded qualities
     t_gen = time.perf_counter() - t_gen
     algo_bytes = cb.algorithmic_bytes(batch)
     bases = cb.aligned_bases(batch)
@@ -481,7 +482,9 @@ def main():
                          "whole_chain_frac": algo_bytes / (dev_ms_max / a.steps * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "aligned bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * float(te.item()) / a.e2e_steps, "h2d_ms": e2e_timers["h2d"], "d2h_ms": e2e_timers["d2h"],
-                    "steps": a.e2e_steps, "host_binding": numa, "how": "cg_process: per-record arrays, then base data in ~96 MB chunks on a copy stream; slice i of the chain starts "
+                    "steps": a.e2e_steps, "host_binding": numa,
+                    "upload": ("compact planes built by the batcher: 2-bit bases + exception list" + (f", {batch.qual_bits}-bit dictionary-coded qualities" if batch.qual_bits else ", 8-bit qualities (more than 16 distinct values)")) if batch.seq2 else "4-bit bases, 8-bit qualities",
+                    "how": "cg_process: per-record arrays, then base data in ~96 MB chunks on a copy stream; slice i of the chain starts "
                     "when chunk i has landed; qualities return on a second copy stream (h2d_ms / d2h_ms are the spans of the two copy streams and overlap)"},
             "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -66,6 +66,10 @@ class Batch(C.Structure):
         ("seq", C.POINTER(C.c_uint8)), ("seq_bytes", C.c_int64),
         ("qual", C.POINTER(C.c_uint8)), ("qual_bytes", C.c_int64),
         ("packed", C.c_int32),
+        ("seq2", C.POINTER(C.c_uint8)), ("seq2_bytes", C.c_int64),
+        ("seq_exc", C.POINTER(C.c_uint64)), ("n_seq_exc", C.c_int64),
+        ("qualp", C.POINTER(C.c_uint8)), ("qualp_bytes", C.c_int64),
+        ("qual_bits", C.c_int32), ("qual_dict", C.c_uint8 * 16),
     ]
 
 
@@ -106,7 +110,7 @@ EXPORTS = [
     "cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_set_params", "cg_strerror", "cg_last_error",
     "cg_set_stream", "cg_process", "cg_process_window", "cg_upload", "cg_run", "cg_download", "cg_sync", "cg_last_ms", "cg_last_launches", "cg_last_h2d_bytes",
     "cg_algorithmic_bytes", "cg_aligned_bases", "cg_n_columns", "cg_params_default", "cg_params_level",
-    "cgb_create", "cgb_destroy", "cgb_reset", "cgb_add", "cgb_add_bam_stream", "cgb_finish", "cgb_bytes", "cgb_reserve",
+    "cgb_create", "cgb_destroy", "cgb_reset", "cgb_add", "cgb_add_bam_stream", "cgb_finish", "cgb_bytes", "cgb_reserve", "cgb_pack",
     "cg_carry_export", "cg_carry_import", "cg_carry_is_neutral", "cg_batch_ends",
 ]
 CARRY_BYTES = 128
@@ -172,6 +176,7 @@ def load_lib():
     lib.cgb_add.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint16, C.c_uint8, C.c_int32, C.c_uint32,
                             C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cgb_finish.argtypes = [C.c_void_p, C.POINTER(Batch)]
+    lib.cgb_pack.argtypes = [C.c_void_p, C.c_int]
     lib.cgb_bytes.restype = C.c_int64
     lib.cgb_bytes.argtypes = [C.c_void_p]
     lib.crumble_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
@@ -219,7 +224,11 @@ class BatchBuilder:
         _check(self.lib, self.lib.cgb_add(self.h, tid, pos, flag, mapq, qual.size, cigar.size,
                                           cigar.ctypes.data, seq4.ctypes.data, qual.ctypes.data))
 
-    def finish(self) -> Batch:
+    def finish(self, pack: bool = False, threads: int = 0) -> Batch:
+        """pack=True also builds the compact planes (2-bit bases + exception list, dictionary-coded qualities when the batch has at
+        most 16 distinct values): the upload then moves those instead of seq / qual"""
+        if pack:
+            _check(self.lib, self.lib.cgb_pack(self.h, threads))
         _check(self.lib, self.lib.cgb_finish(self.h, C.byref(self.batch)))
         return self.batch
 
@@ -405,7 +414,22 @@ def sub_batch(batch: Batch, i0: int, i1: int):
     b.seq = at(batch.seq, C.c_uint8, q0 // 2); b.seq_bytes = (q1 - q0) // 2
     b.qual = at(batch.qual, C.c_uint8, q0); b.qual_bytes = q1 - q0
     b.packed = batch.packed                            # running sums stay running sums after rebasing
-    return b, (off2, coff2)
+    keep = [off2, coff2]
+    if batch.seq2:                                     # compact planes: positions are quality-buffer offsets, so they rebase with q0
+        b.seq2 = at(batch.seq2, C.c_uint8, q0 // 4); b.seq2_bytes = (q1 - q0) // 4
+        ne = int(batch.n_seq_exc)
+        exc = np.ctypeslib.as_array(batch.seq_exc, shape=(ne,)) if ne else np.zeros(0, np.uint64)
+        e0, e1 = np.searchsorted(exc >> np.uint64(4), [q0, q1]) if ne else (0, 0)
+        exc2 = (exc[e0:e1] - np.uint64(q0 << 4)).astype(np.uint64)
+        keep.append(exc2)
+        b.seq_exc = exc2.ctypes.data_as(C.POINTER(C.c_uint64)) if exc2.size else None
+        b.n_seq_exc = int(exc2.size)
+        b.qual_bits = batch.qual_bits
+        if batch.qual_bits:
+            b.qualp = at(batch.qualp, C.c_uint8, q0 * batch.qual_bits // 8); b.qualp_bytes = (q1 - q0) * batch.qual_bits // 8
+            for k in range(16):
+                b.qual_dict[k] = batch.qual_dict[k]
+    return b, tuple(keep)
 
 
 def plan_region_shards(batch: Batch, n_shards: int):

@@ -81,15 +81,14 @@ CG_HD uint32_t cg_funnel_r(uint32_t lo, uint32_t hi, unsigned sh) {    /* sh in 
  * of two cells each.  d_first = 8k - (col0 & 7) is the offset inside the read of the group's first cell (negative in the first
  * group of a read that does not start on a group boundary).  Two aligned 64-bit quality loads and two 32-bit sequence loads are
  * funnel-shifted into place (both buffers are padded, see CG_FRONT_PAD), the nt16 codes are mapped to bases in one
- * SIMD-within-register pass, quality x mapq goes through the host-built effective-quality table (a pure function of both,
- * snp_score.c:632-642). */
+ * SIMD-within-register pass, quality x mapq goes through the host-built cell table (effective quality, a pure function of both,
+ * snp_score.c:632-642, with the valid and low-mapq bits folded in).  Only the first and last group of a read are ragged. */
 CG_HD void cg_cells8_simple(const CgDev *D, const CgRead *q, int d_first, int doB, uint32_t out[4]) {
     const int span = q->span;
     const int ka = -d_first, kb = span - d_first;                        /* cells k in [ka, kb) lie on the read */
     out[0] = out[1] = out[2] = out[3] = 0;
     if (ka >= 8 || kb <= 0) return;
     const int mapq = q->mapq;
-    const uint32_t rowf = CELL_VALID | (mapq <= D->P.min_mqual ? CELL_LOWMQ : 0u);
     const int64_t A = CG_OFF(q) + d_first;                              /* byte address of the first quality */
     const int64_t Bb = (A >> 1) & ~(int64_t)3;
     const uint32_t *qa = (const uint32_t *)(D->qual + (A & ~(int64_t)7));
@@ -105,29 +104,50 @@ CG_HD void cg_cells8_simple(const CgDev *D, const CgRead *q, int d_first, int do
     const int s = (int)(A & 7);
     const uint32_t Wa = (s & 4) ? w0y : w0x, Wb = (s & 4) ? w1x : w0y, Wc = (s & 4) ? w1y : w1x;
     const uint32_t qlo = cg_funnel_r(Wa, Wb, (s & 3) * 8), qhi = cg_funnel_r(Wb, Wc, (s & 3) * 8);
-    const int m0 = (int)(A - (Bb << 1));                                /* first nibble inside the 64-bit word, 0..7 */
-    v0 = ((v0 & 0x0f0f0f0fu) << 4) | ((v0 >> 4) & 0x0f0f0f0fu);         /* high nibble first -> little-endian nibbles */
-    v1 = ((v1 & 0x0f0f0f0fu) << 4) | ((v1 >> 4) & 0x0f0f0f0fu);
-    const uint32_t Bs = doB ? cg_bases8(cg_funnel_r(v0, v1, 4 * m0)) : 0x77777777u;
-    const uint8_t *er = D->T->effB + (mapq << 8);
-    uint32_t c[8];
+    uint32_t c[4];
+    if (doB) {
+        const int m0 = (int)(A - (Bb << 1));                            /* first nibble inside the 64-bit word, 0..7 */
+        v0 = ((v0 & 0x0f0f0f0fu) << 4) | ((v0 >> 4) & 0x0f0f0f0fu);     /* high nibble first -> little-endian nibbles */
+        v1 = ((v1 & 0x0f0f0f0fu) << 4) | ((v1 >> 4) & 0x0f0f0f0fu);
+        const uint32_t Bs = cg_bases8(cg_funnel_r(v0, v1, 4 * m0));      /* base of cell k in nibble k */
+        const uint16_t *er = D->T->cellB + (mapq << 8);
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-    for (int k = 0; k < 8; k++) {
-        const uint32_t qv = ((k < 4 ? qlo >> (8 * k) : qhi >> (8 * (k - 4)))) & 0xff;
+        for (int w = 0; w < 4; w++) {
+            const uint32_t qq = w < 2 ? qlo >> (16 * w) : qhi >> (16 * (w - 2));
 #ifdef __CUDA_ARCH__
-        const uint32_t e = doB ? __ldg(er + qv) : 0u;
+            const uint32_t e0 = __ldg(er + (qq & 0xff)), e1 = __ldg(er + ((qq >> 8) & 0xff));
 #else
-        const uint32_t e = doB ? er[qv] : 0u;
+            const uint32_t e0 = er[qq & 0xff], e1 = er[(qq >> 8) & 0xff];
 #endif
-        const uint32_t b = (4 * k <= CELL_BASE_SH) ? (Bs << (CELL_BASE_SH - 4 * k)) : (Bs >> (4 * k - CELL_BASE_SH));
-        uint32_t v = (b & CELL_BASE_M) | (e << CELL_E_SH) | rowf;
-        if (k > ka && k < kb - 1) v |= CELL_MID;                        /* the read's first and last column are not "mid" */
-        if (k < ka || k >= kb) v = 0;                                   /* ragged ends */
-        c[k] = v;
+            /* the two base nibbles of this word to bits 12..14 and 28..30 */
+            const uint32_t bb = (((Bs >> (8 * w)) & 0xffu) * 0x01001000u) & 0x70007000u;
+            c[w] = e0 | (e1 << 16) | bb;
+        }
+    } else {
+        const uint32_t rowf = CELL_VALID | (7u << CELL_BASE_SH) | (mapq <= D->P.min_mqual ? CELL_LOWMQ : 0u);   /* no contribution */
+        c[0] = c[1] = c[2] = c[3] = rowf | (rowf << 16);
     }
-    out[0] = c[0] | c[1] << 16; out[1] = c[2] | c[3] << 16; out[2] = c[4] | c[5] << 16; out[3] = c[6] | c[7] << 16;
+    const uint32_t MIDW = CELL_MID | (CELL_MID << 16);
+    if (ka < 0 && kb > 8) {                                              /* interior group: all eight cells valid and "mid" */
+        out[0] = c[0] | MIDW; out[1] = c[1] | MIDW; out[2] = c[2] | MIDW; out[3] = c[3] | MIDW;
+        return;
+    }
+    /* ragged ends: valid cells [ka, kb), of which the read's first and last column are not "mid" */
+    const int va = ka < 0 ? 0 : ka, vb = kb > 8 ? 8 : kb;
+    const int ma = ka + 1 < 0 ? 0 : ka + 1, mb = kb - 1 > 8 ? 8 : kb - 1;
+    const uint32_t v8 = ((1u << vb) - 1u) & ~((1u << va) - 1u);
+    const uint32_t m8 = mb > ma ? ((1u << mb) - 1u) & ~((1u << ma) - 1u) : 0u;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int w = 0; w < 4; w++) {
+        const uint32_t tv = (v8 >> (2 * w)) & 3u, tm = (m8 >> (2 * w)) & 3u;
+        const uint32_t vm = ((tv & 1u) * 0xffffu) | ((tv >> 1) * 0xffff0000u);
+        const uint32_t mm = ((tm & 1u) * (uint32_t)CELL_MID) | ((tm >> 1) * ((uint32_t)CELL_MID << 16));
+        out[w] = (c[w] & vm) | mm;
+    }
 }
 
 /* group k of any read */

@@ -11,7 +11,7 @@
  * exactly the six adds of the reference's switch (656-683), in the same order per slot, so every slot sees the same IEEE
  * add sequence.  Nearly all cells of a column carry its first base, so the fast path is taken by whole warps whatever the
  * reference base under each lane is.  sumsE of the reference is dead (never read after the loop) and is not computed.
- * A column holding an N base (which adds to 14 slots) is recomputed by the plain body.
+ * An N base adds to 14 slots; it first hands a rank to every base that has none yet.
  */
 #ifndef CG_COLUMN_LEAN_H
 #define CG_COLUMN_LEAN_H
@@ -25,10 +25,11 @@ __align__(16)
 ColTabRow { double MM, hM, om, pad; } ColTabRow;       /* per effective quality: pMM-p__, p_M-p__, 1-q2p (snp_score.c:644-651); row 0 is zero */
 
 /* sums of ranks 0 and 1 (and their pairs) live in registers; H2 H3 H4 C2 C3 C4 P23 P24 P34 in `rare` (shared memory on the device) */
+#define CG_NO_BASE 0x1000u           /* a base without the valid bit: no cell looks like this (an uncovered cell is all zero) */
 typedef struct CgRankAcc {
     double H0, H1, C0, C1, P01, P02, P03, P04, P12, P13, P14;
     uint32_t pi, nseen;               /* base -> rank, 4 bits per base, 15 = not seen yet */
-    uint32_t b0s, b1s;                /* first and second base of the column, in cell position (CELL_BASE_M), ~0 = none yet */
+    uint32_t b0s, b1s;                /* first and second base of the column as cell bits (CELL_VALID | base << CELL_BASE_SH), CG_NO_BASE = none yet */
     int n_plp, n_skip, n_none, nN, low_mq, n_overlap, indel_cnt, clipped;
     uint32_t ins_seen;
 } CgRankAcc;
@@ -42,7 +43,7 @@ template <int RS>
 CG_HD void cg_rank_init(CgRankAcc *a, double *rare) {
     a->H0 = a->H1 = a->C0 = a->C1 = 0;
     a->P01 = a->P02 = a->P03 = a->P04 = a->P12 = a->P13 = a->P14 = 0;
-    a->pi = 0xfffffu; a->nseen = 0; a->b0s = 0xffffffffu; a->b1s = 0xffffffffu;
+    a->pi = 0xfffffu; a->nseen = 0; a->b0s = CG_NO_BASE; a->b1s = CG_NO_BASE;
     a->n_plp = a->n_skip = a->n_none = a->nN = a->low_mq = a->n_overlap = a->indel_cnt = a->clipped = 0; a->ins_seen = 0;
 #ifdef __CUDA_ARCH__
 #pragma unroll
@@ -70,8 +71,8 @@ CG_HD void cg_rank_slow(CgRankAcc *a, double *rare, uint32_t cell, double mm, do
         uint32_t rank = (a->pi >> (base << 2)) & 0xfu;
         if (rank == 15u) {
             rank = a->nseen++; a->pi = (a->pi & ~(0xfu << (base << 2))) | (rank << (base << 2));
-            if (rank == 0) a->b0s = cell & CELL_BASE_M;
-            if (rank == 1) a->b1s = cell & CELL_BASE_M;
+            if (rank == 0) a->b0s = cell & (CELL_VALID | CELL_BASE_M);
+            if (rank == 1) a->b1s = cell & (CELL_VALID | CELL_BASE_M);
         }
         if (rank == 0)      { a->H0 += mm; a->P01 += hm; a->P02 += hm; a->P03 += hm; a->P04 += hm; a->C0 += om; }
         else if (rank == 1) { a->P01 += hm; a->H1 += mm; a->P12 += hm; a->P13 += hm; a->P14 += hm; a->C1 += om; }
@@ -82,7 +83,44 @@ CG_HD void cg_rank_slow(CgRankAcc *a, double *rare, uint32_t cell, double mm, do
             else if (rank == 3) { a->P03 += hm; a->P13 += hm; }
             else                { a->P04 += hm; a->P14 += hm; }
         }
-    } else if (base == 5u) a->nN++;
+    } else if (base == 5u) {
+        /* N: MM to every genotype without a pad, _M to the pad-containing hets, nothing to ** and to the discrepancy sums
+         * (snp_score.c:677-682).  Every base needs a rank for that: the unseen ones get theirs now, in base order - ranks are
+         * arbitrary labels, the un-permute at the end of the column does not care when they were handed out. */
+        a->nN++;
+        int rk[5];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int b = 0; b < 5; b++) {
+            uint32_t r = (a->pi >> (4 * b)) & 0xfu;
+            if (r == 15u) {
+                r = a->nseen++; a->pi = (a->pi & ~(0xfu << (4 * b))) | (r << (4 * b));
+                if (r == 0) a->b0s = CELL_VALID | ((uint32_t)b << CELL_BASE_SH);
+                if (r == 1) a->b1s = CELL_VALID | ((uint32_t)b << CELL_BASE_SH);
+            }
+            rk[b] = (int)r;
+        }
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+        for (int x = 0; x < 5; x++) {
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+            for (int y = x; y < 5; y++) {
+                if (x == 4) continue;                                   /* ** */
+                const double v = y == 4 ? hm : mm;
+                const int u = rk[x] < rk[y] ? rk[x] : rk[y], w = rk[x] < rk[y] ? rk[y] : rk[x];
+                if (x == y) { if (u == 0) a->H0 += v; else if (u == 1) a->H1 += v; else rare[(u - 2) * RS] += v; }
+                else switch (CG_RK_P(u, w) - 5) {
+                    case 0: a->P01 += v; break; case 1: a->P02 += v; break; case 2: a->P03 += v; break; case 3: a->P04 += v; break;
+                    case 4: a->P12 += v; break; case 5: a->P13 += v; break; case 6: a->P14 += v; break;
+                    default: rare[(CG_RK_P(u, w) - 5 - 7 + 6) * RS] += v; break;     /* P23 P24 P34 -> rare 6 7 8 */
+                }
+            }
+        }
+    }
     else if (base == 6u) a->n_skip++;
     else a->n_none++;
 }
@@ -96,12 +134,14 @@ CG_HD void cg_rank_peek(CgRankAcc *a, const uint16_t *col, int n) {
     while (r < n && !((cell = col[r * CS]) & CELL_VALID)) r++;
     if (r < n && ((cell >> CELL_BASE_SH) & 7u) < 5u) {
         const uint32_t base = (cell >> CELL_BASE_SH) & 7u;
-        a->b0s = cell & CELL_BASE_M; a->nseen = 1; a->pi = (a->pi & ~(0xfu << (base << 2)));
+        a->b0s = cell & (CELL_VALID | CELL_BASE_M); a->nseen = 1; a->pi = (a->pi & ~(0xfu << (base << 2)));
     }
 }
 
 /* rows [0, n) of one column: col[r * CS] is the cell of row r (row n must be readable: the loop looks one row ahead).
- * Flag counters: five 6-bit fields in one word (ins | clip | indel | mid | lowmq), flushed every 32 rows. */
+ * Flag counters: five 6-bit fields in one word (ins | clip | indel | mid | lowmq), flushed every 32 rows.
+ * An uncovered cell is all zero: it counts nothing, carries no flags, and matches neither b0x nor b1x (which include the valid
+ * bit), so the common row - every lane on its column's first base, or off the read - runs without a divergent branch. */
 template <int CS, int RS, class Tab>
 CG_HD void cg_rank_rows(CgRankAcc *a, double *rare, const uint16_t *col, int n, Tab tab) {
     for (int rb = 0; rb < n; rb += 32) {
@@ -110,21 +150,20 @@ CG_HD void cg_rank_rows(CgRankAcc *a, double *rare, const uint16_t *col, int n, 
         const uint16_t *cp = col + rb * CS;
         uint32_t nxt = cp[0];
 #ifdef __CUDA_ARCH__
-#pragma unroll 1
+#pragma unroll 2
 #endif
         for (int r = 0; r < re; r++) {
             const uint32_t cell = nxt;
             nxt = cp[(r + 1) * CS];                      /* next row's cell: its latency overlaps this row's arithmetic */
-            if (cell & CELL_VALID) {
-                a->n_plp++;
-                pk += ((cell & 0x1fu) * 0x00108421u) & 0x01041041u;
-                double mm, hm, om;
-                cg_tab_load(tab, cell, mm, hm, om);
-                if ((cell & CELL_BASE_M) == a->b0s) {
-                    a->H0 += mm; a->P01 += hm; a->P02 += hm; a->P03 += hm; a->P04 += hm; a->C0 += om;
-                } else if ((cell & CELL_BASE_M) == a->b1s) {
-                    a->P01 += hm; a->H1 += mm; a->P12 += hm; a->P13 += hm; a->P14 += hm; a->C1 += om;
-                } else cg_rank_slow<RS>(a, rare, cell, mm, hm, om);
+            a->n_plp += (int)(cell >> 15);
+            pk += ((cell & 0x1fu) * 0x00108421u) & 0x01041041u;
+            double mm, hm, om;
+            cg_tab_load(tab, cell, mm, hm, om);
+            if (((cell ^ a->b0s) & (CELL_VALID | CELL_BASE_M)) == 0) {
+                a->H0 += mm; a->P01 += hm; a->P02 += hm; a->P03 += hm; a->P04 += hm; a->C0 += om;
+            } else if (cell & CELL_VALID) {
+                if (((cell ^ a->b1s) & (CELL_VALID | CELL_BASE_M)) == 0) { a->P01 += hm; a->H1 += mm; a->P12 += hm; a->P13 += hm; a->P14 += hm; a->C1 += om; }
+                else cg_rank_slow<RS>(a, rare, cell, mm, hm, om);
             }
         }
         a->low_mq += pk & 0x3f; a->n_overlap += (pk >> 6) & 0x3f; a->indel_cnt += (pk >> 12) & 0x3f; a->clipped += (pk >> 18) & 0x3f; a->ins_seen |= pk >> 24;
@@ -196,14 +235,14 @@ CG_HDN void cg_col_gather_generic(const CgDev *D, int c, int lo, int hi, CgConsA
     }
 }
 
-/* calculate_consensus_pileup's tail (snp_score.c:690-794) for a column without N bases, from the un-permuted sums.
+/* calculate_consensus_pileup's tail (snp_score.c:690-794) from the un-permuted sums.
  * Same IEEE operation sequence as cg_cons_finalize (cg_core.h), arranged so that nothing is indexed dynamically:
  *   - shift = max over all 15 = max(hom max, het max); both arg-max chains keep the first maximum (strict <);
  *   - norm[j] = (sum of S[0..j-1], left to right) + (sum of S[14..j+1], right to left): only norm[call] and norm[het_call]
  *     are ever used, so the two running sums are captured as they pass those slots instead of being stored for all 15;
  *   - call is one of the hom slots 0 5 9 12 14, het_call one of the other ten. */
-CG_HD void cg_cons_finalize_lean(const CgTables *T, const CgConsAcc *a, int depth, CgCons *o) {
-    if (!depth) { o->call = 5; o->het_call = 0; o->het_phred = 0; o->phred = 0; o->depth = 0; o->discrep = 0; return; }
+CG_HD void cg_cons_finalize_lean(const CgTables *T, const CgConsAcc *a, int depth, int nN, CgCons *o) {
+    if (!depth || depth == nN) {                            /* snp_score.c:751: nothing but N bases counts as no depth */ o->call = 5; o->het_call = 0; o->het_phred = 0; o->phred = 0; o->depth = 0; o->discrep = 0; return; }
     double S[15];
     double mx = -DBL_MAX, mx_het = -DBL_MAX;
     int call = 0, het_call = 0;
@@ -221,7 +260,7 @@ CG_HD void cg_cons_finalize_lean(const CgTables *T, const CgConsAcc *a, int dept
 #endif
     for (int j = 0; j < 15; j++) {
         const double y = S[j] - shift;
-        const double e = cg_fast_exp(T, y);
+        const double e = cg_fast_exp_neg(T, y);         /* y <= 0: S[j] <= shift */
         S[j] = (y > T->min_e_exp) ? e : DBL_MIN;
     }
     double tot = 0, pre_c = 0, pre_h = 0, suf_c = 0, suf_h = 0, shet = 0;

@@ -45,6 +45,7 @@ typedef struct CgTables {
     double  min_e_exp;        /* DBL_MIN_EXP*log(2)+1       (snp_score.c:540) */
     double  log_c1, log_c2;   /* (double)(-1.0f/3), (double)(2.0f/3)    (snp_score.c:515) */
     uint8_t effB[65536];      /* [mapq<<8|qual] -> max(1, (uint8_t)ph_log(1-(_m*_p+(1-_m)/4))) (632-642), qual capped first (1325-1332) */
+    uint16_t cellB[65536];    /* [mapq<<8|qual] -> the read-and-quality part of a pileup cell (cg_cells.h): valid | effB << 5 | (mapq <= -m) */
     uint8_t effA[256];        /* mode A: max(1,qual), clamped to the table size */
     uint8_t bin2[256];        /* snp_score.c:234-247 (values are < 256 for sane -l/-u) */
     uint8_t preserve_qual[256];
@@ -164,6 +165,13 @@ CG_HD double cg_fast_exp(const CgTables *T, double y) {
     if (yc > 500) yc = 500;
     const int idx = fine ? 1002 + 500 + (int)(y * 10) : 500 + (int)yc;
     return T->e_tab[idx];
+}
+
+/* the same for y <= 0 (a genotype sum minus the largest one): the upper clamps of fast_exp are dead and drop out */
+CG_HD double cg_fast_exp_neg(const CgTables *T, double y) {
+    const bool fine = y >= -50;
+    const double t = fine ? y * 10 : (y < -500 ? -500 : y);
+    return T->e_tab[(fine ? 1002 + 500 : 500) + (int)t];
 }
 
 CG_HD double cg_fast_log2(const CgTables *T, double val) {
@@ -481,6 +489,78 @@ CG_HDN void cg_mask_lc(const uint8_t *seq4, int l_qseq, int phantom, const uint3
         if (!(rpos + add >= L->start[k] + start && rpos - add <= L->end[k] + start)) continue;
         int s = cg_qpos2rpos(cig, n_cigar, read_pos, L->start[k] + start);
         int e = cg_qpos2rpos(cig, n_cigar, read_pos, L->end[k] + start);
+        if (*lo > s) *lo = s;
+        if (*hi < e) *hi = e;
+    }
+}
+
+/* mask_LC_regions again, without the repeat list (the device path: one thread per (trigger column, read)).
+ * What the caller wants from find_STR's list is only min start / max end over the FINAL entries that overlap Q = [rpos - add,
+ * rpos + add].  Three facts about add_rep (str_finder.c:34-127) make the list unnecessary:
+ *  1. the skip test (41-45) looks at the LAST entry only, i.e. the most recently added repeat;
+ *  2. the pruning (106-122) drops exactly the earlier entries whose start is >= the new entry's start, and every such entry starts
+ *     within the last 15 positions (a repeat found at position i with period p starts at i + 1 - 2p >= i - 15).  Entries that start
+ *     before i - 15 are therefore final; at most one live entry exists per start value, so the live ones fit 16 slots indexed by
+ *     start mod 16 (an older entry with the same start is itself dropped by the rule);
+ *  3. a repeat found at position i starts at >= i - 15, so nothing found beyond rpos + add + 15 can overlap Q, and nothing found
+ *     there can prune an entry that does (its start would have to be <= rpos + add): the scan stops there.
+ * qpos2rpos is monotone in qpos, so mapping the two extreme window positions equals taking min / max over the mapped entries.
+ * live: 16 slots (value = end of the live entry with that start mod 16, -1 = none), LS = stride between slots. */
+template <int LS>
+CG_HD void cg_mask_lc_lean(const uint8_t *seq4, int l_qseq, int phantom, const uint32_t *cig, int n_cigar,
+                           int read_pos, int rpos, int add, int16_t *live, int *lo, int *hi) {
+    int start = rpos - CG_MASK_WIN; if (start < 0) start = 0;
+    int end = rpos + CG_MASK_WIN;   if (end > l_qseq) end = l_qseq;
+    const int len = end - start + 1;
+    const int qlo = rpos - start - add, qhi = rpos - start + add;          /* Q in window coordinates */
+    int imax = qhi + 15; if (imax > len - 1) imax = len - 1;
+    const uint32_t ph2 = cg_nt16_to_2bit(phantom);
+#define CG_B2(wi_) (((wi_) + start) < l_qseq ? (uint32_t)cg_nt16_to_2bit((seq4[((wi_) + start) >> 1] >> ((~((wi_) + start) & 1) << 2)) & 0xf) : ph2)
+    for (int k = 0; k < 16; k++) live[k * LS] = -1;
+    int tail_s = INT_MAX, tail_e = -1;                                     /* no entry yet: the skip test fails */
+    int rlo = INT_MAX, rhi = -1;
+    uint32_t w = 0;
+    for (int i = 0; i <= imax; i++) {
+        {   /* the entry that started at i - 16 can no longer be pruned: final */
+            const int en = live[(i & 15) * LS];
+            if (en >= 0) { const int st = i - 16; if (qhi >= st && qlo <= en) { if (rlo > st) rlo = st; if (rhi < en) rhi = en; } live[(i & 15) * LS] = -1; }
+        }
+        w = (w << 2) | CG_B2(i);
+        /* candidate periods at this position: all matching ones (shortest first) while fewer than 15 bases have been consumed
+         * (str_finder.c:140-162), only the longest afterwards (164-186) */
+        uint32_t cand = 0;
+        if (i < 15) {
+            for (int p = 1; p <= 7; p++) if (i >= 2 * p - 1 && ((w ^ (w >> (2 * p))) & ((1u << (2 * p)) - 1u)) == 0) cand |= 1u << p;
+        } else {
+            for (int p = 8; p >= 1; p--) if (((w ^ (w >> (2 * p))) & (p == 16 ? 0xffffffffu : ((1u << (2 * p)) - 1u))) == 0) { cand = 1u << p; break; }
+        }
+        while (cand) {
+#ifdef __CUDA_ARCH__
+            const int p = __ffs((int)cand) - 1;
+#else
+            const int p = __builtin_ctz(cand);
+#endif
+            cand &= cand - 1;
+            const int ps = i + 1 - 2 * p;
+            if (tail_s <= ps && tail_e >= i) continue;                     /* str_finder.c:41-45 */
+            int c1 = i - p + 1, c2 = i + 1;                                /* 49-74 */
+            while (c2 < len && CG_B2(c1) == CG_B2(c2)) { c1++; c2++; }
+            const int en = c2 - 1;
+            for (int x = ps; x < i; x++) live[(x & 15) * LS] = -1;         /* 106-122: earlier entries starting at or after ps */
+            live[(ps & 15) * LS] = (int16_t)en;
+            tail_s = ps; tail_e = en;
+        }
+    }
+    for (int k = 0; k < 16; k++) {                                         /* whatever is still live at the end of the scan */
+        const int en = live[k * LS];
+        if (en < 0) continue;
+        const int st = imax - ((imax - k) & 15);
+        if (qhi >= st && qlo <= en) { if (rlo > st) rlo = st; if (rhi < en) rhi = en; }
+    }
+#undef CG_B2
+    if (rhi >= 0) {
+        const int s = cg_qpos2rpos(cig, n_cigar, read_pos, rlo + start);
+        const int e = cg_qpos2rpos(cig, n_cigar, read_pos, rhi + start);
         if (*lo > s) *lo = s;
         if (*hi < e) *hi = e;
     }

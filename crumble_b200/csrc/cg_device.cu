@@ -198,11 +198,8 @@ __global__ void k_tile_index(const __grid_constant__ CgDev D) {
     if (j < D.n_pile) cg_tile_index(&D, j);
 }
 
-/* the plain finalisation, out of line: columns holding an N base (recomputed exactly) and mode A (-q) */
-__device__ __noinline__ CgColOut col_finish_plain(const CgDev *D, int c, int lo, int hi, const CgColStats *st, CgConsAcc *A, int nN) {
-    if (nN) cg_col_gather_generic(D, c, lo, hi, A);
-    return cg_column_finish(D, c, lo, hi, st, A);
-}
+/* the plain body, out of line: mode A (-q) columns are recomputed from the records */
+__device__ __noinline__ CgColOut col_body_plain(const CgDev *D, int c) { return cg_column_body(D, c); }
 
 /* ============================== column stage ============================================
  * Two kernels (cell format and per-lane bodies: cg_cells.h, cg_column_lean.h):
@@ -285,6 +282,13 @@ __global__ void __launch_bounds__(256) k_cells_general(const __grid_constant__ C
     }
 }
 
+/* asm volatile: the load is issued where it is written (ahead of the column loop), not sunk to its first use */
+__device__ __forceinline__ CgCellRec ld_crec(const CgCellRec *p) {
+    CgCellRec r;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(r.cpos8), "=r"(r.col0), "=r"(r.span), "=r"(r.ngrp) : "l"(p));
+    return r;
+}
+
 /* Stage rows [j0, j0 + n) of the read window for tile t into buf: lane l owns rows l and 32 + l (their records were loaded ahead) */
 __device__ __forceinline__ void col_issue(const CgDev &D, uint16_t (*buf)[32], int tile_c0, int n, const CgCellRec &ra, const CgCellRec &rb, int lane) {
     const uint4 *cells = reinterpret_cast<const uint4 *>(D.cells);
@@ -320,28 +324,32 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
     const uint32_t tab = (uint32_t)__cvta_generic_to_shared(S.tab);
     double *rare = &S.rare[w][0][lane];
     int depth_max = 0;
+    unsigned long long items_ub = 0;
     const CgCellRec zrec = { 0u, 0, 0, 0u };
 
-    /* work items: (tile, chunk of its read window).  `nt` is the tile after the current one, claimed one tile ahead. */
-    auto claim = [&]() -> int {
-        int v = 0;
-        if (lane == 0) v = t_begin + atomicAdd(tile_counter, 1);
-        return __shfl_sync(0xffffffffu, v, 0);
-    };
-    int t = claim();
+    /* Work items: (tile, chunk of its read window).  Tiles are claimed from a global counter THREE ahead: the atomic of tile i+3 is
+     * issued when tile i starts and read when it ends, the window bounds of tile i+2 are loaded then and used a tile later, so
+     * neither latency is ever waited for.  t = current tile, nt = next (bounds loaded), n2 = after that (bounds in flight). */
+    int pend = 0;
+    auto claim_issue = [&]() { if (lane == 0) pend = t_begin + atomicAdd(tile_counter, 1); };
+    auto claim_read = [&]() -> int { return __shfl_sync(0xffffffffu, pend, 0); };
+    claim_issue(); int t = claim_read();
     if (t >= t_end) return;
-    int nt = claim();
+    claim_issue(); int nt = claim_read();
+    claim_issue(); int n2 = claim_read();
     int lo = D.tile_lo[t], hi = D.tile_start[t + 1];
-    int nlo = 0, nhi = 0;
+    int nlo = 0, nhi = 0, n2lo = 0, n2hi = 0;
     if (nt < t_end) { nlo = D.tile_lo[nt]; nhi = D.tile_start[nt + 1]; }
+    if (n2 < t_end) { n2lo = D.tile_lo[n2]; n2hi = D.tile_start[n2 + 1]; }
     int j0 = lo, cur = 0;
     {   /* prologue: first chunk of the first tile */
         const int n = hi - j0 < COL_R ? hi - j0 : COL_R;
-        const CgCellRec ra = lane < n ? D.crec[j0 + lane] : zrec, rb = 32 + lane < n ? D.crec[j0 + 32 + lane] : zrec;
+        const CgCellRec ra = lane < n ? ld_crec(D.crec + j0 + lane) : zrec, rb = 32 + lane < n ? ld_crec(D.crec + j0 + 32 + lane) : zrec;
         col_issue(D, S.cell[w][0], t * 32, n, ra, rb, lane);
     }
     CgRankAcc A;
     cg_rank_init<32>(&A, rare);
+    claim_issue();
     for (;;) {
         const int n = hi - j0 < COL_R ? hi - j0 : COL_R;          /* rows of the current item (<= 0 for an empty window) */
         const bool last = j0 + COL_R >= hi;
@@ -351,10 +359,10 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
         const bool more = xt < t_end;
         int xn = 0;
         CgCellRec ra = zrec, rb = zrec;
-        if (more) {
+        if (more) {                                               /* its row records: requested now, used after this item's rows have been walked */
             xn = xhi - xj0 < COL_R ? xhi - xj0 : COL_R;
-            if (lane < xn) ra = D.crec[xj0 + lane];
-            if (32 + lane < xn) rb = D.crec[xj0 + 32 + lane];
+            if (lane < xn) ra = ld_crec(D.crec + xj0 + lane);
+            if (32 + lane < xn) rb = ld_crec(D.crec + xj0 + 32 + lane);
         }
         cp_async_wait_all();
         __syncwarp();
@@ -366,19 +374,22 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
         if (more) col_issue(D, S.cell[w][cur ^ 1], xt * 32, xn, ra, rb, lane);
         if (last) {
             const int c = t * 32 + lane;
-            CgColOut o; o.cnt = 0; o.n_plp = 0;
+            CgColOut o; o.cnt = 0; o.n_plp = 0; o.items = 0;
             if (c < D.n_cols) {
-                double *dump = reinterpret_cast<double *>(&S.cell[w][cur][0][0]) + lane;      /* the walked buffer is dead: lane-private scratch */
-                int rk[5];
-                CgConsAcc C;
-                cg_rank_of_bases(A.pi, A.nseen, rk);
-                cg_rank_dump_S<32, 32>(&A, rare, dump); cg_rank_unpermute_S<32>(dump, rk, C.S);
-                cg_rank_dump_C<32, 32>(&A, rare, dump); cg_rank_unpermute_C<32>(dump, rk, C.sumsC);
-                CgColStats st; st.cp = 0; st.n_plp = A.n_plp; st.n_skip = A.n_skip; st.low_mq = A.low_mq; st.had_indel = A.indel_cnt > 0; st.indel_cnt = A.indel_cnt;
-                st.clipped = A.clipped; st.n_overlap = A.n_overlap; st.ins_seen = A.ins_seen != 0;
-                C.depth = A.n_plp - A.n_skip - A.n_none - A.nN; C.nN = 0; C.sumsE = 0;
-                if (A.nN || !lean) o = col_finish_plain(&D, c, lo, hi, &st, &C, A.nN);        /* N bases add to 14 slots; mode A: the plain body */
-                else { CgCons cB; cg_cons_finalize_lean(T, &C, C.depth, &cB); o = cg_column_finish(&D, c, lo, hi, &st, (CgConsAcc *)0, &cB); }
+                if (!lean) o = col_body_plain(&D, c);                                        /* mode A (-q): the plain body */
+                else {
+                    double *dump = reinterpret_cast<double *>(&S.cell[w][cur][0][0]) + lane;  /* the walked buffer is dead: lane-private scratch */
+                    int rk[5];
+                    CgConsAcc C;
+                    cg_rank_of_bases(A.pi, A.nseen, rk);
+                    cg_rank_dump_S<32, 32>(&A, rare, dump); cg_rank_unpermute_S<32>(dump, rk, C.S);
+                    cg_rank_dump_C<32, 32>(&A, rare, dump); cg_rank_unpermute_C<32>(dump, rk, C.sumsC);
+                    CgColStats st; st.cp = 0; st.n_plp = A.n_plp; st.n_skip = A.n_skip; st.low_mq = A.low_mq; st.had_indel = A.indel_cnt > 0; st.indel_cnt = A.indel_cnt;
+                    st.clipped = A.clipped; st.n_overlap = A.n_overlap; st.ins_seen = A.ins_seen != 0;
+                    CgCons cB;
+                    cg_cons_finalize_lean(T, &C, A.n_plp - A.n_skip - A.n_none, A.nN, &cB);
+                    o = cg_column_finish(&D, c, lo, hi, &st, (CgConsAcc *)0, &cB);
+                }
             }
             /* counters: per warp in shared memory, flushed once when the warp runs out of tiles */
             unsigned un = __reduce_or_sync(0xffffffffu, o.cnt);
@@ -389,17 +400,22 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
             }
             int mx = __reduce_max_sync(0xffffffffu, o.n_plp);
             depth_max = mx > depth_max ? mx : depth_max;
+            items_ub += (unsigned)__reduce_add_sync(0xffffffffu, o.items);
             if (!more) break;
             cg_rank_init<32>(&A, rare);
+            const int n3 = claim_read();
             t = nt; lo = nlo; hi = nhi; j0 = lo;
-            nt = claim();
-            if (nt < t_end) { nlo = D.tile_lo[nt]; nhi = D.tile_start[nt + 1]; }
+            nt = n2; nlo = n2lo; nhi = n2hi;
+            n2 = n3;
+            if (n2 < t_end) { n2lo = D.tile_lo[n2]; n2hi = D.tile_start[n2 + 1]; }
+            claim_issue();
         } else j0 += COL_R;
         cur ^= 1;
     }
     __syncwarp();
     if (lane < CG_N_COUNTERS && S.cntw[w][lane]) atomicAdd(&D.counters[lane], (unsigned long long)S.cntw[w][lane]);
     if (lane == 0 && depth_max > 0) atomicMax(D.maxdepth, depth_max);
+    if (lane == 0 && items_ub) atomicAdd(D.item_bound, items_ub);
 }
 
 /* Options outside the hand-tuned kernels (-S, -k/-K/-y, -N, -R; cg_params_generic): one column / one record per thread
@@ -407,8 +423,10 @@ __global__ void __launch_bounds__(COL_WARPS * 32, COL_MINB) k_column(const __gri
 __global__ void __launch_bounds__(128) k_column_generic(const __grid_constant__ CgDev D, int t_begin, int t_end) {
     const int c = t_begin * 32 + blockIdx.x * blockDim.x + threadIdx.x;
     const int c_end = t_end * 32 < D.n_cols ? t_end * 32 : D.n_cols;
-    CgColOut o; o.cnt = 0; o.n_plp = 0;
+    CgColOut o; o.cnt = 0; o.n_plp = 0; o.items = 0;
     if (c < c_end) o = cg_column_body(&D, c);
+    const unsigned it = (unsigned)__reduce_add_sync(0xffffffffu, o.items);
+    if ((threadIdx.x & 31) == 0 && it) atomicAdd(D.item_bound, (unsigned long long)it);
     unsigned un = __reduce_or_sync(0xffffffffu, o.cnt);
     while (un) {
         const int b = __ffs(un) - 1; un &= un - 1;
@@ -429,12 +447,13 @@ __global__ void __launch_bounds__(128) k_rewrite_generic(const __grid_constant__
  *               which reads trigger.  What the reference computes read by read is order-free except for two things,
  *               both recovered from the index of the LAST triggering read of each type (jI, jS): the running STR
  *               extents as seen by that read (PI/QI, PS/QS = min/max over the triggering reads up to it) and the
- *               column variable `indel`.  The column's number of (column, read) STR work items goes to items[k].
- *  k_str_items  one THREAD per work item (after an exclusive scan of items[]): mask_LC_regions + find_STR of one
- *               read at one column — the expensive, strictly sequential part — with every lane busy whatever the
- *               number of triggering reads per column; extents are folded into the trigger record with atomics. */
+ *               column variable `indel`.  Every triggering read becomes one work item (flagged entry, read, query
+ *               position, type) appended to the slice's item list; the list is unordered, its order does not matter.
+ *  k_str_items  one THREAD per work item: mask_LC_regions + find_STR of one read at one column in the list-free form
+ *               (cg_mask_lc_lean, cg_core.h: last entry + 16 live slots instead of the repeat list, scan cut at
+ *               rpos + add + 15), all 32 lanes busy; extents are folded into the trigger record with atomics. */
 #define FL_WARPS 4
-__global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant__ CgDev D, int32_t *items, int k_begin, int k_end) {
+__global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant__ CgDev D, int k_begin, int k_end) {
     __shared__ int hist[FL_WARPS][104];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int gw = blockIdx.x * FL_WARPS + w, nw = gridDim.x * FL_WARPS;
@@ -452,7 +471,7 @@ __global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant
         for (int i = lane; i < 104; i += 32) hist[w][i] = 0;
         __syncwarp();
         /* indel count, insertion-size spectrum, last triggering read of each type, `indel` */
-        int indel_cnt = 0, jI = -1, jS = -1, maxsz = 0, nIq = 0, nitem = 0;
+        int indel_cnt = 0, jI = -1, jS = -1, maxsz = 0, nIq = 0;
         for (int j = lo + lane; j < hi; j += 32) {
             const CgRead q = D.rd[j]; CgCell cell;
             if (!cg_cell(&D, &q, c, &cell)) continue;
@@ -465,22 +484,40 @@ __global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant
             }
             if ((is_indel || strall) && lowscore) {                            /* 1718-1720 */
                 if (is_indel) { jI = j; nIq++; } else jS = j;
-                if (q.l_qseq > 0) nitem++;
             }
         }
-        indel_cnt = __reduce_add_sync(FULL, indel_cnt); nIq = __reduce_add_sync(FULL, nIq); nitem = __reduce_add_sync(FULL, nitem);
+        indel_cnt = __reduce_add_sync(FULL, indel_cnt); nIq = __reduce_add_sync(FULL, nIq);
         jI = __reduce_max_sync(FULL, jI); jS = __reduce_max_sync(FULL, jS); maxsz = __reduce_max_sync(FULL, maxsz);
-        const int gate = indel_cnt >= n_plp * P->indel_fract;                  /* 1732 */
+        const int gate = indel_cnt >= n_plp * P->indel_fract;                  /* 1732: no STR search below the indel fraction */
         int vall = 0, vafter = 0;
         if (jI >= 0 || jS >= 0) {
-            for (int j = lo + lane; j < hi; j += 32) {
-                const CgRead q = D.rd[j]; CgCell cell;
-                if ((unsigned)(c - q.col0) < (unsigned)q.span) D.r_bf[j] = 1;  /* every read of a trigger column is back-filled (1870-1879) */
-                if (!cg_cell(&D, &q, c, &cell)) continue;
-                if (cell.is_refskip || !(cell.indel || cell.is_del)) continue;
-                const int v = (cell.indel < 0 ? -cell.indel : cell.indel) + cell.is_del;
-                if (v > vall) vall = v;
-                if (j > jS && v > vafter) vafter = v;
+            for (int j0 = lo; j0 < hi; j0 += 32) {
+                const int j = j0 + lane;
+                int emit = 0, rpos = 0, isi = 0;
+                if (j < hi) {
+                    const CgRead q = D.rd[j]; CgCell cell;
+                    if ((unsigned)(c - q.col0) < (unsigned)q.span) D.r_bf[j] = 1;  /* every read of a trigger column is back-filled (1870-1879) */
+                    if (cg_cell(&D, &q, c, &cell) && !cell.is_refskip) {
+                        isi = (cell.indel || cell.is_del);
+                        if (isi) {
+                            const int v = (cell.indel < 0 ? -cell.indel : cell.indel) + cell.is_del;
+                            if (v > vall) vall = v;
+                            if (j > jS && v > vafter) vafter = v;
+                        }
+                        emit = gate && (isi || strall) && q.l_qseq > 0;        /* lowscore holds: a trigger exists */
+                        rpos = cell.qpos + 1;
+                    }
+                }
+                const unsigned em = __ballot_sync(FULL, emit);
+                if (em) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(D.n_sitem, __popc(em));
+                    base = __shfl_sync(FULL, base, 0) + __popc(em & ((1u << lane) - 1u));
+                    if (emit) {
+                        if (base < D.sitem_cap) { CgStrItem it; it.k = k; it.j = j; it.rpos = rpos; it.is_indel = isi; D.sitem[base] = it; }
+                        else *D.err = CG_ERR_OVERFLOW;                          /* cannot happen: the list is sized from the columns' own bound */
+                    }
+                }
             }
             vall = __reduce_max_sync(FULL, vall); vafter = __reduce_max_sync(FULL, vafter);
         }
@@ -491,7 +528,6 @@ __global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant
             tr.PI = tr.QI = tr.PS = tr.QS = tr.A = tr.B = pos;                /* k_str_items widens them */
             tr.indel = tr.hasS ? (vafter > 1 ? vafter : 1) : vall;             /* 1725-1730: a SNP-type trigger resets it to 1 */
             D.trig[k] = tr;
-            items[k - k_begin] = ((tr.hasI || tr.hasS) && gate) ? nitem : 0;   /* 1732: no STR search below the indel fraction */
             uint32_t cnt = 0;
             if (nIq) cnt |= 1u << CG_CNT_INDEL_QUAL;                           /* 1762 */
             uint16_t ev_add = 0; int keep = 0;
@@ -517,57 +553,25 @@ __global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant
     }
 }
 
-/* item_off = inclusive scan of items[] over the slice's flagged entries; *n_items = total */
 #ifndef STR_THREADS
 #define STR_THREADS 128
 #endif
-#ifndef STR_BPS
-#define STR_BPS 8                   /* blocks per SM in the grid */
-#endif
-#ifndef STR_LANES
-#define STR_LANES 8                 /* working lanes per warp */
-#endif
-#define STR_WIN_STRIDE 516          /* 2 * CG_MASK_WIN + 1 window bytes, padded so that threads at the same offset use different banks */
-__global__ void __launch_bounds__(STR_THREADS) k_str_items(const __grid_constant__ CgDev D, const int32_t *item_off, const int32_t *n_items, int k_begin, int k_end) {
-    /* The search is a chain of short data-dependent branches (which period repeats here, how far does it extend), so the lanes of
-     * a warp spend most of their time waiting for each other: only STR_LANES lanes per warp take items, and the grid supplies the
-     * parallelism in warps instead.  The 2-bit window of each working lane lives in shared memory, its repeat list in local memory. */
-    __shared__ __align__(4) uint8_t win_all[(STR_THREADS / 32) * STR_LANES * STR_WIN_STRIDE];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    if (lane >= STR_LANES) return;
-    CgRepList reps;
-    uint8_t *win = win_all + (wib * STR_LANES + lane) * STR_WIN_STRIDE;
-    const int gt = (blockIdx.x * (STR_THREADS / 32) + wib) * STR_LANES + lane, nt = gridDim.x * (STR_THREADS / 32) * STR_LANES;
+__global__ void __launch_bounds__(STR_THREADS) k_str_items(const __grid_constant__ CgDev D) {
+    __shared__ int16_t live[16 * STR_THREADS];                                 /* slot-major: lane-adjacent threads use adjacent half-words */
     const CgDevParams *P = &D.P;
-    const int total = *n_items, nk = k_end - k_begin;
-    for (int it = gt; it < total; it += nt) {
-        /* flagged entry of this item: first k with item_off[k] > it */
-        int lo_ = 0, hi_ = nk - 1;
-        while (lo_ < hi_) { int mid = (lo_ + hi_) >> 1; if (item_off[mid] > it) hi_ = mid; else lo_ = mid + 1; }
-        const int kl = lo_, k = k_begin + kl;
-        int m = it - (kl ? item_off[kl - 1] : 0);                              /* m-th triggering read of the column */
-        CgTrig *tr = &D.trig[k];
-        const int c = tr->col, pos = tr->pos, jI = tr->jI, jS = tr->jS;
-        const int strall = (D.ev[c] & CG_EV_STRALL) != 0;
-        const int t = c >> 5;
-        const int lo = D.tile_lo[t], hi = D.tile_start[t + 1];
-        for (int j = lo; j < hi; j++) {
-            const CgRead q = D.rd[j]; CgCell cell;
-            if (!cg_cell(&D, &q, c, &cell)) continue;
-            if (cell.is_refskip) continue;
-            const int is_indel = (cell.indel || cell.is_del);
-            if (!(is_indel || strall) || q.l_qseq <= 0) continue;
-            if (m-- > 0) continue;
-            const int phantom = (q.l_qseq & 1) ? (D.seq[(CG_OFF(&q) >> 1) + (q.l_qseq >> 1)] & 0xf)
-                                               : (cg_cap_qual(D.qual[CG_OFF(&q)], P, D.T) >> 4);
-            int lo_r = pos, hi_r = pos;                                        /* 1732-1739: the two calls are identical in effect */
-            cg_mask_lc(D.seq + (CG_OFF(&q) >> 1), q.l_qseq, phantom, D.cigar + q.cig_off, q.n_cigar, q.pos,
-                       cell.qpos + 1, is_indel ? P->iSTR_add : P->sSTR_add, win, &reps, &lo_r, &hi_r);
-            if (reps.overflow) *D.err = CG_ERR_OVERFLOW;
-            if (lo_r < pos) { atomicMin(&tr->A, lo_r); if (j <= jI) atomicMin(&tr->PI, lo_r); if (j <= jS) atomicMin(&tr->PS, lo_r); }
-            if (hi_r > pos) { atomicMax(&tr->B, hi_r); if (j <= jI) atomicMax(&tr->QI, hi_r); if (j <= jS) atomicMax(&tr->QS, hi_r); }
-            break;
-        }
+    const int total = *D.n_sitem;
+    for (int it = blockIdx.x * STR_THREADS + threadIdx.x; it < total; it += gridDim.x * STR_THREADS) {
+        const CgStrItem im = D.sitem[it];
+        CgTrig *tr = &D.trig[im.k];
+        const int pos = tr->pos, jI = tr->jI, jS = tr->jS, j = im.j;
+        const CgRead q = D.rd[j];
+        const int phantom = (q.l_qseq & 1) ? (D.seq[(CG_OFF(&q) >> 1) + (q.l_qseq >> 1)] & 0xf)
+                                           : (cg_cap_qual(D.qual[CG_OFF(&q)], P, D.T) >> 4);
+        int lo_r = pos, hi_r = pos;                                            /* 1732-1739: the two calls are identical in effect */
+        cg_mask_lc_lean<STR_THREADS>(D.seq + (CG_OFF(&q) >> 1), q.l_qseq, phantom, D.cigar + q.cig_off, q.n_cigar, q.pos,
+                                     im.rpos, im.is_indel ? P->iSTR_add : P->sSTR_add, live + threadIdx.x, &lo_r, &hi_r);
+        if (lo_r < pos) { atomicMin(&tr->A, lo_r); if (j <= jI) atomicMin(&tr->PI, lo_r); if (j <= jS) atomicMin(&tr->PS, lo_r); }
+        if (hi_r > pos) { atomicMax(&tr->B, hi_r); if (j <= jI) atomicMax(&tr->QI, hi_r); if (j <= jS) atomicMax(&tr->QS, hi_r); }
     }
 }
 
@@ -1115,6 +1119,57 @@ __global__ void k_dump_flags(const __grid_constant__ CgDev D) {
     D.coldump[c] = z;
 }
 
+/* ---- compact planes (cg_batch.seq2 / qualp, include/crumble_gpu.h) -> the 4-bit / 8-bit working arrays --------------------------
+ * One thread per 8 positions [8g, 8g + 8): 2 bytes of 2-bit bases become 4 bytes of nt16 codes (high nibble first), 2 or 4 bytes of
+ * dictionary codes become 8 quality bytes through byte permutes of the dictionary held in registers. */
+struct CgDict { uint32_t w[4]; };
+__global__ void __launch_bounds__(256) k_unpack(const uint8_t *__restrict__ seq2, const uint8_t *__restrict__ qualp, uint8_t *__restrict__ seq, uint8_t *__restrict__ qual,
+                                                int64_t g_begin, int64_t g_end, int bits, const __grid_constant__ CgDict dict) {
+    const int64_t g = g_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g_end) return;
+    const uint32_t s = reinterpret_cast<const uint16_t *>(seq2)[g];
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+        const uint32_t hi = 1u << ((s >> (2 * k)) & 3u), lo = 1u << ((s >> (2 * k + 2)) & 3u);   /* nt16: A=1 C=2 G=4 T=8 */
+        out |= ((hi << 4) | lo) << (4 * k);
+    }
+    reinterpret_cast<uint32_t *>(seq)[g] = out;
+    if (bits == 2) {
+        const uint32_t c = reinterpret_cast<const uint16_t *>(qualp)[g];
+        /* 2-bit codes -> byte selectors of one permute per four positions */
+        const uint32_t x0 = c & 0xffu, x1 = c >> 8;
+        const uint32_t s0 = ((x0 & 0xc0u) << 6) | ((x0 & 0x30u) << 4) | ((x0 & 0x0cu) << 2) | (x0 & 0x03u);
+        const uint32_t s1 = ((x1 & 0xc0u) << 6) | ((x1 & 0x30u) << 4) | ((x1 & 0x0cu) << 2) | (x1 & 0x03u);
+        reinterpret_cast<uint2 *>(qual)[g] = make_uint2(__byte_perm(dict.w[0], 0, s0), __byte_perm(dict.w[0], 0, s1));
+    } else if (bits == 4) {
+        const uint32_t c = reinterpret_cast<const uint32_t *>(qualp)[g];
+        uint32_t r[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t x = (c >> (16 * h)) & 0xffffu;                 /* four 4-bit codes */
+            const uint32_t sel = x & 0x7777u, hi8 = x & 0x8888u;           /* selector inside an 8-byte half, and which half */
+            const uint32_t a = __byte_perm(dict.w[0], dict.w[1], sel), b = __byte_perm(dict.w[2], dict.w[3], sel);
+            /* byte mask from bit 3 of every nibble */
+            const uint32_t m = ((hi8 >> 3) & 1u) * 0xffu | ((hi8 >> 7) & 1u) * 0xff00u | ((hi8 >> 11) & 1u) * 0xff0000u | ((hi8 >> 15) & 1u) * 0xff000000u;
+            r[h] = (a & ~m) | (b & m);
+        }
+        reinterpret_cast<uint2 *>(qual)[g] = make_uint2(r[0], r[1]);
+    }
+}
+/* the positions whose base is not A/C/G/T: patch the nibble (two exceptions may share a byte, never a nibble) */
+__global__ void __launch_bounds__(256) k_unpack_exc(const uint64_t *__restrict__ exc, int64_t e_begin, int64_t e_end, uint8_t *seq) {
+    const int64_t i = e_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e_end) return;
+    const uint64_t v = exc[i];
+    const int64_t pos = (int64_t)(v >> 4); const uint32_t code = (uint32_t)(v & 15u);
+    const int64_t byte = pos >> 1;
+    uint32_t *word = reinterpret_cast<uint32_t *>(seq + (byte & ~(int64_t)3));
+    const int sh = (int)(byte & 3) * 8 + ((pos & 1) ? 0 : 4);
+    atomicAnd(word, ~(0xfu << sh));
+    atomicOr(word, code << sh);
+}
+
 /* ============================== context ================================================ */
 /* the staging loads of k_column / k_rewrite read whole aligned words around a read: pad both ends of seq and qual */
 #define CG_FRONT_PAD 256
@@ -1128,7 +1183,7 @@ struct cg_ctx {
     dbuf b_tid, b_pos, b_flag, b_mapq, b_lq, b_nc, b_off, b_coff, b_cigar, b_seq, b_qual, b_qout;
     dbuf b_jmap, b_rspan, b_rd, b_ks, b_ke, b_gap, b_gapraw, b_pmax, b_orig, b_rbf;
     dbuf b_tlo, b_tstart, b_isl, b_cb, b_ev, b_depth, b_dump, b_dsum, b_csum, b_fcol, b_trig, b_twin;
-    dbuf b_aggr, b_scal, b_scratch, b_epoch, b_events, b_chain, b_items, b_bed, b_bedpm, b_crec, b_cells;
+    dbuf b_aggr, b_scal, b_scratch, b_epoch, b_events, b_chain, b_items, b_bed, b_bedpm, b_crec, b_cells, b_seq2, b_qualp, b_exc;
     int generic;                  /* cg_params_generic(): column and rewrite stages through the plain bodies */
     /* host mirrors */
     int32_t *d_hdims;             /* device alias of h_dims (mapped pinned memory) */
@@ -1140,6 +1195,7 @@ struct cg_ctx {
     int need_depth, epoch_cap, nf_total;
     int64_t chunk_bytes;
     int win_on, have_saved, depth_matters; cg_window win; dbuf b_saved;
+    int has_planes, qual_bits; CgDict dict;                                     /* compact planes travel instead of seq / qual */
     int packed, offsets_ready; int64_t h2d_bytes;                           /* offsets rebuilt on the device; bytes copied up by the last call */       /* chained calls: this call's window, the carries of the previous one */
     cudaStream_t s_h2d, s_d2h; cudaEvent_t ev_up[32], ev_done[32], ev_misc;
     char h_carry_init[64];
@@ -1241,7 +1297,7 @@ extern "C" void cg_destroy(cg_ctx *ctx) {
     dbuf *all[] = { &ctx->b_tid, &ctx->b_pos, &ctx->b_flag, &ctx->b_mapq, &ctx->b_lq, &ctx->b_nc, &ctx->b_off, &ctx->b_coff, &ctx->b_cigar,
         &ctx->b_seq, &ctx->b_qual, &ctx->b_qout, &ctx->b_jmap, &ctx->b_rspan, &ctx->b_rd, &ctx->b_ks, &ctx->b_ke, &ctx->b_gap, &ctx->b_gapraw,
         &ctx->b_pmax, &ctx->b_orig, &ctx->b_rbf, &ctx->b_tlo, &ctx->b_tstart, &ctx->b_isl, &ctx->b_cb, &ctx->b_ev, &ctx->b_depth, &ctx->b_dump,
-        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain, &ctx->b_items, &ctx->b_bed, &ctx->b_bedpm, &ctx->b_saved, &ctx->b_crec, &ctx->b_cells };
+        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain, &ctx->b_items, &ctx->b_bed, &ctx->b_bedpm, &ctx->b_saved, &ctx->b_crec, &ctx->b_cells, &ctx->b_seq2, &ctx->b_qualp, &ctx->b_exc };
     for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); i++) if (all[i]->p) cudaFree(all[i]->p);
     if (ctx->dT) cudaFree(ctx->dT);
     if (ctx->h_dims) cudaFreeHost(ctx->h_dims);
@@ -1301,6 +1357,16 @@ static int alloc_inputs(cg_ctx *ctx, const cg_batch *in) {
     D->mapq = (const uint8_t *)ctx->b_mapq.p; D->l_qseq = (const int32_t *)ctx->b_lq.p; D->n_cigar = (const uint16_t *)ctx->b_nc.p;
     D->off = (const int64_t *)ctx->b_off.p; D->cigar_off = (const int32_t *)ctx->b_coff.p; D->cigar = (const uint32_t *)ctx->b_cigar.p;
     D->seq = (const uint8_t *)ctx->b_seq.p + CG_FRONT_PAD; D->qual = (const uint8_t *)ctx->b_qual.p + CG_FRONT_PAD; D->qual_out = (uint8_t *)ctx->b_qout.p;
+    ctx->has_planes = in->seq2 != NULL; ctx->qual_bits = ctx->has_planes ? in->qual_bits : 0;
+    if (ctx->has_planes) {
+        if (in->seq2_bytes < in->qual_bytes / 4 || (in->qual_bits != 0 && in->qual_bits != 2 && in->qual_bits != 4) || (in->qual_bytes & 7) ||
+            (in->qual_bits && (!in->qualp || in->qualp_bytes < in->qual_bytes * in->qual_bits / 8)) || in->n_seq_exc < 0 || (in->n_seq_exc && !in->seq_exc)) {
+            snprintf(ctx->err, sizeof ctx->err, "compact planes do not cover the quality buffer"); return CG_ERR_BAD_ARG;
+        }
+        if ((e = ensure(ctx, &ctx->b_seq2, (size_t)in->qual_bytes / 4 + 64)) || (e = ensure(ctx, &ctx->b_exc, ((size_t)in->n_seq_exc + 1) * 8)) ||
+            (in->qual_bits && (e = ensure(ctx, &ctx->b_qualp, (size_t)in->qual_bytes * in->qual_bits / 8 + 64)))) return e;
+        memcpy(ctx->dict.w, in->qual_dict, 16);
+    }
     ctx->qual_bytes = in->qual_bytes; ctx->cigar_total = in->n_cigar_total;
     ctx->packed = in->packed == 1; ctx->offsets_ready = 0;
     ctx->h2d_bytes = 0;
@@ -1324,17 +1390,53 @@ static int upload_meta(cg_ctx *ctx, const cg_batch *in, cudaStream_t st) {
         ctx->h2d_bytes += n * 12;
     }
     if (in->n_cigar_total) CG_CHECK(cudaMemcpyAsync(ctx->b_cigar.p, in->cigar, (size_t)in->n_cigar_total * 4, cudaMemcpyHostToDevice, st));
+    if (ctx->has_planes && in->n_seq_exc) {
+        CG_CHECK(cudaMemcpyAsync(ctx->b_exc.p, in->seq_exc, (size_t)in->n_seq_exc * 8, cudaMemcpyHostToDevice, st));
+        ctx->h2d_bytes += in->n_seq_exc * 8;
+    }
     return 0;
 }
 
 /* bytes [b0, b1) of the quality buffer and the matching half of the packed sequences */
 static int upload_bases(cg_ctx *ctx, const cg_batch *in, int64_t b0, int64_t b1, cudaStream_t st) {
     if (b1 <= b0) return 0;
+    if (ctx->has_planes) {                                     /* chunk bounds are record offsets: multiples of 8 positions */
+        CG_CHECK(cudaMemcpyAsync((char *)ctx->b_seq2.p + b0 / 4, in->seq2 + b0 / 4, (size_t)(b1 - b0) / 4, cudaMemcpyHostToDevice, st));
+        ctx->h2d_bytes += (b1 - b0) / 4;
+        if (ctx->qual_bits) {
+            const int64_t q0 = b0 * ctx->qual_bits / 8, q1 = b1 * ctx->qual_bits / 8;
+            CG_CHECK(cudaMemcpyAsync((char *)ctx->b_qualp.p + q0, in->qualp + q0, (size_t)(q1 - q0), cudaMemcpyHostToDevice, st));
+            ctx->h2d_bytes += q1 - q0;
+        } else {
+            CG_CHECK(cudaMemcpyAsync((char *)ctx->b_qual.p + CG_FRONT_PAD + b0, in->qual + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+            ctx->h2d_bytes += b1 - b0;
+        }
+        return 0;
+    }
     CG_CHECK(cudaMemcpyAsync((char *)ctx->b_qual.p + CG_FRONT_PAD + b0, in->qual + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
     int64_t s0 = b0 >> 1, s1 = (b1 + 1) >> 1;
     if (s1 > in->seq_bytes) s1 = in->seq_bytes;
     if (s1 > s0) CG_CHECK(cudaMemcpyAsync((char *)ctx->b_seq.p + CG_FRONT_PAD + s0, in->seq + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, st));
     ctx->h2d_bytes += (b1 - b0) + (s1 > s0 ? s1 - s0 : 0);
+    return 0;
+}
+
+/* positions [b0, b1) have landed as compact planes: expand them into the working arrays (on the compute stream) */
+static int expand_bases(cg_ctx *ctx, const cg_batch *in, int64_t b0, int64_t b1, cudaStream_t st) {
+    if (!ctx->has_planes || b1 <= b0) return 0;
+    const int64_t g0 = b0 >> 3, g1 = b1 >> 3;
+    k_unpack<<<(unsigned)((g1 - g0 + 255) / 256), 256, 0, st>>>((const uint8_t *)ctx->b_seq2.p, (const uint8_t *)ctx->b_qualp.p, (uint8_t *)ctx->b_seq.p + CG_FRONT_PAD,
+                                                                 (uint8_t *)ctx->b_qual.p + CG_FRONT_PAD, g0, g1, ctx->qual_bits, ctx->dict);
+    ctx->launches++;
+    if (in->n_seq_exc) {                                       /* the exceptions inside [b0, b1): the list is ascending */
+        int64_t lo = 0, hi = in->n_seq_exc, e0, e1;
+        while (lo < hi) { const int64_t m = (lo + hi) >> 1; if ((int64_t)(in->seq_exc[m] >> 4) < b0) lo = m + 1; else hi = m; }
+        e0 = lo; hi = in->n_seq_exc;
+        while (lo < hi) { const int64_t m = (lo + hi) >> 1; if ((int64_t)(in->seq_exc[m] >> 4) < b1) lo = m + 1; else hi = m; }
+        e1 = lo;
+        if (e1 > e0) { k_unpack_exc<<<(unsigned)((e1 - e0 + 255) / 256), 256, 0, st>>>((const uint64_t *)ctx->b_exc.p, e0, e1, (uint8_t *)ctx->b_seq.p + CG_FRONT_PAD); ctx->launches++; }
+    }
+    CG_CHECK(cudaGetLastError());
     return 0;
 }
 
@@ -1345,7 +1447,7 @@ extern "C" int cg_upload(cg_ctx *ctx, const cg_batch *in) {
     int e;
     if ((e = alloc_inputs(ctx, in))) return e;
     T0(CG_T_H2D);
-    if ((e = upload_meta(ctx, in, st)) || (e = upload_bases(ctx, in, 0, in->qual_bytes, st))) return e;
+    if ((e = upload_meta(ctx, in, st)) || (e = upload_bases(ctx, in, 0, in->qual_bytes, st)) || (e = expand_bases(ctx, in, 0, in->qual_bytes, st))) return e;
     T1(CG_T_H2D);
     ctx->resident = 1;
     return 0;
@@ -1406,7 +1508,7 @@ struct StI32Carry { int32_t *p; const CgEpochCarry *cy; __device__ void operator
 
 /* scalars on the device (b_scal): int32 [0] n_pile [1] n_cols [2] n_islands [3] n_flagged of the slice [4] maxdepth [5] err
  * [6] n_events [7] - [8] beyond [9] window max [10] STR items [12..13] packed quality bytes [14] packed CIGAR ops
- * [16..17] cell groups [18] tile counter of k_column; counters at +128 B; chain carry at +512 B; epoch carry at +640 B; bounds at +768 B */
+ * [16..17] cell groups [18] tile counter of k_column [20..21] STR item bound of the slice; counters at +128 B; chain carry at +512 B; epoch carry at +640 B; bounds at +768 B */
 static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
     cudaStream_t st = ctx->stream;
     CgDev *D = &ctx->D;
@@ -1560,13 +1662,14 @@ static int run_slice(cg_ctx *ctx, int t0, int t1, int c0, int c1, int64_t r0, in
         ctx->launches += 2;
     }
     if (timed) { T1(CG_T_CELLS); T0(CG_T_COLUMNS); }
+    D->item_bound = (unsigned long long *)(scal + 20);
     if (t1 > t0) {
+        CG_CHECK(cudaMemsetAsync(scal + 18, 0, 16, st));        /* tile counter, STR item bound of this slice */
         if (ctx->generic) k_column_generic<<<nblk((int64_t)(t1 - t0) * 32, 128), 128, 0, st>>>(*D, t0, t1);
         else {
             /* persistent warps claim tiles from a counter: one warp slot per resident warp, never more warps than tiles */
             int blocks = nblk(t1 - t0, COL_WARPS);
             if (blocks > 148 * COL_MINB) blocks = 148 * COL_MINB;
-            CG_CHECK(cudaMemsetAsync(scal + 18, 0, 4, st));
             k_column<<<blocks, COL_WARPS * 32, 0, st>>>(*D, t0, t1, scal + 18);
         }
         ctx->launches++;
@@ -1575,7 +1678,7 @@ static int run_slice(cg_ctx *ctx, int t0, int t1, int c0, int c1, int64_t r0, in
     if (ncs > 0) {
         LdEvFlagOff lf = { D->ev + c0, CG_EV_FLAGGED }; StCompactOff sc = { D->fcol + kb, D->ev + c0, CG_EV_FLAGGED, c0 };
         if ((e = run_scan<int32_t, OpSum>(ctx, lf, sc, ncs, 0, scal + 3))) return e;
-        k_publish<<<1, 32, 0, st>>>(scal, ctx->d_hdims, 8); ctx->launches++;
+        k_publish<<<1, 32, 0, st>>>(scal, ctx->d_hdims, 24); ctx->launches++;
         CG_CHECK(cudaStreamSynchronize(st));
         nfs = ctx->h_dims[3];
     }
@@ -1587,13 +1690,18 @@ static int run_slice(cg_ctx *ctx, int t0, int t1, int c0, int c1, int64_t r0, in
     if (nfs > 0) {
         int threads = FL_WARPS * 32, blocks = nblk(nfs, FL_WARPS);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        const int sblocks = 148 * STR_BPS, sthreads = STR_THREADS;
-        if ((e = ensure(ctx, &ctx->b_items, ((size_t)nfs + 1) * 8))) return e;
-        int32_t *items = (int32_t *)ctx->b_items.p, *item_off = items + nfs;
-        k_flagged<<<blocks, threads, 0, st>>>(*D, items, kb, ke); ctx->launches++;
-        LdI32 li = { items }; StI32Incl si = { item_off };
-        if ((e = run_scan<int32_t, OpSum>(ctx, li, si, nfs, 0, scal + 10))) return e;
-        k_str_items<<<sblocks, sthreads, 0, st>>>(*D, item_off, scal + 10, kb, ke); ctx->launches++;
+        /* the item list holds at most what the slice's columns announced (their bound came over with n_flagged) */
+        int64_t ub; memcpy(&ub, ctx->h_dims + 20, 8);
+        if (ub > 0x7fffff00LL) { snprintf(ctx->err, sizeof ctx->err, "too many STR searches in one slice"); return CG_ERR_OVERFLOW; }
+        if ((e = ensure(ctx, &ctx->b_items, ((size_t)ub + 1) * sizeof(CgStrItem)))) return e;
+        D->sitem = (CgStrItem *)ctx->b_items.p; D->sitem_cap = ub; D->n_sitem = scal + 10;
+        CG_CHECK(cudaMemsetAsync(scal + 10, 0, 4, st));
+        k_flagged<<<blocks, threads, 0, st>>>(*D, kb, ke); ctx->launches++;
+        if (ub > 0) {
+            int sblocks = nblk(ub, STR_THREADS);
+            if (sblocks > 148 * 8) sblocks = 148 * 8;
+            k_str_items<<<sblocks, STR_THREADS, 0, st>>>(*D); ctx->launches++;
+        }
     }
     if (timed) { T1(CG_T_FLAGGED); T0(CG_T_DEPTH); }
     if (ctx->need_depth && ncs > 0) {
@@ -1812,6 +1920,7 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
         if (r1 < rprev) r1 = rprev;
         if (j1 < jprev) j1 = jprev;
         CG_CHECK(cudaStreamWaitEvent(st, ctx->ev_up[i], 0));
+        if ((e = expand_bases(ctx, in, boff[i], boff[i + 1], st))) { ctx->win_on = 0; return e; }
         const int c0 = tprev * 32 < ctx->D.n_cols ? tprev * 32 : ctx->D.n_cols, c1 = t1 * 32 < ctx->D.n_cols ? t1 * 32 : ctx->D.n_cols;
         if (cS >= 0 && cS < c1) {
             /* the next call's first column lies in this slice: sparse passes up to it, save both carries, then the rest */

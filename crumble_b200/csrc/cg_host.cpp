@@ -8,6 +8,8 @@
 #include <stdio.h>
 #include <math.h>
 #include <float.h>
+#include <pthread.h>
+#include <unistd.h>
 #include "cg_pipeline.h"
 #include "cg_host.h"
 
@@ -112,6 +114,7 @@ void cg_tables_init(CgTables *T, const cg_params *p) {
             if (e < 1) e = 1;
             if (e > 100) e = 100;          /* the reference would index past its 101-entry tables here */
             T->effB[(mq << 8) | q] = e;
+            T->cellB[(mq << 8) | q] = (uint16_t)(0x8000u | ((unsigned)e << 5) | (mq <= p->min_mqual ? 1u : 0u));   /* CELL_VALID | e << CELL_E_SH | CELL_LOWMQ */
         }
     for (int q = 0; q < 256; q++) { int qc = (q > p->qcap && !p->preserve_qual[q]) ? p->qcap : q; int e = qc < 1 ? 1 : (qc > 100 ? 100 : qc); T->effA[q] = (uint8_t)e; }
     for (int i = 0; i < 256; i++) {                                                  /* init_bins 234-247 */
@@ -155,6 +158,8 @@ template <class T> struct vec {
 struct cg_batch_builder {
     vec<int32_t> tid, pos, l_qseq, cigar_off; vec<uint16_t> flag, n_cigar; vec<uint8_t> mapq; vec<int64_t> off;
     vec<uint32_t> cigar; vec<uint8_t> seq, qual;
+    vec<uint8_t> seq2, qualp; vec<uint64_t> seq_exc;        /* compact planes (cgb_pack) */
+    int have_pack, qual_bits; uint8_t qual_dict[16];
     int64_t last_key; int unsorted; int seen_unplaced;
 };
 
@@ -165,18 +170,21 @@ extern "C" cg_batch_builder *cgb_create(int pinned) {
     int pin = pinned && cg_pinned_alloc_hook;
     b->tid.init(pin); b->pos.init(pin); b->l_qseq.init(pin); b->cigar_off.init(pin); b->flag.init(pin); b->n_cigar.init(pin);
     b->mapq.init(pin); b->off.init(pin); b->cigar.init(pin); b->seq.init(pin); b->qual.init(pin);
+    b->seq2.init(pin); b->qualp.init(pin); b->seq_exc.init(pin);
     b->last_key = INT64_MIN;
     return b;
 }
 extern "C" void cgb_reset(cg_batch_builder *b) {
     b->tid.n = b->pos.n = b->l_qseq.n = b->cigar_off.n = b->flag.n = b->n_cigar.n = b->mapq.n = b->off.n = 0;
     b->cigar.n = b->seq.n = b->qual.n = 0;
+    b->seq2.n = b->qualp.n = b->seq_exc.n = 0; b->have_pack = 0; b->qual_bits = 0;
     b->last_key = INT64_MIN; b->unsorted = 0; b->seen_unplaced = 0;
 }
 extern "C" void cgb_destroy(cg_batch_builder *b) {
     if (!b) return;
     b->tid.release(); b->pos.release(); b->l_qseq.release(); b->cigar_off.release(); b->flag.release(); b->n_cigar.release();
     b->mapq.release(); b->off.release(); b->cigar.release(); b->seq.release(); b->qual.release();
+    b->seq2.release(); b->qualp.release(); b->seq_exc.release();
     free(b);
 }
 
@@ -184,6 +192,7 @@ extern "C" int cgb_add(cg_batch_builder *b, int32_t tid, int32_t pos, uint16_t f
                        uint32_t n_cigar, const uint32_t *cigar, const uint8_t *seq4, const uint8_t *qual) {
     size_t i = b->tid.n;
     if (n_cigar > 65535 || l_qseq < 0) return CG_ERR_BAD_ARG;
+    b->have_pack = 0;
     if (b->tid.reserve(i + 1) || b->pos.reserve(i + 1) || b->l_qseq.reserve(i + 1) || b->cigar_off.reserve(i + 1) ||
         b->flag.reserve(i + 1) || b->n_cigar.reserve(i + 1) || b->mapq.reserve(i + 1) || b->off.reserve(i + 1)) return CG_ERR_NOMEM;
     /* quality bytes padded to 8 so that off is 8-aligned and seq sits at off/2 */
@@ -272,6 +281,118 @@ extern "C" int cgb_finish(cg_batch_builder *b, cg_batch *o) {
     o->seq = b->seq.p; o->seq_bytes = (int64_t)b->seq.n;
     o->qual = b->qual.p; o->qual_bytes = (int64_t)b->qual.n;
     o->packed = 1;                                   /* cgb_add lays records out back to back */
+    if (b->have_pack) {
+        o->seq2 = b->seq2.p; o->seq2_bytes = (int64_t)b->seq2.n;
+        o->seq_exc = b->seq_exc.p; o->n_seq_exc = (int64_t)b->seq_exc.n;
+        o->qual_bits = b->qual_bits;
+        if (b->qual_bits) { o->qualp = b->qualp.p; o->qualp_bytes = (int64_t)b->qualp.n; memcpy(o->qual_dict, b->qual_dict, 16); }
+    }
+    return 0;
+}
+
+/* ---- compact planes -------------------------------------------------------------------------
+ * Workers own contiguous ranges of RECORDS; a range's positions are a contiguous, 8-aligned range of the quality buffer, so the
+ * planes are written without overlap (8 positions = 2 bytes of seq2, 2 or 4 bytes of qualp).  Exceptions are collected per worker
+ * and concatenated in worker order, which is position order. */
+struct pack_job {
+    cg_batch_builder *b; size_t r0, r1; int pass; int bits; const uint8_t *code;     /* code[value] -> dictionary code */
+    uint64_t seen[4]; uint64_t *exc; size_t n_exc, cap_exc; int err;
+};
+static void *pack_worker(void *v) {
+    pack_job *J = (pack_job *)v;
+    cg_batch_builder *b = J->b;
+    if (J->pass == 0) {                                  /* which quality values occur (real bases only, not the padding) */
+        for (size_t r = J->r0; r < J->r1; r++) {
+            const uint8_t *q = b->qual.p + b->off.p[r]; const int l = b->l_qseq.p[r];
+            for (int x = 0; x < l; x++) J->seen[q[x] >> 6] |= 1ULL << (q[x] & 63);
+        }
+        return NULL;
+    }
+    static const uint8_t n2[16] = { 0xff, 0, 1, 0xff, 2, 0xff, 0xff, 0xff, 3, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff };   /* nt16 -> 2 bit */
+    for (size_t r = J->r0; r < J->r1; r++) {
+        const size_t o = (size_t)b->off.p[r]; const int l = b->l_qseq.p[r], lp = (l + 7) & ~7;
+        const uint8_t *q = b->qual.p + o, *s4 = b->seq.p + o / 2;
+        uint8_t *s2 = b->seq2.p + o / 4;
+        for (int x = 0; x < lp; x += 4) {
+            unsigned byte = 0;
+            for (int k = 0; k < 4; k++) {
+                const int xx = x + k;
+                if (xx >= l) continue;                   /* padding: A */
+                const unsigned nib = (s4[xx >> 1] >> ((~xx & 1) << 2)) & 0xf;
+                unsigned c = n2[nib];
+                if (c == 0xff) {
+                    c = 0;
+                    if (J->n_exc == J->cap_exc) {
+                        size_t nc = J->cap_exc ? J->cap_exc * 2 : 1024;
+                        uint64_t *ne = (uint64_t *)realloc(J->exc, nc * 8);
+                        if (!ne) { J->err = 1; return NULL; }
+                        J->exc = ne; J->cap_exc = nc;
+                    }
+                    J->exc[J->n_exc++] = ((uint64_t)(o + (size_t)xx) << 4) | nib;
+                }
+                byte |= c << (2 * k);
+            }
+            s2[x >> 2] = (uint8_t)byte;
+        }
+        if (J->bits == 2) {
+            uint8_t *qp = b->qualp.p + o / 4;
+            for (int x = 0; x < lp; x += 4) {
+                unsigned byte = 0;
+                for (int k = 0; k < 4; k++) if (x + k < l) byte |= (unsigned)J->code[q[x + k]] << (2 * k);
+                qp[x >> 2] = (uint8_t)byte;
+            }
+        } else if (J->bits == 4) {
+            uint8_t *qp = b->qualp.p + o / 2;
+            for (int x = 0; x < lp; x += 2) {
+                unsigned byte = 0;
+                if (x < l) byte |= J->code[q[x]];
+                if (x + 1 < l) byte |= (unsigned)J->code[q[x + 1]] << 4;
+                qp[x >> 1] = (uint8_t)byte;
+            }
+        }
+    }
+    return NULL;
+}
+
+extern "C" int cgb_pack(cg_batch_builder *b, int threads) {
+    const size_t n = b->tid.n;
+    b->have_pack = 0; b->qual_bits = 0;
+    if (threads <= 0) threads = (int)sysconf(_SC_NPROCESSORS_ONLN);
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    if ((size_t)threads > n) threads = n ? (int)n : 1;
+    if (b->seq2.reserve(b->qual.n / 4 + 16) || b->qualp.reserve(b->qual.n / 2 + 16)) return CG_ERR_NOMEM;
+    pack_job jobs[64]; pthread_t th[64];
+    uint8_t code[256]; memset(code, 0, sizeof code);
+    int bits = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int t = 0; t < threads; t++) {
+            pack_job *J = &jobs[t];
+            if (pass == 0) { memset(J, 0, sizeof *J); J->b = b; J->r0 = n * (size_t)t / (size_t)threads; J->r1 = n * (size_t)(t + 1) / (size_t)threads; }
+            J->pass = pass; J->bits = bits; J->code = code;
+            if (pthread_create(&th[t], NULL, pack_worker, J) != 0) { pack_worker(J); th[t] = 0; }
+        }
+        for (int t = 0; t < threads; t++) if (th[t]) pthread_join(th[t], NULL);
+        if (pass == 0) {
+            uint64_t seen[4] = { 0, 0, 0, 0 };
+            for (int t = 0; t < threads; t++) for (int k = 0; k < 4; k++) seen[k] |= jobs[t].seen[k];
+            int nv = 0; uint8_t dict[256];
+            for (int v = 0; v < 256; v++) if (seen[v >> 6] >> (v & 63) & 1) dict[nv++] = (uint8_t)v;
+            bits = nv <= 4 ? 2 : (nv <= 16 ? 4 : 0);
+            memset(b->qual_dict, 0, 16);
+            if (bits) for (int k = 0; k < nv; k++) { b->qual_dict[k] = dict[k]; code[dict[k]] = (uint8_t)k; }
+        }
+    }
+    size_t ne = 0; int err = 0;
+    for (int t = 0; t < threads; t++) { ne += jobs[t].n_exc; err |= jobs[t].err; }
+    if (err || b->seq_exc.reserve(ne + 1)) { for (int t = 0; t < threads; t++) free(jobs[t].exc); return CG_ERR_NOMEM; }
+    ne = 0;
+    for (int t = 0; t < threads; t++) { if (jobs[t].n_exc) memcpy(b->seq_exc.p + ne, jobs[t].exc, jobs[t].n_exc * 8); ne += jobs[t].n_exc; free(jobs[t].exc); }
+    b->seq_exc.n = ne;
+    b->seq2.n = b->qual.n / 4;
+    b->qual_bits = bits;
+    b->qualp.n = bits == 2 ? b->qual.n / 4 : (bits == 4 ? b->qual.n / 2 : 0);
+    b->have_pack = 1;
     return 0;
 }
 

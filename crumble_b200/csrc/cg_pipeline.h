@@ -37,6 +37,7 @@ typedef struct CgRead {       /* 32 bytes, one per pileup read (compacted, input
 } CgRead;
 #define CG_OFF(q) ((int64_t)(q)->off8 << 3)
 
+typedef struct CgStrItem { int32_t k, j, rpos, is_indel; } CgStrItem;   /* flagged entry, pileup read, 1-based query position (qpos + 1), trigger type */
 typedef struct CgIsland { int32_t col_start, tid, pos_start, pad; } CgIsland;
 struct CgCellRec;             /* cg_cells.h */
 
@@ -79,6 +80,10 @@ typedef struct CgDev {
     /* sparse */
     int32_t *fcol;            /* flagged dense columns, ascending */
     CgTrig  *trig;            /* one per flagged column (hasI=hasS=0 when it does not trigger) */
+    struct CgStrItem *sitem;  /* (trigger column, read) STR searches of the slice, any order */
+    int32_t *n_sitem;         /* how many */
+    int64_t sitem_cap;
+    unsigned long long *item_bound;   /* running upper bound of the searches the columns processed so far will ask for */
     CgWin   *twin;            /* window state after each flagged column */
     /* scalars on the device */
     unsigned long long *counters;   /* CG_N_COUNTERS */
@@ -224,7 +229,7 @@ CG_HD int cg_bed_hit(const CgDev *D, int tid, int pos) {
  * transcode's column loop up to the point where cross-column state is needed
  * (snp_score.c:1466-1472, 1490-1500, 1520-1649, 1658-1669, 1694-1713, 1764-1773).
  * Returns a bit mask of CG_CNT_* counters to increment.                                  */
-typedef struct CgColOut { uint32_t cnt; int32_t n_plp; } CgColOut;
+typedef struct CgColOut { uint32_t cnt; int32_t n_plp; int32_t items; /* upper bound of the (column, read) STR searches this column will ask for */ } CgColOut;
 
 template <int MODE_B>
 CG_HD void cg_column_cons(const CgDev *D, int c, int lo, int hi, CgCons *out) {
@@ -251,7 +256,7 @@ typedef struct CgColStats { int n_plp, n_skip, low_mq, had_indel, indel_cnt, cli
 CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgColStats *st, CgConsAcc *acc, const CgCons *cB_ready = NULL) {
     const CgDevParams *P = &D->P;
     const CgTables *T = D->T;
-    CgColOut o; o.cnt = 0; o.n_plp = 0;
+    CgColOut o; o.cnt = 0; o.n_plp = 0; o.items = 0;
     const int n_plp = st->n_plp, n_skip = st->n_skip, low_mq = st->low_mq, had_indel = st->had_indel;
     const int clipped = st->clipped, n_overlap = st->n_overlap, ins_seen = st->ins_seen;
     const int doB = P->min_qual_B != 0;
@@ -342,6 +347,9 @@ CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgC
             ev |= CG_EV_FLAGGED;
         }
         if (ins_seen) ev |= CG_EV_FLAGGED;                                 /* indel-size spectrum tests (1777-1819) */
+        /* every read that triggers at this column gets one mask_LC_regions search (1718-1739): all of them when str_snp && preserve,
+         * else the reads with an indel here; none below the -Y indel fraction (1732).  Sizes the item list of the flagged stage. */
+        if (lowscore && (had_indel || strall) && st->indel_cnt >= n_plp * P->indel_fract) o.items = strall ? n_plp : st->indel_cnt;
         cb = (uint8_t)code;
         if (preserve) cb |= CG_CB_PRESERVE;
         if (keep) cb |= CG_CB_KEEP;
@@ -365,7 +373,7 @@ CG_HD CgColOut cg_column_finish(const CgDev *D, int c, int lo, int hi, const CgC
 CG_HD CgColOut cg_column_body(const CgDev *D, int c) {
     const CgDevParams *P = &D->P;
     const CgTables *T = D->T;
-    CgColOut o; o.cnt = 0; o.n_plp = 0;
+    CgColOut o; o.cnt = 0; o.n_plp = 0; o.items = 0;
     const int t = c >> 5;
     const int lo = D->tile_lo[t], hi = D->tile_start[t + 1];
     int n_plp = 0, n_skip = 0, low_mq = 0, had_indel = 0, indel_cnt = 0, clipped = 0, n_overlap = 0;

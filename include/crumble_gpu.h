@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CG_ABI_VERSION 1
+#define CG_ABI_VERSION 2
 
 /* ---- error codes (negative; 0 = ok).  transcode_gpu() maps any of these to -1, the
  * value transcode() returns on failure (snp_score.c:1480-1481,1979-1980). ------------- */
@@ -96,6 +96,18 @@ typedef struct cg_batch {
     const uint8_t  *qual;   int64_t qual_bytes;
     int32_t  packed;            /* 1: off[] and cigar_off[] are the running sums of ((l_qseq + 7) & ~7) and n_cigar starting at 0 (what the
                                    cgb_* batcher builds): the device rebuilds them with two scans instead of receiving 12 bytes per record */
+    /* Optional COMPACT PLANES of the two big arrays (cgb_pack builds them next to seq / qual).  When present the upload moves these
+     * instead and the device expands them into its 4-bit / 8-bit working arrays: 0.25 + 0.25..0.5 bytes per base cross PCIe in place
+     * of 1.5.  Both are indexed like qual[] (position = byte offset in the quality buffer, padding included).
+     *   seq2     2-bit bases A0 C1 G2 T3, four per byte, position i at bits 2*(i&3) of byte i>>2; every other nt16 code is an
+     *            exception: seq_exc[] = (position << 4 | code), ascending (padding positions are A and never listed);
+     *   qualp    dictionary codes of the qualities, qual_bits (2 or 4) per position, low bits first; qual_dict[code] = value
+     *            (padding positions carry code 0).  qual_bits = 0: no such plane (more than 16 distinct values), qual[] travels. */
+    const uint8_t  *seq2;     int64_t seq2_bytes;
+    const uint64_t *seq_exc;  int64_t n_seq_exc;
+    const uint8_t  *qualp;    int64_t qualp_bytes;
+    int32_t  qual_bits;
+    uint8_t  qual_dict[16];
 } cg_batch;
 
 /* BED_DIST-expanded suspicious-region events (snp_score.c:1496-1498,1676-1678,
@@ -216,6 +228,9 @@ int   cgb_add(cg_batch_builder *b, int32_t tid, int32_t pos, uint16_t flag, uint
 /* every record of an uncompressed BAM stream (BAM\1 magic + header + records) */
 int   cgb_add_bam_stream(cg_batch_builder *b, const uint8_t *buf, size_t len);
 int   cgb_finish(cg_batch_builder *b, cg_batch *out);    /* out points into the builder */
+/* build the compact planes (cg_batch.seq2 / seq_exc / qualp) of everything added so far, with `threads` workers (0 = all cores);
+ * the next cgb_finish hands them out.  Optional: costs one pass over the base data on the host, saves two thirds of the upload. */
+int   cgb_pack(cg_batch_builder *b, int threads);
 int64_t cgb_bytes(const cg_batch_builder *b);
 
 #ifdef __cplusplus

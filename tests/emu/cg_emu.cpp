@@ -157,11 +157,10 @@ static int emu_process(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg
                 cg_rank_dump_C<1, 1>(&a, rare[l], dmp); cg_rank_unpermute_C<1>(dmp, rk, A.sumsC);
                 CgColStats st; st.cp = 0; st.n_plp = a.n_plp; st.n_skip = a.n_skip; st.low_mq = a.low_mq; st.had_indel = a.indel_cnt > 0; st.indel_cnt = a.indel_cnt;
                 st.clipped = a.clipped; st.n_overlap = a.n_overlap; st.ins_seen = a.ins_seen != 0;
-                A.depth = a.n_plp - a.n_skip - a.n_none - a.nN; A.nN = 0; A.sumsE = 0;
+                A.depth = a.n_plp - a.n_skip - a.n_none; A.nN = a.nN; A.sumsE = 0;
                 CgColOut o;
-                if (a.nN) { cg_col_gather_generic(&D2, c, lo, hi, &A); o = cg_column_finish(&D2, c, lo, hi, &st, &A); }
-                else if (lean) { CgCons cB; cg_cons_finalize_lean(&ctx->T, &A, A.depth, &cB); o = cg_column_finish(&D2, c, lo, hi, &st, NULL, &cB); }
-                else o = cg_column_finish(&D2, c, lo, hi, &st, &A);
+                if (lean) { CgCons cB; cg_cons_finalize_lean(&ctx->T, &A, A.depth, A.nN, &cB); o = cg_column_finish(&D2, c, lo, hi, &st, NULL, &cB); }
+                else o = cg_column_body(&D2, c);
                 for (int i = 0; i < CG_N_COUNTERS; i++) if (o.cnt >> i & 1) counters2[i]++;
                 if (o.n_plp > maxdepth2) maxdepth2 = o.n_plp;
             }

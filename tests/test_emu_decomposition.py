@@ -121,3 +121,14 @@ def test_chained_calls_sparse_coverage(depth):
         for batch in ("1", "7"):
             r = run_oracle(data, args, binary=EMU_BIN, kind="emu", env_extra={"CRUMBLE_BATCH_READS": batch})
             assert (r["qual"][m] == ref["qual"][m]).all() and r["bed"] == ref["bed"] and r["counters"] == ref["counters"], (args, batch)
+
+
+def test_list_free_str_search_equals_find_str():
+    """cg_mask_lc_lean (what k_str_items runs: last entry + 16 live slots instead of find_STR's repeat list, scan cut at
+    rpos + add + 15) against cg_mask_lc (the full list, pinned to str_finder.c by the golden vectors) on 6e5 random, repeat-rich,
+    noisy, N-containing, short and long reads with random CIGARs, positions and -i/-s additions"""
+    import subprocess
+    from util import ROOT
+    r = subprocess.run([str(ROOT / "tests" / "emu" / "str_check"), "200000"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "mismatches=0" in r.stdout

@@ -390,3 +390,51 @@ def test_gpu_chained_calls_sparse_coverage(depth):
         for batch in ("1", "7"):
             r = run_oracle(data, args, binary=ROOT / "crumble_b200" / "lib" / "crumble_gpu", kind="gpu-cli", env_extra={"CRUMBLE_BATCH_READS": batch})
             assert (r["qual"][m] == ref["qual"][m]).all() and r["bed"] == ref["bed"] and r["counters"] == ref["counters"], (args, batch)
+
+
+@pytest.mark.parametrize("name,args,chunk", [("c2s", ["-9"], 1 << 18), ("c2s", ["-1", "-B"], None), ("c1s", ["-9"], 1 << 19), ("tiny", ["-3", "-P1.5"], 1 << 16), ("c4s", ["-9"], None)],
+                         ids=lambda v: "".join(v) if isinstance(v, list) else str(v))
+def test_gpu_compact_planes(name, args, chunk):
+    """cg_batch with the compact planes (2-bit bases + exceptions, dictionary-coded qualities): the device expands them into its
+    working arrays; results equal the oracle's, resident and streamed, and the upload shrinks"""
+    data, bb0, batch0, mask = dataset(name)
+    bb = cb.BatchBuilder(); bb.add_bam_stream(data); batch = bb.finish(pack=True)
+    g = cb.Crumble(params_from_args(args), device=0)
+    if chunk:
+        g.set_chunk_bytes(chunk)
+    out = g.process(batch); up_packed = g.h2d_bytes()
+    ref = run_oracle(data, args)
+    assert int((out["qual"][mask] != ref["qual"][mask]).sum()) == 0
+    assert cb.bed_text(out["events"], ref["names"]) == ref["bed"] and out["counters"] == ref["counters"]
+    g.process(batch0); up_plain = g.h2d_bytes()
+    saved = int(batch.qual_bytes) // 4 + (int(batch.qual_bytes) * (8 - batch.qual_bits) // 8 if batch.qual_bits else 0) - 8 * int(batch.n_seq_exc)
+    assert up_plain - up_packed == saved
+    g.upload(batch); g.run(); res = g.download(batch)
+    assert np.array_equal(res["qual"][mask], out["qual"][mask]) and res["counters"] == out["counters"]
+    # region shards carry their share of the planes
+    ctxs = [cb.Crumble(params_from_args(args), device=0) for _ in range(3)]
+    sh = cb.run_region_shards(ctxs, batch, 3)
+    assert np.array_equal(sh["qual"][mask], out["qual"][mask]) and sh["counters"] == out["counters"]
+    for c in ctxs + [g]:
+        c.close()
+    bb.close()
+
+
+@pytest.mark.parametrize("name,rate", [("tiny", 0.01), ("c4s", 0.002), ("c1s", 0.05)])
+def test_gpu_ambiguity_codes(name, rate):
+    """N and other non-ACGT codes: an N adds to 14 of the 15 genotype sums (snp_score.c:677-682), which the column kernel does in
+    rank space after handing every base a rank; the STR search maps them to 'A'; the compact planes list them as exceptions"""
+    from util import add_ambiguity_codes
+    data0 = dataset(name)[0]
+    data, n = add_ambiguity_codes(data0, rate, seed=7)
+    assert n > 1000
+    bb = cb.BatchBuilder(); bb.add_bam_stream(data); batch = bb.finish(pack=True); mask = valid_mask(bb)
+    assert int(batch.n_seq_exc) > 0
+    for args in (["-9"], ["-1", "-B"], ["-3"]):
+        g = cb.Crumble(params_from_args(args), device=0)
+        out = g.process(batch, want_columns=(args == ["-9"]))
+        ref = run_oracle(data, args)
+        assert int((out["qual"][mask] != ref["qual"][mask]).sum()) == 0, args
+        assert cb.bed_text(out["events"], ref["names"]) == ref["bed"] and out["counters"] == ref["counters"], args
+        g.close()
+    bb.close()

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
     assert set(cb.EXPORTS) <= declared
-    assert lib.cg_abi_version() == 1
+    assert lib.cg_abi_version() == 2
 
 
 def test_no_device_fails_loudly():
@@ -205,3 +205,40 @@ def test_streaming_driver_error_paths():
         assert r.returncode == 1 and "Error while reducing file" in r.stderr
         r = subprocess.run([str(EMU_BIN), "-z", "-9", good, "/nonexistent_dir/out.bam"], env=env, stderr=subprocess.PIPE, text=True)
         assert r.returncode == 1
+
+
+@pytest.mark.parametrize("preset,scale,bits", [("C2", 1 / 256, 2), ("C1", 0.05, 0), ("tiny", 1.0, 0)])
+def test_batcher_compact_planes_decode_back(preset, scale, bits):
+    """cgb_pack: 2-bit bases + exception list and dictionary-coded qualities decode back to exactly the 4-bit / 8-bit arrays the
+    kernels work on (checked on the host with numpy; the device expansion is checked against the same arrays in the GPU suite)"""
+    data, nr, nb = cb.simulate(preset, scale, seed=21, threads=2)
+    bb = cb.BatchBuilder(pinned=False)
+    bb.add_bam_stream(data)
+    b = bb.finish(pack=True, threads=3)
+    n = int(b.qual_bytes)
+    assert b.seq2 and int(b.seq2_bytes) == n // 4 and b.qual_bits == bits
+    off, ln = bb.offsets(), bb.lengths()
+    valid = np.zeros(n + 1, np.int32); np.add.at(valid, off, 1); np.add.at(valid, off + ln, -1); valid = np.cumsum(valid[:-1]) > 0
+    seq = np.ctypeslib.as_array(b.seq, shape=(int(b.seq_bytes),))
+    nib = np.empty(n, np.uint8); nib[0::2] = seq[: n // 2] >> 4; nib[1::2] = seq[: n // 2] & 15
+    s2 = np.ctypeslib.as_array(b.seq2, shape=(n // 4,))
+    code = np.empty(n, np.uint8)
+    for k in range(4):
+        code[k::4] = (s2 >> (2 * k)) & 3
+    dec = (1 << code).astype(np.uint8)
+    ne = int(b.n_seq_exc)
+    if ne:
+        exc = np.ctypeslib.as_array(b.seq_exc, shape=(ne,))
+        assert np.all(np.diff(exc >> np.uint64(4)).astype(np.int64) > 0)
+        dec[(exc >> np.uint64(4)).astype(np.int64)] = (exc & np.uint64(15)).astype(np.uint8)
+    assert np.array_equal(dec[valid], nib[valid])
+    assert ne == int((~np.isin(nib[valid], [1, 2, 4, 8])).sum())
+    if bits:
+        qp = np.ctypeslib.as_array(b.qualp, shape=(int(b.qualp_bytes),))
+        per = 8 // bits
+        qc = np.empty(n, np.uint8)
+        for k in range(per):
+            qc[k::per] = (qp >> (bits * k)) & ((1 << bits) - 1)
+        dq = np.array(list(b.qual_dict), np.uint8)[qc]
+        assert np.array_equal(dq[valid], bb.qual()[valid])
+    bb.close()

@@ -104,3 +104,25 @@ def valid_mask(bb):
     np.add.at(m, off, 1)
     np.add.at(m, off + ln, -1)
     return np.cumsum(m[:-1]) > 0
+
+
+def add_ambiguity_codes(data: np.ndarray, rate: float, seed: int = 1):
+    """a copy of an uncompressed BAM stream with a fraction of the bases replaced by N (mostly), other ambiguity codes and '='"""
+    import struct
+    d = data.copy(); rng = np.random.default_rng(seed)
+    b = d.tobytes(); p = 8 + struct.unpack_from('<i', b, 4)[0]
+    nref = struct.unpack_from('<i', b, p)[0]; p += 4
+    for _ in range(nref):
+        p += 4 + struct.unpack_from('<i', b, p)[0] + 4
+    n = 0
+    while p + 4 <= len(b):
+        bs = struct.unpack_from('<i', b, p)[0]; r = p + 4
+        lname = b[r + 8]; ncig = struct.unpack_from('<H', b, r + 12)[0]; lseq = struct.unpack_from('<i', b, r + 16)[0]
+        so = r + 32 + lname + 4 * ncig
+        for x in rng.integers(0, max(lseq, 1), rng.binomial(lseq, rate) if lseq else 0):
+            code = [15, 15, 15, 3, 0, 14][rng.integers(0, 6)]
+            i = so + (int(x) >> 1)
+            d[i] = (d[i] & 0xf0) | code if x & 1 else (d[i] & 0x0f) | (code << 4)
+            n += 1
+        p += 4 + bs
+    return d, n
