@@ -5,6 +5,6 @@ kernels, see ``csrc/``); this package is the thin Python mirror used by the test
 ``bench.py``.  See DESIGN.md.
 """
 from .api import (  # noqa: F401
-    BatchBuilder, Crumble, CrumbleError, Params, Window, default_params, simulate, algorithmic_bytes,
+    BatchBuilder, Crumble, MultiCrumble, CrumbleError, Params, Window, default_params, simulate, algorithmic_bytes,
     aligned_bases, bed_text, batch_ends, sub_batch, plan_region_shards, run_region_shards, shard_window, shard_final_mask, crumble_cli, load_lib, lib_path, COUNTER_NAMES, BED_TAGS, EXPORTS,
 )

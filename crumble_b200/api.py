@@ -70,6 +70,7 @@ class Batch(C.Structure):
         ("seq_exc", C.POINTER(C.c_uint64)), ("n_seq_exc", C.c_int64),
         ("qualp", C.POINTER(C.c_uint8)), ("qualp_bytes", C.c_int64),
         ("qual_bits", C.c_int32), ("qual_dict", C.c_uint8 * 16),
+        ("pmax_end", C.POINTER(C.c_int32)),
     ]
 
 
@@ -94,6 +95,7 @@ class Result(C.Structure):
         ("events", C.POINTER(BedEvent)), ("events_cap", C.c_int64), ("n_events", C.c_int64),
         ("counters", C.c_int64 * N_COUNTERS),
         ("columns", C.POINTER(Column)), ("columns_cap", C.c_int64), ("n_columns", C.c_int64),
+        ("qual_head", C.POINTER(C.c_uint8)), ("head_bytes", C.c_int64),
     ]
 
 
@@ -111,7 +113,8 @@ EXPORTS = [
     "cg_set_stream", "cg_process", "cg_process_window", "cg_upload", "cg_run", "cg_download", "cg_sync", "cg_last_ms", "cg_last_launches", "cg_last_h2d_bytes",
     "cg_algorithmic_bytes", "cg_aligned_bases", "cg_n_columns", "cg_params_default", "cg_params_level",
     "cgb_create", "cgb_destroy", "cgb_reset", "cgb_add", "cgb_add_bam_stream", "cgb_finish", "cgb_bytes", "cgb_reserve", "cgb_pack",
-    "cg_carry_export", "cg_carry_import", "cg_carry_is_neutral", "cg_batch_ends",
+    "cg_carry_export", "cg_carry_import", "cg_carry_is_neutral", "cg_batch_ends", "cg_shard_begin", "cg_shard_carry", "cg_shard_end",
+    "cgm_create", "cgm_destroy", "cgm_n_devices", "cgm_process", "cgm_process_window", "cgm_last_error", "cgm_last_ms", "cgm_last_h2d_bytes", "cgm_context",
 ]
 CARRY_BYTES = 128
 
@@ -149,6 +152,21 @@ def load_lib():
     lib.cg_carry_import.argtypes = [C.c_void_p, C.c_void_p]
     lib.cg_carry_is_neutral.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
     lib.cg_batch_ends.argtypes = [C.POINTER(Batch), C.c_void_p]
+    lib.cg_shard_begin.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Window), C.POINTER(Result)]
+    lib.cg_shard_carry.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cg_shard_end.argtypes = [C.c_void_p, C.POINTER(Result)]
+    lib.cgm_create.restype = C.c_void_p
+    lib.cgm_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.cgm_destroy.argtypes = [C.c_void_p]
+    lib.cgm_n_devices.argtypes = [C.c_void_p]
+    lib.cgm_process.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Result)]
+    lib.cgm_process_window.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Window), C.POINTER(Result)]
+    lib.cgm_last_error.restype = C.c_char_p
+    lib.cgm_last_error.argtypes = [C.c_void_p]
+    lib.cgm_last_ms.restype = C.c_float
+    lib.cgm_last_ms.argtypes = [C.c_void_p]
+    lib.cgm_last_h2d_bytes.restype = C.c_int64
+    lib.cgm_last_h2d_bytes.argtypes = [C.c_void_p]
     lib.cg_upload.argtypes = [C.c_void_p, C.POINTER(Batch)]
     lib.cg_run.argtypes = [C.c_void_p]
     lib.cg_sync.argtypes = [C.c_void_p]
@@ -329,6 +347,28 @@ class Crumble:
         return {"qual": qout[: int(batch.qual_bytes)], "events": ev[: int(res.n_events)],
                 "counters": {k: int(res.counters[i]) for i, k in enumerate(COUNTER_NAMES)}}
 
+    # region shards without speculation: begin (state-free part) on all shards, carry from left to right, end on all shards
+    def shard_begin(self, batch: Batch, window: Window, events_cap: int = 1 << 16, pinned_out=None):
+        self._shard = (batch, self._result(batch, False, events_cap, pinned_out))
+        _check(self.lib, self.lib.cg_shard_begin(self.h, C.byref(batch), C.byref(window), C.byref(self._shard[1][0])), self.h)
+
+    def shard_carry(self, carry_in: bytes | None, want_out: bool = True) -> bytes | None:
+        cin = C.create_string_buffer(carry_in, CARRY_BYTES) if carry_in is not None else None
+        cout = C.create_string_buffer(CARRY_BYTES) if want_out else None
+        _check(self.lib, self.lib.cg_shard_carry(self.h, cin, cout), self.h)
+        return cout.raw if want_out else None
+
+    def shard_end(self):
+        batch, (res, qout, ev, _) = self._shard
+        _check(self.lib, self.lib.cg_shard_end(self.h, C.byref(res)), self.h)
+        if res.n_events > res.events_cap:
+            res2, qout2, ev, _ = self._result(batch, False, int(res.n_events), qout)
+            _check(self.lib, self.lib.cg_download(self.h, C.byref(res2)), self.h)
+            res = res2
+        self._shard = None
+        return {"qual": qout[: int(batch.qual_bytes)], "events": ev[: int(res.n_events)],
+                "counters": {k: int(res.counters[i]) for i, k in enumerate(COUNTER_NAMES)}}
+
     def carry_export(self) -> bytes:
         """the cross-column state the last ``process_window`` saved at its ``next_lo_pos`` (opaque, CARRY_BYTES long)"""
         buf = C.create_string_buffer(CARRY_BYTES)
@@ -377,6 +417,62 @@ class Crumble:
     def close(self):
         if getattr(self, "h", None):
             self.lib.cg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiCrumble:
+    """cg_multi: one batch over several devices (region shards scheduled in C, crumble_b200/csrc/cg_multi.c).  ``devices`` may name a
+    device more than once (several contexts on one GPU)."""
+
+    def __init__(self, params: Params | None = None, devices=None):
+        self.lib = load_lib()
+        if self.lib.cg_device_count() <= 0:
+            raise CrumbleError("no usable CUDA device: the GPU path is mandatory, there is no CPU fallback")
+        self.params = params if params is not None else default_params()
+        err = C.c_int(0)
+        if devices is None:
+            self.h = self.lib.cgm_create(C.byref(self.params), 0, None, C.byref(err))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            self.h = self.lib.cgm_create(C.byref(self.params), len(devices), arr, C.byref(err))
+        if not self.h:
+            raise CrumbleError(f"cgm_create failed: {self.lib.cg_strerror(err.value).decode()}")
+
+    def n_devices(self) -> int:
+        return int(self.lib.cgm_n_devices(self.h))
+
+    def process(self, batch: Batch, events_cap: int = 1 << 16, pinned_out=None, window: Window | None = None):
+        while True:
+            res = Result()
+            qout = pinned_out if pinned_out is not None else np.empty(max(int(batch.qual_bytes), 1), dtype=np.uint8)
+            res.qual_out = qout.ctypes.data_as(C.POINTER(C.c_uint8))
+            ev = np.zeros(events_cap, dtype=EVENT_DTYPE)
+            res.events = ev.ctypes.data_as(C.POINTER(BedEvent)); res.events_cap = events_cap
+            code = self.lib.cgm_process(self.h, C.byref(batch), C.byref(res)) if window is None else \
+                self.lib.cgm_process_window(self.h, C.byref(batch), C.byref(window), C.byref(res))
+            if code != 0:
+                raise CrumbleError(f"{self.lib.cg_strerror(code).decode()} [{code}] {self.lib.cgm_last_error(self.h).decode()}")
+            if res.n_events > events_cap and window is None:
+                events_cap = int(res.n_events); continue
+            break
+        return {"qual": qout[: int(batch.qual_bytes)], "events": ev[: min(int(res.n_events), events_cap)], "n_events": int(res.n_events),
+                "counters": {k: int(res.counters[i]) for i, k in enumerate(COUNTER_NAMES)}}
+
+    def ms(self) -> float:
+        return float(self.lib.cgm_last_ms(self.h))
+
+    def h2d_bytes(self) -> int:
+        return int(self.lib.cgm_last_h2d_bytes(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cgm_destroy(self.h)
             self.h = None
 
     def __del__(self):

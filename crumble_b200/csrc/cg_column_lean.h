@@ -25,6 +25,10 @@ __align__(16)
 ColTabRow { double MM, hM, om, pad; } ColTabRow;       /* per effective quality: pMM-p__, p_M-p__, 1-q2p (snp_score.c:644-651); row 0 is zero */
 
 /* sums of ranks 0 and 1 (and their pairs) live in registers; H2 H3 H4 C2 C3 C4 P23 P24 P34 in `rare` (shared memory on the device) */
+#ifndef COL_UNROLL
+#define COL_UNROLL 1            /* rows of the column loop per iteration: the kernel is instruction-fetch bound, the smaller loop wins (A/B: 6.96 / 7.29 / 8.73 ms at 1 / 2 / 4) */
+#endif
+static const int cg_col_unroll = COL_UNROLL;
 #define CG_NO_BASE 0x1000u           /* a base without the valid bit: no cell looks like this (an uncovered cell is all zero) */
 typedef struct CgRankAcc {
     double H0, H1, C0, C1, P01, P02, P03, P04, P12, P13, P14;
@@ -63,6 +67,36 @@ CG_HD void cg_tab_load(const ColTabRow *tab, uint32_t cell, double &mm, double &
     mm = r->MM; hm = r->hM; om = r->om;
 }
 
+/* N: MM to every genotype without a pad, _M to the pad-containing hets, nothing to ** and to the discrepancy sums
+ * (snp_score.c:677-682).  Every base needs a rank for that: the unseen ones get theirs now, in base order - ranks are
+ * arbitrary labels, the un-permute at the end of the column does not care when they were handed out. */
+template <int RS>
+CG_HDN void cg_rank_add_N(CgRankAcc *a, double *rare, double mm, double hm) {
+    a->nN++;
+    int rk[5];
+    for (int b = 0; b < 5; b++) {
+        uint32_t r = (a->pi >> (4 * b)) & 0xfu;
+        if (r == 15u) {
+            r = a->nseen++; a->pi = (a->pi & ~(0xfu << (4 * b))) | (r << (4 * b));
+            if (r == 0) a->b0s = CELL_VALID | ((uint32_t)b << CELL_BASE_SH);
+            if (r == 1) a->b1s = CELL_VALID | ((uint32_t)b << CELL_BASE_SH);
+        }
+        rk[b] = (int)r;
+    }
+    for (int x = 0; x < 4; x++) {
+        for (int y = x; y < 5; y++) {
+            const double v = y == 4 ? hm : mm;
+            const int u = rk[x] < rk[y] ? rk[x] : rk[y], w = rk[x] < rk[y] ? rk[y] : rk[x];
+            if (x == y) { if (u == 0) a->H0 += v; else if (u == 1) a->H1 += v; else rare[(u - 2) * RS] += v; }
+            else switch (CG_RK_P(u, w) - 5) {
+                case 0: a->P01 += v; break; case 1: a->P02 += v; break; case 2: a->P03 += v; break; case 3: a->P04 += v; break;
+                case 4: a->P12 += v; break; case 5: a->P13 += v; break; case 6: a->P14 += v; break;
+                default: rare[(CG_RK_P(u, w) - 5 - 7 + 6) * RS] += v; break;     /* P23 P24 P34 -> rare 6 7 8 */
+            }
+        }
+    }
+}
+
 /* third and later bases of a column, N, ref-skip, no-contribution cells: out of line of the hot loop */
 template <int RS>
 CG_HD void cg_rank_slow(CgRankAcc *a, double *rare, uint32_t cell, double mm, double hm, double om) {
@@ -84,42 +118,10 @@ CG_HD void cg_rank_slow(CgRankAcc *a, double *rare, uint32_t cell, double mm, do
             else                { a->P04 += hm; a->P14 += hm; }
         }
     } else if (base == 5u) {
-        /* N: MM to every genotype without a pad, _M to the pad-containing hets, nothing to ** and to the discrepancy sums
-         * (snp_score.c:677-682).  Every base needs a rank for that: the unseen ones get theirs now, in base order - ranks are
-         * arbitrary labels, the un-permute at the end of the column does not care when they were handed out. */
-        a->nN++;
-        int rk[5];
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-        for (int b = 0; b < 5; b++) {
-            uint32_t r = (a->pi >> (4 * b)) & 0xfu;
-            if (r == 15u) {
-                r = a->nseen++; a->pi = (a->pi & ~(0xfu << (4 * b))) | (r << (4 * b));
-                if (r == 0) a->b0s = CELL_VALID | ((uint32_t)b << CELL_BASE_SH);
-                if (r == 1) a->b1s = CELL_VALID | ((uint32_t)b << CELL_BASE_SH);
-            }
-            rk[b] = (int)r;
-        }
-#ifdef __CUDA_ARCH__
-#pragma unroll 1
-#endif
-        for (int x = 0; x < 5; x++) {
-#ifdef __CUDA_ARCH__
-#pragma unroll 1
-#endif
-            for (int y = x; y < 5; y++) {
-                if (x == 4) continue;                                   /* ** */
-                const double v = y == 4 ? hm : mm;
-                const int u = rk[x] < rk[y] ? rk[x] : rk[y], w = rk[x] < rk[y] ? rk[y] : rk[x];
-                if (x == y) { if (u == 0) a->H0 += v; else if (u == 1) a->H1 += v; else rare[(u - 2) * RS] += v; }
-                else switch (CG_RK_P(u, w) - 5) {
-                    case 0: a->P01 += v; break; case 1: a->P02 += v; break; case 2: a->P03 += v; break; case 3: a->P04 += v; break;
-                    case 4: a->P12 += v; break; case 5: a->P13 += v; break; case 6: a->P14 += v; break;
-                    default: rare[(CG_RK_P(u, w) - 5 - 7 + 6) * RS] += v; break;     /* P23 P24 P34 -> rare 6 7 8 */
-                }
-            }
-        }
+        /* rare and bulky: out of line, through a copy, so that the accumulators of the hot loop stay in registers */
+        CgRankAcc tmp = *a;
+        cg_rank_add_N<RS>(&tmp, rare, mm, hm);
+        *a = tmp;
     }
     else if (base == 6u) a->n_skip++;
     else a->n_none++;
@@ -150,7 +152,7 @@ CG_HD void cg_rank_rows(CgRankAcc *a, double *rare, const uint16_t *col, int n, 
         const uint16_t *cp = col + rb * CS;
         uint32_t nxt = cp[0];
 #ifdef __CUDA_ARCH__
-#pragma unroll 2
+#pragma unroll cg_col_unroll
 #endif
         for (int r = 0; r < re; r++) {
             const uint32_t cell = nxt;

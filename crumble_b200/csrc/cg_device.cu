@@ -1175,6 +1175,10 @@ __global__ void __launch_bounds__(256) k_unpack_exc(const uint64_t *__restrict__
 #define CG_FRONT_PAD 256
 struct dbuf { void *p; size_t cap; };
 
+#define CG_MAX_CHUNKS 32
+struct CgBounds { int64_t rb[CG_MAX_CHUNKS]; int32_t n; };
+struct CgSlice { int t0, t1, c0, c1, jb, je, kb, ke, chunk, save_after; int64_t r0, r1; };   /* see slice_A / slice_B */
+
 struct cg_ctx {
     int device; cudaStream_t stream; int own_stream;
     cg_params params; CgTables *hT; CgTables *dT;
@@ -1199,6 +1203,8 @@ struct cg_ctx {
     int packed, offsets_ready; int64_t h2d_bytes;                           /* offsets rebuilt on the device; bytes copied up by the last call */       /* chained calls: this call's window, the carries of the previous one */
     cudaStream_t s_h2d, s_d2h; cudaEvent_t ev_up[32], ev_done[32], ev_misc;
     char h_carry_init[64];
+    char *h_carry_io;                                           /* pinned: [0, 128) the state a shard imported, [128, 256) the one it exports */
+    CgSlice sl[2 * CG_MAX_CHUNKS + 2]; int n_sl, shard_state, shard_next, shard_save_end; const cg_batch *shard_in;
     cudaEvent_t ev[CG_N_TIMERS][2];
     float ms[CG_N_TIMERS];
     int64_t launches;
@@ -1283,6 +1289,7 @@ extern "C" cg_ctx *cg_create(const cg_params *p, int device, int *err) {
     if (!e && cudaHostAlloc((void **)&ctx->h_dims, 128, cudaHostAllocMapped) != cudaSuccess) e = CG_ERR_CUDA;
     if (!e && cudaHostGetDevicePointer((void **)&ctx->d_hdims, ctx->h_dims, 0) != cudaSuccess) e = CG_ERR_CUDA;
     if (!e && cudaHostAlloc((void **)&ctx->h_counters, sizeof(unsigned long long) * 32, cudaHostAllocDefault) != cudaSuccess) e = CG_ERR_CUDA;
+    if (!e && cudaHostAlloc((void **)&ctx->h_carry_io, 2 * CG_CARRY_BYTES, cudaHostAllocDefault) != cudaSuccess) e = CG_ERR_CUDA;
     for (int i = 0; i < CG_N_TIMERS && !e; i++)
         for (int k = 0; k < 2; k++) if (cudaEventCreate(&ctx->ev[i][k]) != cudaSuccess) e = CG_ERR_CUDA;
     if (!e) e = cg_set_params(ctx, p);
@@ -1302,6 +1309,7 @@ extern "C" void cg_destroy(cg_ctx *ctx) {
     if (ctx->dT) cudaFree(ctx->dT);
     if (ctx->h_dims) cudaFreeHost(ctx->h_dims);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_carry_io) cudaFreeHost(ctx->h_carry_io);
     for (int i = 0; i < CG_N_TIMERS; i++) for (int k = 0; k < 2; k++) if (ctx->ev[i][k]) cudaEventDestroy(ctx->ev[i][k]);
     if (ctx->s_h2d) { cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h); for (int i = 0; i < 32; i++) { cudaEventDestroy(ctx->ev_up[i]); cudaEventDestroy(ctx->ev_done[i]); } cudaEventDestroy(ctx->ev_misc); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1477,8 +1485,6 @@ static inline int nblk(int64_t n, int t) { int64_t b = (n + t - 1) / t; return (
  * device, then the rewrite of every record whose last column lies below the slice end.  A resident batch is one
  * slice; cg_process cuts the batch so that slice i starts as soon as upload chunk i has landed and its qualities
  * travel back while later chunks are still arriving (H2D, kernels and D2H overlap, PCIe is full duplex). */
-#define CG_MAX_CHUNKS 32
-struct CgBounds { int64_t rb[CG_MAX_CHUNKS]; int32_t n; };
 /* upload chunk i ends before record rb[i]; out[3i] = tiles complete once it has landed, out[3i+1] = records final then,
  * out[3i+2] = pileup reads whose bases are on the device then (their cell rows can be built) */
 __global__ void k_bounds(const __grid_constant__ CgDev D, const __grid_constant__ CgBounds B, int64_t *out) {
@@ -1644,47 +1650,50 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
     return 0;
 }
 
-/* one slice: tiles [t0,t1) -> their columns -> sparse passes -> records [r0,r1) */
-static int run_slice(cg_ctx *ctx, int t0, int t1, int c0, int c1, int64_t r0, int64_t r1, int jb, int je, int timed) {
+/* One slice: tiles [t0,t1) -> their columns -> sparse passes over columns [c0,c1) -> records [r0,r1).  The work falls in three parts:
+ *   A   (no carried state)  cell rows, column stage, flagged columns + their STR searches;
+ *   B1  (the carry)         depth prefix sums + epochs, keep-window chain: small, and all the NEXT slice / call / region shard needs;
+ *   B2  (the rest)          over-depth test, window painting, per-read rewrite.
+ * A single context runs A, B1, B2 slice after slice.  Region shards on several devices (cg_shard_*) run A for all their slices at
+ * once, pass the carry from shard to shard through B1 alone, and run B2 concurrently again. */
+
+static int slice_A(cg_ctx *ctx, CgSlice *s, int timed) {
     cudaStream_t st = ctx->stream;
     CgDev *D = &ctx->D;
     int32_t *scal = (int32_t *)ctx->b_scal.p;
-    CgChainCarry *ccarry = (CgChainCarry *)((char *)ctx->b_scal.p + 512);
-    CgEpochCarry *ecarry = (CgEpochCarry *)((char *)ctx->b_scal.p + 640);
     int e;
-    const int ncs = c1 > c0 ? c1 - c0 : 0;                      /* columns of the sparse passes: the tiles' own, except in chained calls */
+    const int ncs = s->c1 > s->c0 ? s->c1 - s->c0 : 0;          /* columns of the sparse passes: the tiles' own, except in chained calls */
     int nfs = 0;
     const int kb = ctx->nf_total;
     if (timed) T0(CG_T_CELLS);
-    if (je > jb && !ctx->generic) {                             /* cell rows of the pileup reads whose bases have landed */
-        k_cells<<<nblk((int64_t)(je - jb) * 4, 256), 256, 0, st>>>(*D, jb, je);
-        k_cells_general<<<nblk((int64_t)(je - jb), 256), 256, 0, st>>>(*D, jb, je);
+    if (s->je > s->jb && !ctx->generic) {                       /* cell rows of the pileup reads whose bases have landed */
+        k_cells<<<nblk((int64_t)(s->je - s->jb) * 4, 256), 256, 0, st>>>(*D, s->jb, s->je);
+        k_cells_general<<<nblk((int64_t)(s->je - s->jb), 256), 256, 0, st>>>(*D, s->jb, s->je);
         ctx->launches += 2;
     }
     if (timed) { T1(CG_T_CELLS); T0(CG_T_COLUMNS); }
     D->item_bound = (unsigned long long *)(scal + 20);
-    if (t1 > t0) {
+    if (s->t1 > s->t0) {
         CG_CHECK(cudaMemsetAsync(scal + 18, 0, 16, st));        /* tile counter, STR item bound of this slice */
-        if (ctx->generic) k_column_generic<<<nblk((int64_t)(t1 - t0) * 32, 128), 128, 0, st>>>(*D, t0, t1);
+        if (ctx->generic) k_column_generic<<<nblk((int64_t)(s->t1 - s->t0) * 32, 128), 128, 0, st>>>(*D, s->t0, s->t1);
         else {
             /* persistent warps claim tiles from a counter: one warp slot per resident warp, never more warps than tiles */
-            int blocks = nblk(t1 - t0, COL_WARPS);
+            int blocks = nblk(s->t1 - s->t0, COL_WARPS);
             if (blocks > 148 * COL_MINB) blocks = 148 * COL_MINB;
-            k_column<<<blocks, COL_WARPS * 32, 0, st>>>(*D, t0, t1, scal + 18);
+            k_column<<<blocks, COL_WARPS * 32, 0, st>>>(*D, s->t0, s->t1, scal + 18);
         }
         ctx->launches++;
     }
     if (timed) { T1(CG_T_COLUMNS); T0(CG_T_FLAGGED); }
     if (ncs > 0) {
-        LdEvFlagOff lf = { D->ev + c0, CG_EV_FLAGGED }; StCompactOff sc = { D->fcol + kb, D->ev + c0, CG_EV_FLAGGED, c0 };
+        LdEvFlagOff lf = { D->ev + s->c0, CG_EV_FLAGGED }; StCompactOff sc = { D->fcol + kb, D->ev + s->c0, CG_EV_FLAGGED, s->c0 };
         if ((e = run_scan<int32_t, OpSum>(ctx, lf, sc, ncs, 0, scal + 3))) return e;
         k_publish<<<1, 32, 0, st>>>(scal, ctx->d_hdims, 24); ctx->launches++;
         CG_CHECK(cudaStreamSynchronize(st));
         nfs = ctx->h_dims[3];
     }
     const int ke = kb + nfs;
-    if ((e = ensure_keep(ctx, &ctx->b_trig, ((size_t)ke + 1) * sizeof(CgTrig))) || (e = ensure_keep(ctx, &ctx->b_twin, ((size_t)ke + 1) * sizeof(CgWin))) ||
-        (e = ensure_keep(ctx, &ctx->b_chain, ((size_t)ke + 1) * 16))) return e;
+    if ((e = ensure_keep(ctx, &ctx->b_trig, ((size_t)ke + 1) * sizeof(CgTrig))) || (e = ensure_keep(ctx, &ctx->b_twin, ((size_t)ke + 1) * sizeof(CgWin)))) return e;
     D->trig = (CgTrig *)ctx->b_trig.p; D->twin = (CgWin *)ctx->b_twin.p;
     D->n_flagged = ke;
     if (nfs > 0) {
@@ -1703,38 +1712,60 @@ static int run_slice(cg_ctx *ctx, int t0, int t1, int c0, int c1, int64_t r0, in
             k_str_items<<<sblocks, STR_THREADS, 0, st>>>(*D); ctx->launches++;
         }
     }
-    if (timed) { T1(CG_T_FLAGGED); T0(CG_T_DEPTH); }
+    if (timed) T1(CG_T_FLAGGED);
+    s->kb = kb; s->ke = ke;
+    ctx->nf_total = ke;
+    CG_CHECK(cudaGetLastError());
+    return 0;
+}
+
+/* what: 1 = B1, 2 = B2, 3 = both */
+static int slice_B(cg_ctx *ctx, const CgSlice *s, int what, int timed) {
+    cudaStream_t st = ctx->stream;
+    CgDev *D = &ctx->D;
+    CgChainCarry *ccarry = (CgChainCarry *)((char *)ctx->b_scal.p + 512);
+    CgEpochCarry *ecarry = (CgEpochCarry *)((char *)ctx->b_scal.p + 640);
+    int e;
+    const int c0 = s->c0, c1 = s->c1, kb = s->kb, ke = s->ke, nfs = ke - kb;
+    const int ncs = c1 > c0 ? c1 - c0 : 0;
+    D->trig = (CgTrig *)ctx->b_trig.p; D->twin = (CgWin *)ctx->b_twin.p;
+    if (D->n_flagged < ke) D->n_flagged = ke;
+    if (timed) T0(CG_T_DEPTH);
     if (ctx->need_depth && ncs > 0) {
-        LdDepthCounted ld = { D->depth + c0, D->ev + c0 }; StI64Carry sd = { D->dsum + c0, ecarry };
-        if ((e = run_scan<int64_t, OpSum>(ctx, ld, sd, ncs, (int64_t)0, (int64_t *)NULL))) return e;
-        LdCounted lc = { D->ev + c0 }; StI32Carry sc2 = { D->csum + c0, ecarry };
-        if ((e = run_scan<int32_t, OpSum>(ctx, lc, sc2, ncs, 0, (int32_t *)NULL))) return e;
-        k_epochs<<<1, 32, 0, st>>>(*D, (CgEpoch *)ctx->b_epoch.p, ecarry, ctx->epoch_cap, c0, c1);
-        k_deep<<<nblk(ncs, 256), 256, 0, st>>>(*D, (const CgEpoch *)ctx->b_epoch.p, ecarry, c0, c1); ctx->launches += 2;
+        if (what & 1) {
+            LdDepthCounted ld = { D->depth + c0, D->ev + c0 }; StI64Carry sd = { D->dsum + c0, ecarry };
+            if ((e = run_scan<int64_t, OpSum>(ctx, ld, sd, ncs, (int64_t)0, (int64_t *)NULL))) return e;
+            LdCounted lc = { D->ev + c0 }; StI32Carry sc2 = { D->csum + c0, ecarry };
+            if ((e = run_scan<int32_t, OpSum>(ctx, lc, sc2, ncs, 0, (int32_t *)NULL))) return e;
+            k_epochs<<<1, 32, 0, st>>>(*D, (CgEpoch *)ctx->b_epoch.p, ecarry, ctx->epoch_cap, c0, c1); ctx->launches++;
+        }
+        if (what & 2) { k_deep<<<nblk(ncs, 256), 256, 0, st>>>(*D, (const CgEpoch *)ctx->b_epoch.p, ecarry, c0, c1); ctx->launches++; }
     }
     if (timed) { T1(CG_T_DEPTH); T0(CG_T_CHAIN); }
     if (nfs > 0) {
-        /* b_chain holds bmax (first half) and umax (second half) per flagged entry, indexed by slice-local position */
-        int64_t *bmax = (int64_t *)ctx->b_chain.p, *umax = bmax + nfs;
-        double mul = ctx->params.iSTR_mul > ctx->params.sSTR_mul ? ctx->params.iSTR_mul : ctx->params.sSTR_mul;
-        double add = ctx->params.iSTR_add > ctx->params.sSTR_add ? ctx->params.iSTR_add : ctx->params.sSTR_add;
-        if (mul < 0) mul = 0;
-        LdTrigB lb = { D->trig + kb, ccarry }; StI64Incl sb = { bmax };
-        if ((e = run_scan<int64_t, OpMax>(ctx, lb, sb, nfs, (int64_t)INT64_MIN, (int64_t *)NULL))) return e;
-        LdTrigU lu = { D->trig + kb, bmax, ccarry, mul, add }; StI64Incl su = { umax };
-        if ((e = run_scan<int64_t, OpMax>(ctx, lu, su, nfs, (int64_t)INT64_MIN, (int64_t *)NULL))) return e;
-        k_chain<<<nblk(nfs, 128), 128, 0, st>>>(*D, umax - kb, ccarry, kb, ke);
-        k_paint<<<nblk(nfs, 128), 128, 0, st>>>(*D, kb, ke);
-        k_chain_carry<<<1, 32, 0, st>>>(*D, bmax - kb, umax - kb, ccarry, kb, ke); ctx->launches += 3;
+        if (what & 1) {
+            /* b_chain holds bmax (first half) and umax (second half) per flagged entry, indexed by slice-local position */
+            if ((e = ensure(ctx, &ctx->b_chain, ((size_t)nfs + 1) * 16))) return e;
+            int64_t *bmax = (int64_t *)ctx->b_chain.p, *umax = bmax + nfs;
+            double mul = ctx->params.iSTR_mul > ctx->params.sSTR_mul ? ctx->params.iSTR_mul : ctx->params.sSTR_mul;
+            double add = ctx->params.iSTR_add > ctx->params.sSTR_add ? ctx->params.iSTR_add : ctx->params.sSTR_add;
+            if (mul < 0) mul = 0;
+            LdTrigB lb = { D->trig + kb, ccarry }; StI64Incl sb = { bmax };
+            if ((e = run_scan<int64_t, OpMax>(ctx, lb, sb, nfs, (int64_t)INT64_MIN, (int64_t *)NULL))) return e;
+            LdTrigU lu = { D->trig + kb, bmax, ccarry, mul, add }; StI64Incl su = { umax };
+            if ((e = run_scan<int64_t, OpMax>(ctx, lu, su, nfs, (int64_t)INT64_MIN, (int64_t *)NULL))) return e;
+            k_chain<<<nblk(nfs, 128), 128, 0, st>>>(*D, umax - kb, ccarry, kb, ke);
+            k_chain_carry<<<1, 32, 0, st>>>(*D, bmax - kb, umax - kb, ccarry, kb, ke); ctx->launches += 2;
+        }
+        if (what & 2) { k_paint<<<nblk(nfs, 128), 128, 0, st>>>(*D, kb, ke); ctx->launches++; }
     }
     if (timed) { T1(CG_T_CHAIN); T0(CG_T_REWRITE); }
-    if (r1 > r0) {
-        if (ctx->generic) k_rewrite_generic<<<nblk(r1 - r0, 128), 128, 0, st>>>(*D, r0, r1);
-        else k_rewrite<<<nblk(r1 - r0, RW_READS), RW_THREADS, 0, st>>>(*D, r0, r1);
+    if ((what & 2) && s->r1 > s->r0) {
+        if (ctx->generic) k_rewrite_generic<<<nblk(s->r1 - s->r0, 128), 128, 0, st>>>(*D, s->r0, s->r1);
+        else k_rewrite<<<nblk(s->r1 - s->r0, RW_READS), RW_THREADS, 0, st>>>(*D, s->r0, s->r1);
         ctx->launches++;
     }
     if (timed) T1(CG_T_REWRITE);
-    ctx->nf_total = ke;
     CG_CHECK(cudaGetLastError());
     return 0;
 }
@@ -1788,7 +1819,9 @@ extern "C" int cg_run(cg_ctx *ctx) {
     int e;
     T0(CG_T_TOTAL);
     if ((e = run_prep(ctx, &B, hb))) return e;
-    if ((e = run_slice(ctx, 0, ctx->D.n_tiles, 0, ctx->D.n_cols, 0, ctx->D.n_reads, 0, ctx->D.n_pile, 1))) return e;
+    CgSlice sl; memset(&sl, 0, sizeof sl);
+    sl.t1 = ctx->D.n_tiles; sl.c1 = ctx->D.n_cols; sl.r1 = ctx->D.n_reads; sl.je = ctx->D.n_pile;
+    if ((e = slice_A(ctx, &sl, 1)) || (e = slice_B(ctx, &sl, 3, 1))) return e;
     return run_finish(ctx, 1);
 }
 
@@ -1835,13 +1868,33 @@ extern "C" int cg_download(cg_ctx *ctx, cg_result *out) {
     return 0;
 }
 
+/* the qualities of records [r0, r1) go home on the download stream once everything queued on the compute stream so far is done;
+ * bytes below out->head_bytes (a region shard's read halo) go to out->qual_head instead of out->qual_out */
+static int enqueue_d2h(cg_ctx *ctx, const cg_batch *in, cg_result *out, int64_t r0, int64_t r1, int chunk) {
+    const int64_t n = in->n_reads;
+    if (r1 <= r0 || (!out->qual_out && !out->qual_head)) return 0;
+    int64_t b0 = in->off[r0], b1 = r1 < n ? in->off[r1] : in->qual_bytes;
+    CG_CHECK(cudaEventRecord(ctx->ev_done[chunk], ctx->stream));
+    CG_CHECK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[chunk], 0));
+    const int64_t hb = out->qual_head ? out->head_bytes : 0;
+    if (b0 < hb) {
+        const int64_t e1 = b1 < hb ? b1 : hb;
+        CG_CHECK(cudaMemcpyAsync(out->qual_head + b0, (char *)ctx->b_qout.p + b0, (size_t)(e1 - b0), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        b0 = e1;
+    }
+    if (b1 > b0 && out->qual_out) CG_CHECK(cudaMemcpyAsync(out->qual_out + b0, (char *)ctx->b_qout.p + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    return 0;
+}
+
 /* End to end, streamed: the base data goes up in chunks on a copy stream; slice i of the chain starts when chunk i has
- * landed; the qualities of the records it finalises go down on a second copy stream while later chunks still arrive. */
-static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, const cg_window *win) {
+ * landed; the qualities of the records it finalises go down on a second copy stream while later chunks still arrive.
+ * phase 0: everything (cg_process / cg_process_window).  phase 1: a region shard's part A only (cg_shard_begin): its slices are
+ * recorded in the context for cg_shard_carry (B1) and cg_shard_end (B2 + downloads). */
+static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, const cg_window *win, int phase) {
     CG_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int e;
-    ctx->resident = 0; ctx->win_on = 0;
+    ctx->resident = 0; ctx->win_on = 0; ctx->n_sl = 0; ctx->shard_state = 0;
     ctx->dump_columns = out->columns != NULL;
     if ((e = alloc_inputs(ctx, in))) return e;
     if (win) {                                                 /* one call of a chain (cg_process_window) */
@@ -1903,7 +1956,7 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
     CgEpochCarry *ecarry = (CgEpochCarry *)((char *)ctx->b_scal.p + 640);
     int cS = -1;                                               /* -1: nothing to save */
     if (win && ctx->D.n_cols > 0) {
-        if (!win->first && ctx->have_saved) { k_paint_carry<<<1, 32, 0, st>>>(ctx->D, ccarry, win->lo_tid, win->lo_pos); ctx->launches++; }
+        if (phase == 0 && !win->first && ctx->have_saved) { k_paint_carry<<<1, 32, 0, st>>>(ctx->D, ccarry, win->lo_tid, win->lo_pos); ctx->launches++; }
         if (win->hi_tid >= 0) {
             k_find_col<<<1, 32, 0, st>>>(ctx->D, win->hi_tid, win->next_lo_pos, ctx->d_hdims + 11); ctx->launches++;
             CG_CHECK(cudaStreamSynchronize(st));
@@ -1911,7 +1964,7 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
         }
     }
     int tprev = 0, jprev = 0; int64_t rprev = 0;
-    cudaEventRecord(ctx->ev[CG_T_D2H][0], ctx->s_d2h);
+    if (phase == 0) cudaEventRecord(ctx->ev[CG_T_D2H][0], ctx->s_d2h);
     for (int i = 0; i < nch; i++) {
         int t1 = (i + 1 == nch) ? ctx->D.n_tiles : (int)hb[3 * i];
         int64_t r1 = (i + 1 == nch) ? n : hb[3 * i + 1];
@@ -1922,22 +1975,31 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
         CG_CHECK(cudaStreamWaitEvent(st, ctx->ev_up[i], 0));
         if ((e = expand_bases(ctx, in, boff[i], boff[i + 1], st))) { ctx->win_on = 0; return e; }
         const int c0 = tprev * 32 < ctx->D.n_cols ? tprev * 32 : ctx->D.n_cols, c1 = t1 * 32 < ctx->D.n_cols ? t1 * 32 : ctx->D.n_cols;
+        /* the slice(s) of this chunk: when the next call's first column cS lies inside, the sparse passes stop there, both carries are
+         * saved, and a second slice (no tiles of its own) finishes the columns from cS on */
+        CgSlice sl[2]; int ns = 1;
+        memset(sl, 0, sizeof sl);
+        sl[0].t0 = tprev; sl[0].t1 = t1; sl[0].c0 = c0; sl[0].c1 = c1; sl[0].jb = jprev; sl[0].je = j1; sl[0].r0 = rprev; sl[0].r1 = r1; sl[0].chunk = i;
         if (cS >= 0 && cS < c1) {
-            /* the next call's first column lies in this slice: sparse passes up to it, save both carries, then the rest */
-            if ((e = run_slice(ctx, tprev, t1, c0, cS, 0, 0, jprev, j1, 0))) { ctx->win_on = 0; return e; }
-            k_carry_save<<<1, 32, 0, st>>>(ccarry, ecarry, (CgSavedCarry *)ctx->b_saved.p); ctx->launches++;
-            e = run_slice(ctx, t1, t1, cS, c1, rprev, r1, j1, j1, 0);
-            cS = -2;                                           /* saved */
-        } else e = run_slice(ctx, tprev, t1, c0, c1, rprev, r1, jprev, j1, 0);
-        if (e) { ctx->win_on = 0; return e; }
-        if (r1 > rprev && out->qual_out) {
-            const int64_t b0 = in->off[rprev], b1 = r1 < n ? in->off[r1] : in->qual_bytes;
-            CG_CHECK(cudaEventRecord(ctx->ev_done[i], st));
-            CG_CHECK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[i], 0));
-            if (b1 > b0) CG_CHECK(cudaMemcpyAsync(out->qual_out + b0, (char *)ctx->b_qout.p + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, ctx->s_d2h));
+            sl[1] = sl[0];
+            sl[0].c1 = cS; sl[0].r0 = sl[0].r1 = 0; sl[0].save_after = 1;
+            sl[1].t0 = sl[1].t1 = t1; sl[1].c0 = cS; sl[1].jb = sl[1].je = j1;
+            ns = 2; cS = -2;                                   /* saved (or about to be) */
         }
+        for (int k = 0; k < ns; k++) {
+            if ((e = slice_A(ctx, &sl[k], 0))) { ctx->win_on = 0; return e; }
+            if (phase == 0) {
+                if ((e = slice_B(ctx, &sl[k], 3, 0))) { ctx->win_on = 0; return e; }
+                if (sl[k].save_after) { k_carry_save<<<1, 32, 0, st>>>(ccarry, ecarry, (CgSavedCarry *)ctx->b_saved.p); ctx->launches++; }
+            } else ctx->sl[ctx->n_sl++] = sl[k];
+        }
+        if (phase == 0 && (e = enqueue_d2h(ctx, in, out, rprev, r1, i))) { ctx->win_on = 0; return e; }
         tprev = t1; rprev = r1; jprev = j1;
         CG_TRACE_AT("slice enqueued (host passed its column sync)", i);
+    }
+    if (phase != 0) {                                          /* a region shard: the rest follows in cg_shard_carry / cg_shard_end */
+        ctx->shard_in = in; ctx->shard_save_end = cS >= 0; ctx->shard_state = 1;
+        return 0;
     }
     cudaEventRecord(ctx->ev[CG_T_D2H][1], ctx->s_d2h);
     if (cS >= 0) { k_carry_save<<<1, 32, 0, st>>>(ccarry, ecarry, (CgSavedCarry *)ctx->b_saved.p); ctx->launches++; }   /* next call starts beyond this batch's columns */
@@ -1957,7 +2019,94 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
     return 0;
 }
 
-extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) { return process_streamed(ctx, in, out, NULL); }
+/* ---- region shards of one contig on several devices at once (include/crumble_gpu.h) -------------------------------------------
+ * cg_shard_begin   upload + part A of every slice (no carried state): all shards run this concurrently;
+ * cg_shard_carry   the true incoming state (from the shard on the left, or none at a contig start) -> part B1 of the slices below the
+ *                  right neighbour's first column -> the outgoing state.  Small (prefix sums, epochs, window chain), and the only
+ *                  thing that runs shard after shard;
+ * cg_shard_end     part B1 of the remaining slices, part B2 (over-depth test, painting, rewrite), downloads: concurrent again. */
+extern "C" int cg_shard_begin(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out) {
+    if (!win) return CG_ERR_BAD_ARG;
+    if (ctx->params.region_tid >= 0) { snprintf(ctx->err, sizeof ctx->err, "region shards and a -r region do not combine"); return CG_ERR_BAD_ARG; }
+    cg_window w = *win;
+    if (w.first == 2) w.first = 0;                             /* there is no speculative start here: the true state arrives in cg_shard_carry */
+    return process_streamed(ctx, in, out, &w, 1);
+}
+
+extern "C" int cg_shard_carry(cg_ctx *ctx, const void *carry_in, void *carry_out) {
+    if (ctx->shard_state != 1) return CG_ERR_STATE;
+    CG_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CgChainCarry *ccarry = (CgChainCarry *)((char *)ctx->b_scal.p + 512);
+    CgEpochCarry *ecarry = (CgEpochCarry *)((char *)ctx->b_scal.p + 640);
+    int e;
+    if (!ctx->win.first) {
+        if (!carry_in) { snprintf(ctx->err, sizeof ctx->err, "this shard continues a contig: it needs the state of the shard on its left"); return CG_ERR_BAD_ARG; }
+        CgSavedCarry sv; memcpy(&sv, carry_in, sizeof sv);
+        memcpy(ctx->h_carry_io, &sv, sizeof sv);
+        CG_CHECK(cudaMemcpyAsync(ccarry, &((CgSavedCarry *)ctx->h_carry_io)->cc, sizeof(CgChainCarry), cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ecarry, &((CgSavedCarry *)ctx->h_carry_io)->ec, sizeof(CgEpochCarry), cudaMemcpyHostToDevice, st));
+        ctx->have_saved = 1;
+    }
+    int k = 0;
+    for (; k < ctx->n_sl; k++) {
+        if ((e = slice_B(ctx, &ctx->sl[k], 1, 0))) return e;
+        if (ctx->sl[k].save_after) { k++; break; }
+    }
+    ctx->shard_next = k;
+    const int saves = (k > 0 && ctx->sl[k - 1].save_after) || ctx->shard_save_end;
+    if (saves) {
+        if (ctx->shard_save_end) for (; k < ctx->n_sl; k++) if ((e = slice_B(ctx, &ctx->sl[k], 1, 0))) return e;    /* the next shard starts beyond these columns */
+        ctx->shard_next = k;
+        k_carry_save<<<1, 32, 0, st>>>(ccarry, ecarry, (CgSavedCarry *)ctx->b_saved.p); ctx->launches++;
+        if (carry_out) {
+            CG_CHECK(cudaMemcpyAsync(ctx->h_carry_io + CG_CARRY_BYTES, ctx->b_saved.p, sizeof(CgSavedCarry), cudaMemcpyDeviceToHost, st));
+            CG_CHECK(cudaStreamSynchronize(st));
+            memset(carry_out, 0, CG_CARRY_BYTES);
+            memcpy(carry_out, ctx->h_carry_io + CG_CARRY_BYTES, sizeof(CgSavedCarry));
+        }
+    } else if (carry_out) memset(carry_out, 0, CG_CARRY_BYTES);
+    ctx->shard_state = 2;
+    return 0;
+}
+
+extern "C" int cg_shard_end(cg_ctx *ctx, cg_result *out) {
+    if (ctx->shard_state != 2) return CG_ERR_STATE;
+    CG_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const cg_batch *in = ctx->shard_in;
+    CgChainCarry *ccarry = (CgChainCarry *)((char *)ctx->b_scal.p + 512);
+    int e;
+    ctx->shard_state = 0;
+    for (int k = ctx->shard_next; k < ctx->n_sl; k++) if ((e = slice_B(ctx, &ctx->sl[k], 1, 0))) { ctx->win_on = 0; return e; }
+    /* the keep window the shard on the left left open stays active from this shard's first column: the carry area now holds the state
+     * after this shard's own triggers, so paint from the imported copy */
+    if (!ctx->win.first && ctx->have_saved && ctx->D.n_cols > 0) {
+        CG_CHECK(cudaMemcpyAsync((char *)ctx->b_scal.p + 1600, &((CgSavedCarry *)ctx->h_carry_io)->cc, sizeof(CgChainCarry), cudaMemcpyHostToDevice, st));
+        k_paint_carry<<<1, 32, 0, st>>>(ctx->D, (const CgChainCarry *)((char *)ctx->b_scal.p + 1600), ctx->win.lo_tid, ctx->win.lo_pos); ctx->launches++;
+    }
+    (void)ccarry;
+    cudaEventRecord(ctx->ev[CG_T_D2H][0], ctx->s_d2h);
+    for (int k = 0; k < ctx->n_sl; k++) {
+        const CgSlice *s = &ctx->sl[k];
+        if ((e = slice_B(ctx, s, 2, 0))) { ctx->win_on = 0; return e; }
+        if (s->r1 > s->r0 && (e = enqueue_d2h(ctx, in, out, s->r0, s->r1, s->chunk))) { ctx->win_on = 0; return e; }
+    }
+    cudaEventRecord(ctx->ev[CG_T_D2H][1], ctx->s_d2h);
+    ctx->have_saved = ctx->win.hi_tid >= 0 && (ctx->D.n_cols > 0 || (!ctx->win.first && ctx->have_saved));
+    e = run_finish(ctx, 0);
+    ctx->win_on = 0;
+    if (e) return e;
+    if ((e = download_results(ctx, out, 0))) return e;
+    CG_CHECK(cudaStreamSynchronize(ctx->s_d2h));
+    CG_CHECK(cudaStreamSynchronize(ctx->s_h2d));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_D2H][0], ctx->ev[CG_T_D2H][1]) == cudaSuccess) ctx->ms[CG_T_D2H] = ms; else cudaGetLastError();
+    if (cudaEventElapsedTime(&ms, ctx->ev[CG_T_H2D][0], ctx->ev[CG_T_H2D][1]) == cudaSuccess) ctx->ms[CG_T_H2D] = ms; else cudaGetLastError();
+    return 0;
+}
+
+extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) { return process_streamed(ctx, in, out, NULL, 0); }
 
 /* One call of a chain (include/crumble_gpu.h): the streamed driver above with a column window.  The column stage runs over all
  * tiles of the batch (columns outside the window come out inert, cg_window_class); the sparse passes of the slice holding the next
@@ -1965,7 +2114,7 @@ extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) { ret
 extern "C" int cg_process_window(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out) {
     if (!win) return CG_ERR_BAD_ARG;
     if (ctx->params.region_tid >= 0) { snprintf(ctx->err, sizeof ctx->err, "chained calls and a -r region do not combine"); return CG_ERR_BAD_ARG; }
-    return process_streamed(ctx, in, out, win);
+    return process_streamed(ctx, in, out, win, 0);
 }
 
 extern "C" int cg_carry_export(cg_ctx *ctx, void *buf) {

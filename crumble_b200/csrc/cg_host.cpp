@@ -159,6 +159,7 @@ struct cg_batch_builder {
     vec<int32_t> tid, pos, l_qseq, cigar_off; vec<uint16_t> flag, n_cigar; vec<uint8_t> mapq; vec<int64_t> off;
     vec<uint32_t> cigar; vec<uint8_t> seq, qual;
     vec<uint8_t> seq2, qualp; vec<uint64_t> seq_exc;        /* compact planes (cgb_pack) */
+    vec<int32_t> pmax;                                      /* running max of pos + span inside the contig */
     int have_pack, qual_bits; uint8_t qual_dict[16];
     int64_t last_key; int unsorted; int seen_unplaced;
 };
@@ -170,21 +171,21 @@ extern "C" cg_batch_builder *cgb_create(int pinned) {
     int pin = pinned && cg_pinned_alloc_hook;
     b->tid.init(pin); b->pos.init(pin); b->l_qseq.init(pin); b->cigar_off.init(pin); b->flag.init(pin); b->n_cigar.init(pin);
     b->mapq.init(pin); b->off.init(pin); b->cigar.init(pin); b->seq.init(pin); b->qual.init(pin);
-    b->seq2.init(pin); b->qualp.init(pin); b->seq_exc.init(pin);
+    b->seq2.init(pin); b->qualp.init(pin); b->seq_exc.init(pin); b->pmax.init(0);
     b->last_key = INT64_MIN;
     return b;
 }
 extern "C" void cgb_reset(cg_batch_builder *b) {
     b->tid.n = b->pos.n = b->l_qseq.n = b->cigar_off.n = b->flag.n = b->n_cigar.n = b->mapq.n = b->off.n = 0;
     b->cigar.n = b->seq.n = b->qual.n = 0;
-    b->seq2.n = b->qualp.n = b->seq_exc.n = 0; b->have_pack = 0; b->qual_bits = 0;
+    b->seq2.n = b->qualp.n = b->seq_exc.n = 0; b->have_pack = 0; b->qual_bits = 0; b->pmax.n = 0;
     b->last_key = INT64_MIN; b->unsorted = 0; b->seen_unplaced = 0;
 }
 extern "C" void cgb_destroy(cg_batch_builder *b) {
     if (!b) return;
     b->tid.release(); b->pos.release(); b->l_qseq.release(); b->cigar_off.release(); b->flag.release(); b->n_cigar.release();
     b->mapq.release(); b->off.release(); b->cigar.release(); b->seq.release(); b->qual.release();
-    b->seq2.release(); b->qualp.release(); b->seq_exc.release();
+    b->seq2.release(); b->qualp.release(); b->seq_exc.release(); b->pmax.release();
     free(b);
 }
 
@@ -208,6 +209,15 @@ extern "C" int cgb_add(cg_batch_builder *b, int32_t tid, int32_t pos, uint16_t f
     b->n_cigar.p[i] = (uint16_t)n_cigar; b->off.p[i] = (int64_t)qoff; b->cigar_off.p[i] = (int32_t)b->cigar.n;
     b->qual.n = qoff + qpad; b->seq.n = (qoff + qpad) / 2; b->cigar.n += n_cigar;
     b->tid.n = b->pos.n = b->l_qseq.n = b->cigar_off.n = b->flag.n = b->n_cigar.n = b->mapq.n = b->off.n = i + 1;
+    {   /* running max of the record ends inside the contig (cg_batch.pmax_end) */
+        if (b->pmax.reserve(i + 1)) return CG_ERR_NOMEM;
+        int span = 0, hasref = 0;
+        for (uint32_t k = 0; k < n_cigar; k++) if (cg_cig_type(cg_cig_op(cigar[k])) & 2) { span += cg_cig_len(cigar[k]); hasref = 1; }
+        const int inp = tid >= 0 && !(flag & 4) && hasref;
+        const int32_t e = pos + (inp ? (span ? span : 1) : 0);
+        b->pmax.p[i] = (i > 0 && b->tid.p[i - 1] == tid && b->pmax.p[i - 1] > e) ? b->pmax.p[i - 1] : e;
+        b->pmax.n = i + 1;
+    }
     /* sortedness of what enters the pileup (htslib's pileup aborts on unsorted input) */
     if (tid >= 0 && !(flag & 4)) {
         int64_t key = cg_key(tid, pos);
@@ -281,6 +291,7 @@ extern "C" int cgb_finish(cg_batch_builder *b, cg_batch *o) {
     o->seq = b->seq.p; o->seq_bytes = (int64_t)b->seq.n;
     o->qual = b->qual.p; o->qual_bytes = (int64_t)b->qual.n;
     o->packed = 1;                                   /* cgb_add lays records out back to back */
+    o->pmax_end = b->pmax.p;
     if (b->have_pack) {
         o->seq2 = b->seq2.p; o->seq2_bytes = (int64_t)b->seq2.n;
         o->seq_exc = b->seq_exc.p; o->n_seq_exc = (int64_t)b->seq_exc.n;

@@ -108,6 +108,9 @@ typedef struct cg_batch {
     const uint8_t  *qualp;    int64_t qualp_bytes;
     int32_t  qual_bits;
     uint8_t  qual_dict[16];
+    /* optional: running maximum of pos + reference span inside each contig (the batcher keeps it): lets cgm_process place region
+     * shard cuts and halos by binary search instead of walking every CIGAR */
+    const int32_t *pmax_end;
 } cg_batch;
 
 /* BED_DIST-expanded suspicious-region events (snp_score.c:1496-1498,1676-1678,
@@ -141,6 +144,10 @@ typedef struct cg_result {
     int64_t       counters[CG_N_COUNTERS];
     cg_column    *columns;         /* caller buffer or NULL (NULL = no dump) */
     int64_t       columns_cap, n_columns;
+    /* optional: bytes [0, head_bytes) of the quality layout go to qual_head[] instead of qual_out[] (a region shard's read halo,
+     * which lies before the shard's own byte range of a shared output buffer: see cgm_process) */
+    uint8_t      *qual_head;
+    int64_t       head_bytes;
 } cg_result;
 
 typedef struct cg_ctx cg_ctx;
@@ -204,6 +211,35 @@ int cg_carry_import(cg_ctx *ctx, const void *buf);                 /* what the n
 int cg_carry_is_neutral(const cg_ctx *ctx, const void *buf, int32_t tid, int32_t lo_pos);
 /* pos + reference span of every record (pos itself for records outside the pileup): what a host needs to plan shards and halos */
 void cg_batch_ends(const cg_batch *in, int32_t *end_out);
+
+/* The same shards without speculation: every shard gets the TRUE state of its left neighbour, yet only a sliver of the work is serial.
+ * A shard's work is split in three (cg_device.cu, slice_A / slice_B):
+ *   cg_shard_begin   upload, pileup, consensus, column decisions, STR searches: nothing here depends on carried state.  All shards
+ *                    run it at the same time (window as for cg_process_window; first = 2 is read as 0);
+ *   cg_shard_carry   state in (NULL for a shard that starts a contig) -> depth prefix sums + epochs and the keep-window chain over the
+ *                    shard's columns below its right neighbour's first column -> state out.  Shard after shard, but tiny;
+ *   cg_shard_end     over-depth test, window painting, per-read rewrite, downloads: all shards at the same time again.
+ * Results are bit-identical to one call on the whole batch at every option level, -1/-3/-5 (depth average) included.
+ * `in` must stay valid until cg_shard_end returns. */
+int cg_shard_begin(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out);
+int cg_shard_carry(cg_ctx *ctx, const void *carry_in, void *carry_out);     /* CG_CARRY_BYTES each; carry_out may be NULL */
+int cg_shard_end(cg_ctx *ctx, cg_result *out);
+
+/* ---- one batch over several GPUs (crumble_b200/csrc/cg_multi.c) -------------------------------------------------------------------
+ * As many region shards as devices, of about equal size, cut at record boundaries; one host thread and one context per device; the three
+ * cg_shard_* phases above; every device downloads its own byte range of out->qual_out.  Same results as cg_process / cg_process_window,
+ * in the same buffers (the per-column dump is not available).  cgm_process_window keeps the state between the calls of a chain inside
+ * the cg_multi object, as a context does for cg_process_window. */
+typedef struct cg_multi cg_multi;
+cg_multi   *cgm_create(const cg_params *p, int n_devices, const int *devices /* NULL: 0 .. n_devices-1 */, int *err);
+void        cgm_destroy(cg_multi *m);
+int         cgm_n_devices(const cg_multi *m);
+int         cgm_process(cg_multi *m, const cg_batch *in, cg_result *out);
+int         cgm_process_window(cg_multi *m, const cg_batch *in, const cg_window *win, cg_result *out);
+const char *cgm_last_error(const cg_multi *m);
+float       cgm_last_ms(const cg_multi *m);                 /* slowest shard's device time of the last call */
+int64_t     cgm_last_h2d_bytes(const cg_multi *m);
+cg_ctx     *cgm_context(cg_multi *m, int i);                /* borrowed */
 
 /* measurement helpers */
 enum { CG_T_TOTAL = 0, CG_T_TILES, CG_T_COLUMNS, CG_T_FLAGGED, CG_T_DEPTH, CG_T_CHAIN, CG_T_REWRITE, CG_T_CELLS, CG_T_EVENTS, CG_T_H2D, CG_T_D2H, CG_N_TIMERS };

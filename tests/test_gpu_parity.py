@@ -438,3 +438,60 @@ def test_gpu_ambiguity_codes(name, rate):
         assert cb.bed_text(out["events"], ref["names"]) == ref["bed"] and out["counters"] == ref["counters"], args
         g.close()
     bb.close()
+
+
+@pytest.mark.parametrize("name,n_dev", [("c1s", 4), ("tiny", 5), ("c2s", 8), ("c4s", 3), ("tiny", 1)])
+@pytest.mark.parametrize("args", [["-9"], ["-1"], ["-1", "-B"], ["-3", "-P1.5"], ["-5", "-q30"]], ids=lambda a: "".join(a))
+def test_gpu_multi_device_scheduler(name, n_dev, args):
+    """cgm_process (crumble_b200/csrc/cg_multi.c): one batch cut into as many region shards as "devices" (here: contexts on one GPU),
+    state-free part on all shards at once, the true 128-byte state passed from shard to shard (cg_shard_begin / _carry / _end), every
+    shard downloading its own byte range of the shared output.  No speculation, so -1 / -3 (depth average in play) run concurrently
+    too.  Compared with the ORACLE, with plain and with compact-plane batches."""
+    data, bb0, batch0, mask = dataset(name)
+    ref = run_oracle(data, args)
+    bb = cb.BatchBuilder(); bb.add_bam_stream(data); packed = bb.finish(pack=True)
+    m = cb.MultiCrumble(params_from_args(args), devices=[0] * n_dev)
+    assert m.n_devices() == n_dev
+    for batch in (batch0, packed):
+        out = m.process(batch)
+        nbad = int((out["qual"][mask] != ref["qual"][mask]).sum())
+        assert nbad == 0, f"{nbad} quality bytes differ from the oracle ({ref['kind']})"
+        assert cb.bed_text(out["events"], ref["names"]) == ref["bed"]
+        assert out["counters"] == ref["counters"]
+    m.close(); bb.close()
+
+
+def test_gpu_shard_phases_by_hand():
+    """the three shard phases driven from Python in the worst order a scheduler could pick: every begin first, then the carries from
+    left to right, then the ends from right to left"""
+    data, bb, batch, mask = dataset("c1s")
+    args = ["-1"]
+    ref = run_oracle(data, args)
+    n_sh = 4
+    shards, end = cb.plan_region_shards(batch, n_sh)
+    subs = [cb.sub_batch(batch, sh["h0"], sh["r1"]) for sh in shards]
+    ctxs = [cb.Crumble(params_from_args(args), device=0) for _ in range(n_sh)]
+    for k, sh in enumerate(shards):
+        ctxs[k].shard_begin(subs[k][0], cb.shard_window(sh))
+    carry = None
+    for k, sh in enumerate(shards):
+        carry = ctxs[k].shard_carry(carry if sh["first"] != 1 else None, want_out=sh["hi_tid"] >= 0)
+    outs = [None] * n_sh
+    for k in reversed(range(n_sh)):
+        outs[k] = ctxs[k].shard_end()
+    n = int(batch.n_reads); off = bb.offsets()
+    qual = np.zeros(int(batch.qual_bytes), np.uint8); done = np.zeros(n, bool)
+    cnt = {k: 0 for k in cb.COUNTER_NAMES}; evs = []
+    for k, sh in enumerate(shards):
+        fin = cb.shard_final_mask(batch, sh, end, done)
+        idx = np.arange(sh["h0"], sh["r1"])[fin]; base = int(off[sh["h0"]])
+        for i in idx:
+            q0 = int(off[i]); q1 = int(off[i + 1]) if i + 1 < n else int(batch.qual_bytes)
+            qual[q0:q1] = outs[k]["qual"][q0 - base: q1 - base]
+        done[idx] = True
+        for c in cnt: cnt[c] += outs[k]["counters"][c]
+        evs.append(outs[k]["events"])
+    assert done.all()
+    assert int((qual[mask] != ref["qual"][mask]).sum()) == 0
+    assert cb.bed_text(np.concatenate(evs), ref["names"]) == ref["bed"] and cnt == ref["counters"]
+    for g in ctxs: g.close()

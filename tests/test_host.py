@@ -18,7 +18,7 @@ GDIR = ROOT / "tests" / "golden"
 
 def test_library_exports_every_declared_symbol():
     hdr = open(ROOT / "include" / "crumble_gpu.h").read()
-    declared = set(re.findall(r"\b(cgb?_[a-z_0-9]+)\s*\(", hdr)) - {"cg_ctx"}
+    declared = set(re.findall(r"\b(cg[bm]?_[a-z_0-9]+)\s*\(", hdr)) - {"cg_ctx"}
     lib = cb.load_lib()
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
