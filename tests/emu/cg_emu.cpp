@@ -39,6 +39,14 @@ extern "C" int64_t cg_last_launches(const cg_ctx *) { return 0; }
 extern "C" int64_t cg_last_h2d_bytes(const cg_ctx *) { return 0; }
 extern "C" int64_t cg_n_columns(const cg_ctx *c) { return c->n_cols; }
 
+/* the multi-GPU scheduler is not emulated (cg_device_count() is 0 here, so the host driver never asks for it): link-time stubs */
+extern "C" cg_multi *cgm_create(const cg_params *, int, const int *, int *err) { if (err) *err = CG_ERR_NO_DEVICE; return NULL; }
+extern "C" void cgm_destroy(cg_multi *) {}
+extern "C" int cgm_process_window(cg_multi *, const cg_batch *, const cg_window *, cg_result *) { return CG_ERR_NO_DEVICE; }
+extern "C" const char *cgm_last_error(const cg_multi *) { return "not emulated"; }
+extern "C" float cgm_last_ms(const cg_multi *) { return 0; }
+extern "C" int64_t cgm_events(const cg_multi *, cg_bed_event *, int64_t) { return 0; }
+
 static int emu_process(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out);
 /* events of the last call again (the caller's buffer was too small); qualities are already in the caller's buffer */
 extern "C" int cg_download(cg_ctx *ctx, cg_result *out) {

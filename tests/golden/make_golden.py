@@ -34,6 +34,9 @@ OPT_ARGS = [["-9", "-S"], ["-1", "-S", "-B"], ["-9", "-k", "37"], ["-9", "-K", "
             ["-1", "-q", "30", "-k", "37", "-S"]]
 KEEP_BED = {"tiny": "chr1\t1000\t3000\nchr1\t2500\t2600\nchr1\t2800\t5000\n# nested + overlapping on purpose (bed.c:20-40)\nchr2\t100\t200\nchr2\t20000\t26000\nchr1\t40000\t41000\n",
             "c1s": "track name=keep\nchr20\t1000\t3000\nchr20\t2500\t2600\nchr20\t2800\t5000\nchr20\t20000\t20100\nchr20\t40000\t49000\nchr20\t90000\t90001\n"}
+# aux-tag options (purge_tags, snp_score.c:989-1054): the reference's whole SAM output for tests/golden/tags.sam
+TAGS = {"plain": ["-9"], "t": ["-9", "-t", "NM,BD"], "T": ["-9", "-T", "MD,XX,ZB"], "efg": ["-9", "-e", "5", "-f", "20", "-g", "40"],
+        "EFGt": ["-9", "-E", "7", "-F", "25", "-G", "45", "-t", "BI,BD,RG"], "all": ["-1", "-e", "1", "-f", "30", "-g", "2", "-E", "3", "-F", "10", "-G", "50", "-T", "BI"]}
 EDGE = {"l9": ["-9"], "l1B": ["-1", "-B"], "l5q30": ["-5", "-q30"], "l3U35": ["-3", "-U35", "-Y0.2"],
         "l9r": ["-9", "-r", "chrA:900-1600"], "l1r": ["-1", "-r", "chrA:1200-2100"]}
 
@@ -71,6 +74,8 @@ def main():
                 if not line.startswith("@"):
                     c = line.rstrip("\n").split("\t"); f.write(c[0] + "\t" + c[10] + "\n")
         out.unlink()
+    for tag, a in TAGS.items():
+        subprocess.run([str(ref), "-z"] + a + [str(HERE / "tags.sam"), str(HERE / f"tags.{tag}.out.sam")], check=True)
     # the reference's own debug dump: "Depth tid pos n_plp \t call score \t[*]\t bases"
     data, _, _ = cb.simulate(*SETS["tiny"], threads=1)
     tmp = HERE / "_tmp.ubam"; data.tofile(tmp)

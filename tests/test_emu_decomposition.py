@@ -132,3 +132,18 @@ def test_list_free_str_search_equals_find_str():
     r = subprocess.run([str(ROOT / "tests" / "emu" / "str_check"), "200000"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "mismatches=0" in r.stdout
+
+
+def test_emulated_pipeline_very_deep_columns():
+    """columns deeper than MAX_DEPTH = 20000 (snp_score.c:92, 1493-1500): counted, reported as VDEEP in the BED, not processed - their
+    reads keep whatever the other columns decided.  Two 16000x amplicons of 250 bp (26 666 reads pile up on the middle columns)."""
+    data, nr, nb = cb.simulate("C4", 0.01, seed=9, amplicon_depth=16000, n_amplicons=2, threads=2)
+    bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data); bb.finish()
+    m = valid_mask(bb)
+    for args in (["-9"], ["-1"]):
+        ref = run_oracle(data, args)
+        assert ref["bed"].count("VDEEP") >= 50
+        r = run_oracle(data, args, binary=EMU_BIN, kind="emu")
+        assert (r["qual"][m] == ref["qual"][m]).all() and r["bed"] == ref["bed"] and r["counters"] == ref["counters"]
+        r = run_oracle(data, args, binary=EMU_BIN, kind="emu", env_extra={"CRUMBLE_BATCH_READS": "7000"})
+        assert (r["qual"][m] == ref["qual"][m]).all() and r["bed"] == ref["bed"] and r["counters"] == ref["counters"]

@@ -242,3 +242,20 @@ def test_batcher_compact_planes_decode_back(preset, scale, bits):
         dq = np.array(list(b.qual_dict), np.uint8)[qc]
         assert np.array_equal(dq[valid], bb.qual()[valid])
     bb.close()
+
+
+TAGS = {"plain": ["-9"], "t": ["-9", "-t", "NM,BD"], "T": ["-9", "-T", "MD,XX,ZB"], "efg": ["-9", "-e", "5", "-f", "20", "-g", "40"],
+        "EFGt": ["-9", "-E", "7", "-F", "25", "-G", "45", "-t", "BI,BD,RG"], "all": ["-1", "-e", "1", "-f", "30", "-g", "2", "-E", "3", "-F", "10", "-G", "50", "-T", "BI"]}
+
+
+@pytest.mark.parametrize("tag", sorted(TAGS))
+def test_aux_tag_options_match_reference(tag):
+    """-t / -T tag lists and -e -f -g / -E -F -G BD / BI binarisation (purge_tags, snp_score.c:989-1054, 2031-2054) through the
+    product's host driver (here on the CPU emulation of the device): the WHOLE SAM output equals the reference's, record for record,
+    for reads carrying i, Z, A, f, H and B-array tags in shuffled order"""
+    from util import EMU_BIN
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "o.sam")
+        r = subprocess.run([str(EMU_BIN), "-z"] + TAGS[tag] + [str(GDIR / "tags.sam"), out], stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out).read() == open(GDIR / f"tags.{tag}.out.sam").read()
