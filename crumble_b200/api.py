@@ -114,7 +114,7 @@ EXPORTS = [
     "cg_algorithmic_bytes", "cg_aligned_bases", "cg_n_columns", "cg_params_default", "cg_params_level",
     "cgb_create", "cgb_destroy", "cgb_reset", "cgb_add", "cgb_add_bam_stream", "cgb_finish", "cgb_bytes", "cgb_reserve", "cgb_pack",
     "cg_carry_export", "cg_carry_import", "cg_carry_is_neutral", "cg_batch_ends", "cg_shard_begin", "cg_shard_carry", "cg_shard_end",
-    "cgm_create", "cgm_destroy", "cgm_n_devices", "cgm_process", "cgm_process_window", "cgm_last_error", "cgm_last_ms", "cgm_last_h2d_bytes", "cgm_context",
+    "cgm_create", "cgm_destroy", "cgm_n_devices", "cgm_process", "cgm_process_window", "cgm_last_error", "cgm_last_ms", "cgm_last_h2d_bytes", "cgm_context", "cgm_events",
 ]
 CARRY_BYTES = 128
 
@@ -348,7 +348,14 @@ class Crumble:
                 "counters": {k: int(res.counters[i]) for i, k in enumerate(COUNTER_NAMES)}}
 
     # region shards without speculation: begin (state-free part) on all shards, carry from left to right, end on all shards
-    def shard_begin(self, batch: Batch, window: Window, events_cap: int = 1 << 16, pinned_out=None):
+    def shard_begin(self, batch: Batch | None, window: Window, events_cap: int = 1 << 16, pinned_out=None):
+        """batch None: the batch ``upload`` left on the device (the chain alone, no copies: what bench.py times as `value`)"""
+        if batch is None:
+            res = Result(); ev = np.zeros(events_cap, dtype=EVENT_DTYPE)
+            res.events = ev.ctypes.data_as(C.POINTER(BedEvent)); res.events_cap = events_cap
+            self._shard = (None, (res, None, ev, None))
+            _check(self.lib, self.lib.cg_shard_begin(self.h, None, C.byref(window), C.byref(res)), self.h)
+            return
         self._shard = (batch, self._result(batch, False, events_cap, pinned_out))
         _check(self.lib, self.lib.cg_shard_begin(self.h, C.byref(batch), C.byref(window), C.byref(self._shard[1][0])), self.h)
 
@@ -361,6 +368,10 @@ class Crumble:
     def shard_end(self):
         batch, (res, qout, ev, _) = self._shard
         _check(self.lib, self.lib.cg_shard_end(self.h, C.byref(res)), self.h)
+        if batch is None:
+            self._shard = None
+            return {"qual": None, "events": ev[: min(int(res.n_events), int(res.events_cap))], "n_events": int(res.n_events),
+                    "counters": {k: int(res.counters[i]) for i, k in enumerate(COUNTER_NAMES)}}
         if res.n_events > res.events_cap:
             res2, qout2, ev, _ = self._result(batch, False, int(res.n_events), qout)
             _check(self.lib, self.lib.cg_download(self.h, C.byref(res2)), self.h)
@@ -662,7 +673,7 @@ class SimCfg(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_contigs", C.c_int), ("contig_len", C.c_int64), ("depth", C.c_double),
                 ("read_len", C.c_int), ("qual_binned", C.c_int), ("features_per_mb", C.c_double), ("amplicon", C.c_int),
                 ("n_amplicons", C.c_int), ("amplicon_len", C.c_int), ("amplicon_depth", C.c_int),
-                ("n_unmapped_tail", C.c_int), ("threads", C.c_int)]
+                ("n_unmapped_tail", C.c_int), ("threads", C.c_int), ("job_first", C.c_int), ("job_count", C.c_int), ("human_like", C.c_int)]
 
 
 def load_sim():

@@ -41,6 +41,7 @@ struct cg_multi {
     cgm_shard *sh; int n_sh;
     unsigned char carry_in0[CG_CARRY_BYTES]; int first_needs_carry;
     float last_ms; int64_t last_h2d;
+    cg_bed_event *ev; int64_t n_ev, cap_ev;                  /* all BED events of the last call, in order */
 };
 
 const char *cgm_last_error(const cg_multi *m) { return m ? m->err : "no context"; }
@@ -52,7 +53,7 @@ cg_ctx *cgm_context(cg_multi *m, int i) { return (m && i >= 0 && i < m->n) ? m->
 void cgm_destroy(cg_multi *m) {
     if (!m) return;
     for (int i = 0; i < m->n; i++) if (m->ctx && m->ctx[i]) cg_destroy(m->ctx[i]);
-    free(m->ctx); free(m->sh);
+    free(m->ctx); free(m->sh); free(m->ev);
     pthread_mutex_destroy(&m->mu); pthread_cond_destroy(&m->cv);
     free(m);
 }
@@ -278,12 +279,18 @@ int cgm_process_window(cg_multi *m, const cg_batch *in, const cg_window *win, cg
                     memcpy(out->qual_out + in->off[i], s->head + (in->off[i] - base), (size_t)in->l_qseq[i]);
                 }
             }
-            for (int64_t j = 0; j < s->res.n_events; j++, ne++) if (out->events && ne < out->events_cap) out->events[ne] = s->res.events[j];
+            if (ne + s->res.n_events > m->cap_ev) {
+                const int64_t nc = (ne + s->res.n_events) * 2 + 1024;
+                cg_bed_event *nv = (cg_bed_event *)realloc(m->ev, sizeof(cg_bed_event) * (size_t)nc);
+                if (!nv) { err = CG_ERR_NOMEM; goto fail; }
+                m->ev = nv; m->cap_ev = nc;
+            }
+            for (int64_t j = 0; j < s->res.n_events; j++, ne++) { m->ev[ne] = s->res.events[j]; if (out->events && ne < out->events_cap) out->events[ne] = s->res.events[j]; }
             for (int c = 0; c < CG_N_COUNTERS; c++) out->counters[c] += s->res.counters[c];
             if (s->ms_total > m->last_ms) m->last_ms = s->ms_total;
             m->last_h2d += cg_last_h2d_bytes(m->ctx[k]);
         }
-        out->n_events = ne; out->n_columns = 0;
+        out->n_events = ne; out->n_columns = 0; m->n_ev = ne;
         cgm_shard *lastS = &m->sh[N - 1];
         m->have_carry = lastS->has_right;
         if (lastS->has_right) memcpy(m->carry, lastS->carry_out, CG_CARRY_BYTES);
@@ -295,3 +302,9 @@ fail:
 }
 
 int cgm_process(cg_multi *m, const cg_batch *in, cg_result *out) { return cgm_process_window(m, in, NULL, out); }
+
+/* the BED events of the last call again (a caller whose event buffer was too small): returns how many there are */
+int64_t cgm_events(const cg_multi *m, cg_bed_event *buf, int64_t cap) {
+    for (int64_t i = 0; i < m->n_ev && i < cap; i++) buf[i] = m->ev[i];
+    return m->n_ev;
+}

@@ -432,11 +432,19 @@ int simgen_preset(simgen_cfg *cfg, const char *name, double scale, uint64_t seed
         cfg->amplicon_len = 250; cfg->amplicon_depth = 1000;
         cfg->contig_len = (int64_t)cfg->n_amplicons * 10000 + 20000; cfg->features_per_mb = 0;
     }
-    else if (!strcmp(name, "C5")) { cfg->n_contigs = 24; cfg->contig_len = (int64_t)(129000000 * scale); cfg->qual_binned = 1; }
+    else if (!strcmp(name, "C5")) { cfg->n_contigs = 24; cfg->contig_len = (int64_t)(129000000 * scale); cfg->qual_binned = 1; cfg->human_like = 1; }
     else if (!strcmp(name, "tiny")) { cfg->contig_len = (int64_t)(50000 * scale); cfg->features_per_mb = 60; cfg->n_contigs = 2; }
     else return -1;
     if (cfg->contig_len < 2000) cfg->contig_len = 2000;
     return 0;
+}
+
+/* human-like contig lengths (Mb, chr1..22, X, Y: sum 3088), scaled to the configured total */
+static int64_t contig_length(const simgen_cfg *cfg, int t) {
+    static const int mb[24] = { 248, 242, 198, 190, 181, 171, 159, 145, 138, 133, 135, 133, 114, 107, 102, 90, 83, 80, 58, 64, 46, 50, 156, 57 };
+    if (!cfg->human_like) return cfg->contig_len;
+    int64_t l = (int64_t)((double)cfg->contig_len * cfg->n_contigs * mb[t % 24] / 3088.0);
+    return l < 2000 ? 2000 : l;
 }
 
 int simgen_generate(const simgen_cfg *cfg, uint8_t **out, size_t *out_len, int64_t *n_reads, int64_t *n_bases) {
@@ -449,8 +457,8 @@ int simgen_generate(const simgen_cfg *cfg, uint8_t **out, size_t *out_len, int64
     /* header */
     char text[8192]; int tl = snprintf(text, sizeof text, "@HD\tVN:1.6\tSO:coordinate\n");
     for (int t = 0; t < cfg->n_contigs; t++) {
-        if (cfg->n_contigs == 1) tl += snprintf(text + tl, sizeof text - (size_t)tl, "@SQ\tSN:chr20\tLN:%lld\n", (long long)cfg->contig_len);
-        else tl += snprintf(text + tl, sizeof text - (size_t)tl, "@SQ\tSN:chr%d\tLN:%lld\n", t + 1, (long long)cfg->contig_len);
+        if (cfg->n_contigs == 1) tl += snprintf(text + tl, sizeof text - (size_t)tl, "@SQ\tSN:chr20\tLN:%lld\n", (long long)contig_length(cfg, t));
+        else tl += snprintf(text + tl, sizeof text - (size_t)tl, "@SQ\tSN:chr%d\tLN:%lld\n", t + 1, (long long)contig_length(cfg, t));
     }
     ob_reserve(&all, (size_t)tl + 64 + 64 * (size_t)cfg->n_contigs);
     memcpy(all.p, "BAM\1", 4); put32(all.p + 4, (uint32_t)tl); memcpy(all.p + 8, text, (size_t)tl);
@@ -460,25 +468,29 @@ int simgen_generate(const simgen_cfg *cfg, uint8_t **out, size_t *out_len, int64
         char nm[32]; int nl = cfg->n_contigs == 1 ? snprintf(nm, sizeof nm, "chr20") : snprintf(nm, sizeof nm, "chr%d", t + 1);
         put32(all.p + all.n, (uint32_t)nl + 1); all.n += 4;
         memcpy(all.p + all.n, nm, (size_t)nl + 1); all.n += (size_t)nl + 1;
-        put32(all.p + all.n, (uint32_t)cfg->contig_len); all.n += 4;
+        put32(all.p + all.n, (uint32_t)contig_length(cfg, t)); all.n += 4;
     }
+    int tail = 1;
     for (int t = 0; t < cfg->n_contigs; t++) {
-        contig c; contig_build(&c, cfg, t, cfg->contig_len);
+        const int64_t clen = contig_length(cfg, t);
+        contig c; contig_build(&c, cfg, t, clen);
         pool_t pl; memset(&pl, 0, sizeof pl); pthread_mutex_init(&pl.mu, NULL);
         if (cfg->amplicon) {
             pl.njobs = cfg->n_amplicons;
             pl.jobs = (job_t *)calloc((size_t)pl.njobs, sizeof(job_t));
             for (int a = 0; a < pl.njobs; a++) { job_t *j = &pl.jobs[a]; j->c = &c; j->cfg = cfg; j->id = a; j->beg = 10000 + a * 10000; j->amp = 1; }
         } else {
-            const int CH = 1 << 18;
-            pl.njobs = (int)((cfg->contig_len + CH - 1) / CH);
+            const int CH = SIMGEN_CHUNK;
+            pl.njobs = (int)((clen + CH - 1) / CH);
             pl.jobs = (job_t *)calloc((size_t)pl.njobs, sizeof(job_t));
             for (int k = 0; k < pl.njobs; k++) {
                 job_t *j = &pl.jobs[k]; j->c = &c; j->cfg = cfg; j->id = k; j->beg = k * CH;
-                int64_t e = (int64_t)(k + 1) * CH, lim = cfg->contig_len - cfg->read_len - 60;
+                int64_t e = (int64_t)(k + 1) * CH, lim = clen - cfg->read_len - 60;
                 if (e > lim) e = lim;
                 j->end = (int)e; if (j->end < j->beg) j->end = j->beg;
+                if (cfg->job_count > 0 && (k < cfg->job_first || k >= cfg->job_first + cfg->job_count)) j->end = j->beg;   /* not this caller's chunk */
             }
+            if (cfg->job_count > 0 && (t + 1 < cfg->n_contigs || cfg->job_first + cfg->job_count < pl.njobs)) tail = 0;
         }
         int nt = nthreads < pl.njobs ? nthreads : pl.njobs;
         pthread_t th[256];
@@ -497,7 +509,7 @@ int simgen_generate(const simgen_cfg *cfg, uint8_t **out, size_t *out_len, int64
     }
     /* trailing unmapped reads (tid = -1) */
     rng_t r; rng_seed(&r, cfg->seed, 77);
-    for (int i = 0; i < cfg->n_unmapped_tail; i++) {
+    for (int i = 0; tail && i < cfg->n_unmapped_tail; i++) {
         rd_t rd; rd.ncig = 0; rd.reflen = 0; rd.l = cfg->read_len;
         for (int k = 0; k < rd.l; k++) { rd.base[k] = (uint8_t)(rng_u32(&r) & 3); rd.qual[k] = (uint8_t)qual_draw(&r, k, rd.l, cfg->qual_binned); }
         char name[32]; snprintf(name, sizeof name, "u%d", i);

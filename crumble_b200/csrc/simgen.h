@@ -15,6 +15,7 @@
 extern "C" {
 #endif
 
+#define SIMGEN_CHUNK (1 << 18)     /* reads are generated per chunk of this many reference positions, each with its own random stream */
 typedef struct {
     uint64_t seed;
     int      n_contigs;          /* contigs are named chr1..chrN (or "chr20" when n_contigs==1 and wgs) */
@@ -29,6 +30,11 @@ typedef struct {
     int      amplicon_depth;     /* 1000 */
     int      n_unmapped_tail;    /* trailing tid=-1 reads */
     int      threads;            /* generator threads (<=0: all cores) */
+    /* whole-genome mode only: generate the reads starting in 256 kb chunks [job_first, job_first + job_count) of every contig
+     * (job_count <= 0: all).  The chunks of a contig concatenate to exactly the full stream, so a rank of a multi-GPU run can make
+     * just its own region shard; the trailing unmapped reads come with the last chunk only. */
+    int      job_first, job_count;
+    int      human_like;         /* 1: contig t gets the length of human chromosome t+1 (1..22, X, Y) scaled so that they sum to n_contigs * contig_len */
 } simgen_cfg;
 
 /* named presets: "C1" (1 Mb 30x continuous quals), "C2" (64 Mb 30x binned), "C4" (amplicon),

@@ -166,6 +166,7 @@ int transcode_gpu(crumble_opts *o, samFile *in, samFile *out, bam_hdr_t *header,
     live_q lq = {0};
     cg_batch_builder *bb = NULL;
     cg_ctx *ctx = NULL;
+    cg_multi *mg = NULL;                                    /* CRUMBLE_GPUS > 1: every call of the chain is spread over the GPUs of the box (cg_multi.c) */
     cg_result res; memset(&res, 0, sizeof(res));
     int64_t qcap = 0;
     int64_t count_in = 0, count_out = 0;
@@ -183,6 +184,13 @@ int transcode_gpu(crumble_opts *o, samFile *in, samFile *out, bam_hdr_t *header,
     int64_t batch_reads = 512 << 10;
     const char *ev = getenv("CRUMBLE_BATCH_READS");
     if (ev && atoll(ev) > 0) batch_reads = atoll(ev);
+    int n_gpus = 1;
+    if (getenv("CRUMBLE_GPUS") && atoi(getenv("CRUMBLE_GPUS")) > 1 && !h_iter) {
+        n_gpus = atoi(getenv("CRUMBLE_GPUS"));
+        if (n_gpus > cg_device_count()) n_gpus = cg_device_count();
+        if (n_gpus < 1) n_gpus = 1;
+        if (!(ev && atoll(ev) > 0)) batch_reads *= n_gpus;  /* one shard of the usual size per device */
+    }
     if (h_iter) batch_reads = INT64_MAX;                    /* a -r region is one call: the region logic owns the column limits */
 
     if (!(bb = cgb_create(1))) goto done;
@@ -190,8 +198,13 @@ int transcode_gpu(crumble_opts *o, samFile *in, samFile *out, bam_hdr_t *header,
         const int64_t rsv = (batch_reads < (4 << 20) ? batch_reads : (4 << 20)) + 4096;
         if (!h_iter && cgb_reserve(bb, rsv, rsv * 160, rsv * 2) != 0) goto done;
     }
-    ctx = cg_create(&p, o->device, &err);
-    if (!ctx) { fprintf(stderr, "crumble: cannot create GPU context: %s\n", cg_strerror(err)); goto done; }
+    if (n_gpus > 1) {
+        mg = cgm_create(&p, n_gpus, NULL, &err);
+        if (!mg) { fprintf(stderr, "crumble: cannot create %d GPU contexts: %s\n", n_gpus, cg_strerror(err)); goto done; }
+    } else {
+        ctx = cg_create(&p, o->device, &err);
+        if (!ctx) { fprintf(stderr, "crumble: cannot create GPU context: %s\n", cg_strerror(err)); goto done; }
+    }
     res.events_cap = 1 << 16;
     if (getenv("CRUMBLE_EVENTS_CAP") && atoll(getenv("CRUMBLE_EVENTS_CAP")) > 0) res.events_cap = atoll(getenv("CRUMBLE_EVENTS_CAP"));   /* tests: force the regrow path */
     res.events = (cg_bed_event *)malloc(sizeof(cg_bed_event) * (size_t)res.events_cap);
@@ -274,17 +287,18 @@ int transcode_gpu(crumble_opts *o, samFile *in, samFile *out, bam_hdr_t *header,
                 break;
             }
         } else {
-            err = cg_process_window(ctx, &batch, &win, &res);
+            err = mg ? cgm_process_window(mg, &batch, &win, &res) : cg_process_window(ctx, &batch, &win, &res);
             if (err == CG_OK && res.n_events > res.events_cap) {                /* the chain's state has moved on: fetch again, do not redo */
                 res.events_cap = res.n_events;
                 cg_bed_event *ne = (cg_bed_event *)realloc(res.events, sizeof(cg_bed_event) * (size_t)res.events_cap);
                 if (!ne) goto done;
                 res.events = ne;
-                err = cg_download(ctx, &res);
+                if (mg) cgm_events(mg, res.events, res.events_cap);
+                else { uint8_t *q = res.qual_out; res.qual_out = NULL; err = cg_download(ctx, &res); res.qual_out = q; }
             }
         }
-        if (err) { fprintf(stderr, "crumble: GPU path failed: %s (%s)\n", cg_strerror(err), cg_last_error(ctx)); goto done; }
-        device_ms += cg_last_ms(ctx, CG_T_TOTAL);
+        if (err) { fprintf(stderr, "crumble: GPU path failed: %s (%s)\n", cg_strerror(err), mg ? cgm_last_error(mg) : cg_last_error(ctx)); goto done; }
+        device_ms += mg ? cgm_last_ms(mg) : cg_last_ms(ctx, CG_T_TOTAL);
         double tk3 = TICK(); t_dev += tk3 - tk2;
         write_bed(o, header, &res);
         for (int i = 0; i < CG_N_COUNTERS; i++) o->counters[i] += res.counters[i];
@@ -371,6 +385,7 @@ done:
     lq_free(&lq);
     free(res.qual_out); free(res.events);
     if (ctx) cg_destroy(ctx);
+    if (mg) cgm_destroy(mg);
     if (bb) cgb_destroy(bb);
     return ret;
 }

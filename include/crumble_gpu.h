@@ -240,6 +240,7 @@ const char *cgm_last_error(const cg_multi *m);
 float       cgm_last_ms(const cg_multi *m);                 /* slowest shard's device time of the last call */
 int64_t     cgm_last_h2d_bytes(const cg_multi *m);
 cg_ctx     *cgm_context(cg_multi *m, int i);                /* borrowed */
+int64_t     cgm_events(const cg_multi *m, cg_bed_event *buf, int64_t cap);   /* the last call's BED events again; returns their number */
 
 /* measurement helpers */
 enum { CG_T_TOTAL = 0, CG_T_TILES, CG_T_COLUMNS, CG_T_FLAGGED, CG_T_DEPTH, CG_T_CHAIN, CG_T_REWRITE, CG_T_CELLS, CG_T_EVENTS, CG_T_H2D, CG_T_D2H, CG_N_TIMERS };
