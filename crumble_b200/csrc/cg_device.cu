@@ -17,6 +17,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <pthread.h>
+#include <unistd.h>
 #include "cg_host.h"
 #include "cg_column_lean.h"
 
@@ -180,6 +182,7 @@ __global__ void k_finish_read(const __grid_constant__ CgDev D, const int32_t *n_
     if (j < np) {
         cg_finish_read(&D, j, D.ks[0]);
         if (j == np - 1) dims[1] = D.pmaxcol[j];     /* n_cols */
+        if (D.glist && !(D.rd[j].rf & CG_RF_SIMPLE)) D.glist[atomicAdd(D.n_glist, 1)] = j;   /* k_cells_general's work list */
     }
     if (j == 0 && np == 0) dims[1] = 0;
 }
@@ -264,16 +267,15 @@ __global__ void __launch_bounds__(256) k_cells(const __grid_constant__ CgDev D, 
         row[k] = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
-/* reads with a non-trivial CIGAR: a warp scans 32 reads and resolves the general ones among them one at a time, lane = column */
+/* reads with a non-trivial CIGAR (listed by k_finish_read, a few percent of all): one warp per read, lane = column; the list is in no
+ * particular order, a launch takes the entries inside its range of pileup reads */
 __global__ void __launch_bounds__(256) k_cells_general(const __grid_constant__ CgDev D, int j_begin, int j_end) {
     const int lane = threadIdx.x & 31;
-    const int jw = j_begin + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5) * 32;
-    if (jw >= j_end) return;
-    const int j = jw + lane;
-    unsigned gm = __ballot_sync(0xffffffffu, j < j_end && !(D.rd[j].rf & CG_RF_SIMPLE));
+    const int nw = (int)((gridDim.x * (unsigned)blockDim.x) >> 5), total = *D.n_glist;
     const int doB = D.P.min_qual_B != 0;
-    while (gm) {
-        const int g = jw + __ffs(gm) - 1; gm &= gm - 1;
+    for (int gi = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5); gi < total; gi += nw) {
+        const int g = D.glist[gi];
+        if (g < j_begin || g >= j_end) continue;
         const CgRead q = D.rd[g];
         const CgCellRec cr = D.crec[g];
         uint16_t *row = D.cells + (size_t)cr.cpos8 * 8;
@@ -581,8 +583,28 @@ struct CgEpoch { int32_t col_begin; int32_t pad; int64_t td_base, tc_base, d_off
 /* what a slice of columns hands to the next one: the contig whose running sums are open, and the prefix sums so far */
 struct CgEpochCarry { int32_t tid, valid; int64_t td, tc, d_off, c_off; int64_t dsum_last; int32_t csum_last, n_ep; };
 
+/* first index in [lo, hi) with csum[index] >= want, by the whole warp: 32-way splits instead of halving (the dependent global loads of
+ * a one-thread binary search were most of this kernel's time, and the kernel sits on the serial path between region shards) */
+__device__ __forceinline__ int epoch_lower_bound(const int32_t *csum, int lo, int hi, int64_t want) {
+    const int lane = threadIdx.x & 31;
+    while (hi - lo > 32) {
+        const int step = (hi - lo + 31) >> 5;
+        const int i = lo + lane * step;                      /* lane probes the first element of its part */
+        const bool ge = i < hi ? (int64_t)csum[i] >= want : true;
+        const unsigned m = __ballot_sync(0xffffffffu, ge);   /* parts whose first element already reaches want */
+        const int f = m ? __ffs(m) - 1 : 32;                 /* the answer lies in part f - 1 (after its first element) or is part f's first element */
+        if (f == 0) return lo;
+        const int nlo = lo + (f - 1) * step + 1, nhi = f < 32 ? lo + f * step : hi;
+        lo = nlo; hi = nhi < hi ? nhi : hi;
+    }
+    const int i = lo + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, i < hi ? (int64_t)csum[i] >= want : true);
+    const int f = m ? __ffs(m) - 1 : 32;                     /* exactly 32 left and none reaches want: hi */
+    return lo + f < hi ? lo + f : hi;
+}
+
 __global__ void k_epochs(const __grid_constant__ CgDev D, CgEpoch *ep, CgEpochCarry *carry, int cap, int cb, int ce) {
-    if (threadIdx.x || blockIdx.x) return;
+    if (blockIdx.x || threadIdx.x >= 32) return;             /* one warp: lanes take part in the searches, lane 0's state is the state */
     int ne = carry->n_ep;
     int is = cg_island_of(&D, cb);
     while (is < D.n_islands && D.isl[is].col_start < ce) {
@@ -606,9 +628,7 @@ __global__ void k_epochs(const __grid_constant__ CgDev D, CgEpoch *ep, CgEpochCa
         for (;;) {
             /* first column in [s,c1) whose counted index makes total_col exceed 2^20 */
             int64_t want = c_off + (1024 * 1024 + 1 - tc);
-            int lo = s, hi = c1;
-            while (lo < hi) { int mid = (lo + hi) >> 1; if ((int64_t)D.csum[mid] < want) lo = mid + 1; else hi = mid; }
-            int c = lo;
+            int c = epoch_lower_bound(D.csum, s, c1, want);
             while (c < c1 && !((D.ev[c] & CG_EV_PROCESSED) && (D.ev[c] & CG_EV_COUNTED))) c++;
             if (c >= c1) break;
             td = (td + (D.dsum[c] - d_off)) >> 1;
@@ -865,7 +885,32 @@ __device__ __forceinline__ void rw_mbar_wait(unsigned long long *bar, uint32_t p
     if (!ok) __trap();
 }
 
-__global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ CgDev D, int64_t rec_begin, int64_t rec_end) {
+/* the compact output of one record (thread per record): mask bytes of its words into mk[], returns the number of exception bytes */
+__device__ __forceinline__ int rw_compact_count(const uint8_t *q, int L, uint32_t dom, uint8_t *mk) {
+    const uint64_t D8 = (uint64_t)dom * 0x0101010101010101ULL;
+    int cnt = 0;
+    for (int w = 0; 8 * w < L; w++) {
+        const uint64_t x = *reinterpret_cast<const uint64_t *>(q + 8 * w) ^ D8;          /* zero bytes where equal */
+        const uint64_t nz = ((x & 0x7f7f7f7f7f7f7f7fULL) + 0x7f7f7f7f7f7f7f7fULL) | x;  /* bit 7 of every non-zero byte */
+        uint32_t m8 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) m8 |= (uint32_t)((~nz >> (8 * k + 7)) & 1ULL) << k;
+        const int rem = L - 8 * w;
+        if (rem < 8) m8 |= 0xffu << rem;                                                 /* padding: "equal" */
+        m8 &= 0xffu;
+        mk[w] = (uint8_t)m8;
+        cnt += 8 - __popc(m8);
+    }
+    return cnt;
+}
+__device__ __forceinline__ void rw_compact_emit(const uint8_t *q, int L, const uint8_t *mk, uint8_t *dst) {
+    for (int w = 0; 8 * w < L; w++) {
+        uint32_t x = (~(uint32_t)mk[w]) & 0xffu;
+        while (x) { const int k = __ffs(x) - 1; x &= x - 1; *dst++ = q[8 * w + k]; }
+    }
+}
+
+__global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ CgDev D, int64_t rec_begin, int64_t rec_end, int64_t blk_base) {
     __shared__ RwSmem S;
     const CgDevParams *P = &D.P;
     const CgTables *T = D.T;
@@ -925,10 +970,26 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
     }
     __syncthreads();
     const long long qa = S.rng[0], qbytes = S.rng[1], sa = S.rng[2], ca = S.rng[4], cbytes = S.rng[5];
-    if (qbytes == 0) return;                                   /* nothing but empty records */
+    if (qbytes == 0) { if (D.cq_mask && threadIdx.x == 0) D.cq_blk[blk_base + blockIdx.x] = 0; return; }   /* nothing but empty records */
     if (cbytes < 0) {                                          /* ranges too long for the staging buffers */
         const int64_t r = base + threadIdx.x;
         if (r < rec_end) cg_rewrite(&D, r, nf);
+        if (D.cq_mask) {                                       /* compact form straight from the flat output (each record's words are its own) */
+            __shared__ int cnts[RW_THREADS];
+            __shared__ unsigned long long fb_base;
+            int cnt = 0;
+            if (r < rec_end && L > 0) cnt = rw_compact_count(D.qual_out + off, L, (uint32_t)D.cq_dom, D.cq_mask + (off >> 3));
+            cnts[threadIdx.x] = cnt;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long tot = 0;
+                for (int i = 0; i < RW_THREADS; i++) { const int c = cnts[i]; cnts[i] = (int)tot; tot += (unsigned long long)c; }
+                fb_base = atomicAdd(D.cq_count, tot);
+                D.cq_blk[blk_base + blockIdx.x] = (int64_t)fb_base;
+            }
+            __syncthreads();
+            if (cnt) rw_compact_emit(D.qual_out + off, L, D.cq_mask + (off >> 3), D.cq_exc + fb_base + (unsigned)cnts[threadIdx.x]);
+        }
         return;
     }
     const int nwords = (int)(qbytes >> 3);
@@ -1089,6 +1150,34 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
             else rw_pblock_rle(S.q + m.qoff, S.wmap + (m.qoff >> 3), (int)(m.lk & RW_L_M), P->pblock, P->qcap);
         }
     }
+    /* ---- phase C': compact output (mask + exceptions) instead of the flat range ---- */
+    if (D.cq_mask) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < (nwords + 3) >> 2; i += RW_THREADS) reinterpret_cast<uint32_t *>(S.wmap)[i] = 0xffffffffu;   /* words of no record: all "equal" */
+        __syncthreads();
+        const RwMeta m = S.m[threadIdx.x];
+        const int Lm = ((m.lk >> RW_KIND_SH) & 3u) ? (int)(m.lk & RW_L_M) : 0;
+        const int cnt = Lm ? rw_compact_count(S.q + m.qoff, Lm, (uint32_t)D.cq_dom, S.wmap + (m.qoff >> 3)) : 0;
+        /* exclusive prefix of the counts over the block's records */
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane == 31) S.red[w][3] = inc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long tot = 0;
+            for (int i = 0; i < RW_THREADS / 32; i++) { const long long c = S.red[i][3]; S.red[i][3] = tot; tot += c; }
+            const unsigned long long b0 = atomicAdd(D.cq_count, (unsigned long long)tot);
+            S.red[0][2] = (long long)b0;
+            D.cq_blk[blk_base + blockIdx.x] = (int64_t)b0;
+        }
+        __syncthreads();
+        if (cnt) rw_compact_emit(S.q + m.qoff, Lm, S.wmap + (m.qoff >> 3), D.cq_exc + S.red[0][2] + S.red[w][3] + (inc - cnt));
+        /* the mask bytes of the block's own words [lo, hi8) */
+        const long long lo = S.red[0][0], hi8 = (S.red[0][1] + 7) & ~7LL;
+        for (long long i = ((lo - qa) >> 3) + threadIdx.x; i < ((hi8 - qa) >> 3); i += RW_THREADS) D.cq_mask[(qa >> 3) + i] = S.wmap[i];
+        return;
+    }
     /* ---- phase C: the block's output range ---- */
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
@@ -1177,7 +1266,7 @@ struct dbuf { void *p; size_t cap; };
 
 #define CG_MAX_CHUNKS 32
 struct CgBounds { int64_t rb[CG_MAX_CHUNKS]; int32_t n; };
-struct CgSlice { int t0, t1, c0, c1, jb, je, kb, ke, chunk, save_after; int64_t r0, r1; };   /* see slice_A / slice_B */
+struct CgSlice { int t0, t1, c0, c1, jb, je, kb, ke, chunk, save_after, synced; int64_t r0, r1; };   /* see slice_A / slice_B */
 
 struct cg_ctx {
     int device; cudaStream_t stream; int own_stream;
@@ -1185,7 +1274,7 @@ struct cg_ctx {
     char err[512];
     /* device buffers */
     dbuf b_tid, b_pos, b_flag, b_mapq, b_lq, b_nc, b_off, b_coff, b_cigar, b_seq, b_qual, b_qout;
-    dbuf b_jmap, b_rspan, b_rd, b_ks, b_ke, b_gap, b_gapraw, b_pmax, b_orig, b_rbf;
+    dbuf b_jmap, b_rspan, b_rd, b_ks, b_ke, b_gap, b_gapraw, b_pmax, b_orig, b_rbf, b_glist;
     dbuf b_tlo, b_tstart, b_isl, b_cb, b_ev, b_depth, b_dump, b_dsum, b_csum, b_fcol, b_trig, b_twin;
     dbuf b_aggr, b_scal, b_scratch, b_epoch, b_events, b_chain, b_items, b_bed, b_bedpm, b_crec, b_cells, b_seq2, b_qualp, b_exc;
     int generic;                  /* cg_params_generic(): column and rewrite stages through the plain bodies */
@@ -1203,8 +1292,16 @@ struct cg_ctx {
     int packed, offsets_ready; int64_t h2d_bytes;                           /* offsets rebuilt on the device; bytes copied up by the last call */       /* chained calls: this call's window, the carries of the previous one */
     cudaStream_t s_h2d, s_d2h; cudaEvent_t ev_up[32], ev_done[32], ev_misc;
     char h_carry_init[64];
+    /* compact download of the rewritten qualities (k_rewrite phase C'): device planes, pinned host copies, the slices in flight */
+    dbuf b_cqmask, b_cqexc, b_cqblk;
+    uint8_t *h_cqmask, *h_cqexc; int64_t *h_cqblk; size_t h_cqmask_cap, h_cqexc_cap, h_cqblk_cap;
+    struct CgCqSlice { int64_t r0, r1, blk0, nblk; } cq_sl[2 * CG_MAX_CHUNKS + 2];
+    int cq_on, cq_n, cq_done; int64_t cq_blk_total; unsigned long long cq_exc_copied; int64_t cq_blk_copied;
+    cudaEvent_t cq_ev[2 * CG_MAX_CHUNKS + 2]; int cq_ev_made;
+    pthread_mutex_t cq_mu; pthread_cond_t cq_cv; int cq_ready, cq_quit, cq_sync_made;
+    const cg_batch *cq_in; cg_result *cq_out;
     char *h_carry_io;                                           /* pinned: [0, 128) the state a shard imported, [128, 256) the one it exports */
-    CgSlice sl[2 * CG_MAX_CHUNKS + 2]; int n_sl, shard_state, shard_next, shard_save_end; const cg_batch *shard_in;
+    CgSlice sl[2 * CG_MAX_CHUNKS + 2]; int n_sl, shard_state, shard_next, shard_save_end, shard_timed; const cg_batch *shard_in;
     cudaEvent_t ev[CG_N_TIMERS][2];
     float ms[CG_N_TIMERS];
     int64_t launches;
@@ -1303,13 +1400,18 @@ extern "C" void cg_destroy(cg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     dbuf *all[] = { &ctx->b_tid, &ctx->b_pos, &ctx->b_flag, &ctx->b_mapq, &ctx->b_lq, &ctx->b_nc, &ctx->b_off, &ctx->b_coff, &ctx->b_cigar,
         &ctx->b_seq, &ctx->b_qual, &ctx->b_qout, &ctx->b_jmap, &ctx->b_rspan, &ctx->b_rd, &ctx->b_ks, &ctx->b_ke, &ctx->b_gap, &ctx->b_gapraw,
-        &ctx->b_pmax, &ctx->b_orig, &ctx->b_rbf, &ctx->b_tlo, &ctx->b_tstart, &ctx->b_isl, &ctx->b_cb, &ctx->b_ev, &ctx->b_depth, &ctx->b_dump,
-        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain, &ctx->b_items, &ctx->b_bed, &ctx->b_bedpm, &ctx->b_saved, &ctx->b_crec, &ctx->b_cells, &ctx->b_seq2, &ctx->b_qualp, &ctx->b_exc };
+        &ctx->b_pmax, &ctx->b_orig, &ctx->b_rbf, &ctx->b_glist, &ctx->b_tlo, &ctx->b_tstart, &ctx->b_isl, &ctx->b_cb, &ctx->b_ev, &ctx->b_depth, &ctx->b_dump,
+        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain, &ctx->b_items, &ctx->b_bed, &ctx->b_bedpm, &ctx->b_saved, &ctx->b_crec, &ctx->b_cells, &ctx->b_seq2, &ctx->b_qualp, &ctx->b_exc, &ctx->b_cqmask, &ctx->b_cqexc, &ctx->b_cqblk };
     for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); i++) if (all[i]->p) cudaFree(all[i]->p);
     if (ctx->dT) cudaFree(ctx->dT);
     if (ctx->h_dims) cudaFreeHost(ctx->h_dims);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_carry_io) cudaFreeHost(ctx->h_carry_io);
+    if (ctx->h_cqmask) cudaFreeHost(ctx->h_cqmask);
+    if (ctx->h_cqexc) cudaFreeHost(ctx->h_cqexc);
+    if (ctx->h_cqblk) cudaFreeHost(ctx->h_cqblk);
+    for (int i = 0; i < ctx->cq_ev_made; i++) cudaEventDestroy(ctx->cq_ev[i]);
+    if (ctx->cq_sync_made) { pthread_mutex_destroy(&ctx->cq_mu); pthread_cond_destroy(&ctx->cq_cv); }
     for (int i = 0; i < CG_N_TIMERS; i++) for (int k = 0; k < 2; k++) if (ctx->ev[i][k]) cudaEventDestroy(ctx->ev[i][k]);
     if (ctx->s_h2d) { cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h); for (int i = 0; i < 32; i++) { cudaEventDestroy(ctx->ev_up[i]); cudaEventDestroy(ctx->ev_done[i]); } cudaEventDestroy(ctx->ev_misc); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1514,7 +1616,8 @@ struct StI32Carry { int32_t *p; const CgEpochCarry *cy; __device__ void operator
 
 /* scalars on the device (b_scal): int32 [0] n_pile [1] n_cols [2] n_islands [3] n_flagged of the slice [4] maxdepth [5] err
  * [6] n_events [7] - [8] beyond [9] window max [10] STR items [12..13] packed quality bytes [14] packed CIGAR ops
- * [16..17] cell groups [18] tile counter of k_column [20..21] STR item bound of the slice; counters at +128 B; chain carry at +512 B; epoch carry at +640 B; bounds at +768 B */
+ * [16..17] cell groups [18] tile counter of k_column [20..21] STR item bound of the slice [22..23] compact-download exception count
+ * [24] reads with a non-trivial CIGAR; counters at +128 B; chain carry at +512 B; epoch carry at +640 B; bounds at +768 B */
 static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
     cudaStream_t st = ctx->stream;
     CgDev *D = &ctx->D;
@@ -1537,11 +1640,12 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
     if ((e = ensure(ctx, &ctx->b_jmap, n1 * 4)) || (e = ensure(ctx, &ctx->b_rspan, n1 * 4)) || (e = ensure(ctx, &ctx->b_rd, n1 * sizeof(CgRead))) ||
         (e = ensure(ctx, &ctx->b_ks, n1 * 8)) || (e = ensure(ctx, &ctx->b_ke, n1 * 8)) || (e = ensure(ctx, &ctx->b_gap, n1 * 8)) ||
         (e = ensure(ctx, &ctx->b_gapraw, n1 * 8)) || (e = ensure(ctx, &ctx->b_pmax, n1 * 4)) || (e = ensure(ctx, &ctx->b_orig, n1 * 4)) ||
-        (e = ensure(ctx, &ctx->b_rbf, n1)) || (e = ensure(ctx, &ctx->b_isl, n1 * sizeof(CgIsland)))) return e;
+        (e = ensure(ctx, &ctx->b_rbf, n1)) || (e = ensure(ctx, &ctx->b_isl, n1 * sizeof(CgIsland))) || (e = ensure(ctx, &ctx->b_glist, n1 * 4))) return e;
     D->jmap = (int32_t *)ctx->b_jmap.p; D->rspan = (int32_t *)ctx->b_rspan.p; D->rd = (CgRead *)ctx->b_rd.p;
     D->ks = (int64_t *)ctx->b_ks.p; D->ke = (int64_t *)ctx->b_ke.p; D->gap = (int64_t *)ctx->b_gap.p;
     D->pmaxcol = (int32_t *)ctx->b_pmax.p; D->orig = (int32_t *)ctx->b_orig.p; D->r_bf = (uint8_t *)ctx->b_rbf.p;
     D->isl = (CgIsland *)ctx->b_isl.p;
+    D->glist = ctx->generic ? NULL : (int32_t *)ctx->b_glist.p; D->n_glist = scal + 24;
     int64_t *gapraw = (int64_t *)ctx->b_gapraw.p;
 
     T0(CG_T_TILES);
@@ -1657,6 +1761,8 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
  * A single context runs A, B1, B2 slice after slice.  Region shards on several devices (cg_shard_*) run A for all their slices at
  * once, pass the carry from shard to shard through B1 alone, and run B2 concurrently again. */
 
+static void cq_bind(cg_ctx *ctx);
+
 static int slice_A(cg_ctx *ctx, CgSlice *s, int timed) {
     cudaStream_t st = ctx->stream;
     CgDev *D = &ctx->D;
@@ -1668,7 +1774,7 @@ static int slice_A(cg_ctx *ctx, CgSlice *s, int timed) {
     if (timed) T0(CG_T_CELLS);
     if (s->je > s->jb && !ctx->generic) {                       /* cell rows of the pileup reads whose bases have landed */
         k_cells<<<nblk((int64_t)(s->je - s->jb) * 4, 256), 256, 0, st>>>(*D, s->jb, s->je);
-        k_cells_general<<<nblk((int64_t)(s->je - s->jb), 256), 256, 0, st>>>(*D, s->jb, s->je);
+        k_cells_general<<<148 * 4, 256, 0, st>>>(*D, s->jb, s->je);
         ctx->launches += 2;
     }
     if (timed) { T1(CG_T_CELLS); T0(CG_T_COLUMNS); }
@@ -1691,6 +1797,7 @@ static int slice_A(cg_ctx *ctx, CgSlice *s, int timed) {
         k_publish<<<1, 32, 0, st>>>(scal, ctx->d_hdims, 24); ctx->launches++;
         CG_CHECK(cudaStreamSynchronize(st));
         nfs = ctx->h_dims[3];
+        s->synced = 1;                                          /* h_dims is current: n_flagged, STR item bound, compact-download exception count */
     }
     const int ke = kb + nfs;
     if ((e = ensure_keep(ctx, &ctx->b_trig, ((size_t)ke + 1) * sizeof(CgTrig))) || (e = ensure_keep(ctx, &ctx->b_twin, ((size_t)ke + 1) * sizeof(CgWin)))) return e;
@@ -1762,7 +1869,7 @@ static int slice_B(cg_ctx *ctx, const CgSlice *s, int what, int timed) {
     if (timed) { T1(CG_T_CHAIN); T0(CG_T_REWRITE); }
     if ((what & 2) && s->r1 > s->r0) {
         if (ctx->generic) k_rewrite_generic<<<nblk(s->r1 - s->r0, 128), 128, 0, st>>>(*D, s->r0, s->r1);
-        else k_rewrite<<<nblk(s->r1 - s->r0, RW_READS), RW_THREADS, 0, st>>>(*D, s->r0, s->r1);
+        else { cq_bind(ctx); k_rewrite<<<nblk(s->r1 - s->r0, RW_READS), RW_THREADS, 0, st>>>(*D, s->r0, s->r1, ctx->cq_blk_total); }
         ctx->launches++;
     }
     if (timed) T1(CG_T_REWRITE);
@@ -1788,7 +1895,7 @@ static int run_finish(cg_ctx *ctx, int timed) {
     }
     if (timed) T1(CG_T_EVENTS);
     T1(CG_T_TOTAL);
-    CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 40, cudaMemcpyDeviceToHost, st));
+    CG_CHECK(cudaMemcpyAsync(ctx->h_dims, scal, 96, cudaMemcpyDeviceToHost, st));
     CG_CHECK(cudaMemcpyAsync(ctx->h_counters, D->counters, sizeof(unsigned long long) * CG_N_COUNTERS, cudaMemcpyDeviceToHost, st));
     CG_CHECK(cudaStreamSynchronize(st));
     CG_CHECK(cudaGetLastError());
@@ -1819,6 +1926,7 @@ extern "C" int cg_run(cg_ctx *ctx) {
     int e;
     T0(CG_T_TOTAL);
     if ((e = run_prep(ctx, &B, hb))) return e;
+    ctx->cq_on = 0;                                            /* resident batch: flat output, fetched by cg_download */
     CgSlice sl; memset(&sl, 0, sizeof sl);
     sl.t1 = ctx->D.n_tiles; sl.c1 = ctx->D.n_cols; sl.r1 = ctx->D.n_reads; sl.je = ctx->D.n_pile;
     if ((e = slice_A(ctx, &sl, 1)) || (e = slice_B(ctx, &sl, 3, 1))) return e;
@@ -1829,7 +1937,8 @@ extern "C" int cg_run(cg_ctx *ctx) {
 static int download_results(cg_ctx *ctx, cg_result *out, int q_too) {
     cudaStream_t st = ctx->stream;
     if (q_too) T0(CG_T_D2H);
-    if (q_too && out->qual_out && ctx->qual_bytes) CG_CHECK(cudaMemcpyAsync(out->qual_out, ctx->b_qout.p, (size_t)ctx->qual_bytes, cudaMemcpyDeviceToHost, st));
+    /* after a compact download the flat device buffer was never written: the qualities are already in the caller's buffer */
+    if (q_too && !ctx->cq_on && out->qual_out && ctx->qual_bytes) CG_CHECK(cudaMemcpyAsync(out->qual_out, ctx->b_qout.p, (size_t)ctx->qual_bytes, cudaMemcpyDeviceToHost, st));
     out->n_events = ctx->h_dims[6];
     if (out->events && out->n_events) {
         int64_t k = out->n_events < out->events_cap ? out->n_events : out->events_cap;
@@ -1868,6 +1977,120 @@ extern "C" int cg_download(cg_ctx *ctx, cg_result *out) {
     return 0;
 }
 
+/* ---- compact download -------------------------------------------------------------------------------------------------------------
+ * After the rewrite most quality bytes of a batch are one value (-u, 40 by default).  k_rewrite can leave, instead of the flat strings, one
+ * bit per byte ("equals the dominant value") and the other bytes in position order; these cross PCIe (about a fifth of the flat bytes at
+ * -9) and a few host threads expand them into the caller's buffer while later slices are still running.  The mask of a slice can be
+ * copied as soon as its rewrite is queued; how many exception bytes it produced is known one host synchronisation later (the counter
+ * travels with n_flagged of the next slice), so the exception copy trails by one slice. */
+static int cq_grow_pinned(cg_ctx *ctx, void **p, size_t *cap, size_t want) {
+    if (want <= *cap) return 0;
+    if (*p) cudaFreeHost(*p);
+    *p = NULL; *cap = 0;
+    const size_t nc = want + (want >> 3) + 4096;
+    CG_CHECK(cudaHostAlloc(p, nc, cudaHostAllocDefault));
+    *cap = nc;
+    return 0;
+}
+static int cq_begin(cg_ctx *ctx, const cg_batch *in, cg_result *out) {
+    ctx->cq_on = 0; ctx->cq_n = 0; ctx->cq_done = 0; ctx->cq_blk_total = 0; ctx->cq_exc_copied = 0; ctx->cq_blk_copied = 0;
+    ctx->cq_ready = 0; ctx->cq_quit = 0; ctx->cq_in = in; ctx->cq_out = out;
+    /* opt-in (CG_COMPACT_D2H=1): expanding on the host costs about 36 ns of CPU per record; four threads need longer for chr20 than the flat
+     * copy needs on a PCIe 5 x16 link (measured: 126 ms against 48 ms end to end).  It pays on hosts with many idle cores or a narrower link. */
+    if (!in || !(out->qual_out || out->qual_head) || ctx->generic || in->qual_bytes == 0 || !getenv("CG_COMPACT_D2H")) return 0;
+    const size_t qb = (size_t)in->qual_bytes, nblocks = (size_t)in->n_reads / RW_READS + 2 * CG_MAX_CHUNKS + 8;
+    int e;
+    if ((e = ensure(ctx, &ctx->b_cqmask, qb / 8 + 64)) || (e = ensure(ctx, &ctx->b_cqexc, qb + 64)) || (e = ensure(ctx, &ctx->b_cqblk, nblocks * 8))) return e;
+    if ((e = cq_grow_pinned(ctx, (void **)&ctx->h_cqmask, &ctx->h_cqmask_cap, qb / 8 + 64)) || (e = cq_grow_pinned(ctx, (void **)&ctx->h_cqexc, &ctx->h_cqexc_cap, qb + 64)) ||
+        (e = cq_grow_pinned(ctx, (void **)&ctx->h_cqblk, &ctx->h_cqblk_cap, nblocks * 8))) return e;
+    while (ctx->cq_ev_made < 2 * CG_MAX_CHUNKS + 2) { CG_CHECK(cudaEventCreateWithFlags(&ctx->cq_ev[ctx->cq_ev_made], cudaEventDisableTiming)); ctx->cq_ev_made++; }
+    if (!ctx->cq_sync_made) { pthread_mutex_init(&ctx->cq_mu, NULL); pthread_cond_init(&ctx->cq_cv, NULL); ctx->cq_sync_made = 1; }
+    if (!in->packed) CG_CHECK(cudaMemsetAsync(ctx->b_cqmask.p, 0xff, qb / 8 + 64, ctx->stream));   /* a caller's own layout may have gaps between records */
+    ctx->cq_on = 1;
+    return 0;
+}
+/* device pointers of the compact planes into the kernel parameter block (before the rewrite of a slice is launched) */
+static void cq_bind(cg_ctx *ctx) {
+    CgDev *D = &ctx->D;
+    if (!ctx->cq_on) { D->cq_mask = NULL; return; }
+    D->cq_mask = (uint8_t *)ctx->b_cqmask.p; D->cq_exc = (uint8_t *)ctx->b_cqexc.p; D->cq_blk = (int64_t *)ctx->b_cqblk.p;
+    D->cq_count = (unsigned long long *)((int32_t *)ctx->b_scal.p + 22); D->cq_dom = ctx->params.qhigh & 0xff;
+}
+/* a slice's rewrite has been queued: its mask can go home now */
+static int cq_slice_queued(cg_ctx *ctx, const cg_batch *in, int64_t r0, int64_t r1, int chunk) {
+    if (!ctx->cq_on || r1 <= r0) return 0;
+    cg_ctx::CgCqSlice *c = &ctx->cq_sl[ctx->cq_n++];
+    c->r0 = r0; c->r1 = r1; c->blk0 = ctx->cq_blk_total; c->nblk = (r1 - r0 + RW_READS - 1) / RW_READS;
+    ctx->cq_blk_total += c->nblk;
+    const int64_t n = in->n_reads, b0 = in->off[r0] >> 3, b1 = (r1 < n ? in->off[r1] : in->qual_bytes) >> 3;
+    CG_CHECK(cudaEventRecord(ctx->ev_done[chunk], ctx->stream));
+    CG_CHECK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[chunk], 0));
+    if (b1 > b0) CG_CHECK(cudaMemcpyAsync(ctx->h_cqmask + b0, (char *)ctx->b_cqmask.p + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    return 0;
+}
+/* the host has just synchronised with the compute stream and h_dims[22..23] holds the exception count of everything rewritten so far:
+ * copy what is new (exceptions and block offsets of the slices queued so far) and hand those slices to the expansion threads */
+static int cq_count_known(cg_ctx *ctx, unsigned long long count) {
+    if (!ctx->cq_on || ctx->cq_done >= ctx->cq_n) return 0;
+    if (count > ctx->cq_exc_copied)
+        CG_CHECK(cudaMemcpyAsync(ctx->h_cqexc + ctx->cq_exc_copied, (char *)ctx->b_cqexc.p + ctx->cq_exc_copied, (size_t)(count - ctx->cq_exc_copied), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    ctx->cq_exc_copied = count;
+    if (ctx->cq_blk_total > ctx->cq_blk_copied)
+        CG_CHECK(cudaMemcpyAsync(ctx->h_cqblk + ctx->cq_blk_copied, (int64_t *)ctx->b_cqblk.p + ctx->cq_blk_copied, (size_t)(ctx->cq_blk_total - ctx->cq_blk_copied) * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    ctx->cq_blk_copied = ctx->cq_blk_total;
+    const int upto = ctx->cq_n;
+    CG_CHECK(cudaEventRecord(ctx->cq_ev[upto - 1], ctx->s_d2h));
+    pthread_mutex_lock(&ctx->cq_mu);
+    ctx->cq_done = upto; ctx->cq_ready = upto;
+    pthread_cond_broadcast(&ctx->cq_cv);
+    pthread_mutex_unlock(&ctx->cq_mu);
+    return 0;
+}
+/* one block of 128 records: memset the dominant value, drop the exceptions in */
+static void cq_expand_block(const cg_batch *in, const cg_result *out, int64_t ra, int64_t rb, const uint8_t *mask, const uint8_t *p, int dom) {
+    for (int64_t r = ra; r < rb; r++) {
+        const int L = in->l_qseq[r];
+        if (L <= 0) continue;
+        const int64_t o = in->off[r];
+        uint8_t *dst = (out->qual_head && o < out->head_bytes) ? out->qual_head + o : (out->qual_out ? out->qual_out + o : NULL);
+        const uint8_t *mk = mask + (o >> 3);
+        if (!dst) { for (int w = 0; 8 * w < L; w++) p += 8 - __builtin_popcount(mk[w]); continue; }
+        memset(dst, dom, (size_t)L);
+        for (int w = 0; 8 * w < L; w++) {
+            unsigned x = (~(unsigned)mk[w]) & 0xffu;
+            while (x) { const int k = __builtin_ctz(x); x &= x - 1; dst[8 * w + k] = *p++; }
+        }
+    }
+}
+struct CqWorker { cg_ctx *ctx; int t, nt; pthread_t th; };
+static void *cq_worker(void *v) {
+    CqWorker *W = (CqWorker *)v;
+    cg_ctx *ctx = W->ctx;
+    cudaSetDevice(ctx->device);
+    int next_ev = -1;                                           /* last event this thread has waited for */
+    for (int i = 0;; i++) {
+        pthread_mutex_lock(&ctx->cq_mu);
+        while (ctx->cq_ready <= i && !ctx->cq_quit) pthread_cond_wait(&ctx->cq_cv, &ctx->cq_mu);
+        const int ready = ctx->cq_ready;
+        pthread_mutex_unlock(&ctx->cq_mu);
+        if (ready <= i) break;                                  /* quit and nothing left */
+        if (next_ev < ready - 1) { cudaEventSynchronize(ctx->cq_ev[ready - 1]); next_ev = ready - 1; }
+        const cg_ctx::CgCqSlice *c = &ctx->cq_sl[i];
+        for (int64_t b = W->t; b < c->nblk; b += W->nt) {
+            const int64_t ra = c->r0 + b * RW_READS, rb = ra + RW_READS < c->r1 ? ra + RW_READS : c->r1;
+            cq_expand_block(ctx->cq_in, ctx->cq_out, ra, rb, ctx->h_cqmask, ctx->h_cqexc + ctx->h_cqblk[c->blk0 + b], ctx->params.qhigh & 0xff);
+        }
+    }
+    return NULL;
+}
+static int cq_threads(void) {
+    const char *e = getenv("CG_EXPAND_THREADS");
+    int t = e ? atoi(e) : 4;
+    const long nc = sysconf(_SC_NPROCESSORS_ONLN);
+    if (t > nc) t = (int)nc;
+    return t < 1 ? 1 : (t > 32 ? 32 : t);
+}
+
 /* the qualities of records [r0, r1) go home on the download stream once everything queued on the compute stream so far is done;
  * bytes below out->head_bytes (a region shard's read halo) go to out->qual_head instead of out->qual_out */
 static int enqueue_d2h(cg_ctx *ctx, const cg_batch *in, cg_result *out, int64_t r0, int64_t r1, int chunk) {
@@ -1894,9 +2117,16 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
     CG_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int e;
-    ctx->resident = 0; ctx->win_on = 0; ctx->n_sl = 0; ctx->shard_state = 0;
+    const int res_mode = in == NULL;                           /* a region shard on the batch cg_upload left on the device (timing the chain alone) */
+    if (res_mode && (!ctx->resident || phase != 1)) return CG_ERR_STATE;
+    ctx->win_on = 0; ctx->n_sl = 0; ctx->shard_state = 0;
     ctx->dump_columns = out->columns != NULL;
-    if ((e = alloc_inputs(ctx, in))) return e;
+    if (!res_mode) { ctx->resident = 0; if ((e = alloc_inputs(ctx, in))) return e; }
+    ctx->cq_on = 0;
+    if (!res_mode && (e = cq_begin(ctx, in, out))) return e;
+    CqWorker cqw[32]; int n_cqw = 0;
+#define CQ_STOP() do { if (n_cqw) { pthread_mutex_lock(&ctx->cq_mu); ctx->cq_quit = 1; pthread_cond_broadcast(&ctx->cq_cv); pthread_mutex_unlock(&ctx->cq_mu); \
+        for (int t_ = 0; t_ < n_cqw; t_++) pthread_join(cqw[t_].th, NULL); n_cqw = 0; } } while (0)
     if (win) {                                                 /* one call of a chain (cg_process_window) */
         if ((e = ensure(ctx, &ctx->b_saved, sizeof(CgSavedCarry)))) return e;
         ctx->win = *win; ctx->win_on = 1; ctx->depth_matters = 0;
@@ -1911,8 +2141,9 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
         CG_CHECK(cudaEventCreateWithFlags(&ctx->ev_misc, cudaEventDisableTiming));
     }
     /* chunk the records by quality bytes (about 96 MB per chunk, at most CG_MAX_CHUNKS) */
-    const int64_t n = in->n_reads;
-    int nch = (int)(in->qual_bytes / (ctx->chunk_bytes > 0 ? ctx->chunk_bytes : (96LL << 20))) + 1;
+    const int64_t n = res_mode ? ctx->D.n_reads : in->n_reads;
+    const int64_t qbytes = res_mode ? ctx->qual_bytes : in->qual_bytes;
+    int nch = res_mode ? 1 : (int)(qbytes / (ctx->chunk_bytes > 0 ? ctx->chunk_bytes : (96LL << 20))) + 1;
     if (nch > CG_MAX_CHUNKS) nch = CG_MAX_CHUNKS;
     if (n < nch) nch = n > 0 ? (int)n : 1;
     CgBounds B; memset(&B, 0, sizeof B); B.n = nch;
@@ -1924,23 +2155,23 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
              * byte has landed (last slice + its download) shrinks with the last chunk */
             const double wtot = nch >= 4 ? (nch - 2) + 0.75 : (double)nch;
             const double wacc = nch >= 4 ? (i + 1 <= nch - 2 ? (double)(i + 1) : (nch - 2) + 0.5) : (double)(i + 1);
-            const int64_t target = (int64_t)((double)in->qual_bytes * (wacc / wtot));
+            const int64_t target = (int64_t)((double)qbytes * (wacc / wtot));
             int64_t lo = i ? B.rb[i - 1] : 0, hi = n;
             while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (in->off[mid] < target) lo = mid + 1; else hi = mid; }
             r = lo;
         }
         B.rb[i] = r;
-        boff[i + 1] = r < n ? in->off[r] : in->qual_bytes;
+        boff[i + 1] = r < n ? in->off[r] : qbytes;
     }
     T0(CG_T_TOTAL);
     cudaEventRecord(ctx->ev[CG_T_H2D][0], st);
-    if ((e = upload_meta(ctx, in, st))) return e;
+    if (!res_mode && (e = upload_meta(ctx, in, st))) return e;
     /* the copy stream must not run ahead of buffer (re)allocation or of earlier users of the buffers: order it after st */
     CG_CHECK(cudaEventRecord(ctx->ev_misc, st));
     CG_CHECK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_misc, 0));
     CG_CHECK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_misc, 0));
     for (int i = 0; i < nch; i++) {
-        if ((e = upload_bases(ctx, in, boff[i], boff[i + 1], ctx->s_h2d))) return e;
+        if (!res_mode && (e = upload_bases(ctx, in, boff[i], boff[i + 1], ctx->s_h2d))) return e;
         CG_CHECK(cudaEventRecord(ctx->ev_up[i], ctx->s_h2d));
     }
     cudaEventRecord(ctx->ev[CG_T_H2D][1], ctx->s_h2d);
@@ -1963,6 +2194,11 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
             cS = ctx->h_dims[11];
         }
     }
+    if (ctx->cq_on && phase == 0) {                            /* the threads that expand the compact download into the caller's buffer */
+        n_cqw = cq_threads();
+        for (int t = 0; t < n_cqw; t++) { cqw[t].ctx = ctx; cqw[t].t = t; cqw[t].nt = n_cqw; if (pthread_create(&cqw[t].th, NULL, cq_worker, &cqw[t]) != 0) { n_cqw = t; break; } }
+        if (n_cqw == 0) ctx->cq_on = 0;                        /* no helper threads: flat download */
+    }
     int tprev = 0, jprev = 0; int64_t rprev = 0;
     if (phase == 0) cudaEventRecord(ctx->ev[CG_T_D2H][0], ctx->s_d2h);
     for (int i = 0; i < nch; i++) {
@@ -1973,7 +2209,7 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
         if (r1 < rprev) r1 = rprev;
         if (j1 < jprev) j1 = jprev;
         CG_CHECK(cudaStreamWaitEvent(st, ctx->ev_up[i], 0));
-        if ((e = expand_bases(ctx, in, boff[i], boff[i + 1], st))) { ctx->win_on = 0; return e; }
+        if (!res_mode && (e = expand_bases(ctx, in, boff[i], boff[i + 1], st))) { ctx->win_on = 0; CQ_STOP(); return e; }
         const int c0 = tprev * 32 < ctx->D.n_cols ? tprev * 32 : ctx->D.n_cols, c1 = t1 * 32 < ctx->D.n_cols ? t1 * 32 : ctx->D.n_cols;
         /* the slice(s) of this chunk: when the next call's first column cS lies inside, the sparse passes stop there, both carries are
          * saved, and a second slice (no tiles of its own) finishes the columns from cS on */
@@ -1987,18 +2223,22 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
             ns = 2; cS = -2;                                   /* saved (or about to be) */
         }
         for (int k = 0; k < ns; k++) {
-            if ((e = slice_A(ctx, &sl[k], 0))) { ctx->win_on = 0; return e; }
+            if ((e = slice_A(ctx, &sl[k], res_mode && k == 0))) { ctx->win_on = 0; CQ_STOP(); return e; }   /* stage timers on a resident batch: the slice that owns the tiles */
+            if (phase == 0 && sl[k].synced) {                    /* the exception count of the slices rewritten so far came over with this slice's n_flagged */
+                unsigned long long cnt; memcpy(&cnt, ctx->h_dims + 22, 8);
+                if ((e = cq_count_known(ctx, cnt))) { ctx->win_on = 0; CQ_STOP(); return e; }
+            }
             if (phase == 0) {
-                if ((e = slice_B(ctx, &sl[k], 3, 0))) { ctx->win_on = 0; return e; }
+                if ((e = slice_B(ctx, &sl[k], 3, 0))) { ctx->win_on = 0; CQ_STOP(); return e; }
                 if (sl[k].save_after) { k_carry_save<<<1, 32, 0, st>>>(ccarry, ecarry, (CgSavedCarry *)ctx->b_saved.p); ctx->launches++; }
             } else ctx->sl[ctx->n_sl++] = sl[k];
         }
-        if (phase == 0 && (e = enqueue_d2h(ctx, in, out, rprev, r1, i))) { ctx->win_on = 0; return e; }
+        if (phase == 0 && (e = ctx->cq_on ? cq_slice_queued(ctx, in, rprev, r1, i) : enqueue_d2h(ctx, in, out, rprev, r1, i))) { ctx->win_on = 0; CQ_STOP(); return e; }
         tprev = t1; rprev = r1; jprev = j1;
         CG_TRACE_AT("slice enqueued (host passed its column sync)", i);
     }
     if (phase != 0) {                                          /* a region shard: the rest follows in cg_shard_carry / cg_shard_end */
-        ctx->shard_in = in; ctx->shard_save_end = cS >= 0; ctx->shard_state = 1;
+        ctx->shard_in = in; ctx->shard_save_end = cS >= 0; ctx->shard_state = 1; ctx->shard_timed = res_mode;
         return 0;
     }
     cudaEventRecord(ctx->ev[CG_T_D2H][1], ctx->s_d2h);
@@ -2007,9 +2247,12 @@ static int process_streamed(cg_ctx *ctx, const cg_batch *in, cg_result *out, con
     if (win) ctx->have_saved = win->hi_tid >= 0 && (ctx->D.n_cols > 0 || (!win->first && ctx->have_saved));
     e = run_finish(ctx, 0);
     ctx->win_on = 0;
-    if (e) return e;
+    if (!e && ctx->cq_on) { unsigned long long cnt; memcpy(&cnt, ctx->h_dims + 22, 8); e = cq_count_known(ctx, cnt); }   /* run_finish has just synchronised */
+    if (e) { CQ_STOP(); return e; }
     CG_TRACE_AT("finish done", 0);
-    if ((e = download_results(ctx, out, 0))) return e;
+    if ((e = download_results(ctx, out, 0))) { CQ_STOP(); return e; }
+    CQ_STOP();
+    CG_TRACE_AT("compact download expanded", 0);
     CG_CHECK(cudaStreamSynchronize(ctx->s_d2h));
     CG_TRACE_AT("d2h drained", 0);
     CG_CHECK(cudaStreamSynchronize(ctx->s_h2d));
@@ -2078,7 +2321,14 @@ extern "C" int cg_shard_end(cg_ctx *ctx, cg_result *out) {
     CgChainCarry *ccarry = (CgChainCarry *)((char *)ctx->b_scal.p + 512);
     int e;
     ctx->shard_state = 0;
-    for (int k = ctx->shard_next; k < ctx->n_sl; k++) if ((e = slice_B(ctx, &ctx->sl[k], 1, 0))) { ctx->win_on = 0; return e; }
+    ctx->cq_out = out;
+    CqWorker cqw[32]; int n_cqw = 0;
+    if (ctx->cq_on && in) {
+        n_cqw = cq_threads();
+        for (int t = 0; t < n_cqw; t++) { cqw[t].ctx = ctx; cqw[t].t = t; cqw[t].nt = n_cqw; if (pthread_create(&cqw[t].th, NULL, cq_worker, &cqw[t]) != 0) { n_cqw = t; break; } }
+        if (n_cqw == 0) ctx->cq_on = 0;
+    } else ctx->cq_on = 0;
+    for (int k = ctx->shard_next; k < ctx->n_sl; k++) if ((e = slice_B(ctx, &ctx->sl[k], 1, 0))) { ctx->win_on = 0; CQ_STOP(); return e; }
     /* the keep window the shard on the left left open stays active from this shard's first column: the carry area now holds the state
      * after this shard's own triggers, so paint from the imported copy */
     if (!ctx->win.first && ctx->have_saved && ctx->D.n_cols > 0) {
@@ -2089,15 +2339,17 @@ extern "C" int cg_shard_end(cg_ctx *ctx, cg_result *out) {
     cudaEventRecord(ctx->ev[CG_T_D2H][0], ctx->s_d2h);
     for (int k = 0; k < ctx->n_sl; k++) {
         const CgSlice *s = &ctx->sl[k];
-        if ((e = slice_B(ctx, s, 2, 0))) { ctx->win_on = 0; return e; }
-        if (s->r1 > s->r0 && (e = enqueue_d2h(ctx, in, out, s->r0, s->r1, s->chunk))) { ctx->win_on = 0; return e; }
+        if ((e = slice_B(ctx, s, 2, ctx->shard_timed && k == ctx->n_sl - 1))) { ctx->win_on = 0; CQ_STOP(); return e; }   /* the last slice holds the rewrite */
+        if (in && s->r1 > s->r0 && (e = ctx->cq_on ? cq_slice_queued(ctx, in, s->r0, s->r1, s->chunk) : enqueue_d2h(ctx, in, out, s->r0, s->r1, s->chunk))) { ctx->win_on = 0; CQ_STOP(); return e; }
     }
     cudaEventRecord(ctx->ev[CG_T_D2H][1], ctx->s_d2h);
     ctx->have_saved = ctx->win.hi_tid >= 0 && (ctx->D.n_cols > 0 || (!ctx->win.first && ctx->have_saved));
-    e = run_finish(ctx, 0);
+    e = run_finish(ctx, ctx->shard_timed);
     ctx->win_on = 0;
-    if (e) return e;
-    if ((e = download_results(ctx, out, 0))) return e;
+    if (!e && ctx->cq_on) { unsigned long long cnt; memcpy(&cnt, ctx->h_dims + 22, 8); e = cq_count_known(ctx, cnt); }
+    if (e) { CQ_STOP(); return e; }
+    if ((e = download_results(ctx, out, 0))) { CQ_STOP(); return e; }
+    CQ_STOP();
     CG_CHECK(cudaStreamSynchronize(ctx->s_d2h));
     CG_CHECK(cudaStreamSynchronize(ctx->s_h2d));
     float ms = 0;

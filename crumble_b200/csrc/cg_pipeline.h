@@ -66,6 +66,7 @@ typedef struct CgDev {
     int32_t *pmaxcol;         /* dense inclusive prefix max of end columns */
     int32_t *orig;            /* compact index -> record index */
     uint8_t *r_bf;            /* read overlaps a trigger column: back-fill path in the rewrite */
+    int32_t *glist, *n_glist; /* pileup reads with a non-trivial CIGAR (any order), and how many */
     struct CgCellRec *crec;   /* cell matrix: row record per pileup read (cg_cells.h) */
     uint16_t *cells;          /* cell matrix: 16-bit pileup cells in groups of 8 */
     int64_t  K0;              /* key of the first pileup read */
@@ -84,6 +85,10 @@ typedef struct CgDev {
     int32_t *n_sitem;         /* how many */
     int64_t sitem_cap;
     unsigned long long *item_bound;   /* running upper bound of the searches the columns processed so far will ask for */
+    /* compact form of the rewritten qualities (k_rewrite, when cq_mask != NULL): one bit per quality byte, set where the byte equals the
+     * dominant value cq_dom (padding counts as equal); the other bytes ("exceptions") in position order, per block of 128 records at
+     * cq_exc[cq_blk[block]], blocks in whatever order they reserved their space */
+    uint8_t *cq_mask; uint8_t *cq_exc; int64_t *cq_blk; unsigned long long *cq_count; int32_t cq_dom;
     CgWin   *twin;            /* window state after each flagged column */
     /* scalars on the device */
     unsigned long long *counters;   /* CG_N_COUNTERS */

@@ -32,6 +32,8 @@ def params_from_args(args):
         elif k == "P": p.over_depth = float(v)
         elif k == "p": p.pblock = int(v)
         elif k == "L": p.reduce_qual = int(v)
+        elif k == "D": p.min_indel_B = int(v)
+        elif k == "X": p.min_discrep_B = float(v)
         else: raise ValueError(a)
     return p
 
@@ -41,7 +43,8 @@ _cache = {}
 
 def dataset(name):
     if name not in _cache:
-        preset, scale, seed = {"tiny": ("tiny", 1.0, 3), "c1s": ("C1", 0.25, 11), "c2s": ("C2", 1 / 128, 5), "c4s": ("C4", 0.05, 4)}[name]
+        preset, scale, seed = {"tiny": ("tiny", 1.0, 3), "c1s": ("C1", 0.25, 11), "c2s": ("C2", 1 / 128, 5), "c4s": ("C4", 0.05, 4),
+                               "c4m": ("C4", 0.15, 6)}[name]       # c4m: 30 amplicons, enough for STR triggers and indel spectra to fire at 1000x
         data, nr, nb = cb.simulate(preset, scale, seed)
         bb = cb.BatchBuilder()
         bb.add_bam_stream(data)
@@ -69,10 +72,21 @@ def test_tiny_all_levels(args):
     check("tiny", args)
 
 
-@pytest.mark.parametrize("name", ["c1s", "c2s", "c4s"])
+@pytest.mark.parametrize("name", ["c1s", "c2s", "c4s", "c4m"])
 @pytest.mark.parametrize("args", [["-9"], ["-1", "-B"], ["-5"]], ids=lambda a: "".join(a))
 def test_configs(name, args):
     check(name, args)
+
+
+@pytest.mark.parametrize("name,args", [("c4m", ["-9", "-D300"]), ("c4m", ["-1", "-D300", "-X0.2"]), ("c4s", ["-1", "-D300", "-Q300"])],
+                         ids=lambda v: "".join(v) if isinstance(v, list) else v)
+def test_str_triggers_at_depth(name, args):
+    """1000x amplicon columns never score below the default indel threshold, so the C4 workload alone runs no STR search at all: -D300 makes
+    every indel column a trigger (a thousand reads each), -Q300 at -1 preserves every column so that EVERY read of every column triggers
+    (str_snp && preserve, snp_score.c:1718): the item list, the list-free search and the window chain under the heaviest load the options
+    allow, against the oracle"""
+    check(name, args)
+    check(name, args, chunk_bytes=1 << 18)
 
 
 @pytest.mark.parametrize("name,chunk", [("tiny", 1 << 16), ("c1s", 1 << 20), ("c2s", 1 << 18), ("c4s", 1 << 17), ("c1s", 3 << 18)])
@@ -351,8 +365,11 @@ def test_gpu_region_shards_on_independent_contexts(name, n_shards, args):
     p = params_from_args(args)
     whole = cb.Crumble(p, device=0)
     ref = whole.process(batch)
+    orc = run_oracle(data, args)                                    # the shards are compared with the ORACLE, not only with the single call
     ctxs = [cb.Crumble(p, device=0) for _ in range(n_shards)]
     out = cb.run_region_shards(ctxs, batch, n_shards)
+    assert int((out["qual"][mask] != orc["qual"][mask]).sum()) == 0
+    assert cb.bed_text(out["events"], orc["names"]) == orc["bed"] and out["counters"] == orc["counters"]
     assert np.array_equal(out["qual"][mask], ref["qual"][mask])
     assert np.array_equal(out["events"], ref["events"])
     assert out["counters"] == ref["counters"]
@@ -495,3 +512,40 @@ def test_gpu_shard_phases_by_hand():
     assert int((qual[mask] != ref["qual"][mask]).sum()) == 0
     assert cb.bed_text(np.concatenate(evs), ref["names"]) == ref["bed"] and cnt == ref["counters"]
     for g in ctxs: g.close()
+
+
+@pytest.mark.parametrize("tag", ["plain", "t", "T", "efg", "EFGt", "all"])
+def test_gpu_cli_aux_tag_options(tag):
+    """-t / -T / -e..-G (purge_tags, snp_score.c:989-1054) through the crumble_gpu command line on the GPU: whole SAM output vs the
+    reference's, for reads with i, Z, A, f, H and B-array tags"""
+    from test_host import TAGS
+    cli = ROOT / "crumble_b200" / "lib" / "crumble_gpu"
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "o.sam")
+        r = subprocess.run([str(cli), "-z"] + TAGS[tag] + [str(GDIR / "tags.sam"), out], stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out).read() == open(GDIR / f"tags.{tag}.out.sam").read()
+
+
+def test_gpu_very_deep_columns():
+    """columns deeper than MAX_DEPTH = 20000 (snp_score.c:92, 1493-1500): VDEEP BED lines, counted but unprocessed columns; one call,
+    streamed in small chunks, chained through the command line, and over region shards"""
+    data, nr, nb = cb.simulate("C4", 0.01, seed=9, amplicon_depth=16000, n_amplicons=2, threads=2)
+    bb = cb.BatchBuilder(); bb.add_bam_stream(data); batch = bb.finish(pack=True); m = valid_mask(bb)
+    for args in (["-9"], ["-1"]):
+        ref = run_oracle(data, args)
+        assert ref["bed"].count("VDEEP") >= 50
+        g = cb.Crumble(params_from_args(args), device=0)
+        g.set_chunk_bytes(1 << 20)
+        out = g.process(batch)
+        assert int((out["qual"][m] != ref["qual"][m]).sum()) == 0
+        assert cb.bed_text(out["events"], ref["names"]) == ref["bed"] and out["counters"] == ref["counters"]
+        g.close()
+        mm = cb.MultiCrumble(params_from_args(args), devices=[0, 0, 0])
+        out = mm.process(batch)
+        assert int((out["qual"][m] != ref["qual"][m]).sum()) == 0
+        assert cb.bed_text(out["events"], ref["names"]) == ref["bed"] and out["counters"] == ref["counters"]
+        mm.close()
+        r = run_oracle(data, args, binary=ROOT / "crumble_b200" / "lib" / "crumble_gpu", kind="gpu-cli", env_extra={"CRUMBLE_BATCH_READS": "7000"})
+        assert (r["qual"][m] == ref["qual"][m]).all() and r["bed"] == ref["bed"] and r["counters"] == ref["counters"]
+    bb.close()
