@@ -369,28 +369,43 @@ def bench_shards(a, rank, world, local):
     barrier(); mbox.open(); barrier()
     seq = [0]
 
+    phase_s = [0.0, 0.0, 0.0, 0.0]                               # host wall clock per phase (CG_BENCH_PHASES=1 prints them): begin, wait, carry, end
+
     def step(resident):
         seq[0] += 1
+        t0 = time.perf_counter()
         g.shard_begin(None if resident else sub, win, pinned_out=None if resident else qout)
+        t1 = time.perf_counter()
         cin = mbox.recv(seq[0], rank - 1) if rank > 0 else None
+        t2 = time.perf_counter()
         cout = g.shard_carry(cin, want_out=rank < world - 1)
         if rank < world - 1:
             mbox.send(seq[0], cout)
-        return g.shard_end()
+        t3 = time.perf_counter()
+        r = g.shard_end()
+        t4 = time.perf_counter()
+        for i, d in enumerate((t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            phase_s[i] += d
+        return r
 
     def timed(resident, steps, warmup):
         for _ in range(warmup):
             step(resident)
         barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
+        ev0.record(stream)
         tm = {}
         for _ in range(steps):
             out = step(resident)
             if resident:
                 for k, v in g.timers().items():
                     tm[k] = tm.get(k, 0.0) + v / steps
+        ev1.record(stream)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if resident:                                             # device clock on the launching stream (idle gaps waiting for the left neighbour included)
+            dt = ev0.elapsed_time(ev1) * 1e-3
         barrier()
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -400,6 +415,10 @@ def bench_shards(a, rank, world, local):
     sampler = ClockSampler(local); sampler.start()
     dev_s, out_r, stage = timed(True, a.steps, a.warmup)
     clocks = sampler.stop()
+    if os.environ.get("CG_BENCH_PHASES"):
+        n_st = a.steps + a.warmup
+        sys.stderr.write(f"[phases] rank {rank}: begin {phase_s[0] / n_st * 1e3:.3f} wait {phase_s[1] / n_st * 1e3:.3f} carry {phase_s[2] / n_st * 1e3:.3f} "
+                         f"end {phase_s[3] / n_st * 1e3:.3f} ms per step; stages {({k: round(v, 3) for k, v in stage.items()})}\n")
     launches = g.launches() * a.steps
     e2e_s, out, _ = timed(False, a.e2e_steps, 1)
     h2d = g.h2d_bytes()

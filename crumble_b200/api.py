@@ -317,16 +317,22 @@ class Crumble:
         if want_columns:
             # first pass sizes the dump
             self._ncols_hint = 1
+        events_cap = max(events_cap, getattr(self, "_events_hint", 0))
         while True:
             res, qout, ev, cols = self._result(batch, want_columns, events_cap, pinned_out)
             _check(self.lib, self.lib.cg_process(self.h, C.byref(batch), C.byref(res)), self.h)
-            redo = False
-            if res.n_events > events_cap:
-                events_cap = int(res.n_events); redo = True
+            if res.n_events > events_cap:                  # the list is still on the device: fetch it again, do not run the call twice
+                events_cap = self._events_hint = int(res.n_events)
+                n_cols, cols_cap = int(res.n_columns), int(res.columns_cap)
+                res2, _, ev, _ = self._result(batch, False, events_cap, qout)
+                res2.qual_out = None                       # the qualities are already home
+                _check(self.lib, self.lib.cg_download(self.h, C.byref(res2)), self.h)
+                res2.n_columns, res2.columns_cap = n_cols, cols_cap
+                res = res2
             if want_columns and res.n_columns > res.columns_cap:
-                self._ncols_hint = int(res.n_columns); redo = True
-            if not redo:
-                break
+                self._ncols_hint = int(res.n_columns)
+                continue
+            break
         out = {
             "qual": qout[: int(batch.qual_bytes)],
             "events": ev[: int(res.n_events)],
@@ -459,6 +465,7 @@ class MultiCrumble:
         return int(self.lib.cgm_n_devices(self.h))
 
     def process(self, batch: Batch, events_cap: int = 1 << 16, pinned_out=None, window: Window | None = None):
+        events_cap = max(events_cap, getattr(self, "_events_hint", 0))
         while True:
             res = Result()
             qout = pinned_out if pinned_out is not None else np.empty(max(int(batch.qual_bytes), 1), dtype=np.uint8)
@@ -470,7 +477,7 @@ class MultiCrumble:
             if code != 0:
                 raise CrumbleError(f"{self.lib.cg_strerror(code).decode()} [{code}] {self.lib.cgm_last_error(self.h).decode()}")
             if res.n_events > events_cap and window is None:
-                events_cap = int(res.n_events); continue
+                events_cap = self._events_hint = int(res.n_events); continue
             break
         return {"qual": qout[: int(batch.qual_bytes)], "events": ev[: min(int(res.n_events), events_cap)], "n_events": int(res.n_events),
                 "counters": {k: int(res.counters[i]) for i, k in enumerate(COUNTER_NAMES)}}

@@ -566,6 +566,134 @@ CG_HD void cg_mask_lc_lean(const uint8_t *seq4, int l_qseq, int phantom, const u
     }
 }
 
+/* ---- mask_LC_regions, bit-parallel ------------------------------------------------------------------------------------------------
+ * The list-free form above still walks the window base by base, and on the device one thread does that per work item: the lanes of a
+ * warp sit at different bases of different reads, so the (rare, long) candidate handling of one lane stalls the other 31.  Here the
+ * per-base part becomes word arithmetic on the window held as 2-bit codes, 32 bases per 64-bit word, and the only loop left runs over
+ * the candidate positions themselves:
+ *   eq_p(x)  = base x equals base x - p                    (one XOR + fold per 32 bases and period)
+ *   R_p(i)   = eq_p holds at i, i-1, .., i-p+1             = the test of str_finder.c:140-186 for period p at position i
+ *   ext(i,p) = first x > i where eq_p fails or x = len     = the extension loop of add_rep (str_finder.c:49-74)
+ * add_rep's list is a stack sorted by start (a new entry drops exactly the entries on top that start at or after it), entries that
+ * start more than 15 bases back can no longer be dropped, so a 16-entry ring of (start, end) is enough; what leaves the ring at the
+ * bottom is final and folded into the answer straight away.  W: >= (len + 31) / 32 words (16 for the 501-base maximum), stride WS;
+ * ring: 16 words, stride RS. */
+#if defined(__CUDA_ARCH__)
+#define CG_CTZ64(x_) (__ffsll((long long)(x_)) - 1)
+#define CG_CTZ32(x_) (__ffs((int)(x_)) - 1)
+#define CG_MSB32(x_) (31 - __clz((int)(x_)))
+#else
+#define CG_CTZ64(x_) __builtin_ctzll(x_)
+#define CG_CTZ32(x_) __builtin_ctz(x_)
+#define CG_MSB32(x_) (31 - __builtin_clz(x_))
+#endif
+
+/* 16 consecutive bases of a packed 4-bit sequence from base index s on, as 2-bit codes of str_finder.c:15-32 (C 1, G 2, T 3, all else 0),
+ * base s + j at bits 2j..2j+1.  Bytes beyond last_byte are not touched (the caller overrides or ignores those bases). */
+CG_HD uint32_t cg_b2x16(const uint8_t *seq4, int s, int last_byte) {
+    const int b0 = s >> 1;
+    uint64_t n = 0;
+    for (int k = 0; k < 8; k++) { int idx = b0 + k; if (idx > last_byte) idx = last_byte; n |= (uint64_t)seq4[idx] << (8 * k); }
+    n = ((n & 0x0f0f0f0f0f0f0f0fULL) << 4) | ((n >> 4) & 0x0f0f0f0f0f0f0f0fULL);          /* nibble j = base 2 * b0 + j */
+    if (s & 1) { int idx = b0 + 8; if (idx > last_byte) idx = last_byte; n = (n >> 4) | ((uint64_t)(seq4[idx] >> 4) << 60); }
+    const uint64_t M1 = 0x1111111111111111ULL;
+    const uint64_t e0 = n & M1, e1 = (n >> 1) & M1, e2 = (n >> 2) & M1, e3 = (n >> 3) & M1;
+    const uint64_t is2 = e1 & ~(e0 | e2 | e3), is4 = e2 & ~(e0 | e1 | e3), is8 = e3 & ~(e0 | e1 | e2);
+    uint64_t x = (is2 | is8) | ((is4 | is8) << 1);                                         /* the code in the low 2 bits of every nibble */
+    x = (x | (x >> 2)) & 0x0f0f0f0f0f0f0f0fULL;
+    x = (x | (x >> 4)) & 0x00ff00ff00ff00ffULL;
+    x = (x | (x >> 8)) & 0x0000ffff0000ffffULL;
+    x = (x | (x >> 16)) & 0x00000000ffffffffULL;
+    return (uint32_t)x;
+}
+
+template <int WS, int RS>
+CG_HD void cg_mask_lc_bits(const uint8_t *seq4, int l_qseq, int phantom, const uint32_t *cig, int n_cigar,
+                           int read_pos, int rpos, int add, uint64_t *W, uint32_t *ring, int *lo, int *hi) {
+    int start = rpos - CG_MASK_WIN; if (start < 0) start = 0;
+    int end = rpos + CG_MASK_WIN;   if (end > l_qseq) end = l_qseq;
+    const int len = end - start + 1;
+    if (len <= 0 || l_qseq <= 0) return;
+    const int qlo = rpos - start - add, qhi = rpos - start + add;          /* Q in window coordinates */
+    int imax = qhi + 15; if (imax > len - 1) imax = len - 1;
+    const int nw = (len + 31) >> 5, last_byte = (l_qseq - 1) >> 1;
+    for (int c = 0; c < nw; c++)
+        W[c * WS] = (uint64_t)cg_b2x16(seq4, start + 32 * c, last_byte) | ((uint64_t)cg_b2x16(seq4, start + 32 * c + 16, last_byte) << 32);
+    if (end == l_qseq) {                                                   /* the window's last base is the one past the read */
+        const int x = len - 1;
+        W[(x >> 5) * WS] = (W[(x >> 5) * WS] & ~(3ULL << (2 * (x & 31)))) | ((uint64_t)cg_nt16_to_2bit(phantom) << (2 * (x & 31)));
+    }
+    const uint64_t M5 = 0x5555555555555555ULL;
+    int tail_s = INT_MAX, tail_e = -1, rlo = INT_MAX, rhi = -1;
+    int rb = 0, rn = 0;                                                    /* ring: bottom index, entries */
+#define CG_FOLD(e_) do { const int st_ = (int)((e_) >> 16), en_ = (int)((e_) & 0xffffu); \
+        if (qhi >= st_ && qlo <= en_) { if (rlo > st_) rlo = st_; if (rhi < en_) rhi = en_; } } while (0)
+    for (int b = 0; 16 * b <= imax; b++) {
+        /* V: the block's 16 bases in the upper half, the 16 before them in the lower half */
+        const uint64_t Wc = W[(b >> 1) * WS];
+        const uint64_t V = (b & 1) ? Wc : ((b ? (W[((b >> 1) - 1) * WS] >> 32) : 0ULL) | (Wc << 32));
+        uint32_t R[9];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int p = 1; p <= 8; p++) {
+            const uint64_t X = V ^ (V << (2 * p));
+            uint64_t eq = ~(X | (X >> 1)) & M5;
+            if (b == 0) eq &= ~0ULL << (2 * (16 + p));                     /* bases before the window have no partner */
+            uint64_t r = eq;
+            if (p >= 2) r &= r << 2;                                       /* runs of 2 */
+            if (p >= 4) r &= r << 4;                                       /* runs of 4 */
+            if (p == 3) r &= eq << 4;
+            if (p == 5) r &= eq << 8;
+            if (p == 6) r &= (eq & (eq << 2)) << 8;
+            if (p == 7) r &= r << 6;                                       /* 4 + 4 overlapping by one */
+            if (p == 8) r &= r << 8;
+            R[p] = (uint32_t)(r >> 32);
+        }
+        uint32_t U = R[1] | R[2] | R[3] | R[4] | R[5] | R[6] | R[7] | R[8];
+        const int nvalid = imax - 16 * b + 1;
+        if (nvalid < 16) U &= (1u << (2 * nvalid)) - 1u;
+        while (U) {
+            const int j2 = CG_CTZ32(U); U &= U - 1;
+            const int i = 16 * b + (j2 >> 1);
+            uint32_t m = 0;                                                /* periods matching at i */
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int p = 1; p <= 8; p++) m |= ((R[p] >> j2) & 1u) << p;
+            if (i >= 15) m = 1u << CG_MSB32(m);                            /* str_finder.c:164-186: the longest only */
+            while (m) {
+                const int p = CG_CTZ32(m); m &= m - 1;
+                const int ps = i + 1 - 2 * p;
+                if (tail_s <= ps && tail_e >= i) continue;                 /* str_finder.c:41-45 */
+                int x = i + 1, xe = len;                                   /* 49-74: first x where base x differs from base x - p */
+                for (int c = x >> 5; c < nw; c++) {
+                    const uint64_t A = W[c * WS], Bp = c ? W[(c - 1) * WS] : 0ULL;
+                    const uint64_t Y = A ^ ((A << (2 * p)) | (Bp >> (64 - 2 * p)));
+                    uint64_t ne = (Y | (Y >> 1)) & M5;
+                    if (c == (x >> 5)) ne &= ~0ULL << (2 * (x & 31));
+                    if (ne) { xe = 32 * c + (CG_CTZ64(ne) >> 1); break; }
+                }
+                if (xe > len) xe = len;
+                const int en = xe - 1;
+                while (rn > 0 && (int)(ring[((rb + rn - 1) & 15) * RS] >> 16) >= ps) rn--;   /* 106-122 */
+                if (rn == 16) { CG_FOLD(ring[rb * RS]); rb = (rb + 1) & 15; rn--; }
+                ring[((rb + rn) & 15) * RS] = ((uint32_t)ps << 16) | (uint32_t)en;
+                rn++;
+                tail_s = ps; tail_e = en;
+            }
+        }
+    }
+    for (int k = 0; k < rn; k++) CG_FOLD(ring[((rb + k) & 15) * RS]);
+#undef CG_FOLD
+    if (rhi >= 0) {
+        const int s = cg_qpos2rpos(cig, n_cigar, read_pos, rlo + start);
+        const int e = cg_qpos2rpos(cig, n_cigar, read_pos, rhi + start);
+        if (*lo > s) *lo = s;
+        if (*hi < e) *hi = e;
+    }
+}
+
 /* ---- keep-window chain (snp_score.c:1508-1511,1741-1755) --------------------------------
  * Per trigger column the device pre-reduces, independently of the incoming state:
  *   A/B   = min/max over pos and every triggered read's STR extents,

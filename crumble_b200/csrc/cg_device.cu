@@ -451,9 +451,10 @@ __global__ void __launch_bounds__(128) k_rewrite_generic(const __grid_constant__
  *               extents as seen by that read (PI/QI, PS/QS = min/max over the triggering reads up to it) and the
  *               column variable `indel`.  Every triggering read becomes one work item (flagged entry, read, query
  *               position, type) appended to the slice's item list; the list is unordered, its order does not matter.
- *  k_str_items  one THREAD per work item: mask_LC_regions + find_STR of one read at one column in the list-free form
- *               (cg_mask_lc_lean, cg_core.h: last entry + 16 live slots instead of the repeat list, scan cut at
- *               rpos + add + 15), all 32 lanes busy; extents are folded into the trigger record with atomics. */
+ *  k_str_items  one THREAD per work item: mask_LC_regions + find_STR of one read at one column in the bit-parallel form
+ *               (cg_mask_lc_bits, cg_core.h: the window as 2-bit codes in 64-bit words, period tests and extensions as word
+ *               arithmetic, a 16-entry ring instead of the repeat list, scan cut at rpos + add + 15); the only loop left runs over
+ *               candidate positions, so the lanes of a warp stay together; extents are folded into the trigger record with atomics. */
 #define FL_WARPS 4
 __global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant__ CgDev D, int k_begin, int k_end) {
     __shared__ int hist[FL_WARPS][104];
@@ -559,7 +560,8 @@ __global__ void __launch_bounds__(FL_WARPS * 32) k_flagged(const __grid_constant
 #define STR_THREADS 128
 #endif
 __global__ void __launch_bounds__(STR_THREADS) k_str_items(const __grid_constant__ CgDev D) {
-    __shared__ int16_t live[16 * STR_THREADS];                                 /* slot-major: lane-adjacent threads use adjacent half-words */
+    __shared__ uint64_t W[16 * STR_THREADS];                                   /* the read window as 2-bit codes; word-major: lane-adjacent threads use adjacent words */
+    __shared__ uint32_t ring[16 * STR_THREADS];                                /* live repeats (start, end) */
     const CgDevParams *P = &D.P;
     const int total = *D.n_sitem;
     for (int it = blockIdx.x * STR_THREADS + threadIdx.x; it < total; it += gridDim.x * STR_THREADS) {
@@ -570,8 +572,8 @@ __global__ void __launch_bounds__(STR_THREADS) k_str_items(const __grid_constant
         const int phantom = (q.l_qseq & 1) ? (D.seq[(CG_OFF(&q) >> 1) + (q.l_qseq >> 1)] & 0xf)
                                            : (cg_cap_qual(D.qual[CG_OFF(&q)], P, D.T) >> 4);
         int lo_r = pos, hi_r = pos;                                            /* 1732-1739: the two calls are identical in effect */
-        cg_mask_lc_lean<STR_THREADS>(D.seq + (CG_OFF(&q) >> 1), q.l_qseq, phantom, D.cigar + q.cig_off, q.n_cigar, q.pos,
-                                     im.rpos, im.is_indel ? P->iSTR_add : P->sSTR_add, live + threadIdx.x, &lo_r, &hi_r);
+        cg_mask_lc_bits<STR_THREADS, STR_THREADS>(D.seq + (CG_OFF(&q) >> 1), q.l_qseq, phantom, D.cigar + q.cig_off, q.n_cigar, q.pos,
+                                                  im.rpos, im.is_indel ? P->iSTR_add : P->sSTR_add, W + threadIdx.x, ring + threadIdx.x, &lo_r, &hi_r);
         if (lo_r < pos) { atomicMin(&tr->A, lo_r); if (j <= jI) atomicMin(&tr->PI, lo_r); if (j <= jS) atomicMin(&tr->PS, lo_r); }
         if (hi_r > pos) { atomicMax(&tr->B, hi_r); if (j <= jI) atomicMax(&tr->QI, hi_r); if (j <= jS) atomicMax(&tr->QS, hi_r); }
     }
@@ -745,8 +747,10 @@ __global__ void k_paint_carry(const __grid_constant__ CgDev D, const CgChainCarr
 }
 
 /* Per-read quality rewrite.  A block owns RW_READS consecutive records; their quality strings, packed sequences
- * and the column bytes under them are three CONTIGUOUS ranges, fetched with three bulk async copies (TMA,
- * cp.async.bulk + mbarrier) into shared memory.  Then
+ * and the column bytes under them are three CONTIGUOUS ranges.  The column bytes (read at arbitrary offsets) come in
+ * with one bulk async copy (TMA, cp.async.bulk + mbarrier) into shared memory; qualities and sequences are read
+ * word by word, in order, in phase A2, so they go from global memory straight to registers (one step ahead), and the
+ * rewritten words are collected in shared memory for the P-block pass and the bulk store.  Then
  *   phase A1 (thread per read):  whole-read facts from the staged column bytes (any keep_qual column, head column
  *            processed) and the word map: which read each staged 8-byte quality word belongs to;
  *   phase A2 (thread per WORD, all lanes busy whatever the read length): single-M reads without back-fill are
@@ -773,9 +777,8 @@ __global__ void k_paint_carry(const __grid_constant__ CgDev D, const CgChainCarr
 struct __align__(16) RwMeta { int32_t qoff, coff; uint32_t lk; int32_t j; };   /* offsets inside the staging buffers */
 struct __align__(128) RwSmem {
     uint8_t q[RW_QCAP + 32];
-    uint8_t s[RW_QCAP / 2 + 32];
     uint8_t c[RW_CCAP + 32];
-    uint8_t wmap[RW_QCAP / 8 + 8];      /* read slot of every staged quality word, 0xff = none */
+    uint8_t wmap[RW_QCAP / 8 + 8];      /* read slot of every staged quality word, 0xff = none, 0xfe = read on the general path */
     RwMeta  m[RW_READS];
     uint8_t glist[RW_READS];            /* slots taking the general path */
     uint8_t gorig[RW_THREADS / 32][RW_GORIG];   /* general path: the read's original qualities, one buffer per warp */
@@ -959,9 +962,7 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
             if (chi > clo) { ca = clo & ~15LL; cbn = ((chi + 15) & ~15LL) - ca; }
             if (qb > RW_QCAP + 16 || sb > RW_QCAP / 2 + 16 || cbn > RW_CCAP + 16) cbn = -1;
             else {
-                rw_mbar_expect(&S.bar, (uint32_t)(qb + sb + cbn));
-                rw_bulk_g2s(S.q, D.qual + qa, (uint32_t)qb, &S.bar);
-                rw_bulk_g2s(S.s, D.seq + sa, (uint32_t)sb, &S.bar);
+                rw_mbar_expect(&S.bar, (uint32_t)cbn);
                 if (cbn > 0) rw_bulk_g2s(S.c, D.cb + ca, (uint32_t)cbn, &S.bar);
             }
         }
@@ -969,7 +970,7 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
         S.red[0][0] = lo; S.red[0][1] = hi;
     }
     __syncthreads();
-    const long long qa = S.rng[0], qbytes = S.rng[1], sa = S.rng[2], ca = S.rng[4], cbytes = S.rng[5];
+    const long long qa = S.rng[0], qbytes = S.rng[1], ca = S.rng[4], cbytes = S.rng[5];
     if (qbytes == 0) { if (D.cq_mask && threadIdx.x == 0) D.cq_blk[blk_base + blockIdx.x] = 0; return; }   /* nothing but empty records */
     if (cbytes < 0) {                                          /* ranges too long for the staging buffers */
         const int64_t r = base + threadIdx.x;
@@ -1026,7 +1027,11 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
         if (kind == 1 || kind == 2) {
             const int w0 = qoff >> 3, nwr = (L + 7) >> 3;
             for (int i = 0; i < nwr; i++) S.wmap[w0 + i] = (uint8_t)threadIdx.x;
-        } else if (kind == 3) S.glist[atomicAdd(&S.n_general, 1)] = (uint8_t)threadIdx.x;
+        } else if (kind == 3) {
+            S.glist[atomicAdd(&S.n_general, 1)] = (uint8_t)threadIdx.x;
+            const int w0 = qoff >> 3, nwr = (L + 7) >> 3;
+            for (int i = 0; i < nwr; i++) S.wmap[w0 + i] = 0xfeu;              /* phase A2 leaves these words to phase A3 */
+        }
     }
     __syncthreads();
 
@@ -1037,18 +1042,22 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
     { int cq = P->qcutoff < 0 ? 0 : (P->qcutoff > 128 ? 128 : P->qcutoff); K.cut = (uint32_t)((128 - cq) & 0xff) * 0x01010101u; }
     K.capadd = P->qcap >= 127 ? 0u : (uint32_t)(127 - (P->qcap < 0 ? 0 : P->qcap)) * 0x01010101u;
     const bool swar_ok = !P->any_preserve_qual;
-    const int sdelta = (int)((qa >> 1) - sa);                  /* staged sequence byte of staged quality byte b: sdelta + b/2 */
+    const uint64_t *gq = reinterpret_cast<const uint64_t *>(D.qual + qa);      /* qa is a multiple of 16, and so is the buffer's base */
+    const uint32_t *gs = reinterpret_cast<const uint32_t *>(D.seq + (qa >> 1));
+    uint64_t q8n = 0; uint32_t s4n = 0;
+    if ((int)threadIdx.x < nwords) { q8n = __ldg(gq + threadIdx.x); s4n = __ldg(gs + threadIdx.x); }
     for (int wi = threadIdx.x; wi < nwords; wi += RW_THREADS) {
         const uint32_t slot = S.wmap[wi];
-        if (slot == 0xffu) continue;
+        const uint64_t q8 = q8n; const uint32_t s4 = s4n;
+        if (wi + RW_THREADS < nwords) { q8n = __ldg(gq + wi + RW_THREADS); s4n = __ldg(gs + wi + RW_THREADS); }   /* next step's words are in flight during this one */
+        if (slot == 0xfeu) continue;
+        if (slot == 0xffu) { *reinterpret_cast<uint64_t *>(S.q + wi * 8) = q8; continue; }   /* bytes of no record travel unchanged */
         const RwMeta m = S.m[slot];
         const int x0 = wi * 8 - m.qoff, nv = (int)(m.lk & RW_L_M) - x0;         /* nv >= 1 */
         const uint64_t vm = nv >= 8 ? ~0ULL : ((1ULL << (8 * nv)) - 1);
-        const uint64_t q8 = *reinterpret_cast<const uint64_t *>(S.q + wi * 8);
         uint64_t res;
         if (((m.lk >> RW_KIND_SH) & 3u) == 1u) res = q8 & 0x7f7f7f7f7f7f7f7fULL;  /* never in the pileup: strip bit 7 only (P-block follows) */
         else {
-            const uint32_t s4 = *reinterpret_cast<const uint32_t *>(S.s + sdelta + wi * 4);
             /* column bytes [coff + x0, +8): two aligned words, funnel-shifted */
             const int cpos = m.coff + x0;
             const uint2 *cw = reinterpret_cast<const uint2 *>(S.c + (cpos & ~7));
@@ -1087,14 +1096,14 @@ __global__ void __launch_bounds__(RW_THREADS) k_rewrite(const __grid_constant__ 
         const CgRead q = D.rd[m.j];
         const uint32_t *cig = D.cigar + q.cig_off;
         const uint8_t *qin = D.qual + (qa + m.qoff);
-        const uint8_t *ss = S.s + sdelta + (m.qoff >> 1);            /* staged sequence of this read (qoff is a multiple of 8) */
+        const uint8_t *ss = D.seq + ((qa + m.qoff) >> 1);            /* qoff is a multiple of 8 */
         if (Lr <= RW_GORIG) {
             __syncwarp();
-            for (int x = lane; x < Lr; x += 32) S.gorig[w][x] = sl[x];
+            for (int x = lane; x < ((Lr + 7) & ~7); x += 32) S.gorig[w][x] = qin[x];      /* with the padding of the last word */
             qin = S.gorig[w];
         }
         __syncwarp();
-        for (int x = lane; x < Lr; x += 32) sl[x] = qin[x] | init_or;
+        for (int x = lane; x < ((Lr + 7) & ~7); x += 32) sl[x] = x < Lr ? (uint8_t)(qin[x] | init_or) : qin[x];   /* the slot starts empty: padding travels unchanged */
         __syncwarp();
 #define RW_NIB(x_) ((ss[(x_) >> 1] >> ((~(x_) & 1) << 2)) & 0xf)
         int c = 0, y = 0;

@@ -34,7 +34,7 @@ typedef struct CgRead {       /* 32 bytes, one per pileup read (compacted, input
     uint16_t n_cigar;
     uint8_t  mapq;
     uint8_t  rf;
-} CgRead;
+} __attribute__((aligned(16))) CgRead;    /* two 16-byte loads / stores per record */
 #define CG_OFF(q) ((int64_t)(q)->off8 << 3)
 
 typedef struct CgStrItem { int32_t k, j, rpos, is_indel; } CgStrItem;   /* flagged entry, pileup read, 1-based query position (qpos + 1), trigger type */

@@ -1,4 +1,4 @@
-/* TEST INFRASTRUCTURE ONLY: cg_mask_lc_lean (the list-free form the device runs) against cg_mask_lc (find_STR + add_rep with the
+/* TEST INFRASTRUCTURE ONLY: cg_mask_lc_bits (the bit-parallel form the device runs) and cg_mask_lc_lean (list-free, base by base) against cg_mask_lc (find_STR + add_rep with the
  * full repeat list, itself pinned to the reference's str_finder.c by the golden vectors) on random and repeat-rich reads. */
 #include <stdio.h>
 #include <stdlib.h>
@@ -49,7 +49,17 @@ int main(int argc, char **argv) {
             if (L->overflow) continue;
             int16_t live[16];
             cg_mask_lc_lean<1>(seq4.data(), l, phantom, cig, nc, read_pos, rpos, add, live, &lo2, &hi2);
+            int lo3 = pos, hi3 = pos;
+            uint64_t W[16]; uint32_t ring[16];
+            cg_mask_lc_bits<1, 1>(seq4.data(), l, phantom, cig, nc, read_pos, rpos, add, W, ring, &lo3, &hi3);
             if (lo1 != pos || hi1 != pos) nonempty++;
+            if (lo1 != lo3 || hi1 != hi3) {
+                if (bad++ < 10) {
+                    fprintf(stderr, "MISMATCH(bits) l=%d rpos=%d add=%d list [%d,%d] bits [%d,%d]\n  ", l, rpos, add, lo1 - pos, hi1 - pos, lo3 - pos, hi3 - pos);
+                    for (int i = 0; i < l && i < 320; i++) fputc("ACGTN"[b[i]], stderr);
+                    fputc('\n', stderr);
+                }
+            }
             if (lo1 != lo2 || hi1 != hi2) {
                 if (bad++ < 10) {
                     fprintf(stderr, "MISMATCH l=%d rpos=%d add=%d list [%d,%d] lean [%d,%d]\n  ", l, rpos, add, lo1, hi1, lo2, hi2);

@@ -343,6 +343,19 @@ def test_gpu_chained_calls_event_buffer_regrow():
     assert r["bed"] == exp["bed"] and r["counters"] == exp["counters"]
 
 
+def test_gpu_small_event_buffer_is_refetched_not_rerun():
+    """More BED events than the caller's buffer holds: the list is fetched again from the device (cg_download), the call is not repeated."""
+    data, bb, batch, mask = dataset("tiny")
+    g = cb.Crumble(params_from_args(["-1"]), device=0)
+    ref = g.process(batch)
+    assert len(ref["events"]) > 1
+    g2 = cb.Crumble(params_from_args(["-1"]), device=0)
+    out = g2.process(batch, events_cap=1)
+    assert np.array_equal(out["events"], ref["events"]) and out["counters"] == ref["counters"]
+    assert np.array_equal(out["qual"][mask], ref["qual"][mask])
+    assert g2._events_hint == len(ref["events"])
+
+
 def test_gpu_chained_calls_options():
     g0 = GOLD["tiny"]
     data, nr, nb = cb.simulate(g0["preset"], g0["scale"], g0["seed"], threads=2)
