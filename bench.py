@@ -255,9 +255,14 @@ def bench_reference(a, rank, world):
 
 class Mailbox:
     """128-byte messages between the ranks of one box through a shared-memory file: the carry of a region shard travels to the rank on
-    its right.  No device collective is involved: NCCL is used for the barrier and the reductions of the results only."""
+    its right.  No device collective is involved: NCCL is used for the barrier and the reductions of the results only.
+    Every sender owns a ring of RING slots (message of step s in slot s % RING) and every receiver publishes the last step it has
+    consumed: a sender never overwrites a message its neighbour has not read yet, however far the ranks drift apart (rank 0 waits
+    for nobody's carry, so without this it can run whole steps ahead)."""
 
-    SLOT = 8 + 128
+    RING = 8
+    MSG = 8 + 128
+    SLOT = 8 + RING * MSG                                        # [consumed step of this rank as a receiver][RING x (step, payload)]
 
     def __init__(self, world, rank, key):
         self.path = f"/dev/shm/crumble_mbox_{key}"
@@ -268,19 +273,26 @@ class Mailbox:
     def open(self):
         self.m = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(self.world * self.SLOT,))
 
-    def _seq(self, r):
-        return self.m[r * self.SLOT: r * self.SLOT + 8].view(np.int64)
+    def _i64(self, byte_off):
+        return self.m[byte_off: byte_off + 8].view(np.int64)
 
     def send(self, step, blob):
-        r = self.rank
-        self.m[r * self.SLOT + 8: (r + 1) * self.SLOT] = np.frombuffer(blob, np.uint8)
-        self._seq(r)[0] = step                                   # x86: stores stay in program order
+        """to rank + 1; steps count from 1"""
+        ack = self._i64((self.rank + 1) * self.SLOT)
+        while int(ack[0]) < step - self.RING:                    # the slot still holds a message the neighbour has not consumed
+            pass
+        o = self.rank * self.SLOT + 8 + (step % self.RING) * self.MSG
+        self.m[o + 8: o + self.MSG] = np.frombuffer(blob, np.uint8)
+        self._i64(o)[0] = step                                   # x86: stores stay in program order
 
     def recv(self, step, src):
-        q = self._seq(src)
+        o = src * self.SLOT + 8 + (step % self.RING) * self.MSG
+        q = self._i64(o)
         while int(q[0]) != step:
             pass
-        return self.m[src * self.SLOT + 8: (src + 1) * self.SLOT].tobytes()
+        blob = self.m[o + 8: o + self.MSG].tobytes()
+        self._i64(self.rank * self.SLOT)[0] = step               # consumed
+        return blob
 
     def close(self):
         if self.rank == 0:

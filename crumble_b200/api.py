@@ -71,6 +71,13 @@ class Batch(C.Structure):
         ("qualp", C.POINTER(C.c_uint8)), ("qualp_bytes", C.c_int64),
         ("qual_bits", C.c_int32), ("qual_dict", C.c_uint8 * 16),
         ("pmax_end", C.POINTER(C.c_int32)),
+        ("meta_planes", C.c_int32),
+        ("tid_runs", C.POINTER(C.c_uint64)), ("n_tid_runs", C.c_int64),
+        ("pos_d8", C.POINTER(C.c_uint8)),
+        ("pos_abs", C.POINTER(C.c_uint64)), ("n_pos_abs", C.c_int64),
+        ("lq8", C.POINTER(C.c_uint8)), ("lq_dict", C.c_int32 * 256),
+        ("nc8", C.POINTER(C.c_uint8)),
+        ("cigar_x", C.POINTER(C.c_uint32)), ("n_cigar_x", C.c_int64),
     ]
 
 

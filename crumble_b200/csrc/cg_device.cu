@@ -145,6 +145,46 @@ struct LdPad8 { const int32_t *lq; __device__ int64_t operator()(int64_t i) cons
 struct LdNCig { const uint16_t *nc; __device__ int32_t operator()(int64_t i) const { return (int32_t)nc[i]; } };
 struct StExcl64 { int64_t *p; __device__ void operator()(int64_t i, int64_t, int64_t ex) const { p[i] = ex; } };
 struct StExcl32 { int32_t *p; __device__ void operator()(int64_t i, int32_t, int32_t ex) const { p[i] = ex; } };
+/* ---- compact planes of the per-record arrays (cg_batch.meta_planes, include/crumble_gpu.h) -> tid / pos / l_qseq / n_cigar / cigar ---- */
+struct LdD8 { const uint8_t *d; __device__ uint32_t operator()(int64_t i) const { const uint32_t v = d[i]; return v == 255u ? 0u : v; } };
+struct StInclU32 { uint32_t *p; __device__ void operator()(int64_t i, uint32_t inc, uint32_t) const { p[i] = inc; } };
+struct LdNcx { const uint8_t *nc8; __device__ int32_t operator()(int64_t i) const { const int v = nc8[i]; return v == 255 ? 0 : v; } };
+/* running sum of the position deltas at every listed record */
+__global__ void k_meta_gather(const uint64_t *__restrict__ pos_abs, int64_t n_abs, const uint32_t *__restrict__ S, uint32_t *__restrict__ absS) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_abs) absS[k] = S[pos_abs[k] >> 32];
+}
+/* last entry of a (record index << 32 | value) list whose index is <= i (entry 0 has index 0) */
+__device__ __forceinline__ int64_t meta_find(const uint64_t *__restrict__ list, int64_t n, int64_t i) {
+    int64_t lo = 0, hi = n;
+    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)(list[mid] >> 32) <= i) lo = mid; else hi = mid; }
+    return lo;
+}
+__global__ void __launch_bounds__(256) k_meta_expand(int64_t n, const uint64_t *__restrict__ tid_runs, int64_t n_runs, const uint64_t *__restrict__ pos_abs, int64_t n_abs,
+                                                    const uint32_t *__restrict__ absS, const uint8_t *__restrict__ lq8, const int32_t *__restrict__ lq_dict,
+                                                    const uint8_t *__restrict__ nc8, int32_t *tid, int32_t *pos /* in: running sums, out: positions */,
+                                                    int32_t *lq, uint16_t *nc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lq[i] = lq_dict[lq8[i]];
+    const int v = nc8[i];
+    nc[i] = (uint16_t)(v == 255 ? 1 : v);
+    tid[i] = (int32_t)(uint32_t)tid_runs[meta_find(tid_runs, n_runs, i)];
+    const int64_t k = meta_find(pos_abs, n_abs, i);
+    pos[i] = (int32_t)((uint32_t)pos_abs[k] + ((uint32_t)pos[i] - absS[k]));
+}
+__global__ void __launch_bounds__(256) k_meta_cigar(int64_t n, const uint8_t *__restrict__ nc8, const int32_t *__restrict__ lq, const int32_t *__restrict__ coff,
+                                                   const int32_t *__restrict__ xoff, const uint32_t *__restrict__ cigar_x, uint32_t *cigar,
+                                                   int64_t cigar_cap, int64_t n_cigar_x) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int v = nc8[i];
+    /* planes that do not add up stay inside the buffers here and are rejected by the totals check that follows */
+    if ((int64_t)coff[i] + (v == 255 ? 1 : v) > cigar_cap || (v != 255 && (int64_t)xoff[i] + v > n_cigar_x)) return;
+    if (v == 255) cigar[coff[i]] = (uint32_t)lq[i] << 4;                       /* one M of l_qseq bases */
+    else for (int k = 0; k < v; k++) cigar[coff[i] + k] = cigar_x[xoff[i] + k];
+}
+
 struct LdEvFlag { const uint16_t *ev; uint16_t mask; __device__ int32_t operator()(int64_t c) const { return (ev[c] & mask) != 0; } };
 struct StCompact { int32_t *out; const uint16_t *ev; uint16_t mask; __device__ void operator()(int64_t c, int32_t, int32_t ex) const { if (ev[c] & mask) out[ex] = (int32_t)c; } };
 struct LdDepthCounted { const uint32_t *depth; const uint16_t *ev; __device__ int64_t operator()(int64_t c) const { return (ev[c] & CG_EV_COUNTED) ? (int64_t)depth[c] : 0; } };
@@ -1286,6 +1326,8 @@ struct cg_ctx {
     dbuf b_jmap, b_rspan, b_rd, b_ks, b_ke, b_gap, b_gapraw, b_pmax, b_orig, b_rbf, b_glist;
     dbuf b_tlo, b_tstart, b_isl, b_cb, b_ev, b_depth, b_dump, b_dsum, b_csum, b_fcol, b_trig, b_twin;
     dbuf b_aggr, b_scal, b_scratch, b_epoch, b_events, b_chain, b_items, b_bed, b_bedpm, b_crec, b_cells, b_seq2, b_qualp, b_exc;
+    dbuf b_truns, b_pabs, b_pd8, b_lq8, b_nc8, b_cigx, b_lqd, b_xoff, b_absS;   /* compact planes of the per-record arrays and what their expansion needs */
+    int has_meta; int64_t n_truns, n_pabs, n_cigx;
     int generic;                  /* cg_params_generic(): column and rewrite stages through the plain bodies */
     /* host mirrors */
     int32_t *d_hdims;             /* device alias of h_dims (mapped pinned memory) */
@@ -1410,7 +1452,8 @@ extern "C" void cg_destroy(cg_ctx *ctx) {
     dbuf *all[] = { &ctx->b_tid, &ctx->b_pos, &ctx->b_flag, &ctx->b_mapq, &ctx->b_lq, &ctx->b_nc, &ctx->b_off, &ctx->b_coff, &ctx->b_cigar,
         &ctx->b_seq, &ctx->b_qual, &ctx->b_qout, &ctx->b_jmap, &ctx->b_rspan, &ctx->b_rd, &ctx->b_ks, &ctx->b_ke, &ctx->b_gap, &ctx->b_gapraw,
         &ctx->b_pmax, &ctx->b_orig, &ctx->b_rbf, &ctx->b_glist, &ctx->b_tlo, &ctx->b_tstart, &ctx->b_isl, &ctx->b_cb, &ctx->b_ev, &ctx->b_depth, &ctx->b_dump,
-        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain, &ctx->b_items, &ctx->b_bed, &ctx->b_bedpm, &ctx->b_saved, &ctx->b_crec, &ctx->b_cells, &ctx->b_seq2, &ctx->b_qualp, &ctx->b_exc, &ctx->b_cqmask, &ctx->b_cqexc, &ctx->b_cqblk };
+        &ctx->b_dsum, &ctx->b_csum, &ctx->b_fcol, &ctx->b_trig, &ctx->b_twin, &ctx->b_aggr, &ctx->b_scal, &ctx->b_scratch, &ctx->b_epoch, &ctx->b_events, &ctx->b_chain, &ctx->b_items, &ctx->b_bed, &ctx->b_bedpm, &ctx->b_saved, &ctx->b_crec, &ctx->b_cells, &ctx->b_seq2, &ctx->b_qualp, &ctx->b_exc, &ctx->b_cqmask, &ctx->b_cqexc, &ctx->b_cqblk,
+        &ctx->b_truns, &ctx->b_pabs, &ctx->b_pd8, &ctx->b_lq8, &ctx->b_nc8, &ctx->b_cigx, &ctx->b_lqd, &ctx->b_xoff, &ctx->b_absS };
     for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); i++) if (all[i]->p) cudaFree(all[i]->p);
     if (ctx->dT) cudaFree(ctx->dT);
     if (ctx->h_dims) cudaFreeHost(ctx->h_dims);
@@ -1486,6 +1529,15 @@ static int alloc_inputs(cg_ctx *ctx, const cg_batch *in) {
             (in->qual_bits && (e = ensure(ctx, &ctx->b_qualp, (size_t)in->qual_bytes * in->qual_bits / 8 + 64)))) return e;
         memcpy(ctx->dict.w, in->qual_dict, 16);
     }
+    ctx->has_meta = n > 0 && in->packed == 1 && in->meta_planes == 1 && in->tid_runs && in->pos_d8 && in->pos_abs && in->lq8 && in->nc8 &&
+                    in->n_tid_runs > 0 && in->n_pos_abs > 0 && in->n_cigar_x >= 0 && (in->n_cigar_x == 0 || in->cigar_x) && in->n_cigar_x <= in->n_cigar_total;
+    if (ctx->has_meta) {
+        if ((e = ensure(ctx, &ctx->b_truns, (size_t)in->n_tid_runs * 8)) || (e = ensure(ctx, &ctx->b_pabs, (size_t)in->n_pos_abs * 8)) ||
+            (e = ensure(ctx, &ctx->b_absS, (size_t)in->n_pos_abs * 4)) || (e = ensure(ctx, &ctx->b_pd8, n1)) || (e = ensure(ctx, &ctx->b_lq8, n1)) ||
+            (e = ensure(ctx, &ctx->b_nc8, n1)) || (e = ensure(ctx, &ctx->b_cigx, ((size_t)in->n_cigar_x + 1) * 4)) || (e = ensure(ctx, &ctx->b_lqd, 1024)) ||
+            (e = ensure(ctx, &ctx->b_xoff, n1 * 4))) return e;
+        ctx->n_truns = in->n_tid_runs; ctx->n_pabs = in->n_pos_abs; ctx->n_cigx = in->n_cigar_x;
+    }
     ctx->qual_bytes = in->qual_bytes; ctx->cigar_total = in->n_cigar_total;
     ctx->packed = in->packed == 1; ctx->offsets_ready = 0;
     ctx->h2d_bytes = 0;
@@ -1496,6 +1548,23 @@ static int alloc_inputs(cg_ctx *ctx, const cg_batch *in) {
 static int upload_meta(cg_ctx *ctx, const cg_batch *in, cudaStream_t st) {
     const int64_t n = in->n_reads;
     if (!n) return 0;
+    if (ctx->has_meta) {                                       /* about 6 bytes per record instead of 21; run_prep expands them */
+        CG_CHECK(cudaMemcpyAsync(ctx->b_truns.p, in->tid_runs, (size_t)in->n_tid_runs * 8, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_pabs.p, in->pos_abs, (size_t)in->n_pos_abs * 8, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_lqd.p, in->lq_dict, 1024, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_pd8.p, in->pos_d8, (size_t)n, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_lq8.p, in->lq8, (size_t)n, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_nc8.p, in->nc8, (size_t)n, cudaMemcpyHostToDevice, st));
+        if (in->n_cigar_x) CG_CHECK(cudaMemcpyAsync(ctx->b_cigx.p, in->cigar_x, (size_t)in->n_cigar_x * 4, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_flag.p, in->flag, (size_t)n * 2, cudaMemcpyHostToDevice, st));
+        CG_CHECK(cudaMemcpyAsync(ctx->b_mapq.p, in->mapq, (size_t)n, cudaMemcpyHostToDevice, st));
+        ctx->h2d_bytes += n * (1 + 1 + 1 + 2 + 1) + (in->n_tid_runs + in->n_pos_abs) * 8 + 1024 + in->n_cigar_x * 4;
+        if (ctx->has_planes && in->n_seq_exc) {
+            CG_CHECK(cudaMemcpyAsync(ctx->b_exc.p, in->seq_exc, (size_t)in->n_seq_exc * 8, cudaMemcpyHostToDevice, st));
+            ctx->h2d_bytes += in->n_seq_exc * 8;
+        }
+        return 0;
+    }
     CG_CHECK(cudaMemcpyAsync(ctx->b_tid.p, in->tid, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CG_CHECK(cudaMemcpyAsync(ctx->b_pos.p, in->pos, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CG_CHECK(cudaMemcpyAsync(ctx->b_flag.p, in->flag, (size_t)n * 2, cudaMemcpyHostToDevice, st));
@@ -1670,10 +1739,26 @@ static int run_prep(cg_ctx *ctx, const CgBounds *bounds, int64_t *h_bounds) {
         }
     }
     if (n > 0 && ctx->packed && !ctx->offsets_ready) {         /* once per uploaded batch: off = running sum of the padded lengths, cigar_off = running sum of n_cigar */
+        if (ctx->has_meta) {                                   /* the per-record arrays from their compact planes first */
+            LdD8 ld8 = { (const uint8_t *)ctx->b_pd8.p }; StInclU32 ss = { (uint32_t *)ctx->b_pos.p };
+            if ((e = run_scan<uint32_t, OpSum>(ctx, ld8, ss, n, 0u, (uint32_t *)NULL))) return e;
+            k_meta_gather<<<nblk(ctx->n_pabs, 256), 256, 0, st>>>((const uint64_t *)ctx->b_pabs.p, ctx->n_pabs, (const uint32_t *)ctx->b_pos.p, (uint32_t *)ctx->b_absS.p);
+            k_meta_expand<<<nblk(n, 256), 256, 0, st>>>(n, (const uint64_t *)ctx->b_truns.p, ctx->n_truns, (const uint64_t *)ctx->b_pabs.p, ctx->n_pabs,
+                (const uint32_t *)ctx->b_absS.p, (const uint8_t *)ctx->b_lq8.p, (const int32_t *)ctx->b_lqd.p, (const uint8_t *)ctx->b_nc8.p,
+                (int32_t *)ctx->b_tid.p, (int32_t *)ctx->b_pos.p, (int32_t *)ctx->b_lq.p, (uint16_t *)ctx->b_nc.p);
+            ctx->launches += 2;
+        }
         LdPad8 lp = { D->l_qseq }; StExcl64 so = { (int64_t *)ctx->b_off.p };
         if ((e = run_scan<int64_t, OpSum>(ctx, lp, so, n, (int64_t)0, (int64_t *)(scal + 12)))) return e;
         LdNCig ln = { D->n_cigar }; StExcl32 sc = { (int32_t *)ctx->b_coff.p };
         if ((e = run_scan<int32_t, OpSum>(ctx, ln, sc, n, 0, scal + 14))) return e;
+        if (ctx->has_meta) {
+            LdNcx lx = { (const uint8_t *)ctx->b_nc8.p }; StExcl32 sx = { (int32_t *)ctx->b_xoff.p };
+            if ((e = run_scan<int32_t, OpSum>(ctx, lx, sx, n, 0, (int32_t *)NULL))) return e;
+            k_meta_cigar<<<nblk(n, 256), 256, 0, st>>>(n, (const uint8_t *)ctx->b_nc8.p, D->l_qseq, (const int32_t *)ctx->b_coff.p, (const int32_t *)ctx->b_xoff.p,
+                (const uint32_t *)ctx->b_cigx.p, (uint32_t *)ctx->b_cigar.p, ctx->cigar_total, ctx->n_cigx);
+            ctx->launches++;
+        }
         ctx->offsets_ready = 1; check_packed = 1;
     }
     if (n > 0) {

@@ -160,6 +160,8 @@ struct cg_batch_builder {
     vec<uint32_t> cigar; vec<uint8_t> seq, qual;
     vec<uint8_t> seq2, qualp; vec<uint64_t> seq_exc;        /* compact planes (cgb_pack) */
     vec<int32_t> pmax;                                      /* running max of pos + span inside the contig */
+    vec<uint64_t> tid_runs, pos_abs; vec<uint8_t> pos_d8, lq8, nc8; vec<uint32_t> cigar_x;   /* compact planes of the per-record arrays (cgb_pack) */
+    int have_meta; int32_t lq_dict[256];
     int have_pack, qual_bits; uint8_t qual_dict[16];
     int64_t last_key; int unsorted; int seen_unplaced;
 };
@@ -172,6 +174,7 @@ extern "C" cg_batch_builder *cgb_create(int pinned) {
     b->tid.init(pin); b->pos.init(pin); b->l_qseq.init(pin); b->cigar_off.init(pin); b->flag.init(pin); b->n_cigar.init(pin);
     b->mapq.init(pin); b->off.init(pin); b->cigar.init(pin); b->seq.init(pin); b->qual.init(pin);
     b->seq2.init(pin); b->qualp.init(pin); b->seq_exc.init(pin); b->pmax.init(0);
+    b->tid_runs.init(pin); b->pos_abs.init(pin); b->pos_d8.init(pin); b->lq8.init(pin); b->nc8.init(pin); b->cigar_x.init(pin);
     b->last_key = INT64_MIN;
     return b;
 }
@@ -179,6 +182,7 @@ extern "C" void cgb_reset(cg_batch_builder *b) {
     b->tid.n = b->pos.n = b->l_qseq.n = b->cigar_off.n = b->flag.n = b->n_cigar.n = b->mapq.n = b->off.n = 0;
     b->cigar.n = b->seq.n = b->qual.n = 0;
     b->seq2.n = b->qualp.n = b->seq_exc.n = 0; b->have_pack = 0; b->qual_bits = 0; b->pmax.n = 0;
+    b->tid_runs.n = b->pos_abs.n = b->pos_d8.n = b->lq8.n = b->nc8.n = b->cigar_x.n = 0; b->have_meta = 0;
     b->last_key = INT64_MIN; b->unsorted = 0; b->seen_unplaced = 0;
 }
 extern "C" void cgb_destroy(cg_batch_builder *b) {
@@ -186,6 +190,7 @@ extern "C" void cgb_destroy(cg_batch_builder *b) {
     b->tid.release(); b->pos.release(); b->l_qseq.release(); b->cigar_off.release(); b->flag.release(); b->n_cigar.release();
     b->mapq.release(); b->off.release(); b->cigar.release(); b->seq.release(); b->qual.release();
     b->seq2.release(); b->qualp.release(); b->seq_exc.release(); b->pmax.release();
+    b->tid_runs.release(); b->pos_abs.release(); b->pos_d8.release(); b->lq8.release(); b->nc8.release(); b->cigar_x.release();
     free(b);
 }
 
@@ -193,7 +198,7 @@ extern "C" int cgb_add(cg_batch_builder *b, int32_t tid, int32_t pos, uint16_t f
                        uint32_t n_cigar, const uint32_t *cigar, const uint8_t *seq4, const uint8_t *qual) {
     size_t i = b->tid.n;
     if (n_cigar > 65535 || l_qseq < 0) return CG_ERR_BAD_ARG;
-    b->have_pack = 0;
+    b->have_pack = 0; b->have_meta = 0;
     if (b->tid.reserve(i + 1) || b->pos.reserve(i + 1) || b->l_qseq.reserve(i + 1) || b->cigar_off.reserve(i + 1) ||
         b->flag.reserve(i + 1) || b->n_cigar.reserve(i + 1) || b->mapq.reserve(i + 1) || b->off.reserve(i + 1)) return CG_ERR_NOMEM;
     /* quality bytes padded to 8 so that off is 8-aligned and seq sits at off/2 */
@@ -298,6 +303,13 @@ extern "C" int cgb_finish(cg_batch_builder *b, cg_batch *o) {
         o->qual_bits = b->qual_bits;
         if (b->qual_bits) { o->qualp = b->qualp.p; o->qualp_bytes = (int64_t)b->qualp.n; memcpy(o->qual_dict, b->qual_dict, 16); }
     }
+    if (b->have_meta) {
+        o->meta_planes = 1;
+        o->tid_runs = b->tid_runs.p; o->n_tid_runs = (int64_t)b->tid_runs.n;
+        o->pos_d8 = b->pos_d8.p; o->pos_abs = b->pos_abs.p; o->n_pos_abs = (int64_t)b->pos_abs.n;
+        o->lq8 = b->lq8.p; memcpy(o->lq_dict, b->lq_dict, sizeof b->lq_dict);
+        o->nc8 = b->nc8.p; o->cigar_x = b->cigar_x.p; o->n_cigar_x = (int64_t)b->cigar_x.n;
+    }
     return 0;
 }
 
@@ -365,9 +377,54 @@ static void *pack_worker(void *v) {
     return NULL;
 }
 
+/* compact planes of the per-record arrays (cg_batch.meta_planes); 0 = built, 1 = this batch does not qualify (the plain arrays travel) */
+static int pack_meta(cg_batch_builder *b) {
+    const size_t n = b->tid.n;
+    b->have_meta = 0;
+    b->tid_runs.n = b->pos_abs.n = b->cigar_x.n = 0;
+    if (n == 0 || n >= (1ULL << 31)) return 1;
+    if (b->pos_d8.reserve(n) || b->lq8.reserve(n) || b->nc8.reserve(n)) return CG_ERR_NOMEM;
+    int nd = 0; memset(b->lq_dict, 0, sizeof b->lq_dict);
+    int last_code = -1; int32_t last_lq = -1;
+    for (size_t i = 0; i < n; i++) {
+        const int32_t tid = b->tid.p[i], pos = b->pos.p[i], lq = b->l_qseq.p[i];
+        const uint32_t nc = b->n_cigar.p[i];
+        if (i == 0 || tid != b->tid.p[i - 1]) {
+            if (b->tid_runs.reserve(b->tid_runs.n + 1)) return CG_ERR_NOMEM;
+            b->tid_runs.p[b->tid_runs.n++] = ((uint64_t)i << 32) | (uint32_t)tid;
+        }
+        const int64_t d = i ? (int64_t)pos - b->pos.p[i - 1] : -1;
+        if (i == 0 || tid != b->tid.p[i - 1] || d < 0 || d > 254) {
+            if (b->pos_abs.reserve(b->pos_abs.n + 1)) return CG_ERR_NOMEM;
+            b->pos_abs.p[b->pos_abs.n++] = ((uint64_t)i << 32) | (uint32_t)pos;
+            b->pos_d8.p[i] = 255;
+        } else b->pos_d8.p[i] = (uint8_t)d;
+        if (lq != last_lq) {
+            int c = 0;
+            while (c < nd && b->lq_dict[c] != lq) c++;
+            if (c == nd) { if (nd == 256) return 1; b->lq_dict[nd++] = lq; }
+            last_code = c; last_lq = lq;
+        }
+        b->lq8.p[i] = (uint8_t)last_code;
+        if (nc > 254) return 1;
+        const uint32_t *cg = b->cigar.p + b->cigar_off.p[i];
+        if (nc == 1 && cg[0] == ((uint32_t)lq << 4)) b->nc8.p[i] = 255;                 /* one M of l_qseq bases: implied */
+        else {
+            b->nc8.p[i] = (uint8_t)nc;
+            if (b->cigar_x.reserve(b->cigar_x.n + nc + 1)) return CG_ERR_NOMEM;
+            memcpy(b->cigar_x.p + b->cigar_x.n, cg, 4u * (size_t)nc); b->cigar_x.n += nc;
+        }
+    }
+    if (b->pos_abs.n > n / 8 + 64 || b->tid_runs.n > n / 8 + 64) return 1;              /* not a coordinate-sorted stream: the per-record searches would cost more than the bytes saved */
+    b->pos_d8.n = b->lq8.n = b->nc8.n = n;
+    b->have_meta = 1;
+    return 0;
+}
+
 extern "C" int cgb_pack(cg_batch_builder *b, int threads) {
     const size_t n = b->tid.n;
     b->have_pack = 0; b->qual_bits = 0;
+    { const int me = pack_meta(b); if (me < 0) return me; }
     if (threads <= 0) threads = (int)sysconf(_SC_NPROCESSORS_ONLN);
     if (threads < 1) threads = 1;
     if (threads > 64) threads = 64;

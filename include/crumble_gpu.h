@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CG_ABI_VERSION 2
+#define CG_ABI_VERSION 3
 
 /* ---- error codes (negative; 0 = ok).  transcode_gpu() maps any of these to -1, the
  * value transcode() returns on failure (snp_score.c:1480-1481,1979-1980). ------------- */
@@ -111,6 +111,23 @@ typedef struct cg_batch {
     /* optional: running maximum of pos + reference span inside each contig (the batcher keeps it): lets cgm_process place region
      * shard cuts and halos by binary search instead of walking every CIGAR */
     const int32_t *pmax_end;
+    /* Optional COMPACT PLANES of the per-record arrays (cgb_pack builds them for a packed batch; meta_planes = 1 says they are all
+     * there).  The upload then moves about 6 bytes per record instead of 21 and the device rebuilds tid / pos / l_qseq / n_cigar /
+     * cigar from them, so the first slice of a streamed call starts (and its results start to travel back) that much earlier.
+     *   tid_runs  (first record index << 32 | (uint32_t)tid), one entry per run of equal tid, ascending;
+     *   pos_d8    pos - pos of the previous record, 0..254; 255: the record is listed in pos_abs (first of a contig, large gaps,
+     *             unsorted stretches): pos_abs[] = (record index << 32 | (uint32_t)pos), ascending;
+     *   lq8       l_qseq = lq_dict[lq8[i]] (at most 256 distinct read lengths);
+     *   nc8       n_cigar (0..254); 255: the CIGAR is one M operation of l_qseq bases and is not listed;
+     *   cigar_x   the CIGAR operations of the other records, back to back in record order.
+     * flag[] and mapq[] travel as they are. */
+    int32_t  meta_planes;
+    const uint64_t *tid_runs; int64_t n_tid_runs;
+    const uint8_t  *pos_d8;
+    const uint64_t *pos_abs;  int64_t n_pos_abs;
+    const uint8_t  *lq8;      int32_t lq_dict[256];
+    const uint8_t  *nc8;
+    const uint32_t *cigar_x;  int64_t n_cigar_x;
 } cg_batch;
 
 /* BED_DIST-expanded suspicious-region events (snp_score.c:1496-1498,1676-1678,

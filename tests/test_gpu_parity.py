@@ -438,6 +438,10 @@ def test_gpu_compact_planes(name, args, chunk):
     assert cb.bed_text(out["events"], ref["names"]) == ref["bed"] and out["counters"] == ref["counters"]
     g.process(batch0); up_plain = g.h2d_bytes()
     saved = int(batch.qual_bytes) // 4 + (int(batch.qual_bytes) * (8 - batch.qual_bits) // 8 if batch.qual_bits else 0) - 8 * int(batch.n_seq_exc)
+    assert batch.meta_planes == 1                                   # and the per-record arrays travel as compact planes too
+    n = int(batch.n_reads)
+    saved += n * (4 + 4 + 2 + 1 + 4 + 2) + 4 * int(batch.n_cigar_total) \
+        - (n * (1 + 1 + 1 + 2 + 1) + 8 * (int(batch.n_tid_runs) + int(batch.n_pos_abs)) + 1024 + 4 * int(batch.n_cigar_x))
     assert up_plain - up_packed == saved
     g.upload(batch); g.run(); res = g.download(batch)
     assert np.array_equal(res["qual"][mask], out["qual"][mask]) and res["counters"] == out["counters"]

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
     assert set(cb.EXPORTS) <= declared
-    assert lib.cg_abi_version() == 2
+    assert lib.cg_abi_version() == 3
 
 
 def test_no_device_fails_loudly():
@@ -244,6 +244,41 @@ def test_batcher_compact_planes_decode_back(preset, scale, bits):
     bb.close()
 
 
+@pytest.mark.parametrize("preset,scale", [("tiny", 1.0), ("C1", 0.2), ("C4", 0.1)])
+def test_batcher_record_planes_decode_back(preset, scale):
+    """cgb_pack: the compact planes of the per-record arrays (tid runs, position deltas + listed positions, read-length codes, CIGAR counts
+    with the implied single-M form, the remaining CIGAR operations) decode back to tid / pos / l_qseq / n_cigar / cigar."""
+    data, nr, nb = cb.simulate(preset, scale, seed=33, threads=2)
+    bb = cb.BatchBuilder(pinned=False)
+    bb.add_bam_stream(data)
+    b = bb.finish(pack=True, threads=2)
+    n = int(b.n_reads)
+    assert b.meta_planes == 1 and n > 0
+    A = lambda p, k: np.ctypeslib.as_array(p, shape=(int(k),))
+    tid, pos, lq, nc = A(b.tid, n), A(b.pos, n), A(b.l_qseq, n), A(b.n_cigar, n)
+    runs = A(b.tid_runs, b.n_tid_runs); idx = (runs >> np.uint64(32)).astype(np.int64); val = (runs & np.uint64(0xffffffff)).astype(np.uint32).astype(np.int32)
+    assert idx[0] == 0 and np.all(np.diff(idx) > 0)
+    assert np.array_equal(val[np.searchsorted(idx, np.arange(n), side="right") - 1], tid)
+    d8 = A(b.pos_d8, n).astype(np.int64); pa = A(b.pos_abs, b.n_pos_abs)
+    ai = (pa >> np.uint64(32)).astype(np.int64); av = (pa & np.uint64(0xffffffff)).astype(np.uint32).astype(np.int32).astype(np.int64)
+    assert ai[0] == 0 and np.all(np.diff(ai) > 0) and np.all(d8[ai] == 255) and int((d8 == 255).sum()) == ai.size
+    S = np.cumsum(np.where(d8 == 255, 0, d8))
+    k = np.searchsorted(ai, np.arange(n), side="right") - 1
+    assert np.array_equal(av[k] + (S - S[ai][k]), pos.astype(np.int64))
+    assert np.array_equal(np.array(list(b.lq_dict), np.int32)[A(b.lq8, n)], lq)
+    nc8 = A(b.nc8, n).astype(np.int64)
+    assert np.array_equal(np.where(nc8 == 255, 1, nc8), nc.astype(np.int64))
+    cig = A(b.cigar, b.n_cigar_total); coff = A(b.cigar_off, n).astype(np.int64)
+    cx = A(b.cigar_x, b.n_cigar_x) if b.n_cigar_x else np.zeros(0, np.uint32)
+    xoff = np.cumsum(np.where(nc8 == 255, 0, nc8)) - np.where(nc8 == 255, 0, nc8)
+    imp = nc8 == 255
+    assert np.array_equal(cig[coff[imp]], (lq[imp].astype(np.uint32) << np.uint32(4)))
+    for i in np.nonzero(~imp)[0][:2000]:
+        assert np.array_equal(cig[coff[i]: coff[i] + nc8[i]], cx[xoff[i]: xoff[i] + nc8[i]])
+    assert int(b.n_cigar_x) == int(np.where(imp, 0, nc8).sum())
+    bb.close()
+
+
 TAGS = {"plain": ["-9"], "t": ["-9", "-t", "NM,BD"], "T": ["-9", "-T", "MD,XX,ZB"], "efg": ["-9", "-e", "5", "-f", "20", "-g", "40"],
         "EFGt": ["-9", "-E", "7", "-F", "25", "-G", "45", "-t", "BI,BD,RG"], "all": ["-1", "-e", "1", "-f", "30", "-g", "2", "-E", "3", "-F", "10", "-G", "50", "-T", "BI"]}
 
@@ -259,3 +294,46 @@ def test_aux_tag_options_match_reference(tag):
         r = subprocess.run([str(EMU_BIN), "-z"] + TAGS[tag] + [str(GDIR / "tags.sam"), out], stderr=subprocess.PIPE, text=True)
         assert r.returncode == 0, r.stderr
         assert open(out).read() == open(GDIR / f"tags.{tag}.out.sam").read()
+
+
+def _mailbox_rank(world, rank, key, steps, out):
+    import random
+    import sys
+    import time
+    sys.path.insert(0, str(ROOT))
+    import bench
+    mb = bench.Mailbox(world, rank, key)
+    time.sleep(0.3 if rank else 0.0)                         # rank 0 creates the file
+    mb.open()
+    rnd = random.Random(rank)
+    acc = 0
+    for s in range(1, steps + 1):
+        if rank and rnd.random() < 0.05:
+            time.sleep(0.003 * rnd.random() * world)         # a slow step now and then: rank 0 (which waits for nobody) runs ahead
+        got = int.from_bytes(mb.recv(s, rank - 1)[:8], "little") if rank else 0
+        val = got + s * (rank + 1)
+        acc += val
+        if rank < world - 1:
+            mb.send(s, val.to_bytes(8, "little") + bytes(120))
+    out.put((rank, acc))
+
+
+def test_bench_mailbox_survives_drifting_ranks():
+    """bench.py's shared-memory mailbox (the carry of a region shard, rank to rank): ranks that drift several steps apart neither lose
+    nor overwrite a message (4 processes, 400 steps, random stalls)."""
+    import multiprocessing as mp
+    world, steps, key = 4, 400, f"test{os.getpid()}"
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_mailbox_rank, args=(world, r, key, steps, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=30)
+    try:
+        os.unlink(f"/dev/shm/crumble_mbox_{key}")
+    except OSError:
+        pass
+    exp = {r: sum(s * sum(k + 1 for k in range(r + 1)) for s in range(1, steps + 1)) for r in range(world)}
+    assert res == exp
