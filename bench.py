@@ -276,11 +276,22 @@ class Mailbox:
     def _i64(self, byte_off):
         return self.m[byte_off: byte_off + 8].view(np.int64)
 
+    def _wait(self, ready, what, timeout_s=300.0):
+        """spin (the carry is on the critical path of every step); a neighbour that died must not hang the job"""
+        n = 0
+        t0 = None
+        while not ready():
+            n += 1
+            if n & 0xfff == 0:
+                if t0 is None:
+                    t0 = time.perf_counter()
+                elif time.perf_counter() - t0 > timeout_s:
+                    raise RuntimeError(f"mailbox: rank {self.rank} waited more than {timeout_s:.0f} s for {what}")
+
     def send(self, step, blob):
         """to rank + 1; steps count from 1"""
         ack = self._i64((self.rank + 1) * self.SLOT)
-        while int(ack[0]) < step - self.RING:                    # the slot still holds a message the neighbour has not consumed
-            pass
+        self._wait(lambda: int(ack[0]) >= step - self.RING, f"rank {self.rank + 1} to consume step {step - self.RING}")   # the slot still holds an unread message
         o = self.rank * self.SLOT + 8 + (step % self.RING) * self.MSG
         self.m[o + 8: o + self.MSG] = np.frombuffer(blob, np.uint8)
         self._i64(o)[0] = step                                   # x86: stores stay in program order
@@ -288,8 +299,7 @@ class Mailbox:
     def recv(self, step, src):
         o = src * self.SLOT + 8 + (step % self.RING) * self.MSG
         q = self._i64(o)
-        while int(q[0]) != step:
-            pass
+        self._wait(lambda: int(q[0]) == step, f"the carry of step {step} from rank {src}")
         blob = self.m[o + 8: o + self.MSG].tobytes()
         self._i64(self.rank * self.SLOT)[0] = step               # consumed
         return blob
