@@ -461,6 +461,14 @@ CG_HDN uint32_t cg_flagged(const CgDev *D, int k, CgFlagScratch *S) {
                 cg_mask_lc(D->seq + (CG_OFF(&q) >> 1), q.l_qseq, phantom, D->cigar + q.cig_off, q.n_cigar, q.pos,
                            cell.qpos + 1, is_indel ? P->iSTR_add : P->sSTR_add, S->win, &S->reps, &lo_r, &hi_r);
                 if (S->reps.overflow) *D->err = CG_ERR_OVERFLOW;
+#ifdef CG_EMU_CROSSCHECK
+                {   /* host emulation only: the bit-parallel search the device runs (k_str_items) must give the same extents on every read the pipeline meets */
+                    uint64_t W_[16]; uint32_t ring_[16]; int lo_b = m_run, hi_b = M_run;
+                    cg_mask_lc_bits<1, 1>(D->seq + (CG_OFF(&q) >> 1), q.l_qseq, phantom, D->cigar + q.cig_off, q.n_cigar, q.pos,
+                                          cell.qpos + 1, is_indel ? P->iSTR_add : P->sSTR_add, W_, ring_, &lo_b, &hi_b);
+                    if (!S->reps.overflow && (lo_b != lo_r || hi_b != hi_r)) *D->err = CG_ERR_STATE;
+                }
+#endif
                 m_run = lo_r; M_run = hi_r;
             }
             if (is_indel) { tr.hasI = 1; tr.PI = m_run; tr.QI = M_run; }
