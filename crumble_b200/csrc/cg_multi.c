@@ -228,9 +228,16 @@ int cgm_process_window(cg_multi *m, const cg_batch *in, const cg_window *win, cg
             const int64_t iS = first_reaching(pmax, a, s->r1, X);
             /* pmax may carry an end from before `a`: the first record of [a, r1) that really reaches X */
             int64_t ii = iS; while (ii < s->r1 && rec_end(in, ii) <= X) ii++;
-            const int32_t S = ii < s->r1 ? in->pos[ii] : X;
+            int32_t S = ii < s->r1 ? in->pos[ii] : X;
+            /* a chained call whose first shards hold nothing but halo records: a cut below the first column this CALL owns (X < cnt_pos) must
+             * neither make the next shard count the columns in between again (the previous call of the chain counted them), nor start its
+             * replay below the call's own: the records that reach such a cut but start below lo_pos were finalised by the previous call, and
+             * the state this call received already contains every column below lo_pos */
+            const int chained_here = win && !win->first && t == win->lo_tid;
+            if (chained_here && S < win->lo_pos) S = win->lo_pos;
             w->hi_tid = t; w->hi_pos = X; w->next_lo_pos = S; s->has_right = 1;
             have_lo = 1; lo_tid = t; lo_S = S; lo_X = X;
+            if (chained_here && lo_X < win->cnt_pos) lo_X = win->cnt_pos;
         } else if (last && win && win->hi_tid >= 0) {
             w->hi_tid = win->hi_tid; w->hi_pos = win->hi_pos; w->next_lo_pos = win->next_lo_pos; s->has_right = 1;
         }

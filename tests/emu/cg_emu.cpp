@@ -17,9 +17,12 @@
 #include "../../crumble_b200/csrc/cg_column_lean.h"
 
 struct EmuCarry { CgWin w; int chain_tid; int64_t td, tc; int depth_tid; };
-struct cg_ctx { cg_params p; CgTables T; char err[256]; int64_t n_cols; std::vector<cg_bed_reg> bed; std::vector<int64_t> bed_pm; EmuCarry carry; std::vector<cg_bed_event> events; };
+struct cg_ctx { cg_params p; CgTables T; char err[256]; int64_t n_cols; std::vector<cg_bed_reg> bed; std::vector<int64_t> bed_pm; EmuCarry carry; std::vector<cg_bed_event> events;
+                const cg_batch *sh_in; cg_window sh_win; cg_result *sh_out; int sh_state; };
 
-extern "C" int cg_device_count(void) { return 0; }
+/* EMU_DEVICES=n makes the host driver (transcode_gpu.c with CRUMBLE_GPUS) and the scheduler (cg_multi.c) believe in n devices: every "device" is
+ * one emulated context, the scheduler's threads, cuts, halos, carries and gather run as they do on a box of GPUs */
+extern "C" int cg_device_count(void) { const char *e = getenv("EMU_DEVICES"); return e ? atoi(e) : 0; }
 extern "C" int cg_enable_pinned(void) { return 0; }
 extern "C" cg_ctx *cg_create(const cg_params *p, int device, int *err) {
     (void)device;
@@ -39,14 +42,6 @@ extern "C" int64_t cg_last_launches(const cg_ctx *) { return 0; }
 extern "C" int64_t cg_last_h2d_bytes(const cg_ctx *) { return 0; }
 extern "C" int64_t cg_n_columns(const cg_ctx *c) { return c->n_cols; }
 
-/* the multi-GPU scheduler is not emulated (cg_device_count() is 0 here, so the host driver never asks for it): link-time stubs */
-extern "C" cg_multi *cgm_create(const cg_params *, int, const int *, int *err) { if (err) *err = CG_ERR_NO_DEVICE; return NULL; }
-extern "C" void cgm_destroy(cg_multi *) {}
-extern "C" int cgm_process_window(cg_multi *, const cg_batch *, const cg_window *, cg_result *) { return CG_ERR_NO_DEVICE; }
-extern "C" const char *cgm_last_error(const cg_multi *) { return "not emulated"; }
-extern "C" float cgm_last_ms(const cg_multi *) { return 0; }
-extern "C" int64_t cgm_events(const cg_multi *, cg_bed_event *, int64_t) { return 0; }
-
 static int emu_process(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out);
 /* events of the last call again (the caller's buffer was too small); qualities are already in the caller's buffer */
 extern "C" int cg_download(cg_ctx *ctx, cg_result *out) {
@@ -55,6 +50,41 @@ extern "C" int cg_download(cg_ctx *ctx, cg_result *out) {
     return 0;
 }
 extern "C" int cg_process(cg_ctx *ctx, const cg_batch *in, cg_result *out) { return emu_process(ctx, in, NULL, out); }
+
+/* the three phases of a region shard (include/crumble_gpu.h).  The emulation is sequential, so everything runs in the middle phase, where the
+ * true state of the left neighbour is known; the protocol (call order, 128-byte state, halo bytes into the side buffer) is the device's */
+extern "C" int cg_shard_begin(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out) {
+    if (!in || !win) return CG_ERR_BAD_ARG;
+    ctx->sh_in = in; ctx->sh_win = *win; ctx->sh_out = out; ctx->sh_state = 1;
+    if (ctx->sh_win.first == 2) ctx->sh_win.first = 0;
+    return 0;
+}
+extern "C" int cg_shard_carry(cg_ctx *ctx, const void *carry_in, void *carry_out) {
+    static_assert(sizeof(EmuCarry) <= CG_CARRY_BYTES, "the emulated state must fit the carry blob");
+    if (ctx->sh_state != 1) return CG_ERR_STATE;
+    if (!ctx->sh_win.first && !carry_in) return CG_ERR_BAD_ARG;
+    if (carry_in && !ctx->sh_win.first) memcpy(&ctx->carry, carry_in, sizeof(EmuCarry));
+    cg_result *out = ctx->sh_out;
+    const int64_t qb = ctx->sh_in->qual_bytes;
+    std::vector<uint8_t> tmp((size_t)qb + 8);
+    cg_result r = *out; r.qual_out = tmp.data(); r.qual_head = NULL; r.head_bytes = 0;
+    int e = emu_process(ctx, ctx->sh_in, &ctx->sh_win, &r);
+    if (e) return e;
+    const int64_t hb = out->qual_head ? (out->head_bytes < qb ? out->head_bytes : qb) : 0;
+    if (hb > 0) memcpy(out->qual_head, tmp.data(), (size_t)hb);
+    if (out->qual_out && qb > hb) memcpy(out->qual_out + hb, tmp.data() + hb, (size_t)(qb - hb));
+    out->n_events = r.n_events; out->n_columns = r.n_columns;
+    memcpy(out->counters, r.counters, sizeof out->counters);
+    if (carry_out) { memset(carry_out, 0, CG_CARRY_BYTES); memcpy(carry_out, &ctx->carry, sizeof(EmuCarry)); }
+    ctx->sh_state = 2;
+    return 0;
+}
+extern "C" int cg_shard_end(cg_ctx *ctx, cg_result *out) {
+    (void)out;
+    if (ctx->sh_state != 2) return CG_ERR_STATE;
+    ctx->sh_state = 0;
+    return 0;
+}
 extern "C" int cg_process_window(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out) { return emu_process(ctx, in, win, out); }
 
 static int emu_process(cg_ctx *ctx, const cg_batch *in, const cg_window *win, cg_result *out) {

@@ -147,3 +147,31 @@ def test_emulated_pipeline_very_deep_columns():
         assert (r["qual"][m] == ref["qual"][m]).all() and r["bed"] == ref["bed"] and r["counters"] == ref["counters"]
         r = run_oracle(data, args, binary=EMU_BIN, kind="emu", env_extra={"CRUMBLE_BATCH_READS": "7000"})
         assert (r["qual"][m] == ref["qual"][m]).all() and r["bed"] == ref["bed"] and r["counters"] == ref["counters"]
+
+
+@pytest.mark.parametrize("name,n_dev,batch", [("tiny", 2, 0), ("tiny", 5, 700), ("tiny", 5, 350), ("tiny", 8, 150), ("c1s", 3, 6000), ("c1s", 8, 0), ("c2s", 4, 9000), ("c4s", 3, 2500)], ids=lambda v: str(v))
+def test_multi_device_scheduler_on_emulated_devices(name, n_dev, batch):
+    """crumble_b200/csrc/cg_multi.c (the scheduler that spreads one batch over the GPUs of a box) and the CRUMBLE_GPUS path of the host driver,
+    with emulated contexts standing in for the devices (EMU_DEVICES): region-shard cuts, read halos, the 128-byte state from shard to shard,
+    halo records that turn final in a later shard, event and counter gather - qualities, BED and counters must equal the golden vectors,
+    for one call per file (batch 0) and for a chain of calls each of which is spread over the devices."""
+    data = sim(name)
+    bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data); bb.finish()
+    m = valid_mask(bb)
+    env = {"EMU_DEVICES": "8", "CRUMBLE_GPUS": str(n_dev), "CRUMBLE_BATCH_READS": str(batch if batch else 1 << 30)}
+    for args in CHAIN_ARGS:
+        exp = GOLD[name]["runs"][args]
+        r = run_oracle(data, args.split(), binary=EMU_BIN, kind="emu", env_extra=env)
+        assert hashlib.sha256(r["qual"][m].tobytes()).hexdigest() == exp["qual_sha256"], args
+        assert r["bed"] == exp["bed"], args
+        assert r["counters"] == exp["counters"], args
+
+
+def test_multi_device_scheduler_edge_cases_on_emulated_devices():
+    """odd CIGARs, FUNMAP-placed and unplaced reads, two contigs: cuts between contigs separate independent pieces, cuts inside get a halo"""
+    for n_dev in (2, 3, 7):
+        for tag in ("l9", "l1B", "l5q30", "l3U35"):
+            quals, bed = run_cli_sam(EMU_BIN, EDGE[tag], GDIR / "edge_cases.sam", env_extra={"EMU_DEVICES": "8", "CRUMBLE_GPUS": str(n_dev)})
+            exp = [tuple(l.rstrip("\n").split("\t")) for l in open(GDIR / f"edge_cases.{tag}.qual.txt")]
+            assert quals == exp, (tag, n_dev)
+            assert bed == open(GDIR / f"edge_cases.{tag}.bed").read(), (tag, n_dev)
