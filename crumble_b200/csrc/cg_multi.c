@@ -25,6 +25,7 @@ typedef struct {
     int64_t h0, r0, r1;                     /* records [h0, r0) = halo, [r0, r1) = the shard's own */
     cg_batch sub; cg_window win; cg_result res;
     int64_t *off2; int32_t *coff2; uint64_t *exc2;
+    const cg_batch *parent; int64_t exc_first;  /* rebasing of the offset arrays and the exception list happens in the shard's own thread */
     uint8_t *head; int64_t head_bytes;
     int needs_left, has_right;
     int status;                             /* error code of this shard */
@@ -90,7 +91,7 @@ static int sub_batch(const cg_batch *in, int64_t i0, int64_t i1, cgm_shard *s) {
     s->off2 = (int64_t *)malloc(sizeof(int64_t) * (size_t)(cnt + 1));
     s->coff2 = (int32_t *)malloc(sizeof(int32_t) * (size_t)(cnt + 1));
     if (!s->off2 || !s->coff2) return CG_ERR_NOMEM;
-    for (int64_t i = 0; i < cnt; i++) { s->off2[i] = in->off[i0 + i] - q0; s->coff2[i] = (int32_t)(in->cigar_off[i0 + i] - c0); }
+    s->parent = in;                                          /* the arrays are filled by sub_batch_rebase in the shard's thread: two stores per record, all shards at once */
     b->n_reads = cnt;
     b->tid = in->tid + i0; b->pos = in->pos + i0; b->flag = in->flag + i0; b->mapq = in->mapq + i0; b->l_qseq = in->l_qseq + i0;
     b->n_cigar = in->n_cigar + i0; b->off = s->off2; b->cigar_off = s->coff2;
@@ -108,13 +109,22 @@ static int sub_batch(const cg_batch *in, int64_t i0, int64_t i1, cgm_shard *s) {
         if (e1 > e0) {
             s->exc2 = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(e1 - e0));
             if (!s->exc2) return CG_ERR_NOMEM;
-            for (int64_t i = e0; i < e1; i++) s->exc2[i - e0] = in->seq_exc[i] - ((uint64_t)q0 << 4);
+            s->exc_first = e0;
             b->seq_exc = s->exc2; b->n_seq_exc = e1 - e0;
         }
         b->qual_bits = in->qual_bits;
         if (in->qual_bits) { b->qualp = in->qualp + q0 * in->qual_bits / 8; b->qualp_bytes = (q1 - q0) * in->qual_bits / 8; memcpy(b->qual_dict, in->qual_dict, 16); }
     }
     return 0;
+}
+
+static void sub_batch_rebase(cgm_shard *s) {
+    const cg_batch *in = s->parent;
+    const int64_t i0 = s->h0, cnt = s->sub.n_reads, n = in->n_reads;
+    const int64_t q0 = i0 < n ? in->off[i0] : in->qual_bytes;
+    const int64_t c0 = i0 < n ? in->cigar_off[i0] : in->n_cigar_total;
+    for (int64_t i = 0; i < cnt; i++) { s->off2[i] = in->off[i0 + i] - q0; s->coff2[i] = (int32_t)(in->cigar_off[i0 + i] - c0); }
+    for (int64_t i = 0; i < s->sub.n_seq_exc; i++) s->exc2[i] = in->seq_exc[s->exc_first + i] - ((uint64_t)q0 << 4);
 }
 
 static void shard_free(cgm_shard *s) {
@@ -133,6 +143,7 @@ static void *shard_main(void *v) {
     cgm_shard *s = (cgm_shard *)v;
     cg_multi *m = s->m;
     cg_ctx *ctx = m->ctx[s->k];
+    sub_batch_rebase(s);
     int e = cg_shard_begin(ctx, &s->sub, &s->win, &s->res);
     const unsigned char *cin = NULL;
     if (!e && s->needs_left) {
