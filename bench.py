@@ -189,6 +189,30 @@ def cpu_baseline(cb, workload, sample_mb=12.0):
             "sample": f"{preset} x{scale:.4g} seed 4242: {nr} reads, {nb} aligned bases, transcode() {secs:.2f} s (memory-backed reader, discarding writer)"}
 
 
+def parity_gate(cb, g, workload):
+    """Part of the cpu_baseline leg: a small sample of the workload through the reference (oracle/_ref) AND through the context the bench
+    has just timed; every quality byte, the BED text and the 19 counters must be equal.  Never raises: the outcome is a string in the
+    bench line (the full-size comparison lives in tests/test_gpu_full_size.py)."""
+    try:
+        sys.path.insert(0, str(ROOT / "tests"))
+        from util import run_oracle, valid_mask
+        preset, args, _ = WORKLOADS[workload]
+        scale = {"C1": 0.5, "C2": 1 / 128, "C3": 1 / 128, "C4": 0.05}.get(preset, 1 / 128)
+        data, nr, nb = cb.simulate(preset, scale, seed=777)
+        bb = cb.BatchBuilder(pinned=False); bb.add_bam_stream(data)
+        batch = bb.finish(pack=True)
+        out = g.process(batch)
+        ref = run_oracle(data, args)
+        m = valid_mask(bb)
+        nbad = int((out["qual"][m] != ref["qual"][m]).sum())
+        ok = nbad == 0 and cb.bed_text(out["events"], ref["names"]) == ref["bed"] and out["counters"] == ref["counters"]
+        bb.close()
+        return (("bit-exact" if ok else f"MISMATCH ({nbad} quality bytes differ)") +
+                f" vs oracle ({ref['kind']}) on {preset} x{scale:.4g} seed 777: {nr} reads, every quality byte, BED text, 19 counters")
+    except Exception as e:  # noqa: BLE001
+        return f"not checked here ({type(e).__name__}: {e}); see tests/test_gpu_full_size.py"
+
+
 def reference_shards(preset, scale, nproc):
     """The workload cut into nproc independent pieces of equal size for the all-cores reference arm (how users parallelise crumble:
     one process per region).  The pieces together are the SAME amount and kind of data the GPU arm processes in one step."""
@@ -700,7 +724,8 @@ def main():
                        "stage_ms": {k: round(v, 4) for k, v in stage.items()}, "datagen_s": round(t_gen, 2)},
             "roofline": {"bound": "hbm", "kernel": "k_column", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic("k_column", a.workload, a.scale), "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": col, "peak_source": peak_src,
-                         "whole_chain_frac": algo_bytes / (dev_ms_max / a.steps * 1e-3) / 1e9 / peak},
+                         "whole_chain_frac": algo_bytes / (dev_ms_max / a.steps * 1e-3) / 1e9 / peak,
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": "aligned bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * float(te.item()) / a.e2e_steps, "h2d_ms": e2e_timers["h2d"], "d2h_ms": e2e_timers["d2h"],
                     "steps": a.e2e_steps, "host_binding": numa,
@@ -714,6 +739,7 @@ def main():
                 line["cpu_baseline"] = cpu_baseline(cb, a.workload)
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"error": str(e)}
+            line["config"]["parity"] = parity_gate(cb, g, a.workload)
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
