@@ -129,6 +129,15 @@ void cg_tables_init(CgTables *T, const cg_params *p) {
 void *(*cg_pinned_alloc_hook)(size_t) = NULL;
 void (*cg_pinned_free_hook)(void *) = NULL;
 
+extern "C" void *cg_host_alloc(size_t bytes) {
+    cg_enable_pinned();                                     /* installs the hooks when a device exists; they stay for the life of the process */
+    return cg_pinned_alloc_hook ? cg_pinned_alloc_hook(bytes) : malloc(bytes);
+}
+extern "C" void cg_host_free(void *p) {
+    if (!p) return;
+    if (cg_pinned_free_hook) cg_pinned_free_hook(p); else free(p);
+}
+
 template <class T> struct vec {
     T *p; size_t n, cap; int pinned;
     void init(int pin) { p = NULL; n = cap = 0; pinned = pin; }

@@ -152,9 +152,10 @@ static void write_bed(crumble_opts *o, bam_hdr_t *header, const cg_result *res) 
 }
 
 static int grow_result(cg_result *res, int64_t *qcap, int64_t qual_bytes) {
-    if (qual_bytes + 16 > *qcap) {
+    if (qual_bytes + 16 > *qcap) {                           /* page-locked: the download of a slice overlaps the kernels of the next (nothing to keep from the last call) */
         int64_t nc = qual_bytes + (qual_bytes >> 2) + 4096;
-        uint8_t *nq = (uint8_t *)realloc(res->qual_out, (size_t)nc);
+        cg_host_free(res->qual_out); res->qual_out = NULL; *qcap = 0;
+        uint8_t *nq = (uint8_t *)cg_host_alloc((size_t)nc);
         if (!nq) return -1;
         res->qual_out = nq; *qcap = nc;
     }
@@ -383,7 +384,7 @@ done:
     free(wc.v);
     if (nx) bam_destroy1(nx);
     lq_free(&lq);
-    free(res.qual_out); free(res.events);
+    cg_host_free(res.qual_out); free(res.events);
     if (ctx) cg_destroy(ctx);
     if (mg) cgm_destroy(mg);
     if (bb) cgb_destroy(bb);

@@ -270,6 +270,11 @@ int64_t cg_n_columns(const cg_ctx *ctx);                 /* covered reference co
 
 /* ---- host batcher: decoded records -> pinned SoA (replaces pileup_callback's bam_dup1
  * into RB-trees, snp_score.c:1113-1153) ------------------------------------------------ */
+/* Host memory for buffers that cross PCIe (cg_result.qual_out, batches laid out by the caller): page-locked when a device exists, so that
+ * cg_process can overlap its copies with the kernels; plain malloc otherwise.  Free with cg_host_free. */
+void *cg_host_alloc(size_t bytes);
+void  cg_host_free(void *p);
+
 typedef struct cg_batch_builder cg_batch_builder;
 cg_batch_builder *cgb_create(int pinned);
 void  cgb_destroy(cg_batch_builder *b);
